@@ -1,0 +1,115 @@
+"""ctypes binding of libclosestmol_b200.so (include/closestmol_b200.h).
+
+There is no CPU fallback: every compute entry point raises if the library is missing or the call
+fails.  torch tensors are only used as owners of device memory; the C ABI sees raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclosestmol_b200.so")
+
+_lib = None
+
+
+class CMError(RuntimeError):
+    pass
+
+
+class PQParamsC(C.Structure):
+    """struct cm_pq_params"""
+    _fields_ = [(n, C.c_double) for n in (
+        "D1", "D2", "inv_dt", "gcoef", "geps", "gs_thr", "gs_cond_scale", "gs_lin", "q_react",
+        "q_adv", "q_x2p", "q_x2q", "q_divr", "q_ibp", "supg_stab", "c0ip_gamma", "pen_stab2", "r2x",
+        "r2y")] + [(n, C.c_int32) for n in ("gkind", "degree", "c0ip_h", "reserved")]
+
+
+class ScalarParamsC(C.Structure):
+    """struct cm_scalar_params"""
+    _fields_ = [("D1", C.c_double), ("D2", C.c_double), ("gcoef", C.c_double),
+                ("degree", C.c_int32), ("reserved", C.c_int32)]
+
+
+class KrylovParamsC(C.Structure):
+    """struct cm_krylov_params"""
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int32),
+                ("restart", C.c_int32), ("method", C.c_int32), ("precond", C.c_int32),
+                ("check_every", C.c_int32), ("verbose", C.c_int32)]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_D = C.c_double
+
+_PROTOS = {
+    "cm_version": ([], C.c_int),
+    "cm_last_error": ([], C.c_char_p),
+    "cm_device_available": ([], C.c_int),
+    "cm_assemble_pq_cells": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I] + [_P] * 7 + [_I, _P], C.c_int),
+    "cm_assemble_scalar_cells": ([C.POINTER(ScalarParamsC), _I, _I] + [_P] * 6 + [_I] + [_P] * 4 + [_P], C.c_int),
+    "cm_assemble_load": ([_I, _I, _D, _I, _I, _I] + [_P] * 6 + [_P], C.c_int),
+    "cm_assemble_c0ip_facets": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 9 + [_P], C.c_int),
+    "cm_assemble_exterior_facets": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 11 + [_P], C.c_int),
+    "cm_apply_dirichlet": ([_I, _I] + [_P] * 7 + [_P], C.c_int),
+    "cm_spmv": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
+}
+
+
+def declared_symbols():
+    """Names of every function include/closestmol_b200.h declares (parsed from the header)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "closestmol_b200.h")
+    txt = open(hdr).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def lib():
+    """Load the shared library (building it is __graft_entry__.build()'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CMError(f"{LIB_PATH} is missing: run `python -m closestmolecule_b200.build` "
+                      "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (args, res) in _PROTOS.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def register(name, args, res=C.c_int):
+    _PROTOS[name] = (args, res)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.argtypes = args
+        fn.restype = res
+
+
+def check(rc):
+    if rc != 0:
+        raise CMError(f"closestmol_b200 error {rc}: {lib().cm_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t):
+    if not t.is_cuda:
+        raise CMError("closestmolecule_b200 computes on CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,115 @@
+// extern "C" entry points declared in include/closestmol_b200.h
+#include <stdarg.h>
+
+#include "cm_common.cuh"
+#include "cm_decl.cuh"
+
+namespace cm {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" {
+
+int cm_version(void) { return 100; }
+
+const char* cm_last_error(void) { return g_err; }
+
+int cm_device_available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n > 0 ? 1 : 0;
+}
+
+int cm_assemble_pq_cells(const cm_pq_params* prm, int32_t nv, int32_t ncells, const int32_t* cells,
+                         const double* coords, const int32_t* v2c_ptr, const int32_t* v2c_ent,
+                         const int32_t* v2c_slot, const int32_t* nrowptr, const int32_t* ncol,
+                         int32_t maxdeg, const double* u, const double* p_old, const double* load,
+                         const double* Kq, const double* cq, double* vals, double* b,
+                         int32_t accumulate, void* stream) {
+  CM_CHECK_ARG(prm && cells && coords && v2c_ptr && v2c_ent && v2c_slot && nrowptr && u && b,
+               "null pointer");
+  CM_CHECK_ARG(nv > 0 && ncells > 0, "empty mesh");
+  CM_CHECK_ARG(maxdeg > 0 && maxdeg <= 48, "row degree outside 1..48");
+  CM_CHECK_ARG(prm->inv_dt == 0.0 || p_old != nullptr, "transient form needs p_old");
+  CM_CHECK_ARG(Kq == nullptr || ncol != nullptr, "facet operator needs ncol");
+  return assemble_pq_rows(*prm, nv, cells, coords, v2c_ptr, v2c_ent, v2c_slot, nrowptr, ncol, u,
+                          p_old, load, Kq, cq, vals, b, accumulate, maxdeg, (cudaStream_t)stream);
+}
+
+int cm_assemble_scalar_cells(const cm_scalar_params* prm, int32_t nv, int32_t ncells,
+                             const int32_t* cells, const double* coords, const int32_t* v2c_ptr,
+                             const int32_t* v2c_ent, const int32_t* v2c_slot,
+                             const int32_t* nrowptr, int32_t maxdeg, const double* u,
+                             const double* load, double* vals, double* b, void* stream) {
+  CM_CHECK_ARG(prm && cells && coords && v2c_ptr && v2c_ent && v2c_slot && nrowptr && u && b,
+               "null pointer");
+  CM_CHECK_ARG(nv > 0 && ncells > 0, "empty mesh");
+  CM_CHECK_ARG(maxdeg > 0 && maxdeg <= 192, "row degree outside 1..192");
+  return assemble_scalar_rows(*prm, nv, cells, coords, v2c_ptr, v2c_ent, v2c_slot, nrowptr, u, load,
+                              vals, b, maxdeg, (cudaStream_t)stream);
+}
+
+int cm_assemble_load(int32_t ncomp, int32_t weighted, double supg_stab, int32_t degree, int32_t nv,
+                     int32_t ncells, const int32_t* cells, const double* coords,
+                     const int32_t* v2c_ptr, const int32_t* v2c_ent, const double* fq, double* load,
+                     void* stream) {
+  CM_CHECK_ARG(cells && coords && v2c_ptr && v2c_ent && fq && load, "null pointer");
+  CM_CHECK_ARG(ncomp == 1 || ncomp == 2, "ncomp must be 1 or 2");
+  CM_CHECK_ARG(nv > 0 && ncells > 0, "empty mesh");
+  return assemble_load(ncomp, weighted, supg_stab, degree, nv, cells, coords, v2c_ptr, v2c_ent, fq,
+                       load, (cudaStream_t)stream);
+}
+
+int cm_assemble_c0ip_facets(const cm_pq_params* prm, int32_t nv, int32_t nf, const int32_t* cells,
+                            const double* coords, const int32_t* fverts, const int32_t* fcell,
+                            const int32_t* v2f_ptr, const int32_t* v2f_ent, const int32_t* nrowptr,
+                            const int32_t* ncol, double* Kq, void* stream) {
+  CM_CHECK_ARG(prm && cells && coords && fverts && fcell && v2f_ptr && v2f_ent && nrowptr && ncol &&
+                   Kq, "null pointer");
+  (void)nf;
+  return assemble_c0ip(*prm, nv, cells, coords, fverts, fcell, v2f_ptr, v2f_ent, nrowptr, ncol, Kq,
+                       (cudaStream_t)stream);
+}
+
+int cm_assemble_exterior_facets(const cm_pq_params* prm, int32_t nv, int32_t nfe,
+                                const double* coords, const int32_t* efverts, const int32_t* efopp,
+                                const int32_t* efkind, const double* qdata, const int32_t* v2e_ptr,
+                                const int32_t* v2e_ent, const int32_t* nrowptr, const int32_t* ncol,
+                                double* Kq, double* cq, void* stream) {
+  CM_CHECK_ARG(prm && coords && efverts && efopp && efkind && v2e_ptr && v2e_ent && nrowptr &&
+                   ncol && Kq && cq, "null pointer");
+  (void)nfe;
+  return assemble_ext(*prm, nv, coords, efverts, efopp, efkind, qdata, v2e_ptr, v2e_ent, nrowptr,
+                      ncol, Kq, cq, (cudaStream_t)stream);
+}
+
+int cm_apply_dirichlet(int32_t bs, int32_t nrows, const int32_t* rows, const int32_t* diag_slot,
+                       const double* g, const double* x, const int32_t* nrowptr, double* vals,
+                       double* b, void* stream) {
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nrows >= 0, "negative row count");
+  if (nrows == 0) return CM_OK;
+  CM_CHECK_ARG(rows && diag_slot && g && x && nrowptr && b, "null pointer");
+  return apply_dirichlet(bs, nrows, rows, diag_slot, g, x, nrowptr, vals, b, (cudaStream_t)stream);
+}
+
+int cm_spmv(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol, const double* vals,
+            const double* x, double* y, void* stream) {
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nrowptr && ncol && vals && x && y, "null pointer");
+  CM_CHECK_ARG(x != y, "x and y must not alias");
+  return spmv(bs, nv, nrowptr, ncol, vals, x, y, 1.0, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

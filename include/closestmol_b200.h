@@ -1,0 +1,173 @@
+/*
+ * closestmol_b200.h -- C ABI of the B200-native closestMolecule FEM hot path.
+ *
+ * The reference (ruizbaier/closestMolecule) has no FFI layer of its own: its scripts program
+ * against the FEniCS 2019.1 Python API, and underneath that against the UFC/DOLFIN C++ interfaces
+ * (tabulate_tensor / GenericTensor::add_local / DirichletBC::apply / GenericLinearSolver::solve).
+ * Every entry point below names the reference call site (file:line under the reference checkout)
+ * whose FEniCS-side work it replaces.  All functions are batched over the whole mesh.
+ *
+ * Conventions
+ *   - every pointer is a CUDA DEVICE pointer owned by the caller unless the name ends in _host;
+ *     the library never allocates or frees caller memory; workspaces are caller-provided after a
+ *     *_workspace_bytes query;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant across
+ *     streams, no global mutable state;
+ *   - return value: 0 = ok, <0 = error (CM_E_*), message via cm_last_error() (thread-local);
+ *   - indices int32, values fp64.  Dof layout of the CG1xCG1 space: dof = 2*vertex + component
+ *     (DOLFIN with reorder_dofs_serial=False).  The P-Q Jacobian value array is laid out exactly
+ *     as the PETSc AIJ CSR DOLFIN produces: for node row v with sorted neighbours w_0<...<w_{d-1}
+ *     (node-level rowptr/col), scalar row 2v+c starts at 4*rowptr[v] + c*2*d and holds
+ *     (w_0,p),(w_0,q),(w_1,p),(w_1,q),...  -- so only the node-level index is ever stored.
+ */
+#ifndef CLOSESTMOL_B200_H
+#define CLOSESTMOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_OK 0
+#define CM_E_INVALID (-1)   /* bad argument */
+#define CM_E_CUDA (-2)      /* CUDA runtime error */
+#define CM_E_UNSUPPORTED (-3)
+#define CM_E_BREAKDOWN (-4) /* Krylov breakdown / NaN */
+
+/* nonlinearity kinds (cm_pq_params.gkind) */
+#define CM_G_NONE 0
+#define CM_G_POWER 1  /* gcoef*x^2*p^2/(q+geps): MixedPrimal_convergence.py:43-44, ..._C0IP.py:46-47 */
+#define CM_G_GSTAR 2  /* conditional Gstar: advection_diffusion_convergence.py:21-27,
+                         advection_diffusion_mixed.py:17-23 */
+
+/* exterior-facet kind bits (per facet) */
+#define CM_EF_ADV 1     /* + (r2vec.n) q w W ds            ..._C0IP.py:146 */
+#define CM_EF_DATA 2    /* + (r2vec.n) q_ex w W ds         test_for_paper_convergence.py:152 */
+#define CM_EF_PENALTY 4 /* + stab2 (hK neg(r2vec.n)^2 + 8/hK)(q-q_ex) w ds   ...:145,153 */
+
+/* Parameters of the P-Q primal form family (host struct, passed by pointer).
+ * p-equation: (p-p_old)*inv_dt*v1*W + D2*(dp/dx + G)*dv1/dx*W + D1*dp/dy*dv1/dy*W
+ *             (advection_diffusion_convergence.py:196-204)
+ * q-equation: [q_react*q + q_adv*dq/dx + x^2*(q_x2p*p + q_x2q*q) - q_divr*(2/x)*q]*(w + tau*dw/dx)*W
+ *             - q_ibp*q*dw/dx*W,   tau = supg_stab*hK/2
+ *             (Galerkin: ...:203; SUPG: ..._SUPG.py:118-129; C0IP cell terms: ..._C0IP.py:144-145)
+ * W = (4*pi*x*y)^2 (advection_diffusion_convergence.py:135), x = r2 = coordinate 0. */
+typedef struct cm_pq_params {
+  double D1, D2;
+  double inv_dt;
+  double gcoef, geps;
+  double gs_thr, gs_cond_scale, gs_lin;
+  double q_react, q_adv, q_x2p, q_x2q, q_divr, q_ibp;
+  double supg_stab;
+  double c0ip_gamma; /* sign*stab/(k_q)^3.5*beta, ..._C0IP.py:147 */
+  double pen_stab2;  /* test_for_paper_convergence.py:145 */
+  double r2x, r2y;   /* r2vec */
+  int32_t gkind;
+  int32_t degree;    /* quadrature degree: 2, 4 (6-point FIAT rule) or 6 (12-point) */
+  int32_t c0ip_h;    /* 0: avg(CellDiameter), 1: avg(FacetArea) */
+  int32_t reserved;
+} cm_pq_params;
+
+/* Parameters of the scalar P1 forms.
+ * F = u*v + D2*du/dx*dv/dx + D1*du/dy*dv/dy - (2*D2/x)*du/dx*v - (2*D1/y)*du/dy*v
+ *     + g(u)*dv/dx - (2/x)*g(u)*v,   g = gcoef*x^2*u^2
+ * (SphericalAdvectionDiffusionReaction_convergence.py:92-100; gcoef=0, D1=D2 gives
+ *  SphericalLaplace_convergence.py:128). */
+typedef struct cm_scalar_params {
+  double D1, D2, gcoef;
+  int32_t degree;
+  int32_t reserved;
+} cm_scalar_params;
+
+int cm_version(void);
+const char* cm_last_error(void);
+/* 1 if a CUDA device is usable, 0 otherwise (never launches work) */
+int cm_device_available(void);
+
+/* ---- a3/a5/a6(i): fused Jacobian+residual of the P-Q cell integrals, unstructured meshes --------
+ * Replaces DOLFIN Assembler::assemble_cells + FFC tabulate_tensor for FF and Tang, triggered by
+ * solver.solve() at advection_diffusion_convergence.py:207-219 (…MixedPrimal_convergence.py:132-140).
+ * Row-owner gather: one thread per vertex accumulates its incident cells in ascending cell order
+ * (DOLFIN's serial summation order), every CSR slot is written exactly once, no atomics.
+ *   v2c_ptr[nv+1], v2c_ent[3*ncells]: vertex -> incident cells, entry = 4*cell + local index
+ *   v2c_slot[3*ncells]: bytes (k0,k1,k2) = slots of (v, next, next-next cell vertex) in row v
+ *   nrowptr[nv+1]: node-level row pointer (cell-only or cell+interior-facet pattern)
+ *   ncol[nnz_node] node-level columns (only read when Kq is given), maxdeg = max row degree
+ *   u[2*nv] state, p_old[nv] or NULL, load[2*nv] or NULL (state-independent forcing, subtracted)
+ *   Kq[nnz_node], cq[nv] or NULL: constant facet operator of the C0IP q-equation (see below):
+ *   J_qq += Kq, F_q += Kq*q + cq, fused into the same pass
+ *   vals[4*nnz_node] or NULL (residual only), b[2*nv]
+ *   accumulate: 0 = overwrite vals/b, 1 = add to existing content (facet terms assembled before) */
+int cm_assemble_pq_cells(const cm_pq_params* prm_host, int32_t nv, int32_t ncells,
+                         const int32_t* cells, const double* coords, const int32_t* v2c_ptr,
+                         const int32_t* v2c_ent, const int32_t* v2c_slot, const int32_t* nrowptr,
+                         const int32_t* ncol, int32_t maxdeg, const double* u, const double* p_old,
+                         const double* load, const double* Kq, const double* cq, double* vals,
+                         double* b, int32_t accumulate, void* stream);
+
+/* ---- a3 on structured meshes (RectangleMesh numbering, create_flat_boundary.py:65; arbitrary
+ * vertex coordinates): same output, bit-identical layout, no connectivity or map is read: cells,
+ * neighbours and CSR slots are derived from (ix,iy).  Each cell's quadrature sums are computed
+ * once per CTA sweep and shared through shared memory; rows leave the SM as contiguous TMA bulk
+ * stores.  nrowptr must be the cell-only P1 pattern of the (nx,ny) mesh. */
+
+/* ---- a4: scalar P1 forms (F-A/F-B), Jacobian+residual, row-owner gather -------------------------
+ * Replaces assemble of FF/Tang at SphericalAdvectionDiffusionReaction_convergence.py:92-110 and of
+ * auv at SphericalLaplace_convergence.py:128-135.  vals[nnz_node] in node CSR order. */
+int cm_assemble_scalar_cells(const cm_scalar_params* prm_host, int32_t nv, int32_t ncells,
+                             const int32_t* cells, const double* coords, const int32_t* v2c_ptr,
+                             const int32_t* v2c_ent, const int32_t* v2c_slot,
+                             const int32_t* nrowptr, int32_t maxdeg, const double* u,
+                             const double* load, double* vals, double* b, void* stream);
+
+/* ---- a1/a12: state-independent load vector  load[i] = sum_cells int f*phi_i (*W) -----------------
+ * fq[ncells*nq*ncomp] holds the forcing at the quadrature points (cell-major, then point, then
+ * component).  ncomp=2 (P-Q: f2 against v1; f3 against w + tau*dw/dx), ncomp=1 scalar.
+ * Replaces the f2_ex/f3_ex terms of …MixedPrimal_convergence.py:126-128 (assembled once per mesh
+ * instead of once per residual evaluation). */
+int cm_assemble_load(int32_t ncomp, int32_t weighted, double supg_stab, int32_t degree, int32_t nv,
+                     int32_t ncells, const int32_t* cells, const double* coords,
+                     const int32_t* v2c_ptr, const int32_t* v2c_ent, const double* fq, double* load,
+                     void* stream);
+
+/* ---- a6(ii,iii): facet integrals of the C0IP q-equation -----------------------------------------
+ * State independent (the q-equation is linear): assembled into a constant operator Kq on the
+ * node-level (cell+interior-facet) pattern and a constant vector cq, so that
+ *   J_qq += Kq,  F_q += Kq*q + cq.
+ * Interior: c0ip_gamma*avg(hK)^2*(jump(grad q).n+)(jump(grad w).n+)*W dS (..._C0IP.py:147).
+ * Exterior: per-facet kind bits CM_EF_*; qdata[nfe*nqf] = q_ex at the facet Gauss points.
+ *   v2f_ptr[nv+1], v2f_ent[...]: vertex -> facets whose macro element contains the vertex
+ *   (ascending facet index); facet tables: fverts[nf*2], fcell[nf*2] (cell1=-1 on the boundary).
+ *   exterior-facet tables: efverts[nfe*2], efopp[nfe] (vertex of the attached cell opposite the
+ *   facet, orients the normal), efkind[nfe]; v2e_ptr/v2e_ent: vertex -> exterior facets (index
+ *   into those arrays) it is an end point of.  Kq and cq must be zeroed by the caller. */
+int cm_assemble_c0ip_facets(const cm_pq_params* prm_host, int32_t nv, int32_t nf,
+                            const int32_t* cells, const double* coords, const int32_t* fverts,
+                            const int32_t* fcell, const int32_t* v2f_ptr, const int32_t* v2f_ent,
+                            const int32_t* nrowptr, const int32_t* ncol, double* Kq, void* stream);
+int cm_assemble_exterior_facets(const cm_pq_params* prm_host, int32_t nv, int32_t nfe,
+                                const double* coords, const int32_t* efverts,
+                                const int32_t* efopp, const int32_t* efkind, const double* qdata,
+                                const int32_t* v2e_ptr, const int32_t* v2e_ent,
+                                const int32_t* nrowptr, const int32_t* ncol, double* Kq, double* cq,
+                                void* stream);
+
+/* ---- a8: DirichletBC::apply(A), apply(b,x) inside NewtonSolver [ext], triggered by bcs=bc at
+ * advection_diffusion_convergence.py:208.  bs = 1 (scalar) or 2 (P-Q).  rows are dof numbers
+ * (unique), g the prescribed values; diag_slot[nrows] = slot of the node in its own node row.
+ * A[row,:]=0, A[row,row]=1, b[row]=x[row]-g  (vals may be NULL: residual only). */
+int cm_apply_dirichlet(int32_t bs, int32_t nrows, const int32_t* rows, const int32_t* diag_slot,
+                       const double* g, const double* x, const int32_t* nrowptr, double* vals,
+                       double* b, void* stream);
+
+/* ---- a11: linear algebra for the Newton linear solve (replaces PETScLUSolver('mumps'|'umfpack'),
+ * advection_diffusion_convergence.py:212, …MixedPrimal_convergence.py:136) ---------------------- */
+/* y = A x for the interleaved P-Q layout (bs=2) or scalar node CSR (bs=1) */
+int cm_spmv(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol, const double* vals,
+            const double* x, double* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOSESTMOL_B200_H */
