@@ -12,3 +12,6 @@ from .space import (Constant, DirichletBC, FiniteElement, Function, FunctionSpac
 from .forms import EF_ADV, EF_DATA, EF_PENALTY, PQPrimalForm, ScalarADRForm
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+from .solver import (LinearVariationalSolver, NonlinearVariationalProblem,  # noqa: E402
+                     NonlinearVariationalSolver, solve)
+__all__ = [n for n in dir() if not n.startswith("_")]

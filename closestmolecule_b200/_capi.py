@@ -56,6 +56,13 @@ _PROTOS = {
     "cm_assemble_exterior_facets": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 11 + [_P], C.c_int),
     "cm_apply_dirichlet": ([_I, _I] + [_P] * 7 + [_P], C.c_int),
     "cm_spmv": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
+    "cm_pqs_workspace_bytes": ([_I, _I, _I], C.c_int64),
+    "cm_pqs_setup": ([_I, _I, _I, _P, _P, _P, _P, C.c_int64, _P], C.c_int),
+    "cm_pqs_solve": ([_I, _I, _I, _P, _P, _D, _D, _I, _P, C.c_int64, C.POINTER(C.c_int32),
+                      C.POINTER(C.c_double), _P], C.c_int),
+    "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
+    "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,
+                         C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
 }
 
 

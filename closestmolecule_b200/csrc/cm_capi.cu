@@ -112,4 +112,54 @@ int cm_spmv(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
   return spmv(bs, nv, nrowptr, ncol, vals, x, y, 1.0, nullptr, (cudaStream_t)stream);
 }
 
+int64_t cm_pqs_workspace_bytes(int32_t nx, int32_t ny, int32_t restart) {
+  if (nx < 2 || ny < 2 || restart < 1) return 0;
+  return (int64_t)pqs_workspace_bytes(nx, ny, restart);
+}
+
+int cm_pqs_setup(int32_t nx, int32_t ny, int32_t restart, const int32_t* nrowptr,
+                 const int32_t* ncol, const double* vals, void* workspace, int64_t workspace_bytes,
+                 void* stream) {
+  CM_CHECK_ARG(nx >= 2 && ny >= 2 && restart >= 1, "bad grid or restart");
+  CM_CHECK_ARG(nrowptr && ncol && vals && workspace, "null pointer");
+  return pqs_setup(nx, ny, restart, nrowptr, ncol, vals, workspace, (size_t)workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+int cm_pqs_solve(int32_t nx, int32_t ny, int32_t restart, const double* b, double* x, double rtol,
+                 double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
+                 int32_t* iters_host, double* resid_host, void* stream) {
+  CM_CHECK_ARG(nx >= 2 && ny >= 2 && restart >= 1 && maxit >= 1, "bad grid, restart or maxit");
+  CM_CHECK_ARG(b && x && workspace, "null pointer");
+  int it = 0;
+  double rr = 0.0;
+  const int rc = pqs_solve(nx, ny, restart, b, x, rtol, atol, maxit, workspace,
+                           (size_t)workspace_bytes, &it, &rr, (cudaStream_t)stream);
+  if (iters_host) *iters_host = it;
+  if (resid_host) *resid_host = rr;
+  return rc;
+}
+
+int64_t cm_krylov_workspace_bytes(int32_t bs, int32_t nv, int32_t restart) {
+  if ((bs != 1 && bs != 2) || nv < 1 || restart < 1) return 0;
+  return (int64_t)krylov_workspace_bytes(bs, nv, restart);
+}
+
+int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
+                    const int32_t* diag_slot, const double* vals, const double* b, double* x,
+                    double rtol, double atol, int32_t maxit, int32_t restart, void* workspace,
+                    int64_t workspace_bytes, int32_t* iters_host, double* resid_host, void* stream) {
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nv >= 1 && restart >= 1 && maxit >= 1, "bad size, restart or maxit");
+  CM_CHECK_ARG(nrowptr && ncol && diag_slot && vals && b && x && workspace, "null pointer");
+  int it = 0;
+  double rr = 0.0;
+  const int rc = krylov_solve(bs, nv, nrowptr, ncol, diag_slot, vals, b, x, rtol, atol, maxit,
+                              restart, workspace, (size_t)workspace_bytes, &it, &rr,
+                              (cudaStream_t)stream);
+  if (iters_host) *iters_host = it;
+  if (resid_host) *resid_host = rr;
+  return rc;
+}
+
 }  // extern "C"

@@ -33,3 +33,55 @@ namespace cm {
 int spmv(int bs, int nv, const int* nrowptr, const int* ncol, const double* vals, const double* x,
          double* y, double alpha, const double* z, cudaStream_t st);
 }  // namespace cm
+
+#include <functional>
+namespace cm {
+using LinOp = std::function<int(const double*, double*)>;
+
+// cm_vec.cu
+int multi_dot(long long n, const double* Vbase, long long vstride, int nvec, const double* w,
+              double* out, double* scratch, cudaStream_t st);
+int multi_axpy(long long n, const double* Vbase, long long vstride, int nvec, const double* h,
+               double sign, double* w, double* norm2_out, double* scratch, cudaStream_t st);
+int vec_scale(long long n, const double* x, const double* a_dev, double a_host, int invert,
+              double* y, cudaStream_t st);
+
+// cm_gmres.cu
+size_t gmres_workspace_doubles(long long n, int restart);
+int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x,
+                double rtol, double atol, int maxit, int restart, int reorth, double* work,
+                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st);
+
+// cm_stencil.cu
+int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
+                      double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
+                      int* err, cudaStream_t st);
+int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
+                   cudaStream_t st);
+int st_interleave(int nv, const double* xs, double* x, cudaStream_t st);
+int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
+               const double* QQ, const double* x, double* y, cudaStream_t st);
+int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
+                cudaStream_t st);
+int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st);
+int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st);
+int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st);
+int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
+                   cudaStream_t st);
+int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
+             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st);
+int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, int* err,
+                     cudaStream_t st);
+int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st);
+
+// cm_pqsolver.cu
+size_t pqs_workspace_bytes(int nx, int ny, int restart);
+int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
+              void* ws, size_t ws_bytes, cudaStream_t st);
+int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
+              int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
+size_t krylov_workspace_bytes(int bs, int nv, int restart);
+int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
+                 const double* vals, const double* b, double* x, double rtol, double atol, int maxit,
+                 int restart, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
+}  // namespace cm

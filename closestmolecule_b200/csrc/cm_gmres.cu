@@ -1,0 +1,163 @@
+// Restarted, right-preconditioned GMRES with classical Gram-Schmidt batched into one fused
+// multi-dot and one fused multi-axpy(+norm) kernel per iteration -> one host synchronisation per
+// iteration (the Hessenberg column).  The operator and the preconditioner are callbacks so the
+// same driver serves the generic CSR path and the structured field-split/multigrid path.
+// Replaces PETScLUSolver::solve inside NewtonSolver [ext] (advection_diffusion_convergence.py:212).
+#include <math.h>
+
+#include <vector>
+
+#include "cm_common.cuh"
+#include "cm_decl.cuh"
+
+namespace cm {
+
+size_t gmres_workspace_doubles(long long n, int restart) {
+  const long long ne = (n + 1) & ~1LL;  // even stride keeps double2 loads aligned
+  return (size_t)ne * (restart + 1)     // Krylov basis
+         + (size_t)ne * 2               // w, z
+         + (size_t)(restart + 4)        // h on the device
+         + (size_t)148 * 4 * 8 + 64;    // reduction scratch
+}
+
+int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x,
+                double rtol, double atol, int maxit, int restart, int reorth, double* work,
+                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st) {
+  const long long ne = (n + 1) & ~1LL;
+  double* V = work;
+  double* w = V + (size_t)ne * (restart + 1);
+  double* z = w + ne;
+  double* hdev = z + ne;
+  double* scratch = hdev + (restart + 4);
+  scratch = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+
+  double* hhost = nullptr;  // pinned staging for the Hessenberg column / coefficients
+  CM_CUDA(cudaMallocHost((void**)&hhost, sizeof(double) * (restart + 4)));
+  struct Guard {
+    double* p;
+    ~Guard() { cudaFreeHost(p); }
+  } guard{hhost};
+
+  const int m = restart;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m);
+  auto Hat = [&](int i, int j) -> double& { return H[(size_t)j * (m + 1) + i]; };
+
+  // x0 = 0: r0 = b
+  CM_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+  CM_CUDA(cudaMemcpyAsync(w, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  int rc = multi_dot(n, w, ne, 1, w, hdev, scratch, st);
+  if (rc) return rc;
+  CM_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CM_CUDA(cudaStreamSynchronize(st));
+  const double bnorm = sqrt(hhost[0]);
+  if (bnorm_out) *bnorm_out = bnorm;
+  const double target = fmax(rtol * bnorm, atol);
+  double beta = bnorm, resid = bnorm;
+  int its = 0;
+  bool converged = !(bnorm > target);
+  if (!isfinite(bnorm)) {
+    set_error("gmres: right-hand side norm is not finite");
+    return CM_E_BREAKDOWN;
+  }
+
+  while (!converged && its < maxit) {
+    // V0 = r / beta  (r is in w)
+    rc = vec_scale(n, w, nullptr, beta, 1, V, st);
+    if (rc) return rc;
+    for (int i = 0; i <= m; ++i) g[i] = 0.0;
+    g[0] = beta;
+    int j = 0;
+    for (; j < m && its < maxit; ++j) {
+      double* vj = V + (size_t)ne * j;
+      rc = Minv(vj, z);
+      if (rc) return rc;
+      rc = A(z, w);
+      if (rc) return rc;
+      rc = multi_dot(n, V, ne, j + 1, w, hdev, scratch, st);
+      if (rc) return rc;
+      rc = multi_axpy(n, V, ne, j + 1, hdev, -1.0, w, hdev + (j + 1), scratch, st);
+      if (rc) return rc;
+      CM_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
+      CM_CUDA(cudaStreamSynchronize(st));
+      for (int i = 0; i <= j; ++i) Hat(i, j) = hhost[i];
+      if (reorth) {  // second classical Gram-Schmidt pass ("twice is enough")
+        rc = multi_dot(n, V, ne, j + 1, w, hdev, scratch, st);
+        if (rc) return rc;
+        rc = multi_axpy(n, V, ne, j + 1, hdev, -1.0, w, hdev + (j + 1), scratch, st);
+        if (rc) return rc;
+        CM_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i <= j; ++i) Hat(i, j) += hhost[i];
+      }
+      const double hn = sqrt(fmax(hhost[j + 1], 0.0));
+      if (!isfinite(hn)) {
+        set_error("gmres: NaN/Inf in the Arnoldi process at iteration %d", its);
+        return CM_E_BREAKDOWN;
+      }
+      Hat(j + 1, j) = hn;
+      // previous rotations, then a new one
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * Hat(i, j) + sn[i] * Hat(i + 1, j);
+        Hat(i + 1, j) = -sn[i] * Hat(i, j) + cs[i] * Hat(i + 1, j);
+        Hat(i, j) = t;
+      }
+      const double d = hypot(Hat(j, j), Hat(j + 1, j));
+      cs[j] = (d == 0.0) ? 1.0 : Hat(j, j) / d;
+      sn[j] = (d == 0.0) ? 0.0 : Hat(j + 1, j) / d;
+      Hat(j, j) = d;
+      Hat(j + 1, j) = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      resid = fabs(g[j + 1]);
+      ++its;
+      const bool lucky = hn <= 1e-300;
+      if (resid <= target || lucky) {
+        converged = true;
+        ++j;
+        break;
+      }
+      if (j + 1 < m || true) {  // next basis vector
+        rc = vec_scale(n, w, nullptr, hn, 1, V + (size_t)ne * (j + 1), st);
+        if (rc) return rc;
+      }
+    }
+    // y = H^{-1} g (upper triangular, j columns); x += Minv(V y)
+    const int k = j;
+    for (int i = k - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int l = i + 1; l < k; ++l) s -= Hat(i, l) * y[l];
+      y[i] = s / Hat(i, i);
+    }
+    for (int i = 0; i < k; ++i) hhost[i] = y[i];
+    CM_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * n, st));
+    rc = multi_axpy(n, V, ne, k, hdev, 1.0, w, nullptr, scratch, st);
+    if (rc) return rc;
+    rc = Minv(w, z);
+    if (rc) return rc;
+    hhost[m + 2] = 1.0;
+    CM_CUDA(cudaMemcpyAsync(hdev + m + 2, hhost + m + 2, sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = multi_axpy(n, z, ne, 1, hdev + m + 2, 1.0, x, nullptr, scratch, st);
+    if (rc) return rc;
+    CM_CUDA(cudaStreamSynchronize(st));
+    if (converged || its >= maxit) break;
+    // restart: r = b - A x
+    rc = A(x, z);
+    if (rc) return rc;
+    CM_CUDA(cudaMemcpyAsync(w, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    hhost[m + 3] = 1.0;
+    CM_CUDA(cudaMemcpyAsync(hdev + m + 3, hhost + m + 3, sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = multi_axpy(n, z, ne, 1, hdev + m + 3, -1.0, w, hdev, scratch, st);
+    if (rc) return rc;
+    CM_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    beta = sqrt(hhost[0]);
+    resid = beta;
+    if (beta <= target) converged = true;
+  }
+  if (iters_out) *iters_out = its;
+  if (resid_out) *resid_out = resid;
+  return converged ? CM_OK : 1;  // 1 = not converged within maxit (caller decides)
+}
+
+}  // namespace cm

@@ -1,0 +1,550 @@
+// Structured-grid kernels of the field-split / geometric-multigrid Newton linear solver.
+//
+// On RectangleMesh-numbered meshes (create_flat_boundary.py:65) every P1 row is a 7-point stencil
+// (W, E, S, N and the two "right diagonal" neighbours), so the four blocks of the row-scaled P-Q
+// Jacobian are stored as diagonals S[k][node] (no column index traffic) and the multigrid
+// hierarchy of the p-block is built by Galerkin coarsening in stencil form.  Smoothing and the
+// q-block solve are zebra x-line relaxations: batched tridiagonal solves along r2, each done by
+// one CTA as two parallel scans over affine maps using factors precomputed once per Jacobian.
+#include "cm_common.cuh"
+#include "cm_decl.cuh"
+
+namespace cm {
+
+// stencil slot k -> (dx,dy):  0:(-1,-1) 1:(0,-1) 2:(-1,0) 3:(0,0) 4:(+1,0) 5:(0,+1) 6:(+1,+1)
+__host__ __device__ __forceinline__ int st_dx(int k) { return (k == 0 || k == 2) ? -1 : ((k == 4 || k == 6) ? 1 : 0); }
+__host__ __device__ __forceinline__ int st_dy(int k) { return (k < 2) ? -1 : (k > 4 ? 1 : 0); }
+__host__ __device__ __forceinline__ int st_slot(int dx, int dy) {
+  if (dy == -1) return dx == -1 ? 0 : (dx == 0 ? 1 : -1);
+  if (dy == 0) return dx == -1 ? 2 : (dx == 0 ? 3 : (dx == 1 ? 4 : -1));
+  if (dy == 1) return dx == 0 ? 5 : (dx == 1 ? 6 : -1);
+  return -1;
+}
+
+constexpr int kSB = 256;
+
+// ------------------------------------------------------------------------------------------------
+// interleaved CSR (DOLFIN layout) -> row-scaled stencil blocks PP, PQ, QP, QQ [7][nv]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSB)
+extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowptr,
+                      const int* __restrict__ ncol, const double2* __restrict__ vals2,
+                      double* __restrict__ PP, double* __restrict__ PQ, double* __restrict__ QP,
+                      double* __restrict__ QQ, double* __restrict__ sp, double* __restrict__ sq,
+                      int* __restrict__ err) {
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  const int n1 = nx + 1;
+  const int rp = nrowptr[v], deg = nrowptr[v + 1] - rp;
+  const double2* prow = vals2 + 2 * (size_t)rp;
+  const double2* qrow = prow + deg;
+  double mp = 0.0, mq = 0.0;
+  for (int k = 0; k < deg; ++k) {
+    const double2 a = prow[k], c = qrow[k];
+    mp = fmax(mp, fmax(fabs(a.x), fabs(a.y)));
+    mq = fmax(mq, fmax(fabs(c.x), fabs(c.y)));
+  }
+  const double s1 = mp > 0.0 ? 1.0 / mp : 1.0, s2 = mq > 0.0 ? 1.0 / mq : 1.0;
+  sp[v] = s1;
+  sq[v] = s2;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    PP[(size_t)k * nv + v] = 0.0; PQ[(size_t)k * nv + v] = 0.0;
+    QP[(size_t)k * nv + v] = 0.0; QQ[(size_t)k * nv + v] = 0.0;
+  }
+  const int ix = v % n1, iy = v / n1;
+  for (int k = 0; k < deg; ++k) {
+    const int w = ncol[rp + k];
+    const int s = st_slot(w % n1 - ix, w / n1 - iy);
+    if (s < 0) { atomicExch(err, 1); continue; }  // not a 7-point row (e.g. C0IP pattern)
+    const double2 a = prow[k], c = qrow[k];
+    PP[(size_t)s * nv + v] = s1 * a.x; PQ[(size_t)s * nv + v] = s1 * a.y;
+    QP[(size_t)s * nv + v] = s2 * c.x; QQ[(size_t)s * nv + v] = s2 * c.y;
+  }
+}
+
+// interleaved b -> split, scaled:  out[v] = sp*b[2v], out[nv+v] = sq*b[2v+1]
+__global__ void __launch_bounds__(kSB)
+split_scale_kernel(const int nv, const double2* __restrict__ b, const double* __restrict__ sp,
+                   const double* __restrict__ sq, double* __restrict__ out) {
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  const double2 t = b[v];
+  out[v] = sp[v] * t.x;
+  out[nv + v] = sq[v] * t.y;
+}
+
+__global__ void __launch_bounds__(kSB)
+interleave_kernel(const int nv, const double* __restrict__ xs, double2* __restrict__ x) {
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  x[v] = make_double2(xs[v], xs[nv + v]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stencil mat-vecs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stencil_offsets(int n1, int* off) {
+  off[0] = -n1 - 1; off[1] = -n1; off[2] = -1; off[3] = 0; off[4] = 1; off[5] = n1; off[6] = n1 + 1;
+}
+
+__device__ __forceinline__ unsigned stencil_valid(int ix, int iy, int nx, int ny) {
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int jx = ix + st_dx(k), jy = iy + st_dy(k);
+    if (jx >= 0 && jx <= nx && jy >= 0 && jy <= ny) m |= 1u << k;
+  }
+  return m;
+}
+
+// full operator on split vectors: y_p = PP x_p + PQ x_q, y_q = QP x_p + QQ x_q
+__global__ void __launch_bounds__(kSB)
+pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP,
+                       const double* __restrict__ PQ, const double* __restrict__ QP,
+                       const double* __restrict__ QQ, const double* __restrict__ x,
+                       double* __restrict__ y) {
+  const int nv = (nx + 1) * (ny + 1);
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  const int n1 = nx + 1;
+  const unsigned valid = stencil_valid(v % n1, v / n1, nx, ny);
+  int off[7];
+  stencil_offsets(n1, off);
+  double yp = 0.0, yq = 0.0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    if (valid & (1u << k)) {
+      const double xp = x[v + off[k]], xq = x[nv + v + off[k]];
+      const size_t e = (size_t)k * nv + v;
+      yp += PP[e] * xp + PQ[e] * xq;
+      yq += QP[e] * xp + QQ[e] * xq;
+    }
+  }
+  y[v] = yp;
+  y[nv + v] = yq;
+}
+
+// r = b - A x  (scalar 7-point stencil; b may be null -> r = -A x)
+__global__ void __launch_bounds__(kSB)
+stencil_residual_kernel(const int nx, const int ny, const double* __restrict__ A,
+                        const double* __restrict__ b, const double* __restrict__ x,
+                        double* __restrict__ r) {
+  const int nv = (nx + 1) * (ny + 1);
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  const int n1 = nx + 1;
+  const unsigned valid = stencil_valid(v % n1, v / n1, nx, ny);
+  int off[7];
+  stencil_offsets(n1, off);
+  double s = b ? b[v] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+    if (valid & (1u << k)) s -= A[(size_t)k * nv + v] * x[v + off[k]];
+  r[v] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transfers: P1 interpolation on nested right-diagonal meshes (weights 1, 1/2 on the 6 neighbours)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSB)
+restrict_kernel(const int nxc, const int nyc, const double* __restrict__ rf, double* __restrict__ rc) {
+  const int nc = (nxc + 1) * (nyc + 1);
+  const int I = blockIdx.x * kSB + threadIdx.x;
+  if (I >= nc) return;
+  const int X = I % (nxc + 1), Y = I / (nxc + 1);
+  const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
+  const int ix = 2 * X, iy = 2 * Y;
+  const int c = iy * n1 + ix;
+  const unsigned valid = stencil_valid(ix, iy, nxf, nyf);
+  int off[7];
+  stencil_offsets(n1, off);
+  double s = rf[c];
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+    if (k != 3 && (valid & (1u << k))) s += 0.5 * rf[c + off[k]];
+  rc[I] = s;
+}
+
+__global__ void __launch_bounds__(kSB)
+prolong_add_kernel(const int nxc, const int nyc, const double* __restrict__ ec, double* __restrict__ xf) {
+  const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
+  const int nf = n1 * (nyf + 1);
+  const int i = blockIdx.x * kSB + threadIdx.x;
+  if (i >= nf) return;
+  const int ix = i % n1, iy = i / n1;
+  const int X = ix >> 1, Y = iy >> 1, m1 = nxc + 1;
+  const int ox = ix & 1, oy = iy & 1;
+  const int c0 = Y * m1 + X;
+  double e;
+  if (!ox && !oy) e = ec[c0];
+  else if (ox && !oy) e = 0.5 * (ec[c0] + ec[c0 + 1]);
+  else if (!ox && oy) e = 0.5 * (ec[c0] + ec[c0 + m1]);
+  else e = 0.5 * (ec[c0] + ec[c0 + m1 + 1]);  // midpoint of the coarse right diagonal
+  xf[i] += e;
+}
+
+// Galerkin coarse operator Ac = P^T A P in stencil form (one thread per coarse node)
+__global__ void __launch_bounds__(kSB)
+rap_kernel(const int nxc, const int nyc, const double* __restrict__ Af, double* __restrict__ Ac) {
+  const int nc = (nxc + 1) * (nyc + 1);
+  const int I = blockIdx.x * kSB + threadIdx.x;
+  if (I >= nc) return;
+  const int X = I % (nxc + 1), Y = I / (nxc + 1);
+  const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
+  const size_t nf = (size_t)n1 * (nyf + 1);
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    const int ax = st_dx(a), ay = st_dy(a);
+    const int ix = 2 * X + ax, iy = 2 * Y + ay;
+    if (ix < 0 || ix > nxf || iy < 0 || iy > nyf) continue;
+    const double wa = (a == 3) ? 1.0 : 0.5;
+    const size_t i = (size_t)iy * n1 + ix;
+#pragma unroll
+    for (int e = 0; e < 7; ++e) {
+      const double av = wa * Af[(size_t)e * nf + i];
+      const int sx = ax + st_dx(e), sy = ay + st_dy(e);  // fine offset of column j from 2I
+#pragma unroll
+      for (int D = 0; D < 7; ++D) {
+        const int bx = sx - 2 * st_dx(D), by = sy - 2 * st_dy(D);
+        if (bx < -1 || bx > 1 || by < -1 || by > 1) continue;
+        const int bs = st_slot(bx, by);
+        if (bs < 0) continue;
+        acc[D] += av * ((bs == 3) ? 1.0 : 0.5);
+      }
+    }
+  }
+#pragma unroll
+  for (int D = 0; D < 7; ++D) Ac[(size_t)D * nc + I] = acc[D];
+}
+
+// ------------------------------------------------------------------------------------------------
+// x-line tridiagonal factors (once per Jacobian): T = L U per grid line, no pivoting
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+line_factor_kernel(const int nx, const int ny, const double* __restrict__ A, double* __restrict__ lf,
+                   double* __restrict__ iu, double* __restrict__ cu, int* __restrict__ err) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > ny) return;
+  const int n1 = nx + 1;
+  const size_t nv = (size_t)n1 * (ny + 1);
+  const size_t base = (size_t)j * n1;
+  double uprev = 1.0, cprev = 0.0;
+  bool bad = false;
+  for (int i = 0; i <= nx; ++i) {
+    const size_t v = base + i;
+    const double a = (i > 0) ? A[2 * nv + v] : 0.0;
+    const double d = A[3 * nv + v];
+    const double c = (i < nx) ? A[4 * nv + v] : 0.0;
+    const double l = (i > 0) ? a / uprev : 0.0;
+    const double u = d - l * cprev;
+    const double inv = 1.0 / u;
+    if (!isfinite(inv) || fabs(u) < 1e-300) bad = true;
+    lf[v] = l;
+    iu[v] = inv;
+    cu[v] = c * inv;
+    uprev = u;
+    cprev = c;
+  }
+  if (bad) atomicExch(err, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// zebra x-line relaxation: for every grid line of one colour solve
+//   T x_line = b_line - (A - T) x      (couplings to the lines above/below use the current x)
+// One CTA per line.  Forward and backward substitution are first-order linear recurrences,
+// evaluated as block-wide scans over affine maps (A,B): v_out = A*v_in + B.
+// ------------------------------------------------------------------------------------------------
+struct Affine {
+  double a, b;
+};
+__device__ __forceinline__ Affine compose(const Affine later, const Affine earlier) {
+  return Affine{later.a * earlier.a, later.a * earlier.b + later.b};
+}
+
+// exclusive scan over threads in thread order; returns the value entering this thread's segment
+// when the value entering thread 0 is 0.  sh must hold 2*32 doubles.
+__device__ __forceinline__ double affine_exclusive_scan(Affine m, double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double pa = __shfl_up_sync(0xffffffffu, m.a, o);
+    const double pb = __shfl_up_sync(0xffffffffu, m.b, o);
+    if (lane >= o) m = compose(m, Affine{pa, pb});
+  }
+  if (lane == 31) { sh[2 * wid] = m.a; sh[2 * wid + 1] = m.b; }
+  __syncthreads();
+  if (wid == 0) {
+    Affine t = (lane < nw) ? Affine{sh[2 * lane], sh[2 * lane + 1]} : Affine{1.0, 0.0};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, t.a, o);
+      const double pb = __shfl_up_sync(0xffffffffu, t.b, o);
+      if (lane >= o) t = compose(t, Affine{pa, pb});
+    }
+    if (lane < nw) { sh[2 * lane] = t.a; sh[2 * lane + 1] = t.b; }
+  }
+  __syncthreads();
+  // inclusive prefix of the previous lane, composed with the inclusive prefix of previous warps
+  double ea = __shfl_up_sync(0xffffffffu, m.a, 1);
+  double eb = __shfl_up_sync(0xffffffffu, m.b, 1);
+  if (lane == 0) { ea = 1.0; eb = 0.0; }
+  double r = eb;
+  if (wid > 0) r = ea * sh[2 * (wid - 1) + 1] + eb;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
+                  const double* __restrict__ A, const double* __restrict__ lf,
+                  const double* __restrict__ iu, const double* __restrict__ cu,
+                  const double* __restrict__ b, double* __restrict__ x, const int x_zero) {
+  extern __shared__ double sm[];
+  const int n1 = nx + 1;
+  double* s_z = sm;
+  double* s_c = sm + n1;
+  __shared__ double sh[64];
+  const int j = 2 * blockIdx.x + colour;
+  if (j > ny) return;
+  const size_t nv = (size_t)n1 * (ny + 1);
+  const size_t base = (size_t)j * n1;
+  const int T = blockDim.x, tid = threadIdx.x;
+  // right-hand side: b minus the couplings to the neighbouring lines
+  for (int i = tid; i < n1; i += T) {
+    const size_t v = base + i;
+    double r = b[v];
+    if (!x_zero) {
+      if (j > 0) {
+        r -= A[1 * nv + v] * x[v - n1];
+        if (i > 0) r -= A[0 * nv + v] * x[v - n1 - 1];
+      }
+      if (j < ny) {
+        r -= A[5 * nv + v] * x[v + n1];
+        if (i < nx) r -= A[6 * nv + v] * x[v + n1 + 1];
+      }
+    }
+    s_z[i] = r;
+    s_c[i] = lf[v];
+  }
+  __syncthreads();
+  // forward: z_i = r_i - l_i z_{i-1}
+  {
+    const int i0 = tid * E, i1 = min(i0 + E, n1);
+    Affine m{1.0, 0.0};
+    for (int i = i0; i < i1; ++i) {
+      const double l = s_c[i];
+      m.b = s_z[i] - l * m.b;
+      m.a = -l * m.a;
+    }
+    double z = affine_exclusive_scan(m, sh);
+    for (int i = i0; i < i1; ++i) {
+      z = s_z[i] - s_c[i] * z;
+      s_z[i] = z;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n1; i += T) {
+    const size_t v = base + i;
+    s_z[i] *= iu[v];
+    s_c[i] = cu[v];
+  }
+  __syncthreads();
+  // backward: x_i = w_i - cu_i x_{i+1}; thread t takes segment T-1-t so scan order = thread order
+  {
+    const int seg = T - 1 - tid;
+    const int i0 = seg * E, i1 = min(i0 + E, n1);
+    Affine m{1.0, 0.0};
+    for (int i = i1 - 1; i >= i0; --i) {
+      const double c = s_c[i];
+      m.b = s_z[i] - c * m.b;
+      m.a = -c * m.a;
+    }
+    double xn = affine_exclusive_scan(m, sh);
+    for (int i = i1 - 1; i >= i0; --i) {
+      xn = s_z[i] - s_c[i] * xn;
+      s_z[i] = xn;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// coarsest level: dense inverse by Gauss-Jordan with partial pivoting (one CTA), then x = Ainv b
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coarse_invert_kernel(const int nx, const int ny, const double* __restrict__ A, double* __restrict__ M,
+                     double* __restrict__ Ainv, int* __restrict__ err) {
+  // M: n x 2n work matrix in global memory ([A | I]), row-major; n <= 256
+  const int n1 = nx + 1, n = n1 * (ny + 1), w = 2 * n;
+  const int tid = threadIdx.x, T = blockDim.x;
+  __shared__ int s_piv;
+  __shared__ double s_pv;
+  __shared__ double s_col[256];
+  for (int e = tid; e < n * w; e += T) M[e] = 0.0;
+  __syncthreads();
+  for (int v = tid; v < n; v += T) {
+    const int ix = v % n1, iy = v / n1;
+    for (int k = 0; k < 7; ++k) {
+      const int jx = ix + st_dx(k), jy = iy + st_dy(k);
+      if (jx < 0 || jx > nx || jy < 0 || jy > ny) continue;
+      M[v * w + jy * n1 + jx] = A[(size_t)k * n + v];
+    }
+    M[v * w + n + v] = 1.0;
+  }
+  __syncthreads();
+  for (int c = 0; c < n; ++c) {
+    if (tid == 0) {
+      int p = c;
+      double best = fabs(M[c * w + c]);
+      for (int r = c + 1; r < n; ++r) {
+        const double t = fabs(M[r * w + c]);
+        if (t > best) { best = t; p = r; }
+      }
+      s_piv = p;
+      s_pv = M[p * w + c];
+      if (!(best > 0.0)) atomicExch(err, 3);
+    }
+    __syncthreads();
+    const int p = s_piv;
+    const double inv = 1.0 / s_pv;
+    if (p != c) {
+      for (int e = tid; e < w; e += T) {
+        const double t = M[c * w + e];
+        M[c * w + e] = M[p * w + e];
+        M[p * w + e] = t;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < w; e += T) M[c * w + e] *= inv;
+    for (int r = tid; r < n; r += T) s_col[r] = (r == c) ? 0.0 : M[r * w + c];
+    __syncthreads();
+    for (int e = tid; e < n * w; e += T) {
+      const int r = e / w, k = e - r * w;
+      const double f = s_col[r];
+      if (f != 0.0) M[e] -= f * M[c * w + k];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * n; e += T) Ainv[e] = M[(e / n) * w + n + (e % n)];
+}
+
+__global__ void __launch_bounds__(256)
+coarse_apply_kernel(const int n, const double* __restrict__ Ainv, const double* __restrict__ b,
+                    double* __restrict__ x) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < n; ++c) s += Ainv[(size_t)r * n + c] * b[c];
+  x[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline int grid_for(long long n) { return (int)((n + kSB - 1) / kSB); }
+
+int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
+                      double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
+                      int* err, cudaStream_t st) {
+  const int nv = (nx + 1) * (ny + 1);
+  extract_blocks_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
+                                                      PP, PQ, QP, QQ, sp, sq, err);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
+                   cudaStream_t st) {
+  split_scale_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, (const double2*)b, sp, sq, out);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_interleave(int nv, const double* xs, double* x, cudaStream_t st) {
+  interleave_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, xs, (double2*)x);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
+               const double* QQ, const double* x, double* y, cudaStream_t st) {
+  const int nv = (nx + 1) * (ny + 1);
+  pq_stencil_spmv_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, x, y);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
+                cudaStream_t st) {
+  const int nv = (nx + 1) * (ny + 1);
+  stencil_residual_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, A, b, x, r);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st) {
+  restrict_kernel<<<grid_for((long long)(nxc + 1) * (nyc + 1)), kSB, 0, st>>>(nxc, nyc, rf, rc);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st) {
+  prolong_add_kernel<<<grid_for((long long)(2 * nxc + 1) * (2 * nyc + 1)), kSB, 0, st>>>(nxc, nyc, ec, xf);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st) {
+  rap_kernel<<<grid_for((long long)(nxc + 1) * (nyc + 1)), kSB, 0, st>>>(nxc, nyc, Af, Ac);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
+                   cudaStream_t st) {
+  line_factor_kernel<<<(ny + 1 + 127) / 128, 128, 0, st>>>(nx, ny, A, lf, iu, cu, err);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
+             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st) {
+  const int n1 = nx + 1;
+  const int nlines = (ny + 1 - colour + 1) / 2;
+  if (nlines <= 0) return CM_OK;
+  const int T = (n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32);
+  int E = (n1 + T - 1) / T;
+  if ((E & 1) == 0) ++E;  // odd stride: at most 2-way shared-memory bank conflicts
+  const size_t smem = 2 * (size_t)n1 * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) {
+    set_error("zebra line relaxation: line of %d unknowns exceeds shared memory", n1);
+    return CM_E_UNSUPPORTED;
+  }
+  zebra_line_kernel<<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, x_zero);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, int* err,
+                     cudaStream_t st) {
+  coarse_invert_kernel<<<1, 256, 0, st>>>(nx, ny, A, M, Ainv, err);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st) {
+  coarse_apply_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, Ainv, b, x);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+}  // namespace cm

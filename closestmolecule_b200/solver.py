@@ -1,0 +1,203 @@
+"""Newton solver front end mirroring NonlinearVariationalProblem / NonlinearVariationalSolver as the
+reference scripts configure them (advection_diffusion_convergence.py:207-215,
+advection_diffusion_mixed.py:219-226, …MixedPrimal_convergence.py:132-140), with DOLFIN's
+NewtonSolver semantics: start from the current u, residual convergence test
+||F|| < atol or ||F||/||F0|| < rtol, full steps x <- x - relaxation*dx, RuntimeError on failure.
+
+There is no sparse LU on the GPU path: linear_solver 'mumps' / 'umfpack' / 'lu' / 'default' are
+aliased to the tightest-tolerance Krylov path ('gmres').
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+from .assembler import make_assembler
+from .forms import PQPrimalForm
+
+
+class LinearSolveError(RuntimeError):
+    pass
+
+
+class StructuredPQLinearSolver:
+    """Field-split GMRES + multigrid on structured meshes (cm_pqs_setup / cm_pqs_solve)."""
+
+    def __init__(self, asm, restart=40):
+        mesh = asm.mesh
+        if not mesh.structured:
+            raise LinearSolveError("the P-Q linear solver needs a structured (RectangleMesh-numbered) mesh")
+        if asm.topo.with_interior_facets:
+            raise LinearSolveError("the structured P-Q solver handles the 7-point (cell) pattern only; "
+                                   "the C0IP interior-facet pattern is not supported yet")
+        self.asm, self.restart = asm, int(restart)
+        self.nx, self.ny = mesh.nx, mesh.ny
+        self.lib = _capi.lib()
+        nbytes = int(self.lib.cm_pqs_workspace_bytes(self.nx, self.ny, self.restart))
+        if nbytes <= 0:
+            raise LinearSolveError("cm_pqs_workspace_bytes failed")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=mesh.device)
+        self.nbytes = nbytes
+        self.last_iterations = 0
+        self.last_residual = 0.0
+
+    def setup(self):
+        t = self.asm.topo
+        _capi.check(self.lib.cm_pqs_setup(self.nx, self.ny, self.restart, _capi.ptr(t.nrowptr),
+                                          _capi.ptr(t.ncol), _capi.ptr(self.asm.vals), _capi.ptr(self.ws),
+                                          self.nbytes, _capi.stream_ptr()))
+
+    def solve(self, b, x, rtol, atol, maxit):
+        it, rr = C.c_int32(0), C.c_double(0.0)
+        rc = self.lib.cm_pqs_solve(self.nx, self.ny, self.restart, _capi.ptr(b), _capi.ptr(x), rtol, atol,
+                                   maxit, _capi.ptr(self.ws), self.nbytes, C.byref(it), C.byref(rr),
+                                   _capi.stream_ptr())
+        self.last_iterations, self.last_residual = it.value, rr.value
+        if rc < 0:
+            _capi.check(rc)
+        return rc == 0
+
+
+class JacobiKrylovLinearSolver:
+    """GMRES + (block-)Jacobi on the node CSR layouts, any mesh (cm_krylov_solve)."""
+
+    def __init__(self, asm, restart=60):
+        self.asm, self.restart = asm, int(restart)
+        self.lib = _capi.lib()
+        t = asm.topo
+        nbytes = int(self.lib.cm_krylov_workspace_bytes(asm.bs, t.nv, self.restart))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=asm.mesh.device)
+        self.nbytes = nbytes
+        self.last_iterations = 0
+        self.last_residual = 0.0
+
+    def setup(self):
+        pass
+
+    def solve(self, b, x, rtol, atol, maxit):
+        t = self.asm.topo
+        it, rr = C.c_int32(0), C.c_double(0.0)
+        rc = self.lib.cm_krylov_solve(self.asm.bs, t.nv, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
+                                      _capi.ptr(t.diag_slot), _capi.ptr(self.asm.vals), _capi.ptr(b),
+                                      _capi.ptr(x), rtol, atol, maxit, self.restart, _capi.ptr(self.ws),
+                                      self.nbytes, C.byref(it), C.byref(rr), _capi.stream_ptr())
+        self.last_iterations, self.last_residual = it.value, rr.value
+        if rc < 0:
+            _capi.check(rc)
+        return rc == 0
+
+
+class NonlinearVariationalProblem:
+    def __init__(self, F, u, bcs=None, J=None):
+        self.form, self.u = F, u
+        if bcs is None:
+            bcs = []
+        self.bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
+
+
+_LU_ALIASES = ("mumps", "umfpack", "lu", "default", "superlu", "petsc")
+
+
+class NonlinearVariationalSolver:
+    def __init__(self, problem):
+        self.problem = problem
+        self.parameters = {
+            "nonlinear_solver": "newton",
+            "newton_solver": self._defaults(),
+            "snes_solver": self._defaults(),
+        }
+        self.asm = make_assembler(problem.form)
+        self._linear = None
+        self.history = []
+        self.linear_iterations = []
+
+    @staticmethod
+    def _defaults():
+        # DOLFIN NewtonSolver defaults + the Krylov controls of this implementation
+        return {"linear_solver": "default", "absolute_tolerance": 1e-10, "relative_tolerance": 1e-9,
+                "maximum_iterations": 50, "relaxation_parameter": 1.0, "error_on_nonconvergence": True,
+                "report": False,
+                "krylov_solver": {"relative_tolerance": 1e-11, "absolute_tolerance": 0.0,
+                                  "maximum_iterations": 400, "restart": 40}}
+
+    def _linear_solver(self, prm):
+        if self._linear is None:
+            name = prm["linear_solver"]
+            if name in _LU_ALIASES or name in ("gmres", "bicgstab"):
+                pass
+            else:
+                raise ValueError(f"unknown linear_solver '{name}'")
+            restart = prm["krylov_solver"]["restart"]
+            if isinstance(self.problem.form, PQPrimalForm):
+                self._linear = StructuredPQLinearSolver(self.asm, restart)
+            else:
+                self._linear = JacobiKrylovLinearSolver(self.asm, restart)
+        return self._linear
+
+    def solve(self):
+        kind = self.parameters["nonlinear_solver"]
+        prm = self.parameters[kind + "_solver"]
+        asm, u = self.asm, self.problem.u.vector()
+        bc = asm._bc_tables(self.problem.bcs)
+        atol, rtol = prm["absolute_tolerance"], prm["relative_tolerance"]
+        maxit, omega = prm["maximum_iterations"], prm["relaxation_parameter"]
+        kp = prm["krylov_solver"]
+        lin = self._linear_solver(prm)
+        dx = torch.empty_like(u)
+        asm.assemble(u, want_jac=False)
+        asm.apply_bcs(bc, u, with_matrix=False)
+        r0 = float(torch.linalg.vector_norm(asm.b))
+        r = r0
+        self.history = [r0]
+        self.linear_iterations = []
+        it = 0
+        conv = r < atol or (r0 > 0 and r / r0 < rtol)
+        while not conv and it < maxit:
+            asm.assemble(u, want_jac=True)
+            asm.apply_bcs(bc, u, with_matrix=True)
+            lin.setup()
+            ok = lin.solve(asm.b, dx, kp["relative_tolerance"], kp["absolute_tolerance"],
+                           kp["maximum_iterations"])
+            self.linear_iterations.append(lin.last_iterations)
+            if not ok:
+                raise LinearSolveError(
+                    f"Krylov solver did not converge in {lin.last_iterations} iterations "
+                    f"(relative residual {lin.last_residual:.3e})")
+            u.add_(dx, alpha=-omega)
+            it += 1
+            asm.assemble(u, want_jac=False)
+            asm.apply_bcs(bc, u, with_matrix=False)
+            r = float(torch.linalg.vector_norm(asm.b))
+            self.history.append(r)
+            if prm["report"]:
+                print(f"Newton iteration {it}: r (abs) = {r:.3e} (tol = {atol:.3e}) "
+                      f"r (rel) = {r / r0:.3e} (tol = {rtol:.3e})  [linear its {lin.last_iterations}]")
+            if r != r:
+                raise RuntimeError("Newton solver diverged (NaN residual)")
+            conv = r < atol or r / r0 < rtol
+        if not conv and prm["error_on_nonconvergence"]:
+            raise RuntimeError("Newton solver did not converge because maximum number of iterations "
+                               "reached")  # DOLFIN's message text
+        return it, conv
+
+
+class LinearVariationalSolver:
+    """solve(a == L, u, bcs) for the linear scalar form (SphericalLaplace_convergence.py:135): one
+    Newton step from u = 0 of the affine residual."""
+
+    def __init__(self, form, u, bcs):
+        self.inner = NonlinearVariationalSolver(NonlinearVariationalProblem(form, u, bcs))
+        self.inner.parameters["newton_solver"]["maximum_iterations"] = 1
+        self.inner.parameters["newton_solver"]["error_on_nonconvergence"] = False
+
+    def solve(self):
+        self.inner.problem.u.vector().zero_()
+        return self.inner.solve()
+
+
+def solve(form, u, bcs=None):
+    """solve(FF == 0, u, bcs) (SphericalAdvectionDiffusionReaction_convergence.py:112 comment) with
+    DOLFIN's default Newton parameters."""
+    return NonlinearVariationalSolver(NonlinearVariationalProblem(form, u, bcs)).solve()

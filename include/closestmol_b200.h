@@ -167,6 +167,34 @@ int cm_apply_dirichlet(int32_t bs, int32_t nrows, const int32_t* rows, const int
 int cm_spmv(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol, const double* vals,
             const double* x, double* y, void* stream);
 
+/* Newton linear solve on structured (RectangleMesh-numbered) meshes: right-preconditioned
+ * GMRES(restart) on the row-equilibrated Jacobian with the block-lower-triangular field split
+ * [[App,0],[Aqp,Aqq]]: p-block = one geometric-multigrid V(1,1) cycle (zebra x-line relaxation,
+ * Galerkin coarse operators, dense coarsest solve), q-block = one zebra x-line sweep.
+ *   cm_pqs_setup : once per Jacobian (vals = assembled J with Dirichlet rows applied): extracts and
+ *                  scales the four stencil blocks, builds the hierarchy and the line factors.
+ *   cm_pqs_solve : J x = b (b, x interleaved dof order); returns 0 when the relative residual of
+ *                  the row-scaled system reached max(rtol*|b|, atol), 1 when maxit was hit (x holds
+ *                  the last iterate), <0 on error.  iters/resid are host outputs.
+ * workspace: device memory of cm_pqs_workspace_bytes(nx,ny,restart) bytes owned by the caller;
+ * its content carries the setup between the two calls. */
+int64_t cm_pqs_workspace_bytes(int32_t nx, int32_t ny, int32_t restart);
+int cm_pqs_setup(int32_t nx, int32_t ny, int32_t restart, const int32_t* nrowptr,
+                 const int32_t* ncol, const double* vals, void* workspace, int64_t workspace_bytes,
+                 void* stream);
+int cm_pqs_solve(int32_t nx, int32_t ny, int32_t restart, const double* b, double* x, double rtol,
+                 double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
+                 int32_t* iters_host, double* resid_host, void* stream);
+
+/* Generic path (any mesh): GMRES(restart) with point (bs=1) or 2x2 node-block (bs=2) Jacobi on the
+ * node-level CSR layouts.  Adequate for the scalar forms (SphericalLaplace_convergence.py:135,
+ * SphericalAdvectionDiffusionReaction_convergence.py:104); NOT for the Galerkin P-Q system. */
+int64_t cm_krylov_workspace_bytes(int32_t bs, int32_t nv, int32_t restart);
+int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
+                    const int32_t* diag_slot, const double* vals, const double* b, double* x,
+                    double rtol, double atol, int32_t maxit, int32_t restart, void* workspace,
+                    int64_t workspace_bytes, int32_t* iters_host, double* resid_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+"""GPU linear solver and Newton loop against the oracle's sparse-LU Newton (SuperLU standing in for
+MUMPS/UMFPACK): Newton solutions within 1e-8 relative L2 (north-star tolerance)."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+import closestmolecule_b200 as cm
+from closestmolecule_b200.solver import JacobiKrylovLinearSolver, StructuredPQLinearSolver
+from oracle import fem, pq, scalar
+from oracle.newton import merge_bcs, newton_solve
+
+from util import np_forcing, oracle_mesh, oracle_params, random_state
+
+pytestmark = pytest.mark.gpu
+P1 = cm.FiniteElement("CG", "triangle", 1)
+
+
+def _supg_problem(nx, ny):
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)   # …_SUPG.py:77
+    form = cm.PQPrimalForm.manufactured(V, "supg")
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    return mesh, V, form, bcs
+
+
+def _oracle_newton(mesh, form, bcs, atol, rtol, maxit=50):
+    om = oracle_mesh(mesh)
+    S = pq.PQSystem(om, oracle_params(form))
+    dofs, vals = cm.DirichletBC.merge(bcs, 2 * mesh.num_vertices())
+    dofs, vals = dofs.cpu().numpy().astype(np.int64), vals.cpu().numpy()
+    f = np_forcing(form)
+    return S, dofs, vals, newton_solve(lambda x, wj: S.assemble(x, wj, None, f), np.zeros(S.N), S.rowptr,
+                                       S.col, dofs, vals, atol=atol, rtol=rtol, maxit=maxit,
+                                       return_history=True)
+
+
+@pytest.mark.parametrize("nx,ny", [(32, 32), (64, 32), (40, 24)])
+def test_structured_linear_solve_matches_lu(nx, ny):
+    mesh, V, form, bcs = _supg_problem(nx, ny)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, cm.Function(V), bcs))
+    asm = s.asm
+    un = random_state(mesh.num_vertices())
+    u = torch.tensor(un, device=mesh.device)
+    bc = asm._bc_tables(bcs)
+    asm.assemble(u, True)
+    asm.apply_bcs(bc, u, True)
+    lin = StructuredPQLinearSolver(asm, restart=40)
+    lin.setup()
+    dx = torch.empty_like(u)
+    assert lin.solve(asm.b, dx, 1e-12, 0.0, 200)
+    rp, col, vals = asm.csr()
+    n = u.numel()
+    A = sp.csr_matrix((vals.cpu().numpy(), col.cpu().numpy(), rp.cpu().numpy()), shape=(n, n))
+    ref = spla.splu(A.tocsc()).solve(asm.b.cpu().numpy())
+    err = np.linalg.norm(dx.cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert err < 1e-9, (err, lin.last_iterations)
+    assert lin.last_iterations < 60
+
+
+@pytest.mark.parametrize("nx,ny", [(32, 32), (128, 64)])
+def test_newton_supg_matches_oracle(nx, ny):
+    mesh, V, form, bcs = _supg_problem(nx, ny)
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    s.parameters["newton_solver"]["linear_solver"] = "umfpack"       # …_SUPG.py:137 (aliased)
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-8
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-8
+    it, conv = s.solve()
+    S, dofs, vals, (x, oit, oconv, hist) = _oracle_newton(mesh, form, bcs, 1e-8, 1e-8)
+    assert conv and oconv and it == oit
+    err = np.linalg.norm(u.vector().cpu().numpy() - x) / np.linalg.norm(x)
+    assert err < 1e-8, err
+    # same residual history as DOLFIN-style Newton with LU
+    assert np.allclose(s.history, hist, rtol=1e-5, atol=1e-12)
+
+
+def test_newton_nonconvergence_raises():
+    mesh, V, form, bcs = _supg_problem(16, 16)
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-30
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-30
+    s.parameters["newton_solver"]["maximum_iterations"] = 2
+    with pytest.raises(RuntimeError, match="maximum number of iterations"):
+        s.solve()
+
+
+def test_galerkin_q_block_reports_breakdown_or_solves():
+    """Unstabilised Galerkin q-block: the reference needs pivoting LU; the structured solver
+    must either converge or fail loudly -- never return garbage silently."""
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), 16, 16)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    form = cm.PQPrimalForm.manufactured(V, "galerkin")
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-7
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-7
+    try:
+        it, conv = s.solve()
+    except RuntimeError:
+        return
+    S, dofs, vals, (x, oit, oconv, hist) = _oracle_newton(mesh, form, bcs, 1e-7, 1e-7)
+    assert np.linalg.norm(u.vector().cpu().numpy() - x) / np.linalg.norm(x) < 1e-6
+
+
+def test_scalar_newton_reproduces_readme_rows():
+    """GPU path for SphericalAdvectionDiffusionReaction_convergence.py: rows of README.md:109-115."""
+    from closestmolecule_b200.manufactured import u_exact
+    rows = {8: ("4.45e-01", "7.51e-03"), 32: ("1.09e-01", "4.29e-04")}
+    for n, (e1s, e0s) in rows.items():
+        mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+        V = cm.FunctionSpace(mesh, "CG", 1)
+        u = cm.Function(V)
+        s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(
+            cm.ScalarADRForm.nonlinear_adr(V), u, [cm.DirichletBC(V, u_exact, "on_boundary")]))
+        s.parameters["newton_solver"]["linear_solver"] = "mumps"
+        s.parameters["newton_solver"]["absolute_tolerance"] = 1e-7
+        s.parameters["newton_solver"]["relative_tolerance"] = 1e-7
+        it, conv = s.solve()
+        assert conv
+        e1, e0 = scalar.errors(oracle_mesh(mesh), u.vector().cpu().numpy(), 4)
+        assert f"{e1:6.2e}" == e1s and f"{e0:6.2e}" == e0s
+        ref = scalar.solve_fb(n)
+        assert np.linalg.norm(u.vector().cpu().numpy() - ref["u"]) / np.linalg.norm(ref["u"]) < 1e-8

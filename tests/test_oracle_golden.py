@@ -107,3 +107,23 @@ def test_pq_manufactured_rates():
         res.append(pq.errors_pq(mesh, x))
     rates = [np.log(a / b) / np.log(0.5) for a, b in zip(res[1], res[0])]
     assert rates[0] > 1.9 and 0.95 < rates[1] < 1.05 and 0.95 < rates[2] < 1.1
+
+
+def test_c_port_matches_numpy_oracle():
+    from oracle import cport
+    mesh = fem.rectangle_mesh(0, 0.1, 5, 5, 12, 9)
+    rng = np.random.default_rng(5)
+    V = mesh.num_vertices
+    u = np.empty(2 * V)
+    u[0::2] = 0.3 + rng.random(V)
+    u[1::2] = 1.0 + rng.random(V)
+    pold = rng.random(V)
+    for prm in (pq.PQParams(**pq.gstar_conv(1.0)),
+                pq.PQParams(D1=1e-3, D2=1.5e-3, gkind=pq.G_POWER, gcoef=0.02, q_react=1.0, q_x2p=0,
+                            q_x2q=1, supg_stab=1.0, inv_dt=10.0),
+                pq.PQParams(D1=1, D2=1.5, gkind=pq.G_POWER, gcoef=1.0, q_adv=0, q_divr=1, q_ibp=1)):
+        S = pq.PQSystem(mesh, prm)
+        ovals, ob = S.assemble(u, True, pold)
+        vals, b = cport.assemble_cells(prm, mesh.cells, mesh.coords, u, S.cell_slots, S.col.size, pold)
+        assert np.max(np.abs(vals - ovals)) / np.max(np.abs(ovals)) < 1e-13
+        assert np.max(np.abs(b - ob)) / np.max(np.abs(ob)) < 1e-13
