@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- cells/s through one Newton step (assemble J+F, Dirichlet rows, sparse linear solve,
+update, residual) of the P-Q system on the 16 Mi-cell structured (r2,r1) mesh.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nx NX]
+
+Workload (BASELINE.json configs[4]): RectangleMesh 4096x2048 on (0,1)^2
+(16 777 216 cells, 16 789 506 dofs, 234 954 756 nnz), manufactured P-Q problem with the SUPG
+q-equation (…MixedPrimal_convergence_SUPG.py:118-129), state = nodal interpolant of the exact
+solution (every step does the same work: one full Newton iteration from that state).
+N > 1: every rank runs an independent problem instance (the concentration sweep of
+advection_diffusion_mixed.py:273-334 is the reference's own data-parallel axis): weak scaling, no
+data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_newton_step_sample(nx, ny, repeats=1):
+    """The CPU restatement of the same step on a bounded sample mesh: plain-C serial cell assembly
+    (oracle/cport, what DOLFIN's serial Assembler does) + SuperLU factor/solve (the only sparse
+    direct solver in the image, standing in for MUMPS/UMFPACK) + update + residual assembly."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import cport, fem, pq
+    from oracle.newton import apply_bc_matrix_vec, apply_bc_residual, merge_bcs
+
+    mesh = fem.rectangle_mesh(0.0, 0.0, 1.0, 1.0, nx, ny)
+    prm = pq.PQParams(D1=1e-3, D2=1.5e-3, gkind=pq.G_POWER, gcoef=1.5e-3 * 4 * np.pi, q_react=1.0,
+                      q_x2p=0.0, q_x2q=1.0, supg_stab=1.0)
+    S = pq.PQSystem(mesh, prm)
+    X = mesh.coords
+    fc = mesh.facets()
+    bv = np.unique(fc.verts[fc.exterior])
+    qv = np.nonzero(fem.near(X[:, 0], 0.0))[0]
+    dofs, gv = merge_bcs([(2 * bv, pq.p_exact(X[bv, 0], X[bv, 1])),
+                          (2 * qv + 1, pq.q_exact(X[qv, 0], X[qv, 1]))])
+    forcing = pq.manufactured_forcing(prm, x2_on_q=True)
+    pts, _ = fem.triangle_rule(4)
+    phi = np.stack([1 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1)
+    P = np.einsum("qi,cid->cqd", phi, X[mesh.cells])
+    f2, f3 = forcing(P[:, :, 0], P[:, :, 1])
+    fq = np.ascontiguousarray(np.stack([f2, f3], -1))
+    u0 = np.empty(S.N)
+    u0[0::2] = pq.p_exact(X[:, 0], X[:, 1])
+    u0[1::2] = pq.q_exact(X[:, 0], X[:, 1])
+    slots = S.cell_slots
+    best = None
+    for _ in range(repeats):
+        u = u0.copy()
+        t0 = time.perf_counter()
+        vals, b = cport.assemble_cells(prm, mesh.cells, mesh.coords, u, slots, S.col.size, None, fq, True)
+        apply_bc_matrix_vec(S.rowptr, S.col, vals, dofs)
+        apply_bc_residual(b, u, dofs, gv)
+        t1 = time.perf_counter()
+        A = sp.csr_matrix((vals, S.col, S.rowptr), shape=(S.N, S.N))
+        dx = spla.splu(A.tocsc()).solve(b)
+        t2 = time.perf_counter()
+        u -= dx
+        _, b = cport.assemble_cells(prm, mesh.cells, mesh.coords, u, slots, S.col.size, None, fq, False)
+        apply_bc_residual(b, u, dofs, gv)
+        float(np.linalg.norm(b))
+        t3 = time.perf_counter()
+        rec = dict(total=t3 - t0, assemble=t1 - t0, lu=t2 - t1, residual=t3 - t2)
+        if best is None or rec["total"] < best["total"]:
+            best = rec
+    best["cells"] = mesh.num_cells
+    return best
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path (FEniCS-equivalent restatement, FEniCS itself is
+    not installable here) timed on this box's host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    nx, ny = 512, 256
+    for _ in range(args.warmup):
+        cpu_newton_step_sample(nx, ny)
+    t = []
+    rec = None
+    for _ in range(args.steps):
+        rec = cpu_newton_step_sample(nx, ny)
+        t.append(rec["total"])
+    ms = 1e3 * float(np.mean(t))
+    val = rec["cells"] / (ms * 1e-3)
+    sample = (f"one Newton step (C serial cell assembly + SuperLU + residual) on RectangleMesh {nx}x{ny} "
+              f"= {rec['cells']} cells; assemble {rec['assemble']:.2f}s lu {rec['lu']:.2f}s")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 4096, 2048),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+METRIC = "cells/s through one Newton step (assemble J+F, BCs, linear solve, update, residual)"
+UNIT = "cells/s"
+
+
+def workload_config(args, nx, ny):
+    return {"workload": f"P-Q CG1xCG1 manufactured SUPG Newton step on RectangleMesh {nx}x{ny} "
+                        f"({2 * nx * ny} cells) per GPU",
+            "nx": nx, "ny": ny, "cells_per_gpu": 2 * nx * ny, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
+            "parallelism": f"independent problem instance per GPU x{args.gpus}",
+            "l2_policy": "inputs larger than L2 (Jacobian 1.9 GB, Krylov basis > 1 GB)",
+            "linear_rtol": LIN_RTOL}
+
+
+LIN_RTOL = 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import closestmolecule_b200 as cm
+    from closestmolecule_b200 import _capi
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
+                         "use --impl reference for the CPU restatement")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    nx = args.nx
+    ny = nx // 2
+    lib = _capi.lib()
+
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny, device=dev)
+    P1 = cm.FiniteElement("CG", mesh.ufl_cell(), 1)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    form = cm.PQPrimalForm.manufactured(V, "supg")
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    u = cm.Function(V)
+    solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
+    X = mesh.coords
+    u0 = torch.empty_like(u.vector())
+    u0[0::2] = p_exact(X[:, 0], X[:, 1])
+    u0[1::2] = q_exact(X[:, 0], X[:, 1])
+    cells = mesh.num_cells()
+    Vn = mesh.num_vertices()
+    nnz = solver.asm.topo.nnz
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step():
+        u.vector().copy_(u0)
+        return solver.newton_step(compute_residual=True)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = int(lib.cm_launch_count())
+    solver.linear_iterations = []
+    solver.phase_events = []      # CUDA events on the launching stream around each phase
+    t0, t1 = ev(), ev()
+    barrier()
+    t0.record()
+    rnorm = None
+    for _ in range(args.steps):
+        rnorm = step()
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(lib.cm_launch_count()) - l0
+    ms_step = t0.elapsed_time(t1) / args.steps
+    ph = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in solver.phase_events])
+    solver.phase_events = None
+    asm_ms, setup_ms, solve_ms, resid_ms = [float(v) for v in ph.mean(0)]
+    lin_its = float(np.mean(solver.linear_iterations))
+
+    # ---- e2e: host buffers in, host buffers out, through the public Newton-step call ------------
+    h_in = torch.empty(u0.numel(), dtype=torch.float64, pin_memory=True)
+    h_in.copy_(u0)
+    h_out = torch.empty_like(h_in)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(e2e_steps):
+        u.vector().copy_(h_in, non_blocking=True)
+        r = solver.newton_step(compute_residual=True)
+        h_out.copy_(u.vector(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+
+    tt = torch.tensor([ms_step, e2e_ms, asm_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms, asm_ms = [float(v) for v in tt.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        bytes_asm = 12 * cells + 16 * Vn + 8 * (2 * Vn) + 8 * (4 * nnz) + 8 * (2 * Vn)
+        achieved = bytes_asm / (asm_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": world * cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, nx, ny),
+            "newton_step_ms": ms_step, "linear_iterations_per_step": lin_its,
+            "assembly_ms": asm_ms, "assembly_cells_per_s": cells / (asm_ms * 1e-3),
+            "phases_ms": {"assemble_J_F": asm_ms, "bc_and_solver_setup": setup_ms,
+                          "krylov_solve": solve_ms, "update_and_residual": resid_ms},
+            "residual_norm_after_step": rnorm,
+            "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8 + 8)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "pq_rows_kernel (cm_assemble_pq_cells, fused J+F)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_asm,
+                         "traffic": TRAFFIC_NCU},
+        }
+        if world == 1 and not args.no_cpu:
+            nxs, nys = 512, 256
+            rec = cpu_newton_step_sample(nxs, nys)
+            out["cpu_baseline"] = {
+                "value": rec["cells"] / rec["total"], "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"one Newton step (C serial cell assembly {rec['assemble']:.2f}s + SuperLU "
+                          f"{rec['lu']:.2f}s + residual {rec['residual']:.2f}s) on RectangleMesh "
+                          f"{nxs}x{nys} = {rec['cells']} cells"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram bytes per launch of the roofline kernel from the committed `ncu --set full` capture
+# (profiles/); None until one exists for the current kernel
+TRAFFIC_NCU = None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096, help="mesh is nx x nx/2 (default: the 16 Mi-cell mesh)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

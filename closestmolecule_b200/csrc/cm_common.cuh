@@ -29,7 +29,12 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define CM_LAUNCH_CHECK() CM_CUDA(cudaGetLastError())
+extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define CM_LAUNCH_CHECK()      \
+  do {                         \
+    ++cm::g_launches;          \
+    CM_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // ---- FIAT "default" triangle rules (15-digit constants as stored by FIAT).
 // Barycentric (l0,l1,l2) = (1-xi-eta, xi, eta) and weight (sums to 1/2).

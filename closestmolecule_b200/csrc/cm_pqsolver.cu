@@ -271,6 +271,7 @@ int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int*
   };
   LinOp Minv = [&](const double* r, double* z) {
     jacobi_apply_kernel<<<grid, 256, 0, st>>>(bs, nv, dinv, r, z);
+    ++g_launches;
     return cudaGetLastError() == cudaSuccess ? CM_OK : CM_E_CUDA;
   };
   double bnorm = 0.0;

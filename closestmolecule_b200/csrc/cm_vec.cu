@@ -146,7 +146,9 @@ int multi_dot(long long n, const double* Vbase, long long vstride, int nvec, con
     CM_K_SWITCH(K, (dot_group_kernel<KK><<<grid, kVecBlock, 0, st>>>(n, Vbase + k0 * vstride,
                                                                     vstride, w, scratch)));
     reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, K, scratch, out + k0);
+    g_launches += 2;
   }
+  --g_launches;
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -161,7 +163,9 @@ int multi_axpy(long long n, const double* Vbase, long long vstride, int nvec, co
     CM_K_SWITCH(K, (axpy_group_kernel<KK><<<grid, kVecBlock, 0, st>>>(
                        n, Vbase + k0 * vstride, vstride, h + k0, sign, w, scratch, last)));
     if (last) reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, 1, scratch, norm2_out);
+    g_launches += last ? 2 : 1;
   }
+  --g_launches;
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -112,6 +112,7 @@ class NonlinearVariationalSolver:
         self._linear = None
         self.history = []
         self.linear_iterations = []
+        self.phase_events = None   # set to [] to collect CUDA events around the phases of each step
 
     @staticmethod
     def _defaults():
@@ -136,40 +137,69 @@ class NonlinearVariationalSolver:
                 self._linear = JacobiKrylovLinearSolver(self.asm, restart)
         return self._linear
 
-    def solve(self):
+    def _prepare(self):
         kind = self.parameters["nonlinear_solver"]
         prm = self.parameters[kind + "_solver"]
-        asm, u = self.asm, self.problem.u.vector()
-        bc = asm._bc_tables(self.problem.bcs)
-        atol, rtol = prm["absolute_tolerance"], prm["relative_tolerance"]
-        maxit, omega = prm["maximum_iterations"], prm["relaxation_parameter"]
+        if getattr(self, "_bc", None) is None:
+            self._bc = self.asm._bc_tables(self.problem.bcs)
+            self._dx = torch.empty_like(self.problem.u.vector())
+        return prm, self._linear_solver(prm)
+
+    def residual_norm(self):
+        """||F(u)||_2 with the Dirichlet rows set to u - g (NewtonSolver's convergence measure)."""
+        prm, _ = self._prepare()
+        u = self.problem.u.vector()
+        self.asm.assemble(u, want_jac=False)
+        self.asm.apply_bcs(self._bc, u, with_matrix=False)
+        return float(torch.linalg.vector_norm(self.asm.b))
+
+    def newton_step(self, compute_residual=True):
+        """One Newton iteration at the current u: fused J+F assembly, Dirichlet rows, linear-solver
+        setup, Krylov solve, u <- u - relaxation*dx, then (optionally) the new residual norm."""
+        prm, lin = self._prepare()
         kp = prm["krylov_solver"]
-        lin = self._linear_solver(prm)
-        dx = torch.empty_like(u)
-        asm.assemble(u, want_jac=False)
-        asm.apply_bcs(bc, u, with_matrix=False)
-        r0 = float(torch.linalg.vector_norm(asm.b))
+        asm, u = self.asm, self.problem.u.vector()
+        marks = [] if self.phase_events is not None else None
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        mark()
+        asm.assemble(u, want_jac=True)
+        mark()
+        asm.apply_bcs(self._bc, u, with_matrix=True)
+        lin.setup()
+        mark()
+        ok = lin.solve(asm.b, self._dx, kp["relative_tolerance"], kp["absolute_tolerance"],
+                       kp["maximum_iterations"])
+        mark()
+        self.linear_iterations.append(lin.last_iterations)
+        if not ok:
+            raise LinearSolveError(
+                f"Krylov solver did not converge in {lin.last_iterations} iterations "
+                f"(relative residual {lin.last_residual:.3e})")
+        u.add_(self._dx, alpha=-prm["relaxation_parameter"])
+        r = self.residual_norm() if compute_residual else None
+        mark()
+        if marks is not None:   # (assemble J+F, BC + solver setup, Krylov solve, update + residual)
+            self.phase_events.append(marks)
+        return r
+
+    def solve(self):
+        prm, lin = self._prepare()
+        atol, rtol = prm["absolute_tolerance"], prm["relative_tolerance"]
+        maxit = prm["maximum_iterations"]
+        r0 = self.residual_norm()
         r = r0
         self.history = [r0]
         self.linear_iterations = []
         it = 0
         conv = r < atol or (r0 > 0 and r / r0 < rtol)
         while not conv and it < maxit:
-            asm.assemble(u, want_jac=True)
-            asm.apply_bcs(bc, u, with_matrix=True)
-            lin.setup()
-            ok = lin.solve(asm.b, dx, kp["relative_tolerance"], kp["absolute_tolerance"],
-                           kp["maximum_iterations"])
-            self.linear_iterations.append(lin.last_iterations)
-            if not ok:
-                raise LinearSolveError(
-                    f"Krylov solver did not converge in {lin.last_iterations} iterations "
-                    f"(relative residual {lin.last_residual:.3e})")
-            u.add_(dx, alpha=-omega)
+            r = self.newton_step()
             it += 1
-            asm.assemble(u, want_jac=False)
-            asm.apply_bcs(bc, u, with_matrix=False)
-            r = float(torch.linalg.vector_norm(asm.b))
             self.history.append(r)
             if prm["report"]:
                 print(f"Newton iteration {it}: r (abs) = {r:.3e} (tol = {atol:.3e}) "

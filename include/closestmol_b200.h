@@ -82,6 +82,8 @@ typedef struct cm_scalar_params {
 
 int cm_version(void);
 const char* cm_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (diagnostics) */
+int64_t cm_launch_count(void);
 /* 1 if a CUDA device is usable, 0 otherwise (never launches work) */
 int cm_device_available(void);
 
