@@ -60,7 +60,10 @@ int st_split_scale(int nv, const double* b, const double* sp, const double* sq, 
                    cudaStream_t st);
 int st_interleave(int nv, const double* xs, double* x, cudaStream_t st);
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
-               const double* QQ, const double* x, double* y, cudaStream_t st);
+               const double* QQ, const double* sp, const double* sq, const double* x, double* y,
+               cudaStream_t st);
+int st_unscale(int nv, const double* r, const double* sp, const double* sq, double* out,
+               cudaStream_t st);
 int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
                 cudaStream_t st);
 int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st);

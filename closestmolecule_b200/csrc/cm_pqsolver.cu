@@ -1,8 +1,8 @@
-// Newton linear solve J dx = F on structured meshes: GMRES on the row-scaled system,
+// Newton linear solve J dx = F on structured meshes: GMRES on the row-equilibrated system,
 // right-preconditioned by the block-lower-triangular field split  [[App, 0], [Aqp, Aqq]]:
 //   p-block: one geometric-multigrid V(1,1) cycle with zebra x-line relaxation (Galerkin coarse
 //            operators in stencil form, dense inverse on the coarsest grid);
-//   q-block: one zebra x-line relaxation sweep (the q-equation is transport along r2).
+//   q-block: two zebra x-line relaxation sweeps (the q-equation is transport along r2).
 // All of it is caller-provided workspace + kernels; nothing is kept between calls except the
 // workspace content written by cm_pqs_setup.  Replaces the sparse LU the reference requests with
 // linear_solver='mumps'|'umfpack' (advection_diffusion_convergence.py:212,
@@ -25,12 +25,13 @@ struct PQSLevel {
 
 struct PQSolver {
   int nx, ny, nv, nlev, restart;
+  int q_sweeps = 2;  // zebra sweeps on the q-block per application
   bool dense_coarse;
   PQSLevel lev[kMaxLevels];
   double *PP, *PQ, *QP, *QQ, *sp, *sq;
   double *qlf, *qiu, *qcu;
   double *Ainv, *Mwork;
-  double *bs, *xs, *tq;
+  double *bs, *xs, *tq, *ru;
   double* gm;
   int* err;
   size_t total_doubles;
@@ -62,6 +63,7 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
   S.bs = take(2 * V);
   S.xs = take(2 * V);
   S.tq = take(V);
+  S.ru = take(2 * V);
   int lx = nx, ly = ny, l = 0;
   for (;;) {
     if (l >= kMaxLevels) return CM_E_UNSUPPORTED;
@@ -181,13 +183,19 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
   const int V = S.nv;
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st))) return rc;
   LinOp A = [&](const double* in, double* out) {
-    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, in, out, st);
+    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st);
   };
+  // M^{-1} = [[App,0],[Aqp,Aqq]]^{-1} (approximately) on the UNSCALED operator, composed with the
+  // inverse row scaling: multigrid needs the true (variational) FE operator to be mesh independent
   LinOp Minv = [&](const double* r, double* z) {
-    int e = vcycle(S, 0, r, z, st);
+    int e = st_unscale(V, r, S.sp, S.sq, S.ru, st);
     if (e) return e;
-    if ((e = st_residual(nx, ny, S.QP, r + V, z, S.tq, st))) return e;
-    return zebra_sweep(S.lev[0], S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, true, st);
+    if ((e = vcycle(S, 0, S.ru, z, st))) return e;
+    if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st))) return e;
+    if ((e = zebra_sweep(S.lev[0], S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, true, st))) return e;
+    for (int s = 1; s < S.q_sweeps && !e; ++s)
+      e = zebra_sweep(S.lev[0], S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, false, st);
+    return e;
   };
   double bnorm = 0.0;
   rc = gmres_solve(2LL * V, A, Minv, S.bs, S.xs, rtol, atol, maxit, restart, 0, S.gm, iters, resid,

@@ -24,7 +24,9 @@ __host__ __device__ __forceinline__ int st_slot(int dx, int dy) {
 constexpr int kSB = 256;
 
 // ------------------------------------------------------------------------------------------------
-// interleaved CSR (DOLFIN layout) -> row-scaled stencil blocks PP, PQ, QP, QQ [7][nv]
+// interleaved CSR (DOLFIN layout) -> stencil blocks PP, PQ, QP, QQ [7][nv] (unscaled: the Galerkin
+// hierarchy must see the true FE operator) + row equilibration factors sp, sq = 1/max|row|, which
+// the outer Krylov operator applies on the fly
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSB)
 extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowptr,
@@ -58,8 +60,8 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
     const int s = st_slot(w % n1 - ix, w / n1 - iy);
     if (s < 0) { atomicExch(err, 1); continue; }  // not a 7-point row (e.g. C0IP pattern)
     const double2 a = prow[k], c = qrow[k];
-    PP[(size_t)s * nv + v] = s1 * a.x; PQ[(size_t)s * nv + v] = s1 * a.y;
-    QP[(size_t)s * nv + v] = s2 * c.x; QQ[(size_t)s * nv + v] = s2 * c.y;
+    PP[(size_t)s * nv + v] = a.x; PQ[(size_t)s * nv + v] = a.y;
+    QP[(size_t)s * nv + v] = c.x; QQ[(size_t)s * nv + v] = c.y;
   }
 }
 
@@ -98,11 +100,12 @@ __device__ __forceinline__ unsigned stencil_valid(int ix, int iy, int nx, int ny
   return m;
 }
 
-// full operator on split vectors: y_p = PP x_p + PQ x_q, y_q = QP x_p + QQ x_q
+// row-scaled operator on split vectors: y_p = sp*(PP x_p + PQ x_q), y_q = sq*(QP x_p + QQ x_q)
 __global__ void __launch_bounds__(kSB)
 pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP,
                        const double* __restrict__ PQ, const double* __restrict__ QP,
-                       const double* __restrict__ QQ, const double* __restrict__ x,
+                       const double* __restrict__ QQ, const double* __restrict__ sp,
+                       const double* __restrict__ sq, const double* __restrict__ x,
                        double* __restrict__ y) {
   const int nv = (nx + 1) * (ny + 1);
   const int v = blockIdx.x * kSB + threadIdx.x;
@@ -121,8 +124,18 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
       yq += QP[e] * xp + QQ[e] * xq;
     }
   }
-  y[v] = yp;
-  y[nv + v] = yq;
+  y[v] = sp[v] * yp;
+  y[nv + v] = sq[v] * yq;
+}
+
+// out = r / s (undo the row equilibration before the unscaled preconditioner)
+__global__ void __launch_bounds__(kSB)
+unscale_kernel(const int nv, const double* __restrict__ r, const double* __restrict__ sp,
+               const double* __restrict__ sq, double* __restrict__ out) {
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  out[v] = r[v] / sp[v];
+  out[nv + v] = r[nv + v] / sq[v];
 }
 
 // r = b - A x  (scalar 7-point stencil; b may be null -> r = -A x)
@@ -470,9 +483,17 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st) {
 }
 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
-               const double* QQ, const double* x, double* y, cudaStream_t st) {
+               const double* QQ, const double* sp, const double* sq, const double* x, double* y,
+               cudaStream_t st) {
   const int nv = (nx + 1) * (ny + 1);
-  pq_stencil_spmv_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, x, y);
+  pq_stencil_spmv_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_unscale(int nv, const double* r, const double* sp, const double* sq, double* out,
+               cudaStream_t st) {
+  unscale_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, r, sp, sq, out);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -127,3 +127,31 @@ def test_c_port_matches_numpy_oracle():
         vals, b = cport.assemble_cells(prm, mesh.cells, mesh.coords, u, S.cell_slots, S.col.size, pold)
         assert np.max(np.abs(vals - ovals)) / np.max(np.abs(ovals)) < 1e-13
         assert np.max(np.abs(b - ob)) / np.max(np.abs(ob)) < 1e-13
+
+
+# convergence/test_for_paper_convergence.py:200-207, verbatim (k=0 table)
+PAPER_K0 = [
+    "    33 & 0.7071 & 2.93e+01 & 0.000 & 1.03e+00 & 0.000 & 4.92e+00 & 0.000 ",
+    "   113 & 0.3536 & 1.73e+01 & 0.763 & 5.56e-01 & 0.888 & 7.08e+00 & -0.526 ",
+    "   417 & 0.1768 & 9.96e+00 & 0.793 & 2.84e-01 & 0.969 & 1.84e+00 & 1.943 ",
+    "  1601 & 0.0884 & 5.93e+00 & 0.747 & 1.43e-01 & 0.992 & 7.10e-01 & 1.375 ",
+    "  6273 & 0.0442 & 3.72e+00 & 0.673 & 7.16e-02 & 0.997 & 3.35e-01 & 1.085 ",
+    " 24833 & 0.0221 & 2.45e+00 & 0.604 & 3.59e-02 & 0.995 & 1.63e-01 & 1.036 ",
+    " 98817 & 0.0110 & 1.67e+00 & 0.551 & 1.82e-02 & 0.981 & 8.13e-02 & 1.004 ",
+]
+
+
+def test_paper_k0_table_pins_facet_terms():
+    """RT1xDG0xCG1 system whose q-block facet tensors come from oracle.pq's facet functions: rows from
+    the third level on match the recorded table digit for digit; the two coarsest differ in the last
+    digit only (analytic data instead of FEniCS's degree-5/6 interpolants)."""
+    from oracle import paper_m0
+    rows = paper_m0.table(6)
+    got = [[float(t) for t in r.replace("&", " ").split()] for r in rows]
+    ref = [[float(t) for t in r.replace("&", " ").split()] for r in PAPER_K0[:6]]
+    for k in range(2, 6):
+        assert rows[k].split() == PAPER_K0[k].split(), (rows[k], PAPER_K0[k])
+    for k in range(2):
+        assert got[k][0] == ref[k][0] and got[k][1] == ref[k][1]
+        for a, b in zip(got[k][2::2], ref[k][2::2]):          # error columns: <= 1 in the 3rd digit
+            assert abs(a - b) <= 0.011 * 10 ** np.floor(np.log10(b)), (a, b)
