@@ -51,6 +51,7 @@ _PROTOS = {
     "cm_device_available": ([], C.c_int),
     "cm_launch_count": ([], C.c_int64),
     "cm_assemble_pq_cells": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I] + [_P] * 7 + [_I, _P], C.c_int),
+    "cm_assemble_pq_cells_structured": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_P], C.c_int),
     "cm_assemble_scalar_cells": ([C.POINTER(ScalarParamsC), _I, _I] + [_P] * 6 + [_I] + [_P] * 4 + [_P], C.c_int),
     "cm_assemble_load": ([_I, _I, _D, _I, _I, _I] + [_P] * 6 + [_P], C.c_int),
     "cm_assemble_c0ip_facets": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 9 + [_P], C.c_int),

@@ -79,8 +79,9 @@ class _Base:
 class PQAssembler(_Base):
     bs = 2
 
-    def __init__(self, form):
+    def __init__(self, form, use_sweep=True):
         super().__init__(form)
+        self.use_sweep = use_sweep
         mesh = self.mesh
         self.topo = t = mesh.topology(form.with_interior_facets)
         dev = mesh.device
@@ -145,6 +146,13 @@ class PQAssembler(_Base):
         """Fused J (self.vals, DOLFIN CSR order) + F (self.b) at state u [2V]."""
         mesh, t, form = self.mesh, self.topo, self.form
         p_old = form.p_old.vector() if form.p_old is not None else None
+        if self.use_sweep and mesh.structured and self.Kq is None and not t.with_interior_facets:
+            # structured fast path: no connectivity / gather tables are read
+            _capi.check(self.lib.cm_assemble_pq_cells_structured(
+                C.byref(form.params), mesh.nx, mesh.ny, _capi.ptr(mesh.coords), _capi.ptr(t.nrowptr),
+                _capi.ptr(u), _capi.ptr(p_old), _capi.ptr(self.load),
+                _capi.ptr(self.vals) if want_jac else None, _capi.ptr(self.b), _capi.stream_ptr()))
+            return (self.vals if want_jac else None), self.b
         _capi.check(self.lib.cm_assemble_pq_cells(
             C.byref(form.params), t.nv, mesh.num_cells(), _capi.ptr(mesh.cells), _capi.ptr(mesh.coords),
             _capi.ptr(t.v2c_ptr), _capi.ptr(t.v2c_ent), _capi.ptr(t.v2c_slot), _capi.ptr(t.nrowptr),

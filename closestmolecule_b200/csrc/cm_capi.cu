@@ -50,6 +50,17 @@ int cm_assemble_pq_cells(const cm_pq_params* prm, int32_t nv, int32_t ncells, co
                           p_old, load, Kq, cq, vals, b, accumulate, maxdeg, (cudaStream_t)stream);
 }
 
+int cm_assemble_pq_cells_structured(const cm_pq_params* prm, int32_t nx, int32_t ny,
+                                    const double* coords, const int32_t* nrowptr, const double* u,
+                                    const double* p_old, const double* load, double* vals,
+                                    double* b, void* stream) {
+  CM_CHECK_ARG(prm && coords && nrowptr && u && b, "null pointer");
+  CM_CHECK_ARG(nx >= 1 && ny >= 1, "empty mesh");
+  CM_CHECK_ARG(prm->inv_dt == 0.0 || p_old != nullptr, "transient form needs p_old");
+  return assemble_pq_sweep(*prm, nx, ny, coords, nrowptr, u, p_old, load, vals, b,
+                           (cudaStream_t)stream);
+}
+
 int cm_assemble_scalar_cells(const cm_scalar_params* prm, int32_t nv, int32_t ncells,
                              const int32_t* cells, const double* coords, const int32_t* v2c_ptr,
                              const int32_t* v2c_ent, const int32_t* v2c_slot,

@@ -77,6 +77,11 @@ int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, i
                      cudaStream_t st);
 int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st);
 
+// cm_sweep.cu
+int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
+                      const int* nrowptr, const double* u, const double* p_old, const double* load,
+                      double* vals, double* b, cudaStream_t st);
+
 // cm_pqsolver.cu
 size_t pqs_workspace_bytes(int nx, int ny, int restart);
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,

@@ -111,8 +111,12 @@ int cm_assemble_pq_cells(const cm_pq_params* prm_host, int32_t nv, int32_t ncell
 /* ---- a3 on structured meshes (RectangleMesh numbering, create_flat_boundary.py:65; arbitrary
  * vertex coordinates): same output, bit-identical layout, no connectivity or map is read: cells,
  * neighbours and CSR slots are derived from (ix,iy).  Each cell's quadrature sums are computed
- * once per CTA sweep and shared through shared memory; rows leave the SM as contiguous TMA bulk
- * stores.  nrowptr must be the cell-only P1 pattern of the (nx,ny) mesh. */
+ * once; element rows meet in shared-memory accumulators in DOLFIN's summation order (no atomics);
+ * every CSR slot is written exactly once.  nrowptr must be the cell-only P1 pattern of the (nx,ny) mesh. */
+int cm_assemble_pq_cells_structured(const cm_pq_params* prm_host, int32_t nx, int32_t ny,
+                                    const double* coords, const int32_t* nrowptr, const double* u,
+                                    const double* p_old, const double* load, double* vals,
+                                    double* b, void* stream);
 
 /* ---- a4: scalar P1 forms (F-A/F-B), Jacobian+residual, row-owner gather -------------------------
  * Replaces assemble of FF/Tang at SphericalAdvectionDiffusionReaction_convergence.py:92-110 and of

@@ -133,3 +133,18 @@ def test_scalar_newton_reproduces_readme_rows():
         assert f"{e1:6.2e}" == e1s and f"{e0:6.2e}" == e0s
         ref = scalar.solve_fb(n)
         assert np.linalg.norm(u.vector().cpu().numpy() - ref["u"]) / np.linalg.norm(ref["u"]) < 1e-8
+
+
+def test_ported_convergence_script_prints_readme_table():
+    """scripts/SphericalAdvectionDiffusionReaction_convergence.py (the reference driver on the GPU
+    path) reproduces README.md:109-115 digit for digit."""
+    import importlib.util
+    import os
+    from test_oracle_golden import README_TABLE
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "SphericalAdvectionDiffusionReaction_convergence.py")
+    spec = importlib.util.spec_from_file_location("sadr_conv", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(7)
+    assert [r.split() for r in rows] == [r.split() for r in README_TABLE]
