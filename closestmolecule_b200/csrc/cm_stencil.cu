@@ -263,6 +263,113 @@ line_factor_kernel(const int nx, const int ny, const double* __restrict__ A, dou
   if (bad) atomicExch(err, 2);
 }
 
+// Parallel version: the pivot recurrence u_i = d_i - a_i c_{i-1} / u_{i-1} is a Moebius map of
+// u_{i-1}; compositions are 2x2 matrix products, so one CTA per grid line evaluates it as a
+// block-wide scan over (projectively normalised) matrices, then every thread replays its own
+// segment with the exact incoming pivot and writes l_i, 1/u_i, c_i/u_i.
+struct Mob {
+  double a, b, c, d;  // u -> (a u + b) / (c u + d)
+};
+__device__ __forceinline__ Mob mob_norm(Mob m) {
+  const double s = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
+  if (s > 0.0 && isfinite(s)) {
+    const double r = 1.0 / s;
+    m.a *= r; m.b *= r; m.c *= r; m.d *= r;
+  }
+  return m;
+}
+__device__ __forceinline__ Mob mob_compose(const Mob l, const Mob e) {  // l after e
+  Mob r;
+  r.a = l.a * e.a + l.b * e.c;
+  r.b = l.a * e.b + l.b * e.d;
+  r.c = l.c * e.a + l.d * e.c;
+  r.d = l.c * e.b + l.d * e.d;
+  return mob_norm(r);
+}
+__device__ __forceinline__ Mob mob_shfl_up(const Mob m, int o) {
+  Mob r;
+  r.a = __shfl_up_sync(0xffffffffu, m.a, o);
+  r.b = __shfl_up_sync(0xffffffffu, m.b, o);
+  r.c = __shfl_up_sync(0xffffffffu, m.c, o);
+  r.d = __shfl_up_sync(0xffffffffu, m.d, o);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+line_factor_scan_kernel(const int nx, const int ny, const int E, const double* __restrict__ A,
+                        double* __restrict__ lf, double* __restrict__ iu, double* __restrict__ cu,
+                        int* __restrict__ err) {
+  extern __shared__ double sm[];
+  const int n1 = nx + 1;
+  double* s_a = sm;
+  double* s_d = sm + n1;
+  double* s_c = sm + 2 * n1;
+  __shared__ double sh[4 * 32];
+  const int j = blockIdx.x;
+  const size_t nv = (size_t)n1 * (ny + 1);
+  const size_t base = (size_t)j * n1;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  for (int i = tid; i < n1; i += T) {
+    const size_t v = base + i;
+    s_a[i] = (i > 0) ? A[2 * nv + v] : 0.0;
+    s_d[i] = A[3 * nv + v];
+    s_c[i] = (i < nx) ? A[4 * nv + v] : 0.0;
+  }
+  __syncthreads();
+  const int i0 = tid * E, i1 = min(i0 + E, n1);
+  Mob m{1.0, 0.0, 0.0, 1.0};
+  for (int i = i0; i < i1; ++i) {
+    const double d = s_d[i], ac = (i > 0) ? s_a[i] * s_c[i - 1] : 0.0;
+    // M_i = [[d, -ac], [1, 0]] applied after m
+    Mob r;
+    r.a = d * m.a - ac * m.c;
+    r.b = d * m.b - ac * m.d;
+    r.c = m.a;
+    r.d = m.b;
+    m = mob_norm(r);
+  }
+  // inclusive scan in thread order
+  Mob inc = m;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const Mob p = mob_shfl_up(inc, o);
+    if (lane >= o) inc = mob_compose(inc, p);
+  }
+  if (lane == 31) { sh[4 * wid] = inc.a; sh[4 * wid + 1] = inc.b; sh[4 * wid + 2] = inc.c; sh[4 * wid + 3] = inc.d; }
+  __syncthreads();
+  if (wid == 0) {
+    Mob t = (lane < nw) ? Mob{sh[4 * lane], sh[4 * lane + 1], sh[4 * lane + 2], sh[4 * lane + 3]}
+                        : Mob{1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const Mob p = mob_shfl_up(t, o);
+      if (lane >= o) t = mob_compose(t, p);
+    }
+    if (lane < nw) { sh[4 * lane] = t.a; sh[4 * lane + 1] = t.b; sh[4 * lane + 2] = t.c; sh[4 * lane + 3] = t.d; }
+  }
+  __syncthreads();
+  Mob ex = mob_shfl_up(inc, 1);
+  if (lane == 0) ex = Mob{1.0, 0.0, 0.0, 1.0};
+  if (wid > 0) ex = mob_compose(ex, Mob{sh[4 * (wid - 1)], sh[4 * (wid - 1) + 1], sh[4 * (wid - 1) + 2], sh[4 * (wid - 1) + 3]});
+  // pivot entering this segment: the prefix map applied to u_{-1} = 1 (a_0 = 0 makes it irrelevant)
+  double uprev = (ex.a + ex.b) / (ex.c + ex.d);
+  bool bad = false;
+  for (int i = i0; i < i1; ++i) {
+    const double a = s_a[i], c = s_c[i];
+    const double l = (i > 0) ? a / uprev : 0.0;
+    const double u = s_d[i] - ((i > 0) ? l * s_c[i - 1] : 0.0);
+    const double inv = 1.0 / u;
+    if (!isfinite(inv) || fabs(u) < 1e-300) bad = true;
+    const size_t v = base + i;
+    lf[v] = l;
+    iu[v] = inv;
+    cu[v] = c * inv;
+    uprev = u;
+  }
+  if (bad) atomicExch(err, 2);
+}
+
 // ------------------------------------------------------------------------------------------------
 // zebra x-line relaxation: for every grid line of one colour solve
 //   T x_line = b_line - (A - T) x      (couplings to the lines above/below use the current x)
@@ -309,7 +416,7 @@ __device__ __forceinline__ double affine_exclusive_scan(Affine m, double* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
                   const double* __restrict__ A, const double* __restrict__ lf,
                   const double* __restrict__ iu, const double* __restrict__ cu,
@@ -325,6 +432,7 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
   const size_t base = (size_t)j * n1;
   const int T = blockDim.x, tid = threadIdx.x;
   // right-hand side: b minus the couplings to the neighbouring lines
+#pragma unroll 4
   for (int i = tid; i < n1; i += T) {
     const size_t v = base + i;
     double r = b[v];
@@ -526,7 +634,22 @@ int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st) {
 
 int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
                    cudaStream_t st) {
-  line_factor_kernel<<<(ny + 1 + 127) / 128, 128, 0, st>>>(nx, ny, A, lf, iu, cu, err);
+  const int n1 = nx + 1;
+  const size_t smem = 3 * (size_t)n1 * sizeof(double);
+  if (smem > 200 * 1024) {  // very long lines: serial Thomas per line
+    line_factor_kernel<<<(ny + 1 + 127) / 128, 128, 0, st>>>(nx, ny, A, lf, iu, cu, err);
+    CM_LAUNCH_CHECK();
+    return CM_OK;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CM_CUDA(cudaFuncSetAttribute(line_factor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    attr_set = true;
+  }
+  const int T = (n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32);
+  const int E = (n1 + T - 1) / T;
+  line_factor_scan_kernel<<<ny + 1, T, smem, st>>>(nx, ny, E, A, lf, iu, cu, err);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -536,7 +659,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   const int n1 = nx + 1;
   const int nlines = (ny + 1 - colour + 1) / 2;
   if (nlines <= 0) return CM_OK;
-  const int T = (n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32);
+  const int T = (n1 > 2048) ? 512 : ((n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32));
   int E = (n1 + T - 1) / T;
   if ((E & 1) == 0) ++E;  // odd stride: at most 2-way shared-memory bank conflicts
   const size_t smem = 2 * (size_t)n1 * sizeof(double);
