@@ -16,6 +16,8 @@ void set_error(const char* fmt, ...) {
 }  // namespace cm
 
 using namespace cm;
+namespace cm { int st_zebra_debug_times(unsigned long long*, int); }
+int cm_zebra_debug_times_impl(unsigned long long* o, int n) { return cm::st_zebra_debug_times(o, n); }
 
 extern "C" {
 
@@ -174,6 +176,31 @@ int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_
   if (iters_host) *iters_host = it;
   if (resid_host) *resid_host = rr;
   return rc;
+}
+
+int cm_stencil_line_factor(int32_t nx, int32_t ny, const double* A, double* lf, double* iu,
+                           double* cu, int32_t* err_flag, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && A && lf && iu && cu && err_flag, "bad argument");
+  return st_line_factor(nx, ny, A, lf, iu, cu, err_flag, (cudaStream_t)stream);
+}
+
+int cm_stencil_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
+                     const double* iu, const double* cu, const double* b, double* x,
+                     int32_t x_is_zero, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && (colour == 0 || colour == 1), "bad argument");
+  CM_CHECK_ARG(A && lf && iu && cu && b && x, "null pointer");
+  return st_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, (cudaStream_t)stream);
+}
+
+int cm_stencil_residual(int32_t nx, int32_t ny, const double* A, const double* b, const double* x,
+                        double* r, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && A && x && r, "bad argument");
+  return st_residual(nx, ny, A, b, x, r, (cudaStream_t)stream);
+}
+
+int cm_dev_zebra_times(unsigned long long* host_out, int32_t n) {
+  extern int cm_zebra_debug_times_impl(unsigned long long*, int);
+  return cm_zebra_debug_times_impl(host_out, n);
 }
 
 }  // extern "C"

@@ -6,6 +6,8 @@
 // hierarchy of the p-block is built by Galerkin coarsening in stencil form.  Smoothing and the
 // q-block solve are zebra x-line relaxations: batched tridiagonal solves along r2, each done by
 // one CTA as two parallel scans over affine maps using factors precomputed once per Jacobian.
+#include <stdlib.h>
+
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
 
@@ -416,11 +418,17 @@ __device__ __forceinline__ double affine_exclusive_scan(Affine m, double* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(512)
+constexpr int kZebraPrefetch = 9;
+__device__ unsigned long long g_zdbg[2048 * 8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define ZT(k) do { if ((dbg & 32) && threadIdx.x == 0) g_zdbg[blockIdx.x * 8 + (k)] = gtime(); } while (0)  // striped elements per thread whose (1/u, c/u) are prefetched
+
+template <bool XZERO>
+__global__ void __launch_bounds__(512, 2)
 zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
                   const double* __restrict__ A, const double* __restrict__ lf,
                   const double* __restrict__ iu, const double* __restrict__ cu,
-                  const double* __restrict__ b, double* __restrict__ x, const int x_zero) {
+                  const double* __restrict__ b, double* __restrict__ x, const int dbg) {
   extern __shared__ double sm[];
   const int n1 = nx + 1;
   double* s_z = sm;
@@ -431,27 +439,73 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
   const size_t nv = (size_t)n1 * (ny + 1);
   const size_t base = (size_t)j * n1;
   const int T = blockDim.x, tid = threadIdx.x;
-  // right-hand side: b minus the couplings to the neighbouring lines
-#pragma unroll 4
-  for (int i = tid; i < n1; i += T) {
-    const size_t v = base + i;
-    double r = b[v];
-    if (!x_zero) {
-      if (j > 0) {
-        r -= A[1 * nv + v] * x[v - n1];
-        if (i > 0) r -= A[0 * nv + v] * x[v - n1 - 1];
+  if ((dbg & 64) && blockIdx.x >= 148 && blockIdx.x < 296) __nanosleep(dbg >> 8);
+  ZT(0);
+  // right-hand side: b minus the couplings to the neighbouring lines.  Branch-free: stencil entries
+  // that point outside the grid are stored as zeros, so the neighbour index is only clamped -- every
+  // load of an iteration is independent and can be in flight at once.
+  {
+    const size_t lo = (size_t)(j > 0 ? j - 1 : 0) * n1;
+    const size_t up = (size_t)(j < ny ? j + 1 : ny) * n1;
+    const double* __restrict__ A0 = A + base;
+    const double* __restrict__ A1 = A + nv + base;
+    const double* __restrict__ A5 = A + 5 * nv + base;
+    const double* __restrict__ A6 = A + 6 * nv + base;
+    if (XZERO && (dbg & 16)) {
+      // all loads of the line in flight at once
+      double rb[kZebraPrefetch], rl[kZebraPrefetch];
+#pragma unroll
+      for (int k = 0; k < kZebraPrefetch; ++k) {
+        const int i = tid + k * T;
+        if (i < n1) { rb[k] = b[base + i]; rl[k] = lf[base + i]; }
       }
-      if (j < ny) {
-        r -= A[5 * nv + v] * x[v + n1];
-        if (i < nx) r -= A[6 * nv + v] * x[v + n1 + 1];
+      double piu2[kZebraPrefetch], pcu2[kZebraPrefetch];
+#pragma unroll
+      for (int k = 0; k < kZebraPrefetch; ++k) {
+        const int i = tid + k * T;
+        if (i < n1) { piu2[k] = iu[base + i]; pcu2[k] = cu[base + i]; }
       }
+#pragma unroll
+      for (int k = 0; k < kZebraPrefetch; ++k) {
+        const int i = tid + k * T;
+        if (i < n1) { s_z[i] = rb[k]; s_c[i] = rl[k]; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kZebraPrefetch; ++k) {
+        const int i = tid + k * T;
+        if (i < n1) { s_z[i] *= piu2[k]; s_c[i] = pcu2[k]; }
+      }
+      __syncthreads();
+      for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
+      return;
     }
-    s_z[i] = r;
-    s_c[i] = lf[v];
+#pragma unroll 3
+    for (int i = tid; i < n1; i += T) {
+      double r = b[base + i];
+      const double l = lf[base + i];
+      if (!XZERO) {
+        const int im = i > 0 ? i - 1 : 0, ip = i < nx ? i + 1 : nx;
+        const double a0 = A0[i], a1 = A1[i], a5 = A5[i], a6 = A6[i];
+        const double x0 = x[lo + im], x1 = x[lo + i], x5 = x[up + i], x6 = x[up + ip];
+        r -= a0 * x0 + a1 * x1 + a5 * x5 + a6 * x6;
+      }
+      s_z[i] = r;
+      s_c[i] = l;
+    }
+  }
+  // prefetch the back-substitution factors of this thread's striped elements: their latency hides
+  // behind the forward scan
+  double piu[kZebraPrefetch], pcu[kZebraPrefetch];
+#pragma unroll
+  for (int k = 0; k < kZebraPrefetch; ++k) {
+    const int i = tid + k * T;
+    if (i < n1) { piu[k] = iu[base + i]; pcu[k] = cu[base + i]; }
   }
   __syncthreads();
+  ZT(1);
   // forward: z_i = r_i - l_i z_{i-1}
-  {
+  if (!(dbg & 1)) {
     const int i0 = tid * E, i1 = min(i0 + E, n1);
     Affine m{1.0, 0.0};
     for (int i = i0; i < i1; ++i) {
@@ -466,14 +520,20 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
     }
   }
   __syncthreads();
-  for (int i = tid; i < n1; i += T) {
-    const size_t v = base + i;
-    s_z[i] *= iu[v];
-    s_c[i] = cu[v];
+  ZT(2);
+#pragma unroll
+  for (int k = 0; k < kZebraPrefetch; ++k) {
+    const int i = tid + k * T;
+    if (i < n1) { s_z[i] *= piu[k]; s_c[i] = pcu[k]; }
+  }
+  for (int i = tid + kZebraPrefetch * T; i < n1; i += T) {
+    s_z[i] *= iu[base + i];
+    s_c[i] = cu[base + i];
   }
   __syncthreads();
+  ZT(3);
   // backward: x_i = w_i - cu_i x_{i+1}; thread t takes segment T-1-t so scan order = thread order
-  {
+  if (!(dbg & 2)) {
     const int seg = T - 1 - tid;
     const int i0 = seg * E, i1 = min(i0 + E, n1);
     Affine m{1.0, 0.0};
@@ -489,7 +549,13 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
     }
   }
   __syncthreads();
+  ZT(4);
   for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
+  ZT(5);
+}
+
+int st_zebra_debug_times(unsigned long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_zdbg, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,15 +731,27 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   const size_t smem = 2 * (size_t)n1 * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
+    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CM_CUDA(cudaFuncSetAttribute(zebra_line_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   if (smem > 200 * 1024) {
     set_error("zebra line relaxation: line of %d unknowns exceeds shared memory", n1);
     return CM_E_UNSUPPORTED;
   }
-  zebra_line_kernel<<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, x_zero);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg = e ? atoi(e) : 0; }
+  int TT = T;
+  if (dbg & 4) { TT = 256; E = (n1 + TT - 1) / TT; if ((E & 1) == 0) ++E; }
+  if (dbg & 8) { TT = 1024; E = (n1 + TT - 1) / TT; if ((E & 1) == 0) ++E; }
+  if (x_zero)
+    zebra_line_kernel<true><<<nlines, TT, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg);
+  else
+    zebra_line_kernel<false><<<nlines, TT, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

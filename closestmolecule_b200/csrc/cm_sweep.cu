@@ -3,12 +3,11 @@
 // On RectangleMesh-numbered meshes (create_flat_boundary.py:65; vertex coordinates arbitrary, so
 // boundary-fitted production-like grids qualify) cells, neighbours and CSR slots follow from
 // (ix,iy): no connectivity, gather table or cell->nnz map is read.  A CTA owns a strip of TX-1
-// vertex columns and sweeps upwards over a segment of vertex rows.  Thread t owns quad
-// (ix0-1+t, jq): it computes the quadrature sums of the quad's two cells ONCE (registers) and adds
-// the element rows into shared-memory accumulators of the two vertex rows the quad touches, in four
-// barrier-separated phases ordered so that every CSR slot receives its contributions in ascending
-// cell index -- the summation order of DOLFIN's serial assembler -- without atomics.  A finished
-// vertex row is written out exactly once in the DOLFIN/PETSc-AIJ value layout.
+// vertex columns and sweeps upwards over a segment of vertex rows.  One thread per CELL computes the
+// cell's quadrature sums ONCE (registers) and adds its three element rows into shared-memory
+// accumulators of the two vertex rows the quad row touches, in three barrier-separated phases with a
+// fixed summation order per CSR slot -- deterministic, no atomics.  A finished vertex row is written
+// out exactly once in the DOLFIN/PETSc-AIJ value layout.
 // Replaces the same reference code as pq_rows_kernel (advection_diffusion_convergence.py:196-207).
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
@@ -123,15 +122,38 @@ __device__ __forceinline__ void acc_add(double* acc, int col, int slot, const do
   a[0] += J4[0]; a[kTX] += J4[1]; a[2 * kTX] += J4[2]; a[3 * kTX] += J4[3];
 }
 
+template <int I, bool QGEN, bool WANTJ>
+__device__ __forceinline__ void add_row(const cm_pq_params& P, const TriGeom& g, const CellSums& S,
+                                        const double* pe, const double* qe, const double* po,
+                                        const bool trans, const double tau, double* acc, const int col,
+                                        const int s0, const int s1, const int s2) {
+  double J[3][4], Fp, Fq;
+  cell_row<I, QGEN>(P, g, S, pe, qe, po, trans, tau, J, Fp, Fq);
+  if (WANTJ) {
+    acc_add(acc, col, s0, J[0]);
+    acc_add(acc, col, s1, J[1]);
+    acc_add(acc, col, s2, J[2]);
+  }
+  acc[28 * kTX + col] += Fp;
+  acc[29 * kTX + col] += Fq;
+}
+
+// 2*kTX threads: thread t < kTX owns cell A = (v0,v1,v3) of quad (ix0-1+t, jq), thread kTX+t owns
+// cell B = (v0,v2,v3) of the same quad.  Three barrier-separated phases add the three element rows
+// of every cell; in each phase the A-threads and the B-threads target different row buffers or
+// different columns, so there are no write conflicts and no atomics, and the summation order per
+// CSR slot is fixed (B1,B2,A2 from the quad row below, then A1,A0,B0): bit-reproducible.
 template <int NQ, int GKIND, bool QGEN, bool WANTJ>
-__global__ void __launch_bounds__(kTX)
+__global__ void __launch_bounds__(2 * kTX, 2)
 pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows_per_seg,
                 const double2* __restrict__ coords, const int* __restrict__ nrowptr,
                 const double2* __restrict__ u, const double* __restrict__ p_old,
                 const double2* __restrict__ load, double* __restrict__ vals,
                 double2* __restrict__ b) {
   extern __shared__ double sm[];  // 2 row buffers x kAccPerVertex x kTX
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x;
+  const bool isB = tid >= kTX;
+  const int t = isB ? tid - kTX : tid;
   const int n1 = nx + 1;
   const int ix0 = blockIdx.x * (kTX - 1);          // first owned vertex column
   const int jy0 = blockIdx.y * rows_per_seg;       // first owned vertex row
@@ -142,23 +164,11 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
   const bool ownL = quad_ok && colL >= 0;          // left vertex (qx) is owned by this strip
   const bool ownR = quad_ok && colR <= kTX - 2;    // right vertex (qx+1)
   const bool trans = P.inv_dt != 0.0;
-  // owned vertex of this thread for the write-out
-  const int vx = ix0 + t;
+  const int vx = ix0 + t;                          // vertex written out by this thread (p-row: A half, q-row: B half)
   const bool vown = t <= kTX - 2 && vx <= nx;
 
-  // lower vertex row of the first quad row
-  double2 X0, X1, U0, U1;
-  double O0 = 0.0, O1 = 0.0;
-  const int jq_first = max(jy0 - 1, 0);
-  if (quad_ok) {
-    const int v0 = jq_first * n1 + qx;
-    X0 = coords[v0]; X1 = coords[v0 + 1];
-    U0 = u[v0]; U1 = u[v0 + 1];
-    if (trans) { O0 = p_old[v0]; O1 = p_old[v0 + 1]; }
-  }
-  // zero the buffer of the first owned vertex row
-  for (int e = 0; e < kAccPerVertex; ++e) sm[((jy0 & 1) * kAccPerVertex + e) * kTX + t] = 0.0;
-  __syncthreads();
+  // zero both row buffers once; afterwards the write-out zeroes what it reads
+  for (int e = tid; e < 2 * kAccPerVertex * kTX; e += 2 * kTX) sm[e] = 0.0;
 
   for (int jq = jy0 - 1; jq < jy1; ++jq) {
     double* accLo = sm + ((jq & 1) * kAccPerVertex) * kTX;        // vertex row jq
@@ -167,66 +177,75 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
     const bool vrow_lo = jq >= jy0 && jq < jy1;                   // vertex row jq exists and is owned
     const bool do_lo = row_ok && vrow_lo;
     const bool do_up = row_ok && jq + 1 < jy1;                    // vertex row jq+1 is owned
-    if (jq >= jy0 - 1) {
-      // fresh accumulators for the upper vertex row (the lower one carries the previous step)
-      if (jq + 1 != jy0)
-        for (int e = 0; e < kAccPerVertex; ++e) accUp[e * kTX + t] = 0.0;
+    // pull the vertex row the NEXT step adds (jq+2) towards L1 while this step computes
+    if (quad_ok && jq + 2 <= ny) {
+      const int vn = (jq + 2) * n1 + qx + (isB ? 0 : 1);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(coords + vn));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(u + vn));
     }
-    double2 X2, X3, U2, U3;
-    double O2 = 0.0, O3 = 0.0;
-    TriGeom gA, gB;
-    CellSums SA, SB;
-    double tauA = 0.0, tauB = 0.0;
-    double pA[3], qA[3], oA[3], pB[3], qB[3], oB[3];
+    TriGeom g;
+    CellSums S;
+    double tau = 0.0;
+    double pe[3], qe[3], po[3] = {0.0, 0.0, 0.0};
     const bool active = quad_ok && row_ok;
     if (active) {
-      const int v2 = (jq + 1) * n1 + qx;
-      X2 = coords[v2]; X3 = coords[v2 + 1];
-      U2 = u[v2]; U3 = u[v2 + 1];
-      if (trans) { O2 = p_old[v2]; O3 = p_old[v2 + 1]; }
-      // cell A = (v0, v1, v3), cell B = (v0, v2, v3)
-      gA.x0 = X0.x; gA.y0 = X0.y; gA.x1 = X1.x; gA.y1 = X1.y; gA.x2 = X3.x; gA.y2 = X3.y; gA.build();
-      gB.x0 = X0.x; gB.y0 = X0.y; gB.x1 = X2.x; gB.y1 = X2.y; gB.x2 = X3.x; gB.y2 = X3.y; gB.build();
-      pA[0] = U0.x; pA[1] = U1.x; pA[2] = U3.x; qA[0] = U0.y; qA[1] = U1.y; qA[2] = U3.y;
-      pB[0] = U0.x; pB[1] = U2.x; pB[2] = U3.x; qB[0] = U0.y; qB[1] = U2.y; qB[2] = U3.y;
-      oA[0] = O0; oA[1] = O1; oA[2] = O3; oB[0] = O0; oB[1] = O2; oB[2] = O3;
-      cell_sums<NQ, GKIND, QGEN>(P, gA, pA[0], pA[1], pA[2], qA[0], qA[1], qA[2], trans, SA);
-      cell_sums<NQ, GKIND, QGEN>(P, gB, pB[0], pB[1], pB[2], qB[0], qB[1], qB[2], trans, SB);
-      if (QGEN && P.supg_stab != 0.0) {
-        tauA = 0.5 * P.supg_stab * gA.hmax();
-        tauB = 0.5 * P.supg_stab * gB.hmax();
+      const int v0 = jq * n1 + qx;
+      const int vm = isB ? v0 + n1 : v0 + 1;  // middle vertex: v1 (A) or v2 (B)
+      const int v3 = v0 + n1 + 1;
+      const double2 X0 = coords[v0], X1 = coords[vm], X2 = coords[v3];
+      const double2 U0 = u[v0], U1 = u[vm], U2 = u[v3];
+      g.x0 = X0.x; g.y0 = X0.y; g.x1 = X1.x; g.y1 = X1.y; g.x2 = X2.x; g.y2 = X2.y;
+      g.build();
+      pe[0] = U0.x; pe[1] = U1.x; pe[2] = U2.x;
+      qe[0] = U0.y; qe[1] = U1.y; qe[2] = U2.y;
+      if (trans) { po[0] = p_old[v0]; po[1] = p_old[vm]; po[2] = p_old[v3]; }
+      cell_sums<NQ, GKIND, QGEN>(P, g, pe[0], pe[1], pe[2], qe[0], qe[1], qe[2], trans, S);
+      if (QGEN && P.supg_stab != 0.0) tau = 0.5 * P.supg_stab * g.hmax();
+    }
+    __syncthreads();  // previous write-out (which re-zeroed its buffer) done
+    // ---- phase 1: A row 1 -> (row jq, right vertex); B row 1 -> (row jq+1, left vertex) ----------
+    if (active) {
+      if (!isB) {
+        if (do_lo && ownR) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colR, 2, 3, 5);
+      } else {
+        if (do_up && ownL) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colL, 1, 3, 4);
       }
     }
-    __syncthreads();  // zeroing done
-    double J[3][4], Fp, Fq;
-    // ---- phase 1: lower-right vertex v1 (row jq): cell A local 1 ------------------------------
-    if (active && do_lo && ownR) {
-      cell_row<1, QGEN>(P, gA, SA, pA, qA, oA, trans, tauA, J, Fp, Fq);
-      if (WANTJ) { acc_add(accLo, colR, 2, J[0]); acc_add(accLo, colR, 3, J[1]); acc_add(accLo, colR, 5, J[2]); }
-      accLo[28 * kTX + colR] += Fp; accLo[29 * kTX + colR] += Fq;
+    __syncthreads();
+    // ---- phase 2: A row 0 -> (row jq, left vertex); B row 2 -> (row jq+1, right vertex) ----------
+    if (active) {
+      if (!isB) {
+        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 4, 6);
+      } else {
+        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 2, 3);
+      }
     }
     __syncthreads();
-    // ---- phase 2: lower-left vertex v0 (row jq): cells A then B, local 0 -----------------------
-    if (active && do_lo && ownL) {
-      cell_row<0, QGEN>(P, gA, SA, pA, qA, oA, trans, tauA, J, Fp, Fq);
-      if (WANTJ) { acc_add(accLo, colL, 3, J[0]); acc_add(accLo, colL, 4, J[1]); acc_add(accLo, colL, 6, J[2]); }
-      accLo[28 * kTX + colL] += Fp; accLo[29 * kTX + colL] += Fq;
-      cell_row<0, QGEN>(P, gB, SB, pB, qB, oB, trans, tauB, J, Fp, Fq);
-      if (WANTJ) { acc_add(accLo, colL, 3, J[0]); acc_add(accLo, colL, 5, J[1]); acc_add(accLo, colL, 6, J[2]); }
-      accLo[28 * kTX + colL] += Fp; accLo[29 * kTX + colL] += Fq;
+    // ---- phase 3: A row 2 -> (row jq+1, right vertex); B row 0 -> (row jq, left vertex) ----------
+    if (active) {
+      if (!isB) {
+        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 1, 3);
+      } else {
+        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 5, 6);
+      }
     }
     __syncthreads();
-    // vertex row jq is complete: write it out (every CSR slot exactly once)
+    // vertex row jq is complete: write it out (every CSR slot exactly once); the A half of the CTA
+    // writes the p-rows (and b), the B half the q-rows
     if (vrow_lo && vown) {
       const int v = jq * n1 + vx;
       const int rp = nrowptr[v];
       const int deg = nrowptr[v + 1] - rp;
-      double2 out = make_double2(accLo[28 * kTX + t], accLo[29 * kTX + t]);
-      if (load != nullptr) { const double2 l = load[v]; out.x -= l.x; out.y -= l.y; }
-      b[v] = out;
+      if (!isB) {
+        double2 out = make_double2(accLo[28 * kTX + t], accLo[29 * kTX + t]);
+        accLo[28 * kTX + t] = 0.0;
+        accLo[29 * kTX + t] = 0.0;
+        if (load != nullptr) { const double2 l = load[v]; out.x -= l.x; out.y -= l.y; }
+        b[v] = out;
+      }
       if (WANTJ) {
-        double2* prow = reinterpret_cast<double2*>(vals + 4 * (size_t)rp);
-        double2* qrow = prow + deg;
+        double2* row = reinterpret_cast<double2*>(vals + 4 * (size_t)rp) + (isB ? deg : 0);
+        const int e0 = isB ? 2 : 0;
         int k = 0;
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
@@ -234,30 +253,13 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
           const int dy = (s < 2) ? -1 : (s > 4 ? 1 : 0);
           const int jx = vx + dx, jy = jq + dy;
           if (jx < 0 || jx > nx || jy < 0 || jy > ny) continue;
-          prow[k] = make_double2(accLo[(4 * s) * kTX + t], accLo[(4 * s + 1) * kTX + t]);
-          qrow[k] = make_double2(accLo[(4 * s + 2) * kTX + t], accLo[(4 * s + 3) * kTX + t]);
+          row[k] = make_double2(accLo[(4 * s + e0) * kTX + t], accLo[(4 * s + e0 + 1) * kTX + t]);
+          accLo[(4 * s + e0) * kTX + t] = 0.0;
+          accLo[(4 * s + e0 + 1) * kTX + t] = 0.0;
           ++k;
         }
       }
     }
-    // ---- phase 3: upper-right vertex v3 (row jq+1): cells A then B, local 2 -------------------
-    if (active && do_up && ownR) {
-      cell_row<2, QGEN>(P, gA, SA, pA, qA, oA, trans, tauA, J, Fp, Fq);
-      if (WANTJ) { acc_add(accUp, colR, 0, J[0]); acc_add(accUp, colR, 1, J[1]); acc_add(accUp, colR, 3, J[2]); }
-      accUp[28 * kTX + colR] += Fp; accUp[29 * kTX + colR] += Fq;
-      cell_row<2, QGEN>(P, gB, SB, pB, qB, oB, trans, tauB, J, Fp, Fq);
-      if (WANTJ) { acc_add(accUp, colR, 0, J[0]); acc_add(accUp, colR, 2, J[1]); acc_add(accUp, colR, 3, J[2]); }
-      accUp[28 * kTX + colR] += Fp; accUp[29 * kTX + colR] += Fq;
-    }
-    __syncthreads();
-    // ---- phase 4: upper-left vertex v2 (row jq+1): cell B local 1 -----------------------------
-    if (active && do_up && ownL) {
-      cell_row<1, QGEN>(P, gB, SB, pB, qB, oB, trans, tauB, J, Fp, Fq);
-      if (WANTJ) { acc_add(accUp, colL, 1, J[0]); acc_add(accUp, colL, 3, J[1]); acc_add(accUp, colL, 4, J[2]); }
-      accUp[28 * kTX + colL] += Fp; accUp[29 * kTX + colL] += Fq;
-    }
-    __syncthreads();
-    if (active) { X0 = X2; X1 = X3; U0 = U2; U1 = U3; O0 = O2; O1 = O3; }
   }
 }
 
@@ -276,12 +278,12 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
   if (vals != nullptr) {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, true>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
+    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
                                   p_old, (const double2*)load, vals, (double2*)b);
   } else {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, false>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
+    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
                                   p_old, (const double2*)load, vals, (double2*)b);
   }
   CM_LAUNCH_CHECK();

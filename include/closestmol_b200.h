@@ -192,6 +192,22 @@ int cm_pqs_solve(int32_t nx, int32_t ny, int32_t restart, const double* b, doubl
                  double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
                  int32_t* iters_host, double* resid_host, void* stream);
 
+/* Building blocks of the structured solver, exported for tests and reuse.  A is a 7-point stencil
+ * stored as diagonals A[k*n + node], n = (nx+1)*(ny+1), k: 0:(-1,-1) 1:(0,-1) 2:(-1,0) 3:(0,0)
+ * 4:(+1,0) 5:(0,+1) 6:(+1,+1); entries pointing outside the grid must be zero.
+ *   cm_stencil_line_factor: LU factors of the tridiagonal x-line blocks (l, 1/u, c/u per node);
+ *     *err_flag (device int, zeroed by the caller) is set to 2 on a zero pivot.
+ *   cm_stencil_zebra: for every grid line of one colour (line index parity) solve
+ *     T x_line = b_line - (A - T) x with the current x on the neighbouring lines (x_is_zero: skip them).
+ *   cm_stencil_residual: r = b - A x (b may be NULL). */
+int cm_stencil_line_factor(int32_t nx, int32_t ny, const double* A, double* lf, double* iu,
+                           double* cu, int32_t* err_flag, void* stream);
+int cm_stencil_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
+                     const double* iu, const double* cu, const double* b, double* x,
+                     int32_t x_is_zero, void* stream);
+int cm_stencil_residual(int32_t nx, int32_t ny, const double* A, const double* b, const double* x,
+                        double* r, void* stream);
+
 /* Generic path (any mesh): GMRES(restart) with point (bs=1) or 2x2 node-block (bs=2) Jacobi on the
  * node-level CSR layouts.  Adequate for the scalar forms (SphericalLaplace_convergence.py:135,
  * SphericalAdvectionDiffusionReaction_convergence.py:104); NOT for the Galerkin P-Q system. */
