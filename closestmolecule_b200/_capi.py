@@ -34,6 +34,13 @@ class ScalarParamsC(C.Structure):
                 ("degree", C.c_int32), ("reserved", C.c_int32)]
 
 
+class DistC(C.Structure):
+    """struct cm_dist"""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("peer_base", C.c_void_p * 8),
+                ("halo_seq", C.c_uint64), ("coll_seq", C.c_uint64), ("row_begin", C.c_int32 * 9),
+                ("reserved", C.c_int32)]
+
+
 class KrylovParamsC(C.Structure):
     """struct cm_krylov_params"""
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int32),
@@ -62,6 +69,19 @@ _PROTOS = {
     "cm_pqs_setup": ([_I, _I, _I, _P, _P, _P, _P, C.c_int64, _P], C.c_int),
     "cm_pqs_solve": ([_I, _I, _I, _P, _P, _D, _D, _I, _P, C.c_int64, C.POINTER(C.c_int32),
                       C.POINTER(C.c_double), _P], C.c_int),
+    "cm_ipc_alloc": ([C.c_int64], C.c_void_p),
+    "cm_ipc_free": ([_P], C.c_int),
+    "cm_ipc_get_handle": ([_P, _P], C.c_int),
+    "cm_ipc_open": ([_P], C.c_void_p),
+    "cm_ipc_close": ([_P], C.c_int),
+    "cm_pqs_state_offset": ([_I, _I, _I], C.c_int64),
+    "cm_assemble_pq_cells_structured_rows": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I, _I, _P], C.c_int),
+    "cm_dist_exchange_rows": ([C.POINTER(DistC), C.c_int64, _I, _I, _I, _P], C.c_int),
+    "cm_dist_allgather_rows": ([C.POINTER(DistC), C.c_int64, _I, _I, _I, _P], C.c_int),
+    "cm_dist_allreduce_sum": ([C.POINTER(DistC), _P, _I, _P], C.c_int),
+    "cm_pqs_setup_dist": ([_I, _I, _I, _P, _P, _P, _P, C.c_int64, C.POINTER(DistC), _P], C.c_int),
+    "cm_pqs_solve_dist": ([_I, _I, _I, _P, _P, _D, _D, _I, _P, C.c_int64, C.POINTER(DistC),
+                           C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
     "cm_stencil_line_factor": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
     "cm_stencil_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P], C.c_int),
     "cm_stencil_residual": ([_I, _I] + [_P] * 4 + [_P], C.c_int),

@@ -203,4 +203,106 @@ int cm_dev_zebra_times(unsigned long long* host_out, int32_t n) {
   return cm_zebra_debug_times_impl(host_out, n);
 }
 
+// ---- multi-GPU (strip-partitioned) entry points ---------------------------------------------------
+void* cm_ipc_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+    set_error("cm_ipc_alloc: cudaMalloc(%lld) failed", (long long)bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  cudaMemset(p, 0, (size_t)bytes);
+  return p;
+}
+
+int cm_ipc_free(void* p) {
+  CM_CUDA(cudaFree(p));
+  return CM_OK;
+}
+
+int cm_ipc_get_handle(void* p, void* handle64_host) {
+  CM_CHECK_ARG(p && handle64_host, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CM_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_host, p));
+  return CM_OK;
+}
+
+void* cm_ipc_open(const void* handle64_host) {
+  void* p = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, sizeof(h));
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    set_error("cm_ipc_open: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+
+int cm_ipc_close(void* p) {
+  CM_CUDA(cudaIpcCloseMemHandle(p));
+  return CM_OK;
+}
+
+int64_t cm_pqs_state_offset(int32_t nx, int32_t ny, int32_t restart) {
+  return (int64_t)pqs_state_offset_bytes(nx, ny, restart);
+}
+
+int cm_assemble_pq_cells_structured_rows(const cm_pq_params* prm, int32_t nx, int32_t ny,
+                                         const double* coords, const int32_t* nrowptr,
+                                         const double* u, const double* p_old, const double* load,
+                                         double* vals, double* b, int32_t row_begin,
+                                         int32_t row_end, void* stream) {
+  CM_CHECK_ARG(prm && coords && nrowptr && u && b, "null pointer");
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && row_begin >= 0 && row_end <= ny + 1, "bad row range");
+  return assemble_pq_sweep(*prm, nx, ny, coords, nrowptr, u, p_old, load, vals, b,
+                           (cudaStream_t)stream, row_begin, row_end);
+}
+
+int cm_dist_exchange_rows(cm_dist* D, int64_t array_offset_bytes, int32_t row_doubles,
+                          int32_t row_begin, int32_t row_end, void* stream) {
+  CM_CHECK_ARG(D && (array_offset_bytes % 8) == 0 && row_doubles > 0 && row_end > row_begin, "bad argument");
+  unsigned long long od = (unsigned long long)(array_offset_bytes / 8) + (unsigned long long)row_begin * row_doubles;
+  unsigned long long ou = (unsigned long long)(array_offset_bytes / 8) + (unsigned long long)(row_end - 1) * row_doubles;
+  int n = row_doubles;
+  return dist_halo2(D, &od, &n, 1, &ou, &n, 1, (cudaStream_t)stream);
+}
+
+int cm_dist_allgather_rows(cm_dist* D, int64_t array_offset_bytes, int32_t row_doubles,
+                           int32_t row_begin, int32_t row_end, void* stream) {
+  CM_CHECK_ARG(D && (array_offset_bytes % 8) == 0 && row_doubles > 0 && row_end > row_begin, "bad argument");
+  unsigned long long off = (unsigned long long)(array_offset_bytes / 8) + (unsigned long long)row_begin * row_doubles;
+  int n = (row_end - row_begin) * row_doubles;
+  return dist_allgather(D, &off, &n, 1, (cudaStream_t)stream);
+}
+
+int cm_dist_allreduce_sum(cm_dist* D, double* vals, int32_t n, void* stream) {
+  CM_CHECK_ARG(D && vals && n > 0 && n <= 64, "bad argument");
+  return dist_allreduce(D, vals, n, (cudaStream_t)stream);
+}
+
+int cm_pqs_setup_dist(int32_t nx, int32_t ny, int32_t restart, const int32_t* nrowptr,
+                      const int32_t* ncol, const double* vals, void* workspace,
+                      int64_t workspace_bytes, cm_dist* D, void* stream) {
+  CM_CHECK_ARG(nx >= 2 && ny >= 2 && restart >= 1, "bad grid or restart");
+  CM_CHECK_ARG(nrowptr && ncol && vals && workspace && D, "null pointer");
+  CM_CHECK_ARG(D->world >= 1 && D->world <= 8 && D->rank >= 0 && D->rank < D->world, "bad rank/world");
+  return pqs_setup_dist(nx, ny, restart, nrowptr, ncol, vals, workspace, (size_t)workspace_bytes, D,
+                        (cudaStream_t)stream);
+}
+
+int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, double* x,
+                      double rtol, double atol, int32_t maxit, void* workspace,
+                      int64_t workspace_bytes, cm_dist* D, int32_t* iters_host, double* resid_host,
+                      void* stream) {
+  CM_CHECK_ARG(nx >= 2 && ny >= 2 && restart >= 1 && maxit >= 1, "bad grid, restart or maxit");
+  CM_CHECK_ARG(b && x && workspace && D, "null pointer");
+  int it = 0;
+  double rr = 0.0;
+  const int rc = pqs_solve_dist(nx, ny, restart, b, x, rtol, atol, maxit, workspace,
+                                (size_t)workspace_bytes, D, &it, &rr, (cudaStream_t)stream);
+  if (iters_host) *iters_host = it;
+  if (resid_host) *resid_host = rr;
+  return rc;
+}
+
 }  // extern "C"

@@ -46,33 +46,53 @@ int multi_axpy(long long n, const double* Vbase, long long vstride, int nvec, co
 int vec_scale(long long n, const double* x, const double* a_dev, double a_host, int invert,
               double* y, cudaStream_t st);
 
+struct VecSlice {
+  long long off0, off1, len;  // indices [off0, off0+len) U [off1, off1+len)
+};
+int multi_dot_slice(VecSlice sl, const double* Vbase, long long vstride, int nvec, const double* w,
+                    double* out, double* scratch, cudaStream_t st);
+int multi_axpy_slice(VecSlice sl, const double* Vbase, long long vstride, int nvec, const double* h,
+                     double sign, double* w, double* norm2_out, double* scratch, cudaStream_t st);
+int vec_scale_slice(VecSlice sl, const double* x, double a, int invert, double* y, cudaStream_t st);
+
+// cm_dist.cu
+size_t dist_ctl_doubles();
+int dist_halo(cm_dist* D, const unsigned long long* offs, const int* ns, int nseg, cudaStream_t st);
+int dist_halo2(cm_dist* D, const unsigned long long* offs_dn, const int* ns_dn, int nseg_dn,
+               const unsigned long long* offs_up, const int* ns_up, int nseg_up, cudaStream_t st);
+int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, int nseg,
+                   cudaStream_t st);
+int dist_allreduce(cm_dist* D, double* vals, int n, cudaStream_t st);
+
 // cm_gmres.cu
 size_t gmres_workspace_doubles(long long n, int restart);
 int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x,
                 double rtol, double atol, int maxit, int restart, int reorth, double* work,
-                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st);
+                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st,
+                const VecSlice* sl = nullptr, cm_dist* D = nullptr);
 
 // cm_stencil.cu
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
-                      int* err, cudaStream_t st);
+                      int* err, cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
-                   cudaStream_t st);
-int st_interleave(int nv, const double* xs, double* x, cudaStream_t st);
+                   cudaStream_t st, int vb = 0, int ve = -1);
+int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb = 0, int ve = -1);
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st);
-int st_unscale(int nv, const double* r, const double* sp, const double* sq, double* out,
-               cudaStream_t st);
+               cudaStream_t st, int r0 = 0, int r1 = -1);
+int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,
+               cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
-                cudaStream_t st);
-int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st);
-int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st);
-int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st);
+                cudaStream_t st, int r0 = 0, int r1 = -1);
+int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st, int R0 = 0, int R1 = -1);
+int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st, int r0 = 0, int r1 = -1);
+int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st, int R0 = 0, int R1 = -1);
 int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
-                   cudaStream_t st);
+                   cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
-             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st);
+             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0 = 0,
+             int r1 = -1);
 int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, int* err,
                      cudaStream_t st);
 int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st);
@@ -80,7 +100,7 @@ int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaS
 // cm_sweep.cu
 int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                       const int* nrowptr, const double* u, const double* p_old, const double* load,
-                      double* vals, double* b, cudaStream_t st);
+                      double* vals, double* b, cudaStream_t st, int row_begin = 0, int row_end = -1);
 
 // cm_pqsolver.cu
 size_t pqs_workspace_bytes(int nx, int ny, int restart);
@@ -88,6 +108,12 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
               void* ws, size_t ws_bytes, cudaStream_t st);
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
               int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
+int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
+                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st);
+int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
+                   int maxit, void* ws, size_t ws_bytes, cm_dist* D, int* iters, double* resid,
+                   cudaStream_t st);
+size_t pqs_state_offset_bytes(int nx, int ny, int restart);
 size_t krylov_workspace_bytes(int bs, int nv, int restart);
 int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
                  const double* vals, const double* b, double* x, double rtol, double atol, int maxit,

@@ -22,7 +22,36 @@ size_t gmres_workspace_doubles(long long n, int restart) {
 
 int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x,
                 double rtol, double atol, int maxit, int restart, int reorth, double* work,
-                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st) {
+                int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st,
+                const VecSlice* sl, cm_dist* D) {
+  // single GPU: the whole vector [0,n); multi GPU: this rank's slices + all-reduced dot products
+  auto multi_dot = [&](long long, const double* Vb, long long vs, int nvec, const double* ww,
+                       double* out, double* scr, cudaStream_t s_) -> int {
+    int e = sl ? multi_dot_slice(*sl, Vb, vs, nvec, ww, out, scr, s_)
+               : cm::multi_dot(n, Vb, vs, nvec, ww, out, scr, s_);
+    if (e) return e;
+    return dist_allreduce(D, out, nvec, s_);
+  };
+  auto multi_axpy = [&](long long, const double* Vb, long long vs, int nvec, const double* hh,
+                        double sign, double* ww, double* n2, double* scr, cudaStream_t s_) -> int {
+    int e = sl ? multi_axpy_slice(*sl, Vb, vs, nvec, hh, sign, ww, n2, scr, s_)
+               : cm::multi_axpy(n, Vb, vs, nvec, hh, sign, ww, n2, scr, s_);
+    if (e) return e;
+    return n2 ? dist_allreduce(D, n2, 1, s_) : CM_OK;
+  };
+  auto vec_scale = [&](long long, const double* xx, const double*, double a, int inv, double* yy,
+                       cudaStream_t s_) -> int {
+    return sl ? vec_scale_slice(*sl, xx, a, inv, yy, s_) : cm::vec_scale(n, xx, nullptr, a, inv, yy, s_);
+  };
+  auto vec_zero = [&](double* yy) -> int {
+    if (sl) return vec_scale_slice(*sl, nullptr, 0.0, 0, yy, st);
+    return cudaMemsetAsync(yy, 0, sizeof(double) * n, st) == cudaSuccess ? CM_OK : CM_E_CUDA;
+  };
+  auto vec_copy = [&](double* yy, const double* xx) -> int {
+    if (sl) return vec_scale_slice(*sl, xx, 1.0, 0, yy, st);
+    return cudaMemcpyAsync(yy, xx, sizeof(double) * n, cudaMemcpyDeviceToDevice, st) == cudaSuccess
+               ? CM_OK : CM_E_CUDA;
+  };
   const long long ne = (n + 1) & ~1LL;
   double* V = work;
   double* w = V + (size_t)ne * (restart + 1);
@@ -43,9 +72,10 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
   auto Hat = [&](int i, int j) -> double& { return H[(size_t)j * (m + 1) + i]; };
 
   // x0 = 0: r0 = b
-  CM_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
-  CM_CUDA(cudaMemcpyAsync(w, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  int rc = multi_dot(n, w, ne, 1, w, hdev, scratch, st);
+  int rc = vec_zero(x);
+  if (rc) return rc;
+  if ((rc = vec_copy(w, b))) return rc;
+  rc = multi_dot(n, w, ne, 1, w, hdev, scratch, st);
   if (rc) return rc;
   CM_CUDA(cudaMemcpyAsync(hhost, hdev, sizeof(double), cudaMemcpyDeviceToHost, st));
   CM_CUDA(cudaStreamSynchronize(st));
@@ -130,7 +160,7 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
     }
     for (int i = 0; i < k; ++i) hhost[i] = y[i];
     CM_CUDA(cudaMemcpyAsync(hdev, hhost, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * n, st));
+    if ((rc = vec_zero(w))) return rc;
     rc = multi_axpy(n, V, ne, k, hdev, 1.0, w, nullptr, scratch, st);
     if (rc) return rc;
     rc = Minv(w, z);
@@ -144,7 +174,7 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
     // restart: r = b - A x
     rc = A(x, z);
     if (rc) return rc;
-    CM_CUDA(cudaMemcpyAsync(w, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if ((rc = vec_copy(w, b))) return rc;
     hhost[m + 3] = 1.0;
     CM_CUDA(cudaMemcpyAsync(hdev + m + 3, hhost + m + 3, sizeof(double), cudaMemcpyHostToDevice, st));
     rc = multi_axpy(n, z, ne, 1, hdev + m + 3, -1.0, w, hdev, scratch, st);

@@ -31,7 +31,7 @@ struct PQSolver {
   double *PP, *PQ, *QP, *QQ, *sp, *sq;
   double *qlf, *qiu, *qcu;
   double *Ainv, *Mwork;
-  double *bs, *xs, *tq, *ru;
+  double *bs, *xs, *tq, *ru, *ustate;
   double* gm;
   int* err;
   size_t total_doubles;
@@ -51,6 +51,8 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
     return p;
   };
   const size_t V = (size_t)S.nv;
+  take(dist_ctl_doubles());  // flags / all-reduce slots of the multi-GPU path (unused on one GPU)
+  S.ustate = take(2 * V);     // Newton state u (interleaved) lives here so its halo rows can be pushed
   S.PP = take(7 * V);
   S.PQ = take(7 * V);
   S.QP = take(7 * V);
@@ -188,7 +190,7 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
   // M^{-1} = [[App,0],[Aqp,Aqq]]^{-1} (approximately) on the UNSCALED operator, composed with the
   // inverse row scaling: multigrid needs the true (variational) FE operator to be mesh independent
   LinOp Minv = [&](const double* r, double* z) {
-    int e = st_unscale(V, r, S.sp, S.sq, S.ru, st);
+    int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st);
     if (e) return e;
     if ((e = vcycle(S, 0, S.ru, z, st))) return e;
     if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st))) return e;
@@ -209,6 +211,194 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
               rtol, maxit, resid ? *resid : -1.0);
   }
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strip-partitioned multi-GPU variant: levels 0..Ld-1 are distributed by vertex rows (every rank
+// works on its own rows of globally indexed arrays and pushes its boundary rows to the neighbours),
+// levels >= Ld are replicated after an all-gather of the level-Ld right-hand side.
+// ------------------------------------------------------------------------------------------------
+struct DistInfo {
+  cm_dist* D;
+  double* base;
+  int Ld;                       // first replicated level
+  int rb[kMaxLevels], re[kMaxLevels];  // owned rows per distributed level
+};
+
+static void dist_info(const PQSolver& S, cm_dist* D, double* base, DistInfo& I) {
+  I.D = D;
+  I.base = base;
+  I.Ld = S.nlev - 1 < 3 ? S.nlev - 1 : 3;
+  for (int l = 0; l <= I.Ld; ++l) {
+    I.rb[l] = D->row_begin[D->rank] >> l;
+    I.re[l] = (D->rank + 1 == D->world) ? S.lev[l].ny + 1 : (D->row_begin[D->rank + 1] >> l);
+  }
+}
+
+// push row rb (downwards) and row re-1 (upwards) of every listed array, wait for the neighbours'
+static int halo_rows(const DistInfo& I, double* const* arrs, int narr, int n1, int rb, int re,
+                     cudaStream_t st) {
+  unsigned long long od[8], ou[8];
+  int nd[8], nu[8];
+  if (narr > 8) return CM_E_INVALID;
+  for (int a = 0; a < narr; ++a) {
+    od[a] = (unsigned long long)(arrs[a] - I.base) + (unsigned long long)rb * n1;
+    ou[a] = (unsigned long long)(arrs[a] - I.base) + (unsigned long long)(re - 1) * n1;
+    nd[a] = nu[a] = n1;
+  }
+  return dist_halo2(I.D, od, nd, narr, ou, nu, narr, st);
+}
+
+static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double* x, cudaStream_t st) {
+  int rc;
+  if (l == I.Ld) {
+    // gather the owned rows of b from every rank, then the ordinary (replicated) cycle
+    PQSLevel& L = S.lev[l];
+    unsigned long long off = (unsigned long long)(b - I.base) + (unsigned long long)I.rb[l] * (L.nx + 1);
+    int n = (I.re[l] - I.rb[l]) * (L.nx + 1);
+    if ((rc = dist_allgather(I.D, &off, &n, 1, st))) return rc;
+    return vcycle(S, l, b, x, st);
+  }
+  PQSLevel& L = S.lev[l];
+  PQSLevel& C = S.lev[l + 1];
+  const int n1 = L.nx + 1, rb = I.rb[l], re = I.re[l];
+  double* xa[1] = {x};
+  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 1, st, rb, re))) return rc;
+  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re))) return rc;
+  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st, rb, re))) return rc;
+  double* ra[1] = {L.r};
+  if ((rc = halo_rows(I, ra, 1, n1, rb, re, st))) return rc;
+  if ((rc = st_restrict(C.nx, C.ny, L.r, C.b, st, I.rb[l + 1], I.re[l + 1]))) return rc;
+  if ((rc = vcycle_dist(S, I, l + 1, C.b, C.x, st))) return rc;
+  if (l + 1 < I.Ld) {  // replicated levels hold the full vector already
+    double* ca[1] = {C.x};
+    if ((rc = halo_rows(I, ca, 1, C.nx + 1, I.rb[l + 1], I.re[l + 1], st))) return rc;
+  }
+  if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st, rb, re))) return rc;
+  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re))) return rc;
+  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  return st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re);
+}
+
+int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
+                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st) {
+  PQSolver S;
+  double* base = align_ws(ws);
+  int rc = pqs_layout(S, nx, ny, restart, base);
+  if (rc) return rc;
+  if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
+    set_error("pqs_setup_dist: workspace too small");
+    return CM_E_INVALID;
+  }
+  if (base != (double*)D->peer_base[D->rank]) {
+    set_error("pqs_setup_dist: workspace must be the (64-byte aligned) IPC allocation registered in cm_dist");
+    return CM_E_INVALID;
+  }
+  DistInfo I;
+  dist_info(S, D, base, I);
+  for (int r = 1; r < D->world; ++r)
+    if (D->row_begin[r] & 7) {
+      set_error("pqs_setup_dist: row_begin[%d] = %d is not a multiple of 8", r, D->row_begin[r]);
+      return CM_E_INVALID;
+    }
+  CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
+  if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err,
+                              st, I.rb[0], I.re[0])))
+    return rc;
+  for (int l = 0; l < I.Ld; ++l) {
+    PQSLevel& L = S.lev[l];
+    const int n1 = L.nx + 1;
+    const size_t n = L.n;
+    double* diag[7];
+    for (int k = 0; k < 7; ++k) diag[k] = L.A + (size_t)k * n;
+    if ((rc = halo_rows(I, diag, 7, n1, I.rb[l], I.re[l], st))) return rc;  // RAP reads ghost rows of A
+    if ((rc = st_line_factor(L.nx, L.ny, L.A, L.lf, L.iu, L.cu, S.err, st, I.rb[l], I.re[l]))) return rc;
+    if ((rc = st_rap(S.lev[l + 1].nx, S.lev[l + 1].ny, L.A, S.lev[l + 1].A, st, I.rb[l + 1], I.re[l + 1])))
+      return rc;
+  }
+  {  // replicate the level-Ld operator
+    PQSLevel& L = S.lev[I.Ld];
+    const int n1 = L.nx + 1;
+    unsigned long long offs[7];
+    int ns[7];
+    for (int k = 0; k < 7; ++k) {
+      offs[k] = (unsigned long long)(L.A + (size_t)k * L.n - base) + (unsigned long long)I.rb[I.Ld] * n1;
+      ns[k] = (I.re[I.Ld] - I.rb[I.Ld]) * n1;
+    }
+    if ((rc = dist_allgather(D, offs, ns, 7, st))) return rc;
+  }
+  for (int l = I.Ld; l < S.nlev; ++l) {
+    PQSLevel& L = S.lev[l];
+    if ((rc = st_line_factor(L.nx, L.ny, L.A, L.lf, L.iu, L.cu, S.err, st))) return rc;
+    if (l + 1 < S.nlev && (rc = st_rap(S.lev[l + 1].nx, S.lev[l + 1].ny, L.A, S.lev[l + 1].A, st)))
+      return rc;
+  }
+  PQSLevel& C = S.lev[S.nlev - 1];
+  if (S.dense_coarse && (rc = st_coarse_invert(C.nx, C.ny, C.A, S.Mwork, S.Ainv, S.err, st))) return rc;
+  if ((rc = st_line_factor(nx, ny, S.QQ, S.qlf, S.qiu, S.qcu, S.err, st, I.rb[0], I.re[0]))) return rc;
+  return check_err_flag(S, st, "cm_pqs_setup_dist");
+}
+
+int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
+                   int maxit, void* ws, size_t ws_bytes, cm_dist* D, int* iters, double* resid,
+                   cudaStream_t st) {
+  PQSolver S;
+  double* base = align_ws(ws);
+  int rc = pqs_layout(S, nx, ny, restart, base);
+  if (rc) return rc;
+  if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
+    set_error("pqs_solve_dist: workspace too small");
+    return CM_E_INVALID;
+  }
+  DistInfo I;
+  dist_info(S, D, base, I);
+  const int V = S.nv, n1 = nx + 1, rb = I.rb[0], re = I.re[0];
+  const int vb = rb * n1, ve = re * n1;
+  if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
+  LinOp A = [&](const double* in, double* out) {
+    double* a2[2] = {const_cast<double*>(in), const_cast<double*>(in) + V};
+    int e = halo_rows(I, a2, 2, n1, rb, re, st);
+    if (e) return e;
+    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st, rb, re);
+  };
+  LinOp Minv = [&](const double* r, double* z) {
+    int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st, rb, re);
+    if (e) return e;
+    if ((e = vcycle_dist(S, I, 0, S.ru, z, st))) return e;
+    double* zp[1] = {z};
+    if ((e = halo_rows(I, zp, 1, n1, rb, re, st))) return e;
+    if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st, rb, re))) return e;
+    double* zq[1] = {z + V};
+    for (int s = 0; s < S.q_sweeps; ++s) {
+      if ((e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, s == 0 ? 1 : 0, st, rb, re)))
+        return e;
+      if ((e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
+      if ((e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, rb, re))) return e;
+      if (s + 1 < S.q_sweeps && (e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
+    }
+    return e;
+  };
+  VecSlice sl{(long long)vb, (long long)V + vb, (long long)(ve - vb)};
+  double bnorm = 0.0;
+  rc = gmres_solve(2LL * V, A, Minv, S.bs, S.xs, rtol, atol, maxit, restart, 0, S.gm, iters, resid,
+                   &bnorm, st, &sl, D);
+  if (rc < 0) return rc;
+  if (resid && bnorm > 0.0) *resid /= bnorm;
+  int rc2 = st_interleave(V, S.xs, x, st, vb, ve);
+  if (rc2) return rc2;
+  if (rc == 1)
+    set_error("cm_pqs_solve_dist: GMRES did not reach rtol=%g in %d iterations (relative residual %g)",
+              rtol, maxit, resid ? *resid : -1.0);
+  return rc;
+}
+
+size_t pqs_state_offset_bytes(int nx, int ny, int restart) {
+  PQSolver S;
+  if (pqs_layout(S, nx, ny, restart, (double*)64)) return 0;
+  return (size_t)((char*)S.ustate - (char*)64);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,9 +35,9 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
                       const int* __restrict__ ncol, const double2* __restrict__ vals2,
                       double* __restrict__ PP, double* __restrict__ PQ, double* __restrict__ QP,
                       double* __restrict__ QQ, double* __restrict__ sp, double* __restrict__ sq,
-                      int* __restrict__ err) {
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+                      int* __restrict__ err, const int vb, const int ve) {
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   const int n1 = nx + 1;
   const int rp = nrowptr[v], deg = nrowptr[v + 1] - rp;
   const double2* prow = vals2 + 2 * (size_t)rp;
@@ -70,18 +70,18 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
 // interleaved b -> split, scaled:  out[v] = sp*b[2v], out[nv+v] = sq*b[2v+1]
 __global__ void __launch_bounds__(kSB)
 split_scale_kernel(const int nv, const double2* __restrict__ b, const double* __restrict__ sp,
-                   const double* __restrict__ sq, double* __restrict__ out) {
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+                   const double* __restrict__ sq, double* __restrict__ out, const int vb, const int ve) {
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   const double2 t = b[v];
   out[v] = sp[v] * t.x;
   out[nv + v] = sq[v] * t.y;
 }
 
 __global__ void __launch_bounds__(kSB)
-interleave_kernel(const int nv, const double* __restrict__ xs, double2* __restrict__ x) {
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+interleave_kernel(const int nv, const double* __restrict__ xs, double2* __restrict__ x, const int vb, const int ve) {
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   x[v] = make_double2(xs[v], xs[nv + v]);
 }
 
@@ -108,10 +108,10 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
                        const double* __restrict__ PQ, const double* __restrict__ QP,
                        const double* __restrict__ QQ, const double* __restrict__ sp,
                        const double* __restrict__ sq, const double* __restrict__ x,
-                       double* __restrict__ y) {
+                       double* __restrict__ y, const int vb, const int ve) {
   const int nv = (nx + 1) * (ny + 1);
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   const int n1 = nx + 1;
   const unsigned valid = stencil_valid(v % n1, v / n1, nx, ny);
   int off[7];
@@ -133,9 +133,9 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
 // out = r / s (undo the row equilibration before the unscaled preconditioner)
 __global__ void __launch_bounds__(kSB)
 unscale_kernel(const int nv, const double* __restrict__ r, const double* __restrict__ sp,
-               const double* __restrict__ sq, double* __restrict__ out) {
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+               const double* __restrict__ sq, double* __restrict__ out, const int vb, const int ve) {
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   out[v] = r[v] / sp[v];
   out[nv + v] = r[nv + v] / sq[v];
 }
@@ -144,10 +144,10 @@ unscale_kernel(const int nv, const double* __restrict__ r, const double* __restr
 __global__ void __launch_bounds__(kSB)
 stencil_residual_kernel(const int nx, const int ny, const double* __restrict__ A,
                         const double* __restrict__ b, const double* __restrict__ x,
-                        double* __restrict__ r) {
+                        double* __restrict__ r, const int vb, const int ve) {
   const int nv = (nx + 1) * (ny + 1);
-  const int v = blockIdx.x * kSB + threadIdx.x;
-  if (v >= nv) return;
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
   const int n1 = nx + 1;
   const unsigned valid = stencil_valid(v % n1, v / n1, nx, ny);
   int off[7];
@@ -163,10 +163,9 @@ stencil_residual_kernel(const int nx, const int ny, const double* __restrict__ A
 // transfers: P1 interpolation on nested right-diagonal meshes (weights 1, 1/2 on the 6 neighbours)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSB)
-restrict_kernel(const int nxc, const int nyc, const double* __restrict__ rf, double* __restrict__ rc) {
-  const int nc = (nxc + 1) * (nyc + 1);
-  const int I = blockIdx.x * kSB + threadIdx.x;
-  if (I >= nc) return;
+restrict_kernel(const int nxc, const int nyc, const double* __restrict__ rf, double* __restrict__ rc, const int vb, const int ve) {
+  const int I = vb + blockIdx.x * kSB + threadIdx.x;
+  if (I >= ve) return;
   const int X = I % (nxc + 1), Y = I / (nxc + 1);
   const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
   const int ix = 2 * X, iy = 2 * Y;
@@ -182,11 +181,10 @@ restrict_kernel(const int nxc, const int nyc, const double* __restrict__ rf, dou
 }
 
 __global__ void __launch_bounds__(kSB)
-prolong_add_kernel(const int nxc, const int nyc, const double* __restrict__ ec, double* __restrict__ xf) {
+prolong_add_kernel(const int nxc, const int nyc, const double* __restrict__ ec, double* __restrict__ xf, const int vb, const int ve) {
   const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
-  const int nf = n1 * (nyf + 1);
-  const int i = blockIdx.x * kSB + threadIdx.x;
-  if (i >= nf) return;
+  const int i = vb + blockIdx.x * kSB + threadIdx.x;
+  if (i >= ve) return;
   const int ix = i % n1, iy = i / n1;
   const int X = ix >> 1, Y = iy >> 1, m1 = nxc + 1;
   const int ox = ix & 1, oy = iy & 1;
@@ -201,10 +199,10 @@ prolong_add_kernel(const int nxc, const int nyc, const double* __restrict__ ec, 
 
 // Galerkin coarse operator Ac = P^T A P in stencil form (one thread per coarse node)
 __global__ void __launch_bounds__(kSB)
-rap_kernel(const int nxc, const int nyc, const double* __restrict__ Af, double* __restrict__ Ac) {
+rap_kernel(const int nxc, const int nyc, const double* __restrict__ Af, double* __restrict__ Ac, const int vb, const int ve) {
   const int nc = (nxc + 1) * (nyc + 1);
-  const int I = blockIdx.x * kSB + threadIdx.x;
-  if (I >= nc) return;
+  const int I = vb + blockIdx.x * kSB + threadIdx.x;
+  if (I >= ve) return;
   const int X = I % (nxc + 1), Y = I / (nxc + 1);
   const int nxf = 2 * nxc, nyf = 2 * nyc, n1 = nxf + 1;
   const size_t nf = (size_t)n1 * (nyf + 1);
@@ -300,14 +298,14 @@ __device__ __forceinline__ Mob mob_shfl_up(const Mob m, int o) {
 __global__ void __launch_bounds__(256)
 line_factor_scan_kernel(const int nx, const int ny, const int E, const double* __restrict__ A,
                         double* __restrict__ lf, double* __restrict__ iu, double* __restrict__ cu,
-                        int* __restrict__ err) {
+                        int* __restrict__ err, const int j0) {
   extern __shared__ double sm[];
   const int n1 = nx + 1;
   double* s_a = sm;
   double* s_d = sm + n1;
   double* s_c = sm + 2 * n1;
   __shared__ double sh[4 * 32];
-  const int j = blockIdx.x;
+  const int j = j0 + blockIdx.x;
   const size_t nv = (size_t)n1 * (ny + 1);
   const size_t base = (size_t)j * n1;
   const int T = blockDim.x, tid = threadIdx.x;
@@ -428,14 +426,16 @@ __global__ void __launch_bounds__(512, 2)
 zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
                   const double* __restrict__ A, const double* __restrict__ lf,
                   const double* __restrict__ iu, const double* __restrict__ cu,
-                  const double* __restrict__ b, double* __restrict__ x, const int dbg) {
+                  const double* __restrict__ b, double* __restrict__ x, const int dbg,
+                  const int jfirst, const int jend) {
   extern __shared__ double sm[];
   const int n1 = nx + 1;
   double* s_z = sm;
   double* s_c = sm + n1;
   __shared__ double sh[64];
-  const int j = 2 * blockIdx.x + colour;
-  if (j > ny) return;
+  const int j = jfirst + 2 * blockIdx.x;  // jfirst has the parity of `colour`
+  if (j >= jend) return;
+  (void)colour;
   const size_t nv = (size_t)n1 * (ny + 1);
   const size_t base = (size_t)j * n1;
   const int T = blockDim.x, tid = threadIdx.x;
@@ -633,76 +633,102 @@ coarse_apply_kernel(const int n, const double* __restrict__ Ainv, const double* 
 // ------------------------------------------------------------------------------------------------
 static inline int grid_for(long long n) { return (int)((n + kSB - 1) / kSB); }
 
+// Row ranges: every launcher works on grid rows [r0, r1) (r1 < 0: the whole grid).  Arrays are
+// always indexed globally, so a strip-partitioned rank simply passes its own rows.
+static inline void row_range(int ny, int n1, int r0, int r1, int& vb, int& ve) {
+  if (r1 < 0) { r0 = 0; r1 = ny + 1; }
+  vb = r0 * n1;
+  ve = r1 * n1;
+}
+
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
-                      int* err, cudaStream_t st) {
+                      int* err, cudaStream_t st, int r0, int r1) {
   const int nv = (nx + 1) * (ny + 1);
-  extract_blocks_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
-                                                      PP, PQ, QP, QQ, sp, sq, err);
+  int vb, ve;
+  row_range(ny, nx + 1, r0, r1, vb, ve);
+  extract_blocks_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
+                                                           PP, PQ, QP, QQ, sp, sq, err, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
 int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
-                   cudaStream_t st) {
-  split_scale_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, (const double2*)b, sp, sq, out);
+                   cudaStream_t st, int vb, int ve) {
+  if (ve < 0) { vb = 0; ve = nv; }
+  split_scale_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nv, (const double2*)b, sp, sq, out, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
-int st_interleave(int nv, const double* xs, double* x, cudaStream_t st) {
-  interleave_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, xs, (double2*)x);
+int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, int ve) {
+  if (ve < 0) { vb = 0; ve = nv; }
+  interleave_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nv, xs, (double2*)x, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st) {
-  const int nv = (nx + 1) * (ny + 1);
-  pq_stencil_spmv_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y);
+               cudaStream_t st, int r0, int r1) {
+  int vb, ve;
+  row_range(ny, nx + 1, r0, r1, vb, ve);
+  pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
-int st_unscale(int nv, const double* r, const double* sp, const double* sq, double* out,
-               cudaStream_t st) {
-  unscale_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, r, sp, sq, out);
+int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,
+               cudaStream_t st, int r0, int r1) {
+  int vb, ve;
+  row_range(ny, nx + 1, r0, r1, vb, ve);
+  unscale_kernel<<<grid_for(ve - vb), kSB, 0, st>>>((nx + 1) * (ny + 1), r, sp, sq, out, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
 int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
-                cudaStream_t st) {
-  const int nv = (nx + 1) * (ny + 1);
-  stencil_residual_kernel<<<grid_for(nv), kSB, 0, st>>>(nx, ny, A, b, x, r);
+                cudaStream_t st, int r0, int r1) {
+  int vb, ve;
+  row_range(ny, nx + 1, r0, r1, vb, ve);
+  stencil_residual_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, A, b, x, r, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
-int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st) {
-  restrict_kernel<<<grid_for((long long)(nxc + 1) * (nyc + 1)), kSB, 0, st>>>(nxc, nyc, rf, rc);
+// coarse rows [R0, R1)
+int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st, int R0, int R1) {
+  int vb, ve;
+  row_range(nyc, nxc + 1, R0, R1, vb, ve);
+  restrict_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, rf, rc, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
-int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st) {
-  prolong_add_kernel<<<grid_for((long long)(2 * nxc + 1) * (2 * nyc + 1)), kSB, 0, st>>>(nxc, nyc, ec, xf);
+// fine rows [r0, r1)
+int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st, int r0, int r1) {
+  int vb, ve;
+  row_range(2 * nyc, 2 * nxc + 1, r0, r1, vb, ve);
+  prolong_add_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, ec, xf, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
-int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st) {
-  rap_kernel<<<grid_for((long long)(nxc + 1) * (nyc + 1)), kSB, 0, st>>>(nxc, nyc, Af, Ac);
+int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st, int R0, int R1) {
+  int vb, ve;
+  row_range(nyc, nxc + 1, R0, R1, vb, ve);
+  rap_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, Af, Ac, vb, ve);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
 int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
-                   cudaStream_t st) {
+                   cudaStream_t st, int r0, int r1) {
+  if (r1 < 0) { r0 = 0; r1 = ny + 1; }
+  if (r1 <= r0) return CM_OK;
   const int n1 = nx + 1;
   const size_t smem = 3 * (size_t)n1 * sizeof(double);
-  if (smem > 200 * 1024) {  // very long lines: serial Thomas per line
+  if (smem > 200 * 1024) {  // very long lines: serial Thomas per line (single-GPU only)
     line_factor_kernel<<<(ny + 1 + 127) / 128, 128, 0, st>>>(nx, ny, A, lf, iu, cu, err);
     CM_LAUNCH_CHECK();
     return CM_OK;
@@ -715,19 +741,22 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
   }
   const int T = (n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32);
   const int E = (n1 + T - 1) / T;
-  line_factor_scan_kernel<<<ny + 1, T, smem, st>>>(nx, ny, E, A, lf, iu, cu, err);
+  line_factor_scan_kernel<<<r1 - r0, T, smem, st>>>(nx, ny, E, A, lf, iu, cu, err, r0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
 
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
-             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st) {
+             const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0,
+             int r1) {
+  if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
-  const int nlines = (ny + 1 - colour + 1) / 2;
+  const int jfirst = r0 + (((r0 & 1) == colour) ? 0 : 1);
+  const int nlines = (r1 - jfirst + 1) / 2;
   if (nlines <= 0) return CM_OK;
   const int T = (n1 > 2048) ? 512 : ((n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32));
   int E = (n1 + T - 1) / T;
-  if ((E & 1) == 0) ++E;  // odd stride: at most 2-way shared-memory bank conflicts
+  if ((E & 1) == 0) ++E;  // odd stride: conflict-free 64-bit shared-memory accesses per half warp
   const size_t smem = 2 * (size_t)n1 * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -745,13 +774,10 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg = e ? atoi(e) : 0; }
-  int TT = T;
-  if (dbg & 4) { TT = 256; E = (n1 + TT - 1) / TT; if ((E & 1) == 0) ++E; }
-  if (dbg & 8) { TT = 1024; E = (n1 + TT - 1) / TT; if ((E & 1) == 0) ++E; }
   if (x_zero)
-    zebra_line_kernel<true><<<nlines, TT, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg);
+    zebra_line_kernel<true><<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg, jfirst, r1);
   else
-    zebra_line_kernel<false><<<nlines, TT, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg);
+    zebra_line_kernel<false><<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg, jfirst, r1);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -146,6 +146,7 @@ __device__ __forceinline__ void add_row(const cm_pq_params& P, const TriGeom& g,
 template <int NQ, int GKIND, bool QGEN, bool WANTJ>
 __global__ void __launch_bounds__(2 * kTX, 2)
 pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows_per_seg,
+                const int row_begin, const int row_end,
                 const double2* __restrict__ coords, const int* __restrict__ nrowptr,
                 const double2* __restrict__ u, const double* __restrict__ p_old,
                 const double2* __restrict__ load, double* __restrict__ vals,
@@ -156,8 +157,8 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
   const int t = isB ? tid - kTX : tid;
   const int n1 = nx + 1;
   const int ix0 = blockIdx.x * (kTX - 1);          // first owned vertex column
-  const int jy0 = blockIdx.y * rows_per_seg;       // first owned vertex row
-  const int jy1 = min(jy0 + rows_per_seg, ny + 1); // one past the last owned vertex row
+  const int jy0 = row_begin + blockIdx.y * rows_per_seg;  // first owned vertex row
+  const int jy1 = min(jy0 + rows_per_seg, row_end);       // one past the last owned vertex row
   const int qx = ix0 - 1 + t;                      // this thread's quad column
   const bool quad_ok = qx >= 0 && qx < nx;
   const int colL = t - 1, colR = t;                // accumulator columns of the quad's left/right vertices
@@ -266,24 +267,28 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
 template <int NQ, int GKIND, bool QGEN>
 static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                         const int* nrowptr, const double* u, const double* p_old,
-                        const double* load, double* vals, double* b, cudaStream_t st) {
+                        const double* load, double* vals, double* b, cudaStream_t st, int row_begin,
+                        int row_end) {
+  if (row_end < 0) { row_begin = 0; row_end = ny + 1; }
+  const int nrows = row_end - row_begin;
+  if (nrows <= 0) return CM_OK;
   const int strips = (nx + 1 + kTX - 2) / (kTX - 1);
   // enough y-segments to fill the machine several times over, at least 32 rows each
   int segs = (148 * 8 + strips - 1) / strips;
-  int rows = (ny + 1 + segs - 1) / segs;
+  int rows = (nrows + segs - 1) / segs;
   if (rows < 32) rows = 32;
-  segs = (ny + 1 + rows - 1) / rows;
+  segs = (nrows + rows - 1) / rows;
   const size_t smem = (size_t)2 * kAccPerVertex * kTX * sizeof(double);
   dim3 grid(strips, segs);
   if (vals != nullptr) {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, true>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
+    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, row_begin, row_end, (const double2*)coords, nrowptr, (const double2*)u,
                                   p_old, (const double2*)load, vals, (double2*)b);
   } else {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, false>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, (const double2*)coords, nrowptr, (const double2*)u,
+    kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, row_begin, row_end, (const double2*)coords, nrowptr, (const double2*)u,
                                   p_old, (const double2*)load, vals, (double2*)b);
   }
   CM_LAUNCH_CHECK();
@@ -292,14 +297,14 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
 
 int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                       const int* nrowptr, const double* u, const double* p_old, const double* load,
-                      double* vals, double* b, cudaStream_t st) {
+                      double* vals, double* b, cudaStream_t st, int row_begin, int row_end) {
   const int nq = nq_of_degree(P.degree);
   const bool plain = P.q_react == 0.0 && P.q_adv == 1.0 && P.q_x2p == 1.0 && P.q_x2q == 0.0 &&
                      P.q_divr == 0.0 && P.q_ibp == 0.0 && P.supg_stab == 0.0;
 #define CM_SW(NQ_, GK_)                                                                          \
   if (nq == NQ_ && P.gkind == GK_)                                                               \
-    return plain ? launch_sweep<NQ_, GK_, false>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st) \
-                 : launch_sweep<NQ_, GK_, true>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st);
+    return plain ? launch_sweep<NQ_, GK_, false>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end) \
+                 : launch_sweep<NQ_, GK_, true>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end);
   CM_SW(6, CM_G_NONE)
   CM_SW(6, CM_G_POWER)
   CM_SW(6, CM_G_GSTAR)

@@ -180,4 +180,118 @@ int vec_scale(long long n, const double* x, const double* a_dev, double a_host, 
   return CM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// slice variants for the strip-partitioned (multi-GPU) path: the vector is the union of two
+// contiguous index ranges [off0, off0+len) and [off1, off1+len) (p-part and q-part rows of this
+// rank in the split layout).  Scalar loads: the offsets need not be 16-byte aligned.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long slice_index(long long i, const VecSlice s) {
+  return i < s.len ? s.off0 + i : s.off1 + (i - s.len);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kVecBlock)
+dot_group_slice_kernel(const VecSlice sl, const double* __restrict__ Vbase, const long long vstride,
+                       const double* __restrict__ w, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  const long long n = 2 * sl.len;
+  for (long long i = blockIdx.x * (long long)kVecBlock + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kVecBlock) {
+    const long long j = slice_index(i, sl);
+    const double ww = w[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += Vbase[k * vstride + j] * ww;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double s = block_sum(acc[k], sh);
+    if (threadIdx.x == 0) partial[blockIdx.x * kGroup + k] = s;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kVecBlock)
+axpy_group_slice_kernel(const VecSlice sl, const double* __restrict__ Vbase, const long long vstride,
+                        const double* __restrict__ h, const double sign, double* __restrict__ w,
+                        double* __restrict__ partial, const int want_norm) {
+  __shared__ double sh[32];
+  double hk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) hk[k] = sign * h[k];
+  double nrm = 0.0;
+  const long long n = 2 * sl.len;
+  for (long long i = blockIdx.x * (long long)kVecBlock + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kVecBlock) {
+    const long long j = slice_index(i, sl);
+    double ww = w[j];
+#pragma unroll
+    for (int k = 0; k < K; ++k) ww += hk[k] * Vbase[k * vstride + j];
+    w[j] = ww;
+    nrm += ww * ww;
+  }
+  if (want_norm) {
+    const double s = block_sum(nrm, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x * kGroup] = s;
+  }
+}
+
+// y = a*x on the slices (a on the host; invert: y = x/a); x == nullptr: y = 0
+__global__ void __launch_bounds__(kVecBlock)
+scale_slice_kernel(const VecSlice sl, const double* __restrict__ x, const double a,
+                   double* __restrict__ y) {
+  const long long n = 2 * sl.len;
+  for (long long i = blockIdx.x * (long long)kVecBlock + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kVecBlock) {
+    const long long j = slice_index(i, sl);
+    y[j] = x ? a * x[j] : 0.0;
+  }
+}
+
+static int slice_grid(const VecSlice sl) {
+  long long g = (2 * sl.len + kVecBlock - 1) / kVecBlock;
+  if (g < 1) g = 1;
+  return (int)(g < kVecGrid ? g : kVecGrid);
+}
+
+int multi_dot_slice(VecSlice sl, const double* Vbase, long long vstride, int nvec, const double* w,
+                    double* out, double* scratch, cudaStream_t st) {
+  const int grid = slice_grid(sl);
+  for (int k0 = 0; k0 < nvec; k0 += kGroup) {
+    const int K = (nvec - k0 < kGroup) ? nvec - k0 : kGroup;
+    CM_K_SWITCH(K, (dot_group_slice_kernel<KK><<<grid, kVecBlock, 0, st>>>(sl, Vbase + k0 * vstride,
+                                                                          vstride, w, scratch)));
+    reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, K, scratch, out + k0);
+    g_launches += 2;
+  }
+  --g_launches;
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int multi_axpy_slice(VecSlice sl, const double* Vbase, long long vstride, int nvec, const double* h,
+                     double sign, double* w, double* norm2_out, double* scratch, cudaStream_t st) {
+  const int grid = slice_grid(sl);
+  for (int k0 = 0; k0 < nvec; k0 += kGroup) {
+    const int K = (nvec - k0 < kGroup) ? nvec - k0 : kGroup;
+    const int last = (k0 + kGroup >= nvec) && norm2_out != nullptr;
+    CM_K_SWITCH(K, (axpy_group_slice_kernel<KK><<<grid, kVecBlock, 0, st>>>(
+                       sl, Vbase + k0 * vstride, vstride, h + k0, sign, w, scratch, last)));
+    if (last) reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, 1, scratch, norm2_out);
+    g_launches += last ? 2 : 1;
+  }
+  --g_launches;
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int vec_scale_slice(VecSlice sl, const double* x, double a, int invert, double* y, cudaStream_t st) {
+  scale_slice_kernel<<<slice_grid(sl), kVecBlock, 0, st>>>(sl, x, invert ? 1.0 / a : a, y);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
 }  // namespace cm
