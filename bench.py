@@ -8,9 +8,11 @@ Workload (BASELINE.json configs[4]): RectangleMesh 4096x2048 on 
 (16 777 216 cells, 16 789 506 dofs, 234 954 756 nnz), manufactured P-Q problem with the SUPG
 q-equation (…MixedPrimal_convergence_SUPG.py:118-129), state = nodal interpolant of the exact
 solution (every step does the same work: one full Newton iteration from that state).
-N > 1: every rank runs an independent problem instance (the concentration sweep of
-advection_diffusion_mixed.py:273-334 is the reference's own data-parallel axis): weak scaling, no
-data-path collective.
+N > 1 (default): the SAME mesh is strip-partitioned by vertex rows over the N GPUs (RCB along r1; halo
+rows, coarse-grid all-gather and Krylov all-reduces by peer-to-peer kernels over NVLink): strong
+scaling.  `--instances`: every rank runs an independent problem instance instead (the concentration
+sweep of advection_diffusion_mixed.py:273-334, the reference's own data-parallel axis): weak scaling,
+no data-path communication.
 """
 from __future__ import annotations
 
@@ -118,7 +120,9 @@ def workload_config(args, nx, ny):
     return {"workload": f"P-Q CG1xCG1 manufactured SUPG Newton step on RectangleMesh {nx}x{ny} "
                         f"({2 * nx * ny} cells) per GPU",
             "nx": nx, "ny": ny, "cells_per_gpu": 2 * nx * ny, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
-            "parallelism": f"independent problem instance per GPU x{args.gpus}",
+            "parallelism": (f"independent problem instance per GPU x{args.gpus}" if getattr(args, "instances", False)
+                            or args.gpus == 1 else f"one mesh strip-partitioned by vertex rows over {args.gpus} GPUs "
+                            "(P2P halo / all-gather / all-reduce kernels over NVLink)"),
             "l2_policy": "inputs larger than L2 (Jacobian 1.9 GB, Krylov basis > 1 GB)",
             "linear_rtol": LIN_RTOL}
 
@@ -207,11 +211,20 @@ def gpu_arm(args):
     cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
     form = cm.PQPrimalForm.manufactured(V, "supg")
     bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
-    u = cm.Function(V)
-    solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
-    solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
+    strong = world > 1 and not args.instances
     X = mesh.coords
-    u0 = torch.empty_like(u.vector())
+    if strong:
+        from closestmolecule_b200.multigpu import DistributedPQNewton
+        solver = DistributedPQNewton(form, bcs, restart=40, rtol_lin=LIN_RTOL)
+        uvec = solver.u
+        own = solver.own
+    else:
+        u = cm.Function(V)
+        solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+        solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
+        uvec = u.vector()
+        own = slice(0, uvec.numel())
+    u0 = torch.empty_like(uvec)
     u0[0::2] = p_exact(X[:, 0], X[:, 1])
     u0[1::2] = q_exact(X[:, 0], X[:, 1])
     cells = mesh.num_cells()
@@ -226,7 +239,7 @@ def gpu_arm(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step():
-        u.vector().copy_(u0)
+        uvec[own] = u0[own]
         return solver.newton_step(compute_residual=True)
 
     for _ in range(args.warmup):
@@ -255,17 +268,17 @@ def gpu_arm(args):
     lin_its = float(np.mean(solver.linear_iterations))
 
     # ---- e2e: host buffers in, host buffers out, through the public Newton-step call ------------
-    h_in = torch.empty(u0.numel(), dtype=torch.float64, pin_memory=True)
-    h_in.copy_(u0)
+    h_in = torch.empty(u0[own].numel(), dtype=torch.float64, pin_memory=True)
+    h_in.copy_(u0[own])
     h_out = torch.empty_like(h_in)
     e2e_steps = max(1, min(args.steps, 3))
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(e2e_steps):
-        u.vector().copy_(h_in, non_blocking=True)
+        uvec[own].copy_(h_in, non_blocking=True)
         r = solver.newton_step(compute_residual=True)
-        h_out.copy_(u.vector(), non_blocking=True)
+        h_out.copy_(uvec[own], non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
@@ -287,17 +300,19 @@ def gpu_arm(args):
         bytes_asm = 12 * cells + 16 * Vn + 8 * (2 * Vn) + 8 * (4 * nnz) + 8 * (2 * Vn)
         achieved = bytes_asm / (asm_ms * 1e-3) / 1e9
         out = {
-            "metric": METRIC, "value": world * cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": (1 if strong else world) * cells / (ms_step * 1e-3), "unit": UNIT,
+            "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, nx, ny),
             "newton_step_ms": ms_step, "linear_iterations_per_step": lin_its,
             "assembly_ms": asm_ms, "assembly_cells_per_s": cells / (asm_ms * 1e-3),
             "phases_ms": {"assemble_J_F": asm_ms, "bc_and_solver_setup": setup_ms,
                           "krylov_solve": solve_ms, "update_and_residual": resid_ms},
             "residual_norm_after_step": rnorm,
-            "e2e": {"value": world * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8 + 8)},
+            "e2e": {"value": (1 if strong else world) * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8 + 8),
+                    "note": "bytes per rank" if world > 1 else "whole state vector"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "pq_rows_kernel (cm_assemble_pq_cells, fused J+F)", "bound": "hbm",
@@ -314,6 +329,8 @@ def gpu_arm(args):
                           f"{rec['lu']:.2f}s + residual {rec['residual']:.2f}s) on RectangleMesh "
                           f"{nxs}x{nys} = {rec['cells']} cells"}
         print(json.dumps(out))
+    if strong:
+        solver.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -331,6 +348,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096, help="mesh is nx x nx/2 (default: the 16 Mi-cell mesh)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--instances", action="store_true",
+                    help="N>1: independent problem instance per GPU (weak scaling) instead of strip partitioning")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -74,6 +74,31 @@ push_kernel(const double* __restrict__ my_base, const Peers peers, const int my_
     st_release_sys(reinterpret_cast<unsigned long long*>(pb) + flag_off + my_rank, seq);
 }
 
+// halo exchange in ONE launch: CTA 0 serves the lower neighbour, CTA 1 the upper one.  Each CTA
+// pushes its segments into the neighbour's workspace, publishes `seq` there, then waits until the
+// same neighbour has published `seq` here.
+__global__ void __launch_bounds__(1024)
+exchange_kernel(const double* __restrict__ my_base, const Peers peers, const int my_rank, const int dn,
+                const int up, const PushSegs segs_dn, const PushSegs segs_up, const size_t flag_off,
+                const unsigned long long seq) {
+  const int dst = blockIdx.x == 0 ? dn : up;
+  if (dst < 0) return;
+  const PushSegs& segs = blockIdx.x == 0 ? segs_dn : segs_up;
+  double* __restrict__ pb = peers.base[dst];
+  for (int s = 0; s < segs.nseg; ++s) {
+    const double* src = my_base + segs.off[s];
+    double* d = pb + segs.off[s];
+    for (int i = threadIdx.x; i < segs.n[s]; i += blockDim.x) d[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + flag_off + my_rank, seq);
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(my_base) + flag_off + dst;
+    while (ld_acquire_sys(f) < seq) __nanosleep(40);
+  }
+}
+
 // one warp: lane s waits until flag[s] >= seq for every source in the mask
 __global__ void wait_kernel(const double* my_base, const size_t flag_off, const unsigned mask,
                             const unsigned long long seq) {
@@ -84,32 +109,33 @@ __global__ void wait_kernel(const double* my_base, const size_t flag_off, const 
   }
 }
 
-// all-reduce (sum) of n <= 64 doubles: publish my values in everybody's slot, wait, sum in rank order
+// all-reduce (sum) of n <= 64 doubles in ONE launch: CTA d publishes my values in rank d's slot
+// (CTA my_rank writes the local slot); CTA 0 then waits for every rank's flag and sums in rank order.
 __global__ void __launch_bounds__(64)
-allreduce_push_kernel(double* __restrict__ my_base, const Peers peers, const int my_rank,
-                      const int world, const double* __restrict__ vals, const int n, const int parity,
-                      const unsigned long long seq) {
+allreduce_kernel(double* __restrict__ my_base, const Peers peers, const int my_rank, const int world,
+                 double* __restrict__ vals, const int n, const int parity, const unsigned long long seq) {
+  __shared__ double mine[kCollMax];
   const int dst = blockIdx.x;
-  if (dst >= world) return;
+  if (threadIdx.x < n) mine[threadIdx.x] = vals[threadIdx.x];
+  __syncthreads();
+  // CTA 0 overwrites vals with the sum: it may do so only after every CTA of this launch has read it
+  unsigned long long* readers = reinterpret_cast<unsigned long long*>(my_base) + (kCtlDoubles - 8);
+  if (threadIdx.x == 0) atomicAdd(readers, 1ull);
   double* pb = (dst == my_rank) ? my_base : peers.base[dst];
   double* slot = pb + kCtlCollBuf + ((size_t)parity * kMaxPeers + my_rank) * kCollMax;
-  if (threadIdx.x < n) slot[threadIdx.x] = vals[threadIdx.x];
+  if (threadIdx.x < n) slot[threadIdx.x] = mine[threadIdx.x];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0)
     st_release_sys(reinterpret_cast<unsigned long long*>(pb) + kCtlCollFlags + my_rank, seq);
-}
-
-__global__ void __launch_bounds__(64)
-allreduce_sum_kernel(const double* __restrict__ my_base, const int world, double* __restrict__ vals,
-                     const int n, const int parity, const unsigned long long seq) {
-  __shared__ int dummy;
+  if (dst != 0) return;
   if (threadIdx.x < world) {
     const unsigned long long* f =
         reinterpret_cast<const unsigned long long*>(my_base) + kCtlCollFlags + threadIdx.x;
-    while (ld_acquire_sys(f) < seq) __nanosleep(100);
+    while (ld_acquire_sys(f) < seq) __nanosleep(40);
   }
-  dummy = 0;
+  if (threadIdx.x == 0)
+    while (atomicAdd(readers, 0ull) < seq * (unsigned long long)world) __nanosleep(20);
   __syncthreads();
   if (threadIdx.x < n) {
     double s = 0.0;
@@ -156,26 +182,13 @@ int dist_halo2(cm_dist* D, const unsigned long long* offs_dn, const int* ns_dn, 
   if (nseg_dn > 8 || nseg_up > 8) return CM_E_INVALID;
   const unsigned long long seq = ++D->halo_seq;
   const int dn = D->rank > 0 ? D->rank - 1 : -1, up = D->rank + 1 < D->world ? D->rank + 1 : -1;
-  const Peers peers = make_peers(D);
-  const double* mb = (const double*)D->peer_base[D->rank];
-  if (dn >= 0) {
-    PushSegs s{};
-    s.nseg = nseg_dn;
-    for (int i = 0; i < nseg_dn; ++i) { s.off[i] = offs_dn[i]; s.n[i] = ns_dn[i]; }
-    push_kernel<<<1, 1024, 0, st>>>(mb, peers, D->rank, dn, -1, 0, D->world, s, kCtlHaloFlags, seq);
-    ++g_launches;
-  }
-  if (up >= 0) {
-    PushSegs s{};
-    s.nseg = nseg_up;
-    for (int i = 0; i < nseg_up; ++i) { s.off[i] = offs_up[i]; s.n[i] = ns_up[i]; }
-    push_kernel<<<1, 1024, 0, st>>>(mb, peers, D->rank, up, -1, 0, D->world, s, kCtlHaloFlags, seq);
-    ++g_launches;
-  }
-  unsigned mask = 0;
-  if (dn >= 0) mask |= 1u << dn;
-  if (up >= 0) mask |= 1u << up;
-  wait_kernel<<<1, 32, 0, st>>>(mb, kCtlHaloFlags, mask, seq);
+  PushSegs sd{}, su{};
+  sd.nseg = nseg_dn;
+  for (int i = 0; i < nseg_dn; ++i) { sd.off[i] = offs_dn[i]; sd.n[i] = ns_dn[i]; }
+  su.nseg = nseg_up;
+  for (int i = 0; i < nseg_up; ++i) { su.off[i] = offs_up[i]; su.n[i] = ns_up[i]; }
+  exchange_kernel<<<2, 1024, 0, st>>>((const double*)D->peer_base[D->rank], make_peers(D), D->rank, dn, up,
+                                      sd, su, kCtlHaloFlags, seq);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -206,9 +219,7 @@ int dist_allreduce(cm_dist* D, double* vals, int n, cudaStream_t st) {
   const unsigned long long seq = ++D->coll_seq;
   const int parity = (int)(seq & 1ull);
   double* mb = (double*)D->peer_base[D->rank];
-  allreduce_push_kernel<<<D->world, 64, 0, st>>>(mb, make_peers(D), D->rank, D->world, vals, n, parity, seq);
-  allreduce_sum_kernel<<<1, 64, 0, st>>>(mb, D->world, vals, n, parity, seq);
-  ++g_launches;
+  allreduce_kernel<<<D->world, 64, 0, st>>>(mb, make_peers(D), D->rank, D->world, vals, n, parity, seq);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -121,6 +121,7 @@ class DistributedPQNewton:
         self.scal = torch.zeros(1, dtype=torch.float64, device=mesh.device)
         self.linear_iterations = []
         self.history = []
+        self.phase_events = None
 
     def _assemble(self, want_jac):
         ctx, asm, form, mesh = self.ctx, self.asm, self.form, self.mesh
@@ -138,13 +139,23 @@ class DistributedPQNewton:
         self.ctx.allreduce(self.scal)
         return float(self.scal.sqrt())
 
-    def newton_step(self):
+    def newton_step(self, compute_residual=True):
         ctx, asm = self.ctx, self.asm
+        marks = [] if self.phase_events is not None else None
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        mark()
         self._assemble(True)
+        mark()
         t = asm.topo
         _capi.check(self.lib.cm_pqs_setup_dist(ctx.nx, ctx.ny, ctx.restart, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
                                                _capi.ptr(asm.vals), ctx.base, ctx.nbytes, C.byref(ctx.D),
                                                _capi.stream_ptr()))
+        mark()
         it, rr = C.c_int32(0), C.c_double(0.0)
         rc = self.lib.cm_pqs_solve_dist(ctx.nx, ctx.ny, ctx.restart, _capi.ptr(asm.b), _capi.ptr(self.dx),
                                         self.rtol_lin, 0.0, self.maxit_lin, ctx.base, ctx.nbytes, C.byref(ctx.D),
@@ -154,8 +165,13 @@ class DistributedPQNewton:
             _capi.check(rc)
         if rc != 0:
             raise LinearSolveError(f"GMRES did not converge in {it.value} iterations (rel. residual {rr.value:.3e})")
+        mark()
         self.u[self.own] -= self.dx[self.own]
-        return self.residual_norm()
+        r = self.residual_norm() if compute_residual else None
+        mark()
+        if marks is not None:
+            self.phase_events.append(marks)
+        return r
 
     def solve(self, atol=1e-10, rtol=1e-9, maxit=50):
         r0 = r = self.residual_norm()
