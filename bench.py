@@ -249,6 +249,8 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     l0 = int(lib.cm_launch_count())
+    lib.cm_profile_reset()
+    lib.cm_profile_enable(1)      # CUDA events around the roofline kernels, on the launching stream
     solver.linear_iterations = []
     solver.phase_events = []      # CUDA events on the launching stream around each phase
     t0, t1 = ev(), ev()
@@ -261,6 +263,17 @@ def gpu_arm(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.cm_launch_count()) - l0
+    lib.cm_profile_enable(0)
+    import ctypes as _C
+    prof = {}
+    for cls, name in ((0, "zebra_line_kernel (fine grid)"), (1, "pq_stencil_spmv_kernel"), (2, "pq_sweep_kernel (J+F)")):
+        n_, ms_, by_ = _C.c_int64(0), _C.c_double(0.0), _C.c_double(0.0)
+        lib.cm_profile_report(cls, _C.byref(n_), _C.byref(ms_), _C.byref(by_))
+        if n_.value:
+            prof[name] = {"launches_per_step": n_.value / args.steps, "avg_us": 1e3 * ms_.value / n_.value,
+                          "ms_per_step": ms_.value / args.steps,
+                          "algorithmic_bytes_per_launch": by_.value / n_.value,
+                          "gbs": by_.value / (ms_.value * 1e-3) / 1e9}
     ms_step = t0.elapsed_time(t1) / args.steps
     ph = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in solver.phase_events])
     solver.phase_events = None
@@ -298,7 +311,7 @@ def gpu_arm(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         bytes_asm = 12 * cells + 16 * Vn + 8 * (2 * Vn) + 8 * (4 * nnz) + 8 * (2 * Vn)
-        achieved = bytes_asm / (asm_ms * 1e-3) / 1e9
+        zk = prof.get("zebra_line_kernel (fine grid)")
         out = {
             "metric": METRIC, "value": (1 if strong else world) * cells / (ms_step * 1e-3), "unit": UNIT,
             "n_gpus": world,
@@ -315,10 +328,16 @@ def gpu_arm(args):
                     "note": "bytes per rank" if world > 1 else "whole state vector"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "pq_rows_kernel (cm_assemble_pq_cells, fused J+F)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_asm,
+            # dominant kernel of the step by time share (profiles/): the zebra x-line relaxation on the
+            # finest grid; durations from CUDA events on the launching stream inside the timed region
+            "roofline": {"kernel": "zebra_line_kernel (x-line relaxation, finest grid)", "bound": "hbm",
+                         "achieved": zk["gbs"] if zk else None, "peak": peak, "unit": "GB/s",
+                         "frac": (zk["gbs"] / peak) if zk else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": zk["algorithmic_bytes_per_launch"] if zk else None,
+                         "avg_launch_us": zk["avg_us"] if zk else None,
+                         "share_of_step": (zk["ms_per_step"] / ms_step) if zk else None,
                          "traffic": TRAFFIC_NCU},
+            "kernels": {**prof, "pq_sweep_kernel roofline frac": (bytes_asm / (asm_ms * 1e-3) / 1e9) / peak},
         }
         if world == 1 and not args.no_cpu:
             nxs, nys = 512, 256
@@ -337,7 +356,8 @@ def gpu_arm(args):
 
 # dram bytes per launch of the roofline kernel from the committed `ncu --set full` capture
 # (profiles/); None until one exists for the current kernel
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 239.7e6  # mean dram read+write of the two fine-grid launch types (150.5 MB zero-guess, 328.9 MB
+# with coupling; ncu --set full, profiles/README.md) -- equal to the algorithmic bytes: no wasted re-reads
 
 
 def main():

@@ -56,6 +56,9 @@ _PROTOS = {
     "cm_version": ([], C.c_int),
     "cm_last_error": ([], C.c_char_p),
     "cm_device_available": ([], C.c_int),
+    "cm_profile_enable": ([_I], C.c_int),
+    "cm_profile_report": ([_I, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
+    "cm_profile_reset": ([], C.c_int),
     "cm_launch_count": ([], C.c_int64),
     "cm_assemble_pq_cells": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I] + [_P] * 7 + [_I, _P], C.c_int),
     "cm_assemble_pq_cells_structured": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_P], C.c_int),

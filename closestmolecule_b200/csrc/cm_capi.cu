@@ -15,6 +15,39 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace cm
 
+#include <vector>
+namespace cm {
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double bytes;
+};
+static bool g_prof_on = false;
+int g_prof_fine_nx = -1;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) {
+    e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int cls, double bytes, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfRec r{prof_event(), prof_event(), cls, bytes};
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty() || g_prof.back().cls != cls) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
+}  // namespace cm
+
 using namespace cm;
 namespace cm { int st_zebra_debug_times(unsigned long long*, int); }
 int cm_zebra_debug_times_impl(unsigned long long* o, int n) { return cm::st_zebra_debug_times(o, n); }
@@ -303,6 +336,36 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
   if (iters_host) *iters_host = it;
   if (resid_host) *resid_host = rr;
   return rc;
+}
+
+/* per-kernel-class timing (diagnostics for bench.py): enable, run, then report.  Classes:
+ * 0 zebra_line_kernel on the finest grid, 1 pq_stencil_spmv_kernel, 2 Jacobian assembly. */
+int cm_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return CM_OK;
+}
+
+int cm_profile_report(int32_t cls, int64_t* launches, double* total_ms, double* total_bytes) {
+  CM_CHECK_ARG(cls >= 0 && cls < kProfClasses && launches && total_ms && total_bytes, "bad argument");
+  CM_CUDA(cudaDeviceSynchronize());
+  int64_t n = 0;
+  double ms = 0.0, by = 0.0;
+  for (auto& r : g_prof) {
+    if (r.cls != cls) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; by += r.bytes; ++n; }
+  }
+  cudaGetLastError();
+  *launches = n;
+  *total_ms = ms;
+  *total_bytes = by;
+  return CM_OK;
+}
+
+int cm_profile_reset(void) {
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof.clear();
+  return CM_OK;
 }
 
 }  // extern "C"

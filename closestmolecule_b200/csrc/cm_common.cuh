@@ -36,6 +36,13 @@ extern long long g_launches;  // kernels launched by this library (bench.py's gp
     CM_CUDA(cudaGetLastError()); \
   } while (0)
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+// object: average launch duration of the dominant kernel measured inside the timed region)
+enum ProfClass { kProfZebraFine = 0, kProfSpmv = 1, kProfAssembly = 2, kProfClasses = 3 };
+void prof_begin(int cls, double bytes, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+extern int g_prof_fine_nx;  // nx of the finest grid of the solve in progress
+
 // ---- FIAT "default" triangle rules (15-digit constants as stored by FIAT).
 // Barycentric (l0,l1,l2) = (1-xi-eta, xi, eta) and weight (sums to 1/2).
 template <int NQ>

@@ -183,6 +183,7 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
     return CM_E_INVALID;
   }
   const int V = S.nv;
+  g_prof_fine_nx = nx;
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st))) return rc;
   LinOp A = [&](const double* in, double* out) {
     return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st);
@@ -357,6 +358,7 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
   dist_info(S, D, base, I);
   const int V = S.nv, n1 = nx + 1, rb = I.rb[0], re = I.re[0];
   const int vb = rb * n1, ve = re * n1;
+  g_prof_fine_nx = nx;
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
   LinOp A = [&](const double* in, double* out) {
     double* a2[2] = {const_cast<double*>(in), const_cast<double*>(in) + V};

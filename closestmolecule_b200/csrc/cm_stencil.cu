@@ -673,7 +673,9 @@ int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double*
                cudaStream_t st, int r0, int r1) {
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
+  prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
   pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve);
+  prof_end(kProfSpmv, st);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -774,10 +776,15 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg = e ? atoi(e) : 0; }
+  // algorithmic bytes of this launch: b, l, 1/u, c/u, x per node (+ 4 stencil diagonals and the two
+  // neighbouring lines when the current iterate is used)
+  const bool prof = nx == g_prof_fine_nx;
+  if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
   if (x_zero)
     zebra_line_kernel<true><<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg, jfirst, r1);
   else
     zebra_line_kernel<false><<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg, jfirst, r1);
+  if (prof) prof_end(kProfZebraFine, st);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -280,11 +280,14 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
   segs = (nrows + rows - 1) / rows;
   const size_t smem = (size_t)2 * kAccPerVertex * kTX * sizeof(double);
   dim3 grid(strips, segs);
+  // algorithmic bytes: 148.05 B per cell of the assembled rows
+  if (vals != nullptr) prof_begin(kProfAssembly, 148.05 * 2.0 * nx * (double)nrows, st);
   if (vals != nullptr) {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, true>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, row_begin, row_end, (const double2*)coords, nrowptr, (const double2*)u,
                                   p_old, (const double2*)load, vals, (double2*)b);
+    prof_end(kProfAssembly, st);
   } else {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, false>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -98,6 +98,12 @@ int cm_version(void);
 const char* cm_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (diagnostics) */
 int64_t cm_launch_count(void);
+/* Diagnostics: CUDA-event timing of selected kernel classes on the launching stream
+ * (0: zebra_line_kernel on the finest grid, 1: pq_stencil_spmv_kernel, 2: Jacobian assembly).
+ * Process-wide state, not thread safe; off by default. */
+int cm_profile_enable(int32_t on);
+int cm_profile_report(int32_t cls, int64_t* launches, double* total_ms, double* total_bytes);
+int cm_profile_reset(void);
 /* 1 if a CUDA device is usable, 0 otherwise (never launches work) */
 int cm_device_available(void);
 

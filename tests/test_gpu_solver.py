@@ -148,3 +148,48 @@ def test_ported_convergence_script_prints_readme_table():
     spec.loader.exec_module(mod)
     rows = mod.main(7)
     assert [r.split() for r in rows] == [r.split() for r in README_TABLE]
+
+
+def test_zebra_line_relaxation_building_blocks():
+    """cm_stencil_line_factor / cm_stencil_zebra / cm_stencil_residual on a random diagonally dominant
+    7-point stencil: after a sweep the residual vanishes on the lines solved last, and one colour solve
+    equals scipy's tridiagonal solve of the same lines."""
+    from closestmolecule_b200 import _capi
+    nx, ny = 200, 37
+    n1, n = nx + 1, (nx + 1) * (ny + 1)
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(2)
+    A = np.zeros((7, ny + 1, n1))
+    offs = [(-1, -1), (0, -1), (-1, 0), (0, 0), (1, 0), (0, 1), (1, 1)]
+    for k, (dx, dy) in enumerate(offs):
+        v = (1.0 + rng.random((ny + 1, n1))) if k == 3 else -(0.1 + 0.05 * rng.random((ny + 1, n1)))
+        if dx == -1: v[:, 0] = 0
+        if dx == 1: v[:, -1] = 0
+        if dy == -1: v[0, :] = 0
+        if dy == 1: v[-1, :] = 0
+        A[k] = v
+    At = torch.tensor(A.reshape(7, n), device=dev)
+    lf, iu, cu = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    b = torch.tensor(rng.standard_normal(n), device=dev)
+    x = torch.zeros(n, dtype=torch.float64, device=dev)
+    r = torch.empty_like(x)
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    _capi.check(lib.cm_stencil_line_factor(nx, ny, P(At), P(lf), P(iu), P(cu), P(err), st))
+    assert int(err.item()) == 0
+    _capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(At), P(lf), P(iu), P(cu), P(b), P(x), 1, st))
+    # colour 0 from a zero guess = plain tridiagonal solves of the even lines
+    import scipy.linalg as sla
+    X = x.cpu().numpy().reshape(ny + 1, n1)
+    B = b.cpu().numpy().reshape(ny + 1, n1)
+    for j in (0, 2, 36):
+        ab = np.zeros((3, n1))
+        ab[0, 1:] = A[4, j, :-1]
+        ab[1] = A[3, j]
+        ab[2, :-1] = A[2, j, 1:]
+        ref = sla.solve_banded((1, 1), ab, B[j])
+        assert np.max(np.abs(X[j] - ref)) < 1e-13 * np.max(np.abs(ref)) + 1e-14
+    _capi.check(lib.cm_stencil_zebra(nx, ny, 1, P(At), P(lf), P(iu), P(cu), P(b), P(x), 0, st))
+    _capi.check(lib.cm_stencil_residual(nx, ny, P(At), P(b), P(x), P(r), st))
+    R = r.cpu().numpy().reshape(ny + 1, n1)
+    assert np.max(np.abs(R[1::2])) < 1e-13 and np.max(np.abs(R[0::2])) > 1e-3
