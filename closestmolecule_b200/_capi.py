@@ -86,7 +86,7 @@ _PROTOS = {
     "cm_pqs_solve_dist": ([_I, _I, _I, _P, _P, _D, _D, _I, _P, C.c_int64, C.POINTER(DistC),
                            C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
     "cm_stencil_line_factor": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
-    "cm_stencil_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P], C.c_int),
+    "cm_stencil_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P, _P], C.c_int),
     "cm_stencil_residual": ([_I, _I] + [_P] * 4 + [_P], C.c_int),
     "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,

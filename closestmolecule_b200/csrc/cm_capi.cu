@@ -219,10 +219,10 @@ int cm_stencil_line_factor(int32_t nx, int32_t ny, const double* A, double* lf, 
 
 int cm_stencil_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
                      const double* iu, const double* cu, const double* b, double* x,
-                     int32_t x_is_zero, void* stream) {
+                     int32_t x_is_zero, double* tmp, void* stream) {
   CM_CHECK_ARG(nx >= 1 && ny >= 1 && (colour == 0 || colour == 1), "bad argument");
   CM_CHECK_ARG(A && lf && iu && cu && b && x, "null pointer");
-  return st_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, (cudaStream_t)stream);
+  return st_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, (cudaStream_t)stream, 0, -1, tmp);
 }
 
 int cm_stencil_residual(int32_t nx, int32_t ny, const double* A, const double* b, const double* x,

@@ -116,11 +116,12 @@ static int check_err_flag(PQSolver& S, cudaStream_t st, const char* what) {
   return CM_OK;
 }
 
+// L.r is free during smoothing: it serves as the scratch of the pipelined sweep
 static int zebra_sweep(const PQSLevel& L, const double* A, const double* lf, const double* iu,
                        const double* cu, const double* b, double* x, bool x_zero, cudaStream_t st) {
-  int rc = st_zebra(L.nx, L.ny, 0, A, lf, iu, cu, b, x, x_zero ? 1 : 0, st);
+  int rc = st_zebra(L.nx, L.ny, 0, A, lf, iu, cu, b, x, x_zero ? 1 : 0, st, 0, -1, L.r);
   if (rc) return rc;
-  return st_zebra(L.nx, L.ny, 1, A, lf, iu, cu, b, x, 0, st);
+  return st_zebra(L.nx, L.ny, 1, A, lf, iu, cu, b, x, 0, st, 0, -1, L.r);
 }
 
 static int vcycle(PQSolver& S, int l, const double* b, double* x, cudaStream_t st) {
@@ -264,9 +265,9 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
   PQSLevel& C = S.lev[l + 1];
   const int n1 = L.nx + 1, rb = I.rb[l], re = I.re[l];
   double* xa[1] = {x};
-  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 1, st, rb, re))) return rc;
+  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 1, st, rb, re, L.r))) return rc;
   if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re))) return rc;
+  if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
   if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
   if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st, rb, re))) return rc;
   double* ra[1] = {L.r};
@@ -279,9 +280,9 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
   }
   if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st, rb, re))) return rc;
   if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re))) return rc;
+  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
   if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  return st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re);
+  return st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r);
 }
 
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
@@ -375,10 +376,10 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
     if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st, rb, re))) return e;
     double* zq[1] = {z + V};
     for (int s = 0; s < S.q_sweeps; ++s) {
-      if ((e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, s == 0 ? 1 : 0, st, rb, re)))
+      if ((e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, s == 0 ? 1 : 0, st, rb, re, S.lev[0].r)))
         return e;
       if ((e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
-      if ((e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, rb, re))) return e;
+      if ((e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, rb, re, S.lev[0].r))) return e;
       if (s + 1 < S.q_sweeps && (e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
     }
     return e;

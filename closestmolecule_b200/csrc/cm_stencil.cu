@@ -559,6 +559,121 @@ int st_zebra_debug_times(unsigned long long* host_out, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pipelined variant of the zebra sweep.  (1) offline_rhs_kernel: the couplings to the neighbouring
+// lines are a plain streaming pass, rhs = b - (A - T) x on the lines of one colour.  (2)
+// line_solve_pipelined_kernel: persistent CTAs, each loops over its lines; the right-hand side and
+// the forward factors of the NEXT line are brought into shared memory by cp.async while the
+// current line is being scanned (double buffering), so HBM keeps streaming during the scans --
+// the lock-step load / scan phases of the one-line-per-CTA kernel left it idle half of the time.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSB)
+offline_rhs_kernel(const int nx, const int ny, const int jfirst, const int nlines,
+                   const double* __restrict__ A, const double* __restrict__ b,
+                   const double* __restrict__ x, double* __restrict__ out) {
+  const int n1 = nx + 1;
+  const long long t = blockIdx.x * (long long)kSB + threadIdx.x;
+  if (t >= (long long)nlines * n1) return;
+  const int l = (int)(t / n1), i = (int)(t - (long long)l * n1);
+  const int j = jfirst + 2 * l;
+  const size_t nv = (size_t)n1 * (ny + 1);
+  const size_t v = (size_t)j * n1 + i;
+  const size_t lo = (size_t)(j > 0 ? j - 1 : 0) * n1, up = (size_t)(j < ny ? j + 1 : ny) * n1;
+  const int im = i > 0 ? i - 1 : 0, ip = i < nx ? i + 1 : nx;
+  const double a0 = A[v], a1 = A[nv + v], a5 = A[5 * nv + v], a6 = A[6 * nv + v];
+  out[v] = b[v] - (a0 * x[lo + im] + a1 * x[lo + i] + a5 * x[up + i] + a6 * x[up + ip]);
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1)
+line_solve_pipelined_kernel(const int nx, const int ny, const int jfirst, const int nlines, const int E,
+                            const double* __restrict__ lf, const double* __restrict__ iu,
+                            const double* __restrict__ cu, const double* __restrict__ rhs,
+                            double* __restrict__ x) {
+  extern __shared__ double sm[];  // 2 stages x (s_z, s_c)
+  const int n1 = nx + 1;
+  __shared__ double sh[64];
+  const int T = blockDim.x, tid = threadIdx.x;
+  int l = blockIdx.x;
+  if (l >= nlines) return;
+  int stage = 0;
+  {
+    const size_t base = (size_t)(jfirst + 2 * l) * n1;
+    double* z = sm;
+    double* c = sm + n1;
+    for (int i = tid; i < n1; i += T) { cp_async8(z + i, rhs + base + i); cp_async8(c + i, lf + base + i); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (; l < nlines; l += gridDim.x) {
+    const size_t base = (size_t)(jfirst + 2 * l) * n1;
+    double* s_z = sm + (size_t)stage * 2 * n1;
+    double* s_c = s_z + n1;
+    const int ln = l + gridDim.x;
+    if (ln < nlines) {  // prefetch the next line into the other stage
+      const size_t bn = (size_t)(jfirst + 2 * ln) * n1;
+      double* z = sm + (size_t)(stage ^ 1) * 2 * n1;
+      double* c = z + n1;
+      for (int i = tid; i < n1; i += T) { cp_async8(z + i, rhs + bn + i); cp_async8(c + i, lf + bn + i); }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // back-substitution factors of this line: in flight during the forward scan
+    double piu[5], pcu[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = tid + k * T;
+      if (i < n1) { piu[k] = iu[base + i]; pcu[k] = cu[base + i]; }
+    }
+    if (ln < nlines) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {
+      const int i0 = tid * E, i1 = min(i0 + E, n1);
+      Affine m{1.0, 0.0};
+      for (int i = i0; i < i1; ++i) {
+        const double lv = s_c[i];
+        m.b = s_z[i] - lv * m.b;
+        m.a = -lv * m.a;
+      }
+      double z = affine_exclusive_scan(m, sh);
+      for (int i = i0; i < i1; ++i) {
+        z = s_z[i] - s_c[i] * z;
+        s_z[i] = z;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = tid + k * T;
+      if (i < n1) { s_z[i] *= piu[k]; s_c[i] = pcu[k]; }
+    }
+    for (int i = tid + 5 * T; i < n1; i += T) { s_z[i] *= iu[base + i]; s_c[i] = cu[base + i]; }
+    __syncthreads();
+    {
+      const int seg = T - 1 - tid;
+      const int i0 = seg * E, i1 = min(i0 + E, n1);
+      Affine m{1.0, 0.0};
+      for (int i = i1 - 1; i >= i0; --i) {
+        const double cv = s_c[i];
+        m.b = s_z[i] - cv * m.b;
+        m.a = -cv * m.a;
+      }
+      double xn = affine_exclusive_scan(m, sh);
+      for (int i = i1 - 1; i >= i0; --i) {
+        xn = s_z[i] - s_c[i] * xn;
+        s_z[i] = xn;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
+    __syncthreads();  // this stage is refilled by the prefetch of the next iteration
+    stage ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // coarsest level: dense inverse by Gauss-Jordan with partial pivoting (one CTA), then x = Ainv b
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -750,12 +865,40 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
 
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
              const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0,
-             int r1) {
+             int r1, double* tmp) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
   const int jfirst = r0 + (((r0 & 1) == colour) ? 0 : 1);
   const int nlines = (r1 - jfirst + 1) / 2;
   if (nlines <= 0) return CM_OK;
+  static int pipe_mode = -1;
+  if (pipe_mode < 0) { const char* e = getenv("CM_ZEBRA_PIPELINED"); pipe_mode = e ? atoi(e) : 1; }
+  if (tmp != nullptr && pipe_mode && n1 >= 1024 && 4 * (size_t)n1 * sizeof(double) <= 200 * 1024) {
+    const bool prof = nx == g_prof_fine_nx;
+    if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
+    const double* rhs = b;
+    if (!x_zero) {
+      const long long nt = (long long)nlines * n1;
+      offline_rhs_kernel<<<(int)((nt + kSB - 1) / kSB), kSB, 0, st>>>(nx, ny, jfirst, nlines, A, b, x, tmp);
+      ++g_launches;
+      rhs = tmp;
+    }
+    static bool attr2 = false;
+    if (!attr2) {
+      CM_CUDA(cudaFuncSetAttribute(line_solve_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+      attr2 = true;
+    }
+    const int T = (n1 > 2048) ? 1024 : 512;
+    int E = (n1 + T - 1) / T;
+    if ((E & 1) == 0) ++E;
+    const int grid = nlines < 148 ? nlines : 148;
+    line_solve_pipelined_kernel<<<grid, T, 4 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, E,
+                                                                                  lf, iu, cu, rhs, x);
+    if (prof) prof_end(kProfZebraFine, st);
+    CM_LAUNCH_CHECK();
+    return CM_OK;
+  }
   const int T = (n1 > 2048) ? 512 : ((n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32));
   int E = (n1 + T - 1) / T;
   if ((E & 1) == 0) ++E;  // odd stride: conflict-free 64-bit shared-memory accesses per half warp

@@ -256,12 +256,14 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
  *     *err_flag (device int, zeroed by the caller) is set to 2 on a zero pivot.
  *   cm_stencil_zebra: for every grid line of one colour (line index parity) solve
  *     T x_line = b_line - (A - T) x with the current x on the neighbouring lines (x_is_zero: skip them).
+ *     tmp: n doubles of scratch or NULL; with scratch the sweep runs as a streaming right-hand-side
+ *     pass + persistent line-solve CTAs that prefetch the next line by cp.async under the scans.
  *   cm_stencil_residual: r = b - A x (b may be NULL). */
 int cm_stencil_line_factor(int32_t nx, int32_t ny, const double* A, double* lf, double* iu,
                            double* cu, int32_t* err_flag, void* stream);
 int cm_stencil_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
                      const double* iu, const double* cu, const double* b, double* x,
-                     int32_t x_is_zero, void* stream);
+                     int32_t x_is_zero, double* tmp, void* stream);
 int cm_stencil_residual(int32_t nx, int32_t ny, const double* A, const double* b, const double* x,
                         double* r, void* stream);
 

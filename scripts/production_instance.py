@@ -1,0 +1,91 @@
+"""Port of solve_problem_instance (convergence/advection_diffusion_convergence.py:105-228, the flat /
+curved-boundary production problem of advection_diffusion_mixed.py:94-269) onto closestmolecule_b200
+for the CG1 x CG1 primal formulation: same mesh labels (right=21, top=22, left=23, bottom=24), same
+Dirichlet list and order (:174-183), same data formulas (PInitial/QInitial :40-44,79-80), same Newton
+parameters (:207-215), steady state or backward-Euler time loop (:196-204,219-226).
+
+The reference's unstabilised Galerkin q-equation needs a pivoting sparse LU; on the GPU
+path the q-equation takes the SUPG test function of …MixedPrimal_convergence_SUPG.py:118-129
+(`supg_stab`, default 1) -- set supg_stab=0 to get the reference's form (assembly works, the
+structured solver then reports a zero pivot).
+"""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from closestmolecule_b200 import *  # noqa: E402,F401,F403
+
+
+def solve_problem_instance(concentration, t_final, dt, mesh, bdry, sigma, deg=1, steady_state=False,
+                           D1=2.0, D2=1.5, r1_max=5.0, supg_stab=1.0, report=False, sigma_fn=None):
+    assert deg == 1, "the GPU hot path is CG1 x CG1"
+    right, top, left, bottom = 21, 22, 23, 24
+    V1 = 4 * math.pi * (r1_max - sigma) ** 3 / 3
+    c = float(concentration)
+    sig = sigma_fn if sigma_fn is not None else (lambda x: sigma)
+
+    def p_initial(x, y):          # PInitial.eval (:40-44)
+        return c / V1 * torch.exp(-4 / 3 * math.pi * c * x ** 3) * (1 - sig(x) / y)
+
+    def p_right(x, y):            # PInitial(right=True)
+        base = c / V1 * torch.exp(-4 / 3 * math.pi * c * x ** 3)
+        return torch.where(y > 0, base * (1 - sig(x) / y), base)
+
+    def q_initial(x, y):          # QInitial.eval (:79-80)
+        return 1 / (4 * math.pi * V1) * torch.exp(-4 / 3 * math.pi * c * x ** 3)
+
+    P0 = FiniteElement('CG', mesh.ufl_cell(), deg)
+    P1 = FiniteElement('CG', mesh.ufl_cell(), deg)
+    mixed_space = FunctionSpace(mesh, MixedElement([P0, P1]))
+    if steady_state:
+        t_final = 0
+    t = 0
+    u = Function(mixed_space)
+    p_old = interpolate(p_initial, mixed_space.sub(0).collapse())
+    bc = [DirichletBC(mixed_space.sub(0), p_right, bdry, right),
+          DirichletBC(mixed_space.sub(0), p_initial, bdry, top),
+          DirichletBC(mixed_space.sub(0), Constant(0.), bdry, bottom),
+          DirichletBC(mixed_space.sub(1), q_initial, bdry, right)]
+    FF = PQPrimalForm(mixed_space, D1, D2, G=("gstar_conv", c), dt=None if steady_state else dt,
+                      p_old=None if steady_state else p_old, supg_stab=supg_stab)
+    problem = NonlinearVariationalProblem(FF, u, bcs=bc)
+    solver = NonlinearVariationalSolver(problem)
+    solver.parameters['nonlinear_solver'] = 'newton'
+    solver.parameters['newton_solver']['linear_solver'] = 'mumps'
+    solver.parameters['newton_solver']['absolute_tolerance'] = 1e-9
+    solver.parameters['newton_solver']['relative_tolerance'] = 1e-9
+    solver.parameters['newton_solver']['maximum_iterations'] = 10
+    solver.parameters['newton_solver']['report'] = report
+    log = []
+    while t <= t_final:
+        print("t=%.3f" % t)
+        its, conv = solver.solve()
+        log.append((its, list(solver.linear_iterations)))
+        p_h, q_h = u.split()
+        p_old.vector().copy_(p_h)          # assign(p_old, p_h)
+        t += dt
+    return u, log
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    sigma, gamma = 0.1, 1.0
+    for kind in ("flat", "curved"):
+        if kind == "flat":
+            mesh = RectangleMesh(Point(0, sigma), Point(5, 5), n, n)
+            sfn = None
+        else:
+            mesh = MappedRectangleMesh(n, n, 5.0, 5.0, sigma, gamma)
+            sfn = lambda x: sigma * torch.exp(-4 / 3 * math.pi * gamma * x ** 3)
+        bdry = structured_boundary_markers(mesh)
+        for c in (1, 4):
+            for steady in (True, False):
+                try:
+                    u, log = solve_problem_instance(c, 0.1, 0.1, mesh, bdry, sigma, steady_state=steady, sigma_fn=sfn)
+                    print(kind, "n", n, "c", c, "steady" if steady else "transient", "Newton/linear its", log,
+                          "max p %.3e" % float(u.split()[0].max()))
+                except Exception as e:  # noqa: BLE001
+                    print(kind, "n", n, "c", c, "steady" if steady else "transient", "FAILED:", str(e)[:150])

@@ -174,10 +174,11 @@ def test_zebra_line_relaxation_building_blocks():
     b = torch.tensor(rng.standard_normal(n), device=dev)
     x = torch.zeros(n, dtype=torch.float64, device=dev)
     r = torch.empty_like(x)
+    tmp = torch.empty_like(x)
     lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
     _capi.check(lib.cm_stencil_line_factor(nx, ny, P(At), P(lf), P(iu), P(cu), P(err), st))
     assert int(err.item()) == 0
-    _capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(At), P(lf), P(iu), P(cu), P(b), P(x), 1, st))
+    _capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(At), P(lf), P(iu), P(cu), P(b), P(x), 1, P(tmp), st))
     # colour 0 from a zero guess = plain tridiagonal solves of the even lines
     import scipy.linalg as sla
     X = x.cpu().numpy().reshape(ny + 1, n1)
@@ -189,7 +190,7 @@ def test_zebra_line_relaxation_building_blocks():
         ab[2, :-1] = A[2, j, 1:]
         ref = sla.solve_banded((1, 1), ab, B[j])
         assert np.max(np.abs(X[j] - ref)) < 1e-13 * np.max(np.abs(ref)) + 1e-14
-    _capi.check(lib.cm_stencil_zebra(nx, ny, 1, P(At), P(lf), P(iu), P(cu), P(b), P(x), 0, st))
+    _capi.check(lib.cm_stencil_zebra(nx, ny, 1, P(At), P(lf), P(iu), P(cu), P(b), P(x), 0, P(tmp), st))
     _capi.check(lib.cm_stencil_residual(nx, ny, P(At), P(b), P(x), P(r), st))
     R = r.cpu().numpy().reshape(ny + 1, n1)
     assert np.max(np.abs(R[1::2])) < 1e-13 and np.max(np.abs(R[0::2])) > 1e-3

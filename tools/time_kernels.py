@@ -26,6 +26,7 @@ err = torch.zeros(1, dtype=torch.int32, device=dev)
 b = torch.randn(n, dtype=torch.float64, device=dev)
 x = torch.zeros(n, dtype=torch.float64, device=dev)
 r = torch.empty_like(x)
+tmp = torch.empty_like(x)
 P = _capi.ptr
 st = _capi.stream_ptr()
 
@@ -46,15 +47,15 @@ print(f"line_factor: {t:.1f} us  ({(3 * 8 + 3 * 8) * n / t / 1e6:.0f} GB/s)")
 assert int(err.item()) == 0
 for colour in (0, 1):
     for xz in (1, 0):
-        t = timeit(lambda: _capi.check(lib.cm_stencil_zebra(nx, ny, colour, P(A), P(lf), P(iu), P(cu), P(b), P(x), xz, st)))
+        t = timeit(lambda: _capi.check(lib.cm_stencil_zebra(nx, ny, colour, P(A), P(lf), P(iu), P(cu), P(b), P(x), xz, P(tmp), st)))
         byts = (n / 2) * (8 + 24 + 8 + (0 if xz else 32 + 16))
         print(f"zebra colour {colour} x_zero {xz}: {t:.1f} us  ({byts / t / 1e6:.0f} GB/s algorithmic)")
 t = timeit(lambda: _capi.check(lib.cm_stencil_residual(nx, ny, P(A), P(b), P(x), P(r), st)))
 print(f"residual: {t:.1f} us ({80 * n / t / 1e6:.0f} GB/s)")
 # correctness of one zebra sweep against the residual: after solving lines of colour c, the residual on those lines is ~0
 x.zero_()
-_capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(A), P(lf), P(iu), P(cu), P(b), P(x), 1, st))
-_capi.check(lib.cm_stencil_zebra(nx, ny, 1, P(A), P(lf), P(iu), P(cu), P(b), P(x), 0, st))
+_capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(A), P(lf), P(iu), P(cu), P(b), P(x), 1, P(tmp), st))
+_capi.check(lib.cm_stencil_zebra(nx, ny, 1, P(A), P(lf), P(iu), P(cu), P(b), P(x), 0, P(tmp), st))
 _capi.check(lib.cm_stencil_residual(nx, ny, P(A), P(b), P(x), P(r), st))
 R = r.reshape(ny + 1, n1)
 print("max |r| on odd lines after the sweep:", float(R[1::2].abs().max()), " even lines:", float(R[0::2].abs().max()))
@@ -62,7 +63,7 @@ if os.environ.get("CM_ZEBRA_DEBUG") and int(os.environ["CM_ZEBRA_DEBUG"]) & 32:
     import ctypes, numpy as np
     lib.cm_dev_zebra_times.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     for xz in (1, 0):
-        _capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(A), P(lf), P(iu), P(cu), P(b), P(x), xz, st))
+        _capi.check(lib.cm_stencil_zebra(nx, ny, 0, P(A), P(lf), P(iu), P(cu), P(b), P(x), xz, P(tmp), st))
         torch.cuda.synchronize()
         buf = np.zeros(1025 * 8, dtype=np.uint64)
         lib.cm_dev_zebra_times(buf.ctypes.data, buf.size)
