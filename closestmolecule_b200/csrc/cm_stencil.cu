@@ -674,6 +674,281 @@ line_solve_pipelined_kernel(const int nx, const int ny, const int jfirst, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Register-resident line solve: thread t owns E consecutive unknowns of the line and keeps the
+// right-hand side and the three factor arrays in registers (blocked loads; the 40-byte per-thread
+// runs are sector-exact through L1), so shared memory only carries the 2 x 32 warp totals of the
+// scans.  Persistent CTAs loop over lines and pull the next line into L2 while scanning.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double affine_exclusive_scan_dir(Affine m, double* sh, const bool rev) {
+  // exclusive scan in thread order (rev: in reverse thread order); returns the incoming value
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int pos = rev ? 31 - lane : lane;       // position inside the warp in scan order
+  const int wpos = rev ? nw - 1 - wid : wid;    // warp position in scan order
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double pa = rev ? __shfl_down_sync(0xffffffffu, m.a, o) : __shfl_up_sync(0xffffffffu, m.a, o);
+    const double pb = rev ? __shfl_down_sync(0xffffffffu, m.b, o) : __shfl_up_sync(0xffffffffu, m.b, o);
+    if (pos >= o) m = compose(m, Affine{pa, pb});
+  }
+  if (pos == 31) { sh[2 * wpos] = m.a; sh[2 * wpos + 1] = m.b; }
+  __syncthreads();
+  if (wid == 0) {
+    Affine t = (lane < nw) ? Affine{sh[2 * lane], sh[2 * lane + 1]} : Affine{1.0, 0.0};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, t.a, o);
+      const double pb = __shfl_up_sync(0xffffffffu, t.b, o);
+      if (lane >= o) t = compose(t, Affine{pa, pb});
+    }
+    if (lane < nw) { sh[2 * lane] = t.a; sh[2 * lane + 1] = t.b; }
+  }
+  __syncthreads();
+  double ea = rev ? __shfl_down_sync(0xffffffffu, m.a, 1) : __shfl_up_sync(0xffffffffu, m.a, 1);
+  double eb = rev ? __shfl_down_sync(0xffffffffu, m.b, 1) : __shfl_up_sync(0xffffffffu, m.b, 1);
+  if (pos == 0) { ea = 1.0; eb = 0.0; }
+  double r = eb;
+  if (wpos > 0) r = ea * sh[2 * (wpos - 1) + 1] + eb;
+  __syncthreads();
+  return r;
+}
+
+template <int E>
+__global__ void __launch_bounds__(1024, 1)
+line_solve_reg_kernel(const int nx, const int ny, const int jfirst, const int nlines,
+                      const double* __restrict__ lf, const double* __restrict__ iu,
+                      const double* __restrict__ cu, const double* __restrict__ rhs,
+                      double* __restrict__ x, const int dbg) {
+  __shared__ double sh[64];
+  const int n1 = nx + 1;
+  const int tid = threadIdx.x;
+  const int i0 = tid * E;
+  const int ne = max(0, min(E, n1 - i0));
+  for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
+    const size_t base = (size_t)(jfirst + 2 * l) * n1 + i0;
+    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 0] = gtime();
+    double r[E], lv[E], iv[E], cv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { r[e] = rhs[base + e]; lv[e] = lf[base + e]; iv[e] = iu[base + e]; cv[e] = cu[base + e]; }
+    // pull this CTA's next line towards L2 while the scans run
+    if (l + gridDim.x < nlines && ne > 0) {
+      const size_t bn = (size_t)(jfirst + 2 * (l + gridDim.x)) * n1 + i0;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rhs + bn));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lf + bn));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(iu + bn));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(cu + bn));
+    }
+    // forward: z_i = r_i - l_i z_{i-1}
+    Affine m{1.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
+    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 1] = gtime();
+    double z = affine_exclusive_scan_dir(m, sh, false);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
+    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 2] = gtime();
+    // backward: x_i = w_i - cu_i x_{i+1}
+    m = Affine{1.0, 0.0};
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
+    double xn = affine_exclusive_scan_dir(m, sh, true);
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { xn = r[e] - cv[e] * xn; r[e] = xn; }
+    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 3] = gtime();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) x[base + e] = r[e];
+    if ((dbg & 32) && tid == 0 && l < 2048) { g_zdbg[l * 8 + 4] = gtime(); g_zdbg[l * 8 + 5] = g_zdbg[l * 8 + 4]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hybrid line solve (the default on long lines): coalesced cp.async brings the four arrays of a line
+// into shared memory; every thread pulls its E consecutive unknowns into registers ONCE, the buffers
+// are immediately refilled with the CTA's next line (the copies fly during the scans), both scans
+// run on registers, and the solution leaves through a shared-memory transpose as coalesced stores.
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(1024, 1)
+line_solve_hybrid_kernel(const int nx, const int ny, const int jfirst, const int nlines,
+                         const double* __restrict__ lf, const double* __restrict__ iu,
+                         const double* __restrict__ cu, const double* __restrict__ rhs,
+                         double* __restrict__ x, const int dbg) {
+  extern __shared__ double sm[];  // s_r, s_l, s_i, s_c, s_x : 5 * n1 doubles
+  __shared__ double sh[64];
+  const int n1 = nx + 1;
+  double* s_r = sm;
+  double* s_l = sm + n1;
+  double* s_i = sm + 2 * n1;
+  double* s_c = sm + 3 * n1;
+  double* s_x = sm + 4 * n1;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int i0 = tid * E;
+  const int ne = max(0, min(E, n1 - i0));
+  int l = blockIdx.x;
+  if (l >= nlines) return;
+  {
+    const size_t b0 = (size_t)(jfirst + 2 * l) * n1;
+    for (int i = tid; i < n1; i += T) {
+      cp_async8(s_r + i, rhs + b0 + i); cp_async8(s_l + i, lf + b0 + i);
+      cp_async8(s_i + i, iu + b0 + i); cp_async8(s_c + i, cu + b0 + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (; l < nlines; l += gridDim.x) {
+    const size_t lbase = (size_t)(jfirst + 2 * l) * n1;
+#define HT(k) do { if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + (k)] = gtime(); } while (0)
+    HT(0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    HT(1);
+    double r[E], lv[E], iv[E], cv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { r[e] = s_r[i0 + e]; lv[e] = s_l[i0 + e]; iv[e] = s_i[i0 + e]; cv[e] = s_c[i0 + e]; }
+    __syncthreads();
+    const int ln = l + gridDim.x;
+    if (ln < nlines) {  // refill the buffers with the next line; the copies overlap the scans
+      const size_t bn = (size_t)(jfirst + 2 * ln) * n1;
+      for (int i = tid; i < n1; i += T) {
+        cp_async8(s_r + i, rhs + bn + i); cp_async8(s_l + i, lf + bn + i);
+        cp_async8(s_i + i, iu + bn + i); cp_async8(s_c + i, cu + bn + i);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    HT(2);
+    Affine m{1.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
+    double z = affine_exclusive_scan_dir(m, sh, false);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
+    HT(3);
+    m = Affine{1.0, 0.0};
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
+    double xn = affine_exclusive_scan_dir(m, sh, true);
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { xn = r[e] - cv[e] * xn; s_x[i0 + e] = xn; }
+    __syncthreads();
+    HT(4);
+    for (int i = tid; i < n1; i += T) x[lbase + i] = s_x[i];
+    HT(5);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant of the hybrid line solve: the four arrays of the next line arrive by four
+// cp.async.bulk copies (UBLKCP) issued by one thread and tracked by an mbarrier -- no per-thread
+// copy instructions at all (8-byte cp.async is issue-bound: ~2.6 us per line).  Lines start on
+// 8-byte boundaries only, so the copy starts at the preceding even element and the shared-memory
+// view is shifted by `sh`; an odd trailing element is fetched by a plain load.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, void* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+template <int E>
+__global__ void __launch_bounds__(1024, 1)
+line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nlines,
+                      const double* __restrict__ lf, const double* __restrict__ iu,
+                      const double* __restrict__ cu, const double* __restrict__ rhs,
+                      double* __restrict__ x, const int dbg) {
+  extern __shared__ __align__(16) double sm[];  // 4 input buffers of npad doubles + s_x
+  __shared__ double sh[64];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int n1 = nx + 1;
+  const int npad = (n1 + 3) & ~1;
+  double* buf[4] = {sm, sm + npad, sm + 2 * npad, sm + 3 * npad};
+  double* s_x = sm + 4 * npad;
+  const double* src[4] = {rhs, lf, iu, cu};
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int i0 = tid * E;
+  const int ne = max(0, min(E, n1 - i0));
+  int l = blockIdx.x;
+  if (l >= nlines) return;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  auto issue = [&](int line) {
+    const size_t base = (size_t)(jfirst + 2 * line) * n1;
+    const int shf = (int)(base & 1);
+    const size_t a0 = base - shf;
+    const int cnt = (n1 + shf) & ~1;  // even number of elements copied by TMA
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const unsigned bytes = (unsigned)cnt * 8u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(4u * bytes) : "memory");
+#pragma unroll
+      for (int a = 0; a < 4; ++a) tma_bulk_g2s(buf[a], src[a] + a0, bytes, &mbar);
+    }
+    if (tid >= 32 && tid < 36 && cnt < n1 + shf)  // odd trailing element
+      buf[tid - 32][cnt] = src[tid - 32][a0 + cnt];
+  };
+  issue(l);
+  for (; l < nlines; l += gridDim.x) {
+    const size_t lbase = (size_t)(jfirst + 2 * l) * n1;
+    const int shf = (int)(lbase & 1);
+    HT(0);
+    {  // wait for the bulk copies of this line
+      unsigned done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(parity) : "memory");
+      }
+      parity ^= 1u;
+    }
+    __syncthreads();  // the plain-load tail element is visible too
+    HT(1);
+    double r[E], lv[E], iv[E], cv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) {
+        r[e] = buf[0][shf + i0 + e]; lv[e] = buf[1][shf + i0 + e];
+        iv[e] = buf[2][shf + i0 + e]; cv[e] = buf[3][shf + i0 + e];
+      }
+    __syncthreads();
+    if (l + gridDim.x < nlines) issue(l + gridDim.x);
+    HT(2);
+    Affine m{1.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
+    double z = affine_exclusive_scan_dir(m, sh, false);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
+    HT(3);
+    m = Affine{1.0, 0.0};
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
+    double xn = affine_exclusive_scan_dir(m, sh, true);
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e)
+      if (e < ne) { xn = r[e] - cv[e] * xn; s_x[i0 + e] = xn; }
+    __syncthreads();
+    HT(4);
+    for (int i = tid; i < n1; i += T) x[lbase + i] = s_x[i];
+    HT(5);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // coarsest level: dense inverse by Gauss-Jordan with partial pivoting (one CTA), then x = Ainv b
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -872,7 +1147,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   const int nlines = (r1 - jfirst + 1) / 2;
   if (nlines <= 0) return CM_OK;
   static int pipe_mode = -1;
-  if (pipe_mode < 0) { const char* e = getenv("CM_ZEBRA_PIPELINED"); pipe_mode = e ? atoi(e) : 1; }
+  if (pipe_mode < 0) { const char* e = getenv("CM_ZEBRA_PIPELINED"); pipe_mode = e ? atoi(e) : 4; }
   if (tmp != nullptr && pipe_mode && n1 >= 1024 && 4 * (size_t)n1 * sizeof(double) <= 200 * 1024) {
     const bool prof = nx == g_prof_fine_nx;
     if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
@@ -889,12 +1164,41 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
                                    200 * 1024));
       attr2 = true;
     }
-    const int T = (n1 > 2048) ? 1024 : 512;
-    int E = (n1 + T - 1) / T;
-    if ((E & 1) == 0) ++E;
+    static int dbg2 = -1;
+    if (dbg2 < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg2 = e ? atoi(e) : 0; }
     const int grid = nlines < 148 ? nlines : 148;
-    line_solve_pipelined_kernel<<<grid, T, 4 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, E,
-                                                                                  lf, iu, cu, rhs, x);
+    if (pipe_mode >= 4 && n1 <= 5 * 1024 && (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
+      static bool attr4 = false;
+      if (!attr4) {
+        CM_CUDA(cudaFuncSetAttribute(line_solve_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+        attr4 = true;
+      }
+      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
+      if (T < 64) T = 64;
+      const int npad = (n1 + 3) & ~1;
+      line_solve_tma_kernel<5><<<grid, T, (4 * (size_t)npad + n1 + 1) * sizeof(double), st>>>(
+          nx, ny, jfirst, nlines, lf, iu, cu, rhs, x, dbg2);
+    } else if (pipe_mode == 3 && n1 <= 5 * 1024 && 5 * (size_t)n1 * sizeof(double) <= 200 * 1024) {
+      static bool attr3 = false;
+      if (!attr3) {
+        CM_CUDA(cudaFuncSetAttribute(line_solve_hybrid_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+        attr3 = true;
+      }
+      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
+      line_solve_hybrid_kernel<5><<<grid, T, 5 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, lf,
+                                                                                    iu, cu, rhs, x, dbg2);
+    } else if (pipe_mode == 2 && n1 <= 5 * 1024) {
+      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
+      line_solve_reg_kernel<5><<<grid, T, 0, st>>>(nx, ny, jfirst, nlines, lf, iu, cu, rhs, x, dbg2);
+    } else {
+      const int T = (n1 > 2048) ? 1024 : 512;
+      int E = (n1 + T - 1) / T;
+      if ((E & 1) == 0) ++E;
+      line_solve_pipelined_kernel<<<grid, T, 4 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, E,
+                                                                                    lf, iu, cu, rhs, x);
+    }
     if (prof) prof_end(kProfZebraFine, st);
     CM_LAUNCH_CHECK();
     return CM_OK;

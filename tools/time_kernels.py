@@ -70,5 +70,5 @@ if os.environ.get("CM_ZEBRA_DEBUG") and int(os.environ["CM_ZEBRA_DEBUG"]) & 32:
         tt = buf.reshape(-1, 8)[:, :6].astype(np.int64)
         t0 = tt[:, 0].min()
         d = np.diff(tt, axis=1)
-        print("x_zero", xz, "phase durations ns (mean): loadA, fwd, mul, bwd, store ->", d.mean(0).round(0), " CTA total", (tt[:, 5] - tt[:, 0]).mean().round(0),
+        print("x_zero", xz, "phase durations ns (mean) [hybrid: wait, LDS+issue, fwd, bwd, store]:", d.mean(0).round(0), " CTA total", (tt[:, 5] - tt[:, 0]).mean().round(0),
               " kernel span", tt[:, 5].max() - t0, " CTA start spread (percentiles 50/90/100)", np.percentile(tt[:, 0] - t0, [50, 90, 100]).round(0))
