@@ -194,3 +194,18 @@ def test_zebra_line_relaxation_building_blocks():
     _capi.check(lib.cm_stencil_residual(nx, ny, P(At), P(b), P(x), P(r), st))
     R = r.cpu().numpy().reshape(ny + 1, n1)
     assert np.max(np.abs(R[1::2])) < 1e-13 and np.max(np.abs(R[0::2])) > 1e-3
+
+
+def test_pq_supg_convergence_rates_on_gpu():
+    """scripts/pq_supg_convergence.py: expected orders of the P1 x P1 SUPG system (2 in L2(p), 1 in
+    H1(p) and H1(q)) with mesh-independent GMRES iteration counts."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "pq_supg_convergence.py")
+    spec = importlib.util.spec_from_file_location("pq_supg_conv", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.main(8)
+    assert 1.9 < r["rp"][-1] < 2.1 and 0.95 < r["r1p"][-1] < 1.05 and 0.9 < r["rq"][-1] < 1.3
+    assert max(max(l) for _, l in r["its"][3:]) <= 20

@@ -3,7 +3,17 @@ import numpy as np
 
 from oracle import fem, pq, scalar
 
-# README.md:109-115 of the reference, verbatim rows (DoF, h, e_1(u), r_1(u), e_0(u), r_0(u))
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _golden(name):
+    return [ln.rstrip("\n") for ln in open(os.path.join(GOLDEN, name)) if ln.strip()]
+
+
+# README.md:109-115 of the reference, verbatim rows (DoF, h, e_1(u), r_1(u), e_0(u), r_0(u));
+# tests/golden/readme_table.txt holds the same rows as a file
 README_TABLE = [
     "     9  0.7071 1.81e+00  0.000  1.74e-01  0.000 ",
     "    25  0.3536 9.23e-01  0.968  3.52e-02  2.305 ",
@@ -13,6 +23,11 @@ README_TABLE = [
     "  4225  0.0221 5.46e-02  1.001  1.09e-04  1.971 ",
     " 16641  0.0110 2.73e-02  0.998  2.95e-05  1.891 ",
 ]
+
+
+def test_golden_files_match_embedded_tables():
+    assert [r.split() for r in _golden("readme_table.txt")] == [r.split() for r in README_TABLE]
+    assert [r.split() for r in _golden("paper_k0_table.txt")] == [r.split() for r in PAPER_K0]
 
 
 def test_readme_table_digit_for_digit():
