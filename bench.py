@@ -117,7 +117,7 @@ UNIT = "cells/s"
 
 
 def workload_config(args, nx, ny):
-    return {"workload": f"P-Q CG1xCG1 manufactured SUPG Newton step on RectangleMesh {nx}x{ny} "
+    return {"workload": f"P-Q CG1xCG1 manufactured {getattr(args, 'variant', 'supg').upper()} Newton step on RectangleMesh {nx}x{ny} "
                         f"({2 * nx * ny} cells) per GPU",
             "nx": nx, "ny": ny, "cells_per_gpu": 2 * nx * ny, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
             "parallelism": (f"independent problem instance per GPU x{args.gpus}" if getattr(args, "instances", False)
@@ -209,8 +209,23 @@ def gpu_arm(args):
     V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
     bd = cm.MeshFunction("size_t", mesh, 1, 0)
     cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
-    form = cm.PQPrimalForm.manufactured(V, "supg")
-    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    if args.variant == "supg":
+        form = cm.PQPrimalForm.manufactured(V, "supg")
+        bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    else:   # C0IP variants of BASELINE config 3 (…_C0IP.py:141-147 / test_for_paper_convergence.py:140-153)
+        cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+        cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+        cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+        if args.variant == "c0ip_minus":
+            form = cm.PQPrimalForm.manufactured(V, "c0ip", D1=0.01, D2=0.015, stab=0.05, sign=-1.0,
+                                                ext_terms=[(bd, 30, cm.EF_ADV)])
+            bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+        else:
+            form = cm.PQPrimalForm.manufactured(
+                V, "c0ip", D1=1.0, D2=1.5, stab=0.05, sign=+1.0, c0ip_h="facet", degree=6, pen_stab2=1.0,
+                ext_terms=[(bd, 30, cm.EF_ADV), (bd, 32, cm.EF_ADV), (bd, 31, cm.EF_DATA),
+                           (bd, "on_boundary", cm.EF_PENALTY)])
+            bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary")]
     strong = world > 1 and not args.instances
     X = mesh.coords
     if strong:
@@ -222,6 +237,8 @@ def gpu_arm(args):
         u = cm.Function(V)
         solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
         solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
+        if args.variant != "supg":
+            solver.parameters["newton_solver"]["krylov_solver"]["restart"] = 100
         uvec = u.vector()
         own = slice(0, uvec.numel())
     u0 = torch.empty_like(uvec)
@@ -381,6 +398,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096, help="mesh is nx x nx/2 (default: the 16 Mi-cell mesh)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", default="supg", choices=["supg", "c0ip_minus", "c0ip_paper"],
+                    help="q-equation variant (default: the SUPG headline workload)")
     ap.add_argument("--instances", action="store_true",
                     help="N>1: independent problem instance per GPU (weak scaling) instead of strip partitioning")
     args = ap.parse_args()

@@ -74,13 +74,15 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
 // cm_stencil.cu
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
-                      int* err, cudaStream_t st, int r0 = 0, int r1 = -1);
+                      int* err, cudaStream_t st, int r0 = 0, int r1 = -1, double* QQx = nullptr,
+                      int* has_extra = nullptr);
 int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
                    cudaStream_t st, int vb = 0, int ve = -1);
 int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb = 0, int ve = -1);
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st, int r0 = 0, int r1 = -1);
+               cudaStream_t st, int r0 = 0, int r1 = -1, const double* QQx = nullptr,
+               const int* has_extra = nullptr);
 int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,
                cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
@@ -92,7 +94,8 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
                    cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
              const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0 = 0,
-             int r1 = -1, double* tmp = nullptr);
+             int r1 = -1, double* tmp = nullptr, const double* Ax = nullptr,
+             const int* has_extra = nullptr);
 int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, int* err,
                      cudaStream_t st);
 int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st);

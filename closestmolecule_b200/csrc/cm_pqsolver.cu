@@ -29,6 +29,8 @@ struct PQSolver {
   bool dense_coarse;
   PQSLevel lev[kMaxLevels];
   double *PP, *PQ, *QP, *QQ, *sp, *sq;
+  double* QQx;      // 6 extra q-q diagonals of the C0IP interior-facet pattern
+  int* has_extra;   // device flag: any of them non-zero
   double *qlf, *qiu, *qcu;
   double *Ainv, *Mwork;
   double *bs, *xs, *tq, *ru, *ustate;
@@ -57,6 +59,8 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
   S.PQ = take(7 * V);
   S.QP = take(7 * V);
   S.QQ = take(7 * V);
+  S.QQx = take(6 * V);
+  S.has_extra = (int*)take(2);
   S.sp = take(V);
   S.sq = take(V);
   S.qlf = take(V);
@@ -160,7 +164,9 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
     return CM_E_INVALID;
   }
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
-  if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err, st)))
+  CM_CUDA(cudaMemsetAsync(S.has_extra, 0, sizeof(int), st));
+  if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err, st, 0,
+                              -1, S.QQx, S.has_extra)))
     return rc;
   for (int l = 0; l < S.nlev; ++l) {
     PQSLevel& L = S.lev[l];
@@ -185,9 +191,12 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
   }
   const int V = S.nv;
   g_prof_fine_nx = nx;
+  int wide = 0;  // C0IP interior-facet couplings present?
+  CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CM_CUDA(cudaStreamSynchronize(st));
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st))) return rc;
   LinOp A = [&](const double* in, double* out) {
-    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st);
+    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st, 0, -1, S.QQx, S.has_extra);
   };
   // M^{-1} = [[App,0],[Aqp,Aqq]]^{-1} (approximately) on the UNSCALED operator, composed with the
   // inverse row scaling: multigrid needs the true (variational) FE operator to be mesh independent
@@ -196,9 +205,16 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
     if (e) return e;
     if ((e = vcycle(S, 0, S.ru, z, st))) return e;
     if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st))) return e;
-    if ((e = zebra_sweep(S.lev[0], S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, true, st))) return e;
-    for (int s = 1; s < S.q_sweeps && !e; ++s)
-      e = zebra_sweep(S.lev[0], S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, false, st);
+    // with the wide pattern a colour also couples to lines of its own colour (two rows away): the
+    // iterate must start from zero there too, or M^{-1} would depend on the previous application
+    if (wide && cudaMemsetAsync(z + V, 0, sizeof(double) * V, st) != cudaSuccess) return (int)CM_E_CUDA;
+    for (int s = 0; s < S.q_sweeps && !e; ++s) {
+      e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, (s == 0 && !wide) ? 1 : 0, st, 0, -1,
+                   S.lev[0].r, wide ? S.QQx : nullptr, S.has_extra);
+      if (!e)
+        e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, 0, -1, S.lev[0].r,
+                     wide ? S.QQx : nullptr, S.has_extra);
+    }
     return e;
   };
   double bnorm = 0.0;
@@ -307,8 +323,9 @@ int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* n
       return CM_E_INVALID;
     }
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
+  CM_CUDA(cudaMemsetAsync(S.has_extra, 0, sizeof(int), st));
   if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err,
-                              st, I.rb[0], I.re[0])))
+                              st, I.rb[0], I.re[0])))  // 7-point rows only on the multi-GPU path
     return rc;
   for (int l = 0; l < I.Ld; ++l) {
     PQSLevel& L = S.lev[l];

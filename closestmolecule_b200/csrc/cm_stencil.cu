@@ -25,6 +25,16 @@ __host__ __device__ __forceinline__ int st_slot(int dx, int dy) {
 
 constexpr int kSB = 256;
 
+// extra q-q couplings of the C0IP interior-facet pattern on right-diagonal meshes: the two vertices
+// opposite an interior facet (..._C0IP.py:147): across the cell diagonal, a horizontal and a vertical edge
+__host__ __device__ __forceinline__ int xq_dx(int e) { return e == 0 ? -1 : (e == 1 ? 1 : (e == 2 ? 1 : (e == 3 ? -1 : (e == 4 ? 2 : -2)))); }
+__host__ __device__ __forceinline__ int xq_dy(int e) { return e == 0 ? 1 : (e == 1 ? -1 : (e == 2 ? 2 : (e == 3 ? -2 : (e == 4 ? 1 : -1)))); }
+__host__ __device__ __forceinline__ int xq_slot(int dx, int dy) {
+  for (int e = 0; e < 6; ++e)
+    if (xq_dx(e) == dx && xq_dy(e) == dy) return e;
+  return -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // interleaved CSR (DOLFIN layout) -> stencil blocks PP, PQ, QP, QQ [7][nv] (unscaled: the Galerkin
 // hierarchy must see the true FE operator) + row equilibration factors sp, sq = 1/max|row|, which
@@ -35,7 +45,8 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
                       const int* __restrict__ ncol, const double2* __restrict__ vals2,
                       double* __restrict__ PP, double* __restrict__ PQ, double* __restrict__ QP,
                       double* __restrict__ QQ, double* __restrict__ sp, double* __restrict__ sq,
-                      int* __restrict__ err, const int vb, const int ve) {
+                      int* __restrict__ err, const int vb, const int ve, double* __restrict__ QQx,
+                      int* __restrict__ has_extra) {
   const int v = vb + blockIdx.x * kSB + threadIdx.x;
   if (v >= ve) return;
   const int n1 = nx + 1;
@@ -57,10 +68,21 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
     QP[(size_t)k * nv + v] = 0.0; QQ[(size_t)k * nv + v] = 0.0;
   }
   const int ix = v % n1, iy = v / n1;
+  if (QQx != nullptr)
+    for (int e = 0; e < 6; ++e) QQx[(size_t)e * nv + v] = 0.0;
   for (int k = 0; k < deg; ++k) {
     const int w = ncol[rp + k];
     const int s = st_slot(w % n1 - ix, w / n1 - iy);
-    if (s < 0) { atomicExch(err, 1); continue; }  // not a 7-point row (e.g. C0IP pattern)
+    if (s < 0) {
+      // interior-facet (C0IP) couple: only the q-q entry can be non-zero there
+      const int e = xq_slot(w % n1 - ix, w / n1 - iy);
+      if (e < 0 || QQx == nullptr) { atomicExch(err, 1); continue; }
+      const double2 a = prow[k], c = qrow[k];
+      if (a.x != 0.0 || a.y != 0.0 || c.x != 0.0) { atomicExch(err, 1); continue; }
+      QQx[(size_t)e * nv + v] = c.y;
+      if (c.y != 0.0) *has_extra = 1;
+      continue;
+    }
     const double2 a = prow[k], c = qrow[k];
     PP[(size_t)s * nv + v] = a.x; PQ[(size_t)s * nv + v] = a.y;
     QP[(size_t)s * nv + v] = c.x; QQ[(size_t)s * nv + v] = c.y;
@@ -108,7 +130,8 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
                        const double* __restrict__ PQ, const double* __restrict__ QP,
                        const double* __restrict__ QQ, const double* __restrict__ sp,
                        const double* __restrict__ sq, const double* __restrict__ x,
-                       double* __restrict__ y, const int vb, const int ve) {
+                       double* __restrict__ y, const int vb, const int ve,
+                       const double* __restrict__ QQx, const int* __restrict__ has_extra) {
   const int nv = (nx + 1) * (ny + 1);
   const int v = vb + blockIdx.x * kSB + threadIdx.x;
   if (v >= ve) return;
@@ -124,6 +147,15 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
       const size_t e = (size_t)k * nv + v;
       yp += PP[e] * xp + PQ[e] * xq;
       yq += QP[e] * xp + QQ[e] * xq;
+    }
+  }
+  if (QQx != nullptr && *has_extra) {
+    const int ix = v % n1, iy = v / n1;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const int jx = ix + xq_dx(e), jy = iy + xq_dy(e);
+      if (jx >= 0 && jx <= nx && jy >= 0 && jy <= ny)
+        yq += QQx[(size_t)e * nv + v] * x[nv + jy * n1 + jx];
     }
   }
   y[v] = sp[v] * yp;
@@ -569,7 +601,8 @@ int st_zebra_debug_times(unsigned long long* host_out, int n) {
 __global__ void __launch_bounds__(kSB)
 offline_rhs_kernel(const int nx, const int ny, const int jfirst, const int nlines,
                    const double* __restrict__ A, const double* __restrict__ b,
-                   const double* __restrict__ x, double* __restrict__ out) {
+                   const double* __restrict__ x, double* __restrict__ out,
+                   const double* __restrict__ Ax, const int* __restrict__ has_extra) {
   const int n1 = nx + 1;
   const long long t = blockIdx.x * (long long)kSB + threadIdx.x;
   if (t >= (long long)nlines * n1) return;
@@ -580,7 +613,15 @@ offline_rhs_kernel(const int nx, const int ny, const int jfirst, const int nline
   const size_t lo = (size_t)(j > 0 ? j - 1 : 0) * n1, up = (size_t)(j < ny ? j + 1 : ny) * n1;
   const int im = i > 0 ? i - 1 : 0, ip = i < nx ? i + 1 : nx;
   const double a0 = A[v], a1 = A[nv + v], a5 = A[5 * nv + v], a6 = A[6 * nv + v];
-  out[v] = b[v] - (a0 * x[lo + im] + a1 * x[lo + i] + a5 * x[up + i] + a6 * x[up + ip]);
+  double r = b[v] - (a0 * x[lo + im] + a1 * x[lo + i] + a5 * x[up + i] + a6 * x[up + ip]);
+  if (Ax != nullptr && *has_extra) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const int jx = i + xq_dx(e), jy = j + xq_dy(e);
+      if (jx >= 0 && jx <= nx && jy >= 0 && jy <= ny) r -= Ax[(size_t)e * nv + v] * x[(size_t)jy * n1 + jx];
+    }
+  }
+  out[v] = r;
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -1033,12 +1074,13 @@ static inline void row_range(int ny, int n1, int r0, int r1, int& vb, int& ve) {
 
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
-                      int* err, cudaStream_t st, int r0, int r1) {
+                      int* err, cudaStream_t st, int r0, int r1, double* QQx, int* has_extra) {
   const int nv = (nx + 1) * (ny + 1);
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   extract_blocks_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
-                                                           PP, PQ, QP, QQ, sp, sq, err, vb, ve);
+                                                           PP, PQ, QP, QQ, sp, sq, err, vb, ve, QQx,
+                                                           has_extra);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1060,11 +1102,12 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, 
 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st, int r0, int r1) {
+               cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra) {
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
-  pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve);
+  pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve,
+                                                            QQx, has_extra);
   prof_end(kProfSpmv, st);
   CM_LAUNCH_CHECK();
   return CM_OK;
@@ -1140,7 +1183,7 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
 
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
              const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0,
-             int r1, double* tmp) {
+             int r1, double* tmp, const double* Ax, const int* has_extra) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
   const int jfirst = r0 + (((r0 & 1) == colour) ? 0 : 1);
@@ -1148,13 +1191,15 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   if (nlines <= 0) return CM_OK;
   static int pipe_mode = -1;
   if (pipe_mode < 0) { const char* e = getenv("CM_ZEBRA_PIPELINED"); pipe_mode = e ? atoi(e) : 4; }
-  if (tmp != nullptr && pipe_mode && n1 >= 1024 && 4 * (size_t)n1 * sizeof(double) <= 200 * 1024) {
+  if (tmp != nullptr && pipe_mode && (n1 >= 1024 || Ax != nullptr) &&
+      (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
     const bool prof = nx == g_prof_fine_nx;
     if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
     const double* rhs = b;
     if (!x_zero) {
       const long long nt = (long long)nlines * n1;
-      offline_rhs_kernel<<<(int)((nt + kSB - 1) / kSB), kSB, 0, st>>>(nx, ny, jfirst, nlines, A, b, x, tmp);
+      offline_rhs_kernel<<<(int)((nt + kSB - 1) / kSB), kSB, 0, st>>>(nx, ny, jfirst, nlines, A, b, x, tmp, Ax,
+                                                                      has_extra);
       ++g_launches;
       rhs = tmp;
     }

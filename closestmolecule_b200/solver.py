@@ -29,9 +29,6 @@ class StructuredPQLinearSolver:
         mesh = asm.mesh
         if not mesh.structured:
             raise LinearSolveError("the P-Q linear solver needs a structured (RectangleMesh-numbered) mesh")
-        if asm.topo.with_interior_facets:
-            raise LinearSolveError("the structured P-Q solver handles the 7-point (cell) pattern only; "
-                                   "the C0IP interior-facet pattern is not supported yet")
         self.asm, self.restart = asm, int(restart)
         self.nx, self.ny = mesh.nx, mesh.ny
         self.lib = _capi.lib()

@@ -209,3 +209,44 @@ def test_pq_supg_convergence_rates_on_gpu():
     r = mod.main(8)
     assert 1.9 < r["rp"][-1] < 2.1 and 0.95 < r["r1p"][-1] < 1.05 and 0.9 < r["rq"][-1] < 1.3
     assert max(max(l) for _, l in r["its"][3:]) <= 20
+
+
+@pytest.mark.parametrize("kind,n", [("minus", 32), ("minus", 64), ("paper", 32)])
+def test_newton_c0ip_matches_oracle(kind, n):
+    """C0IP q-equation (13-point interior-facet pattern, constant facet operator) solved on the GPU:
+    …MixedPrimal_convergence_C0IP.py:141-147 (minus sign, strong q data at x=1) and the "paper"
+    variant test_for_paper_convergence.py:140-153 (plus sign, weak data, boundary penalty)."""
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+    from util import np_qdata, oracle_ext
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    mf = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(mf, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(mf, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(mf, 32)
+    if kind == "minus":
+        form = cm.PQPrimalForm.manufactured(V, "c0ip", D1=0.01, D2=0.015, stab=0.05, sign=-1.0,
+                                            ext_terms=[(mf, 30, cm.EF_ADV)])
+        bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, mf, 31)]
+    else:
+        form = cm.PQPrimalForm.manufactured(
+            V, "c0ip", D1=1.0, D2=1.5, stab=0.05, sign=+1.0, c0ip_h="facet", degree=6, pen_stab2=1.0,
+            ext_terms=[(mf, 30, cm.EF_ADV), (mf, 32, cm.EF_ADV), (mf, 31, cm.EF_DATA),
+                       (mf, "on_boundary", cm.EF_PENALTY)])
+        bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary")]
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-8
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-8
+    s.parameters["newton_solver"]["krylov_solver"]["restart"] = 120
+    it, conv = s.solve()
+    om = oracle_mesh(mesh)
+    ef, ek = oracle_ext(form, om)
+    S = pq.PQSystem(om, oracle_params(form), ef, ek)
+    dofs, vals = cm.DirichletBC.merge(bcs, 2 * mesh.num_vertices())
+    f, qd = np_forcing(form), np_qdata(form)
+    x, oit, oconv = newton_solve(lambda xx, wj: S.assemble(xx, wj, None, f, qd), np.zeros(S.N), S.rowptr, S.col,
+                                 dofs.cpu().numpy().astype(np.int64), vals.cpu().numpy(), atol=1e-8, rtol=1e-8)
+    assert conv and oconv and it == oit
+    err = np.linalg.norm(u.vector().cpu().numpy() - x) / np.linalg.norm(x)
+    assert err < 1e-8, (err, s.linear_iterations)
