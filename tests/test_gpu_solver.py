@@ -250,3 +250,58 @@ def test_newton_c0ip_matches_oracle(kind, n):
     assert conv and oconv and it == oit
     err = np.linalg.norm(u.vector().cpu().numpy() - x) / np.linalg.norm(x)
     assert err < 1e-8, (err, s.linear_iterations)
+
+
+def test_transient_backward_euler_steps_match_oracle():
+    """Two backward-Euler steps of the transient form (advection_diffusion_convergence.py:196-199: the
+    (p - p_old)/dt term, assign(p_old, p_h) after every solve :225), SUPG q-equation, warm-started Newton."""
+    import math
+    from closestmolecule_b200.manufactured import forcing_torch, p_exact, q_exact
+    n, dt = 48, 0.1
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n // 2)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    p_old = cm.interpolate(lambda x, y: 0.8 * p_exact(x, y), V.sub(0).collapse())
+    D1, D2 = 1e-3, 1.5e-3
+    gc = D2 * 4.0 * math.pi
+    form = cm.PQPrimalForm(V, D1, D2, G=("power", gc), dt=dt, p_old=p_old,
+                           forcing=forcing_torch(D1, D2, gc, q_react=1.0, x2_on_q=True),
+                           q_react=1.0, q_x2p=0.0, q_x2q=1.0, supg_stab=1.0)
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-9
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-9
+    om = oracle_mesh(mesh)
+    S = pq.PQSystem(om, oracle_params(form))
+    dofs, vals = cm.DirichletBC.merge(bcs, 2 * mesh.num_vertices())
+    dofs, vals = dofs.cpu().numpy().astype(np.int64), vals.cpu().numpy()
+    f = np_forcing(form)
+    xo = np.zeros(S.N)
+    po = p_old.vector().cpu().numpy().copy()
+    for step in range(2):
+        it, conv = s.solve()
+        xo, oit, oconv = newton_solve(lambda xx, wj: S.assemble(xx, wj, po, f), xo, S.rowptr, S.col, dofs, vals,
+                                      atol=1e-9, rtol=1e-9)
+        assert conv and oconv and it == oit
+        err = np.linalg.norm(u.vector().cpu().numpy() - xo) / np.linalg.norm(xo)
+        assert err < 1e-8, (step, err)
+        p_old.vector().copy_(u.split()[0])      # assign(p_old, p_h)
+        po = xo[0::2].copy()
+
+
+def test_production_constants_fail_loudly():
+    """The reference's production form (unstabilised Galerkin q-equation, advection-dominated p-block)
+    needs a pivoting sparse LU: the GPU solver must raise, never return garbage."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "production_instance.py")
+    spec = importlib.util.spec_from_file_location("prod_inst", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mesh = cm.RectangleMesh(cm.Point(0, 0.1), cm.Point(5, 5), 64, 64)
+    bdry = cm.structured_boundary_markers(mesh)
+    with pytest.raises(RuntimeError):
+        mod.solve_problem_instance(1, 0.1, 0.1, mesh, bdry, 0.1, steady_state=True, supg_stab=0.0)
