@@ -266,6 +266,7 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     l0 = int(lib.cm_launch_count())
+    by0 = float(lib.cm_algorithmic_bytes())
     lib.cm_profile_reset()
     lib.cm_profile_enable(1)      # CUDA events around the roofline kernels, on the launching stream
     solver.linear_iterations = []
@@ -280,6 +281,7 @@ def gpu_arm(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.cm_launch_count()) - l0
+    step_bytes = (float(lib.cm_algorithmic_bytes()) - by0) / args.steps
     lib.cm_profile_enable(0)
     import ctypes as _C
     prof = {}
@@ -367,6 +369,11 @@ def gpu_arm(args):
                          "avg_launch_us": zk["avg_us"] if zk else None,
                          "share_of_step": (zk["ms_per_step"] / ms_step) if zk else None,
                          "traffic": TRAFFIC_NCU},
+            # whole Newton step: algorithmic bytes of every kernel launched by the library in the step
+            # (each array once per pass; per rank) over the step time and the measured HBM peak
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "gbs": step_bytes / (ms_step * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "peak": peak,
+                              "gmres_iterations": lin_its},
             "kernels": {**prof, "pq_sweep_kernel roofline frac": (bytes_asm / (asm_ms * 1e-3) / 1e9) / peak},
         }
         if world == 1 and not args.no_cpu:

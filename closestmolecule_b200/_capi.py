@@ -60,6 +60,7 @@ _PROTOS = {
     "cm_profile_report": ([_I, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
     "cm_profile_reset": ([], C.c_int),
     "cm_launch_count": ([], C.c_int64),
+    "cm_algorithmic_bytes": ([], C.c_double),
     "cm_assemble_pq_cells": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I] + [_P] * 7 + [_I, _P], C.c_int),
     "cm_assemble_pq_cells_structured": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_P], C.c_int),
     "cm_assemble_scalar_cells": ([C.POINTER(ScalarParamsC), _I, _I] + [_P] * 6 + [_I] + [_P] * 4 + [_P], C.c_int),

@@ -185,6 +185,7 @@ static int launch_pq_rows(const cm_pq_params& P, int nv, const int* cells, const
                           const double* load, const double* Kq, const double* cq, double* vals,
                           double* b, int accumulate, int maxdeg, cudaStream_t st) {
   const int grid = (nv + kRowBlock - 1) / kRowBlock;
+  CM_BYTES((vals != nullptr ? 148.05 : 36.0) * 2.0 * (double)nv);  // ~2 cells per vertex
   if (vals != nullptr) {
     const size_t smem = (size_t)4 * maxdeg * kRowBlock * sizeof(double);
     auto kern = pq_rows_kernel<NQ, GKIND, QGEN, true>;

@@ -7,6 +7,7 @@
 namespace cm {
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+double g_alg_bytes = 0.0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -59,6 +60,8 @@ int cm_version(void) { return 100; }
 const char* cm_last_error(void) { return g_err; }
 
 int64_t cm_launch_count(void) { return (int64_t)g_launches; }
+
+double cm_algorithmic_bytes(void) { return g_alg_bytes; }
 
 int cm_device_available(void) {
   int n = 0;

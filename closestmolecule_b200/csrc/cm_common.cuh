@@ -30,6 +30,8 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+extern double g_alg_bytes;    // algorithmic (compulsory) bytes of the kernels launched so far (Newton-step roofline)
+#define CM_BYTES(x) (cm::g_alg_bytes += (double)(x))
 #define CM_LAUNCH_CHECK()      \
   do {                         \
     ++cm::g_launches;          \

@@ -1081,6 +1081,7 @@ int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const
   extract_blocks_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
                                                            PP, PQ, QP, QQ, sp, sq, err, vb, ve, QQx,
                                                            has_extra);
+  CM_BYTES((double)(ve - vb) * (2 * 28 * 8.0 + 16.0));  // CSR values in, 4 stencil blocks + scalings out
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1089,6 +1090,7 @@ int st_split_scale(int nv, const double* b, const double* sp, const double* sq, 
                    cudaStream_t st, int vb, int ve) {
   if (ve < 0) { vb = 0; ve = nv; }
   split_scale_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nv, (const double2*)b, sp, sq, out, vb, ve);
+  CM_BYTES((double)(ve - vb) * 48.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1096,6 +1098,7 @@ int st_split_scale(int nv, const double* b, const double* sp, const double* sq, 
 int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, int ve) {
   if (ve < 0) { vb = 0; ve = nv; }
   interleave_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nv, xs, (double2*)x, vb, ve);
+  CM_BYTES((double)(ve - vb) * 32.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1106,6 +1109,7 @@ int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double*
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
+  CM_BYTES((double)(ve - vb) * 288.0);
   pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve,
                                                             QQx, has_extra);
   prof_end(kProfSpmv, st);
@@ -1118,6 +1122,7 @@ int st_unscale(int nx, int ny, const double* r, const double* sp, const double* 
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   unscale_kernel<<<grid_for(ve - vb), kSB, 0, st>>>((nx + 1) * (ny + 1), r, sp, sq, out, vb, ve);
+  CM_BYTES((double)(ve - vb) * 48.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1127,6 +1132,7 @@ int st_residual(int nx, int ny, const double* A, const double* b, const double* 
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   stencil_residual_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, A, b, x, r, vb, ve);
+  CM_BYTES((double)(ve - vb) * 80.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1136,6 +1142,7 @@ int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st,
   int vb, ve;
   row_range(nyc, nxc + 1, R0, R1, vb, ve);
   restrict_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, rf, rc, vb, ve);
+  CM_BYTES((double)(ve - vb) * (4 * 8.0 + 8.0));  // fine residual read once, coarse rhs written
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1145,6 +1152,7 @@ int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t 
   int vb, ve;
   row_range(2 * nyc, 2 * nxc + 1, r0, r1, vb, ve);
   prolong_add_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, ec, xf, vb, ve);
+  CM_BYTES((double)(ve - vb) * (16.0 + 2.0));  // fine x read+write, coarse correction read once
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1153,6 +1161,7 @@ int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st, int 
   int vb, ve;
   row_range(nyc, nxc + 1, R0, R1, vb, ve);
   rap_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nxc, nyc, Af, Ac, vb, ve);
+  CM_BYTES((double)(ve - vb) * (4 * 56.0 + 56.0));  // fine operator read once, coarse operator written
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1177,6 +1186,7 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
   const int T = (n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32);
   const int E = (n1 + T - 1) / T;
   line_factor_scan_kernel<<<r1 - r0, T, smem, st>>>(nx, ny, E, A, lf, iu, cu, err, r0);
+  CM_BYTES((double)(r1 - r0) * n1 * 48.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -1194,6 +1204,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   if (tmp != nullptr && pipe_mode && (n1 >= 1024 || Ax != nullptr) &&
       (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
     const bool prof = nx == g_prof_fine_nx;
+    CM_BYTES((double)nlines * n1 * (x_zero ? 40.0 : 88.0));
     if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
     const double* rhs = b;
     if (!x_zero) {
@@ -1271,6 +1282,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   // algorithmic bytes of this launch: b, l, 1/u, c/u, x per node (+ 4 stencil diagonals and the two
   // neighbouring lines when the current iterate is used)
   const bool prof = nx == g_prof_fine_nx;
+  CM_BYTES((double)nlines * n1 * (x_zero ? 40.0 : 88.0));
   if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
   if (x_zero)
     zebra_line_kernel<true><<<nlines, T, smem, st>>>(nx, ny, colour, E, A, lf, iu, cu, b, x, dbg, jfirst, r1);
@@ -1290,6 +1302,7 @@ int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, i
 
 int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st) {
   coarse_apply_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, Ainv, b, x);
+  CM_BYTES((double)n * n * 8.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -281,6 +281,8 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
   const size_t smem = (size_t)2 * kAccPerVertex * kTX * sizeof(double);
   dim3 grid(strips, segs);
   // algorithmic bytes: 148.05 B per cell of the assembled rows
+  // J+F: 148.05 B/cell; F only: coordinates + state + residual = 12 + 16 + 16 + 16 B per vertex-ish = 36 B/cell
+  CM_BYTES((vals != nullptr ? 148.05 : 36.0) * 2.0 * nx * (double)nrows);
   if (vals != nullptr) prof_begin(kProfAssembly, 148.05 * 2.0 * nx * (double)nrows, st);
   if (vals != nullptr) {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, true>;

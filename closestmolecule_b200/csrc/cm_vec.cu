@@ -147,6 +147,7 @@ int multi_dot(long long n, const double* Vbase, long long vstride, int nvec, con
                                                                     vstride, w, scratch)));
     reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, K, scratch, out + k0);
     g_launches += 2;
+    CM_BYTES((double)n * 8.0 * (K + 1));
   }
   --g_launches;
   CM_LAUNCH_CHECK();
@@ -164,6 +165,7 @@ int multi_axpy(long long n, const double* Vbase, long long vstride, int nvec, co
                        n, Vbase + k0 * vstride, vstride, h + k0, sign, w, scratch, last)));
     if (last) reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, 1, scratch, norm2_out);
     g_launches += last ? 2 : 1;
+    CM_BYTES((double)n * 8.0 * (K + 2));
   }
   --g_launches;
   CM_LAUNCH_CHECK();
@@ -176,6 +178,7 @@ int vec_scale(long long n, const double* x, const double* a_dev, double a_host, 
   long long g = (n + kVecBlock - 1) / kVecBlock;
   const int grid = (int)(g < kVecGrid ? g : kVecGrid);
   scale_kernel<<<grid, kVecBlock, 0, st>>>(n, x, a_dev, a_host, invert, y);
+  CM_BYTES((double)n * 16.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -266,6 +269,7 @@ int multi_dot_slice(VecSlice sl, const double* Vbase, long long vstride, int nve
                                                                           vstride, w, scratch)));
     reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, K, scratch, out + k0);
     g_launches += 2;
+    CM_BYTES((double)sl.len * 16.0 * (K + 1));
   }
   --g_launches;
   CM_LAUNCH_CHECK();
@@ -282,6 +286,7 @@ int multi_axpy_slice(VecSlice sl, const double* Vbase, long long vstride, int nv
                        sl, Vbase + k0 * vstride, vstride, h + k0, sign, w, scratch, last)));
     if (last) reduce_partials_kernel<<<1, kVecBlock, 0, st>>>(grid, 1, scratch, norm2_out);
     g_launches += last ? 2 : 1;
+    CM_BYTES((double)sl.len * 16.0 * (K + 2));
   }
   --g_launches;
   CM_LAUNCH_CHECK();
@@ -290,6 +295,7 @@ int multi_axpy_slice(VecSlice sl, const double* Vbase, long long vstride, int nv
 
 int vec_scale_slice(VecSlice sl, const double* x, double a, int invert, double* y, cudaStream_t st) {
   scale_slice_kernel<<<slice_grid(sl), kVecBlock, 0, st>>>(sl, x, invert ? 1.0 / a : a, y);
+  CM_BYTES((double)sl.len * (x ? 32.0 : 16.0));
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

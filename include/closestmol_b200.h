@@ -98,6 +98,9 @@ int cm_version(void);
 const char* cm_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (diagnostics) */
 int64_t cm_launch_count(void);
+/* algorithmic (compulsory) bytes of all kernels launched so far: every array counted once per pass,
+ * index/gather tables and cache re-reads not counted */
+double cm_algorithmic_bytes(void);
 /* Diagnostics: CUDA-event timing of selected kernel classes on the launching stream
  * (0: zebra_line_kernel on the finest grid, 1: pq_stencil_spmv_kernel, 2: Jacobian assembly).
  * Process-wide state, not thread safe; off by default. */
