@@ -9,6 +9,7 @@ from .mesh import (CompiledSubDomain, MappedRectangleMesh, Mesh, MeshFunction, P
                    UnitSquareMesh, flat_boundary_markers, structured_boundary_markers, DOLFIN_EPS)
 from .space import (Constant, DirichletBC, FiniteElement, Function, FunctionSpace, MixedElement,
                     interpolate)
+from .meshio import read_facet_function, read_mesh, write_facet_function, write_mesh
 from .forms import EF_ADV, EF_DATA, EF_PENALTY, PQPrimalForm, ScalarADRForm
 
 __all__ = [n for n in dir() if not n.startswith("_")]

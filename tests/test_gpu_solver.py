@@ -305,3 +305,27 @@ def test_production_constants_fail_loudly():
     bdry = cm.structured_boundary_markers(mesh)
     with pytest.raises(RuntimeError):
         mod.solve_problem_instance(1, 0.1, 0.1, mesh, bdry, 0.1, steady_state=True, supg_stab=0.0)
+
+
+def test_unstructured_xml_mesh_scalar_newton(tmp_path):
+    """Mesh(xml) path (advection_diffusion_mixed.py:313): a mesh read from DOLFIN XML has no structured
+    index, so assembly runs through the row-owner gather kernels and the solve through Jacobi-GMRES."""
+    from closestmolecule_b200.manufactured import u_exact
+    src = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), 32, 32)
+    cm.write_mesh(src, tmp_path / "m.xml")
+    mesh = cm.read_mesh(tmp_path / "m.xml")
+    assert not mesh.structured
+    V = cm.FunctionSpace(mesh, "CG", 1)
+    u = cm.Function(V)
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(
+        cm.ScalarADRForm.nonlinear_adr(V), u, [cm.DirichletBC(V, u_exact, "on_boundary")]))
+    s.parameters["newton_solver"]["absolute_tolerance"] = 1e-7
+    s.parameters["newton_solver"]["relative_tolerance"] = 1e-7
+    it, conv = s.solve()
+    ref = scalar.solve_fb(32)
+    assert conv and np.linalg.norm(u.vector().cpu().numpy() - ref["u"]) / np.linalg.norm(ref["u"]) < 1e-8
+    # the P-Q solver refuses unstructured meshes loudly
+    W = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    with pytest.raises(RuntimeError):
+        cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(
+            cm.PQPrimalForm.manufactured(W, "supg"), cm.Function(W), [])).solve()
