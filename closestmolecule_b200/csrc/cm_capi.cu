@@ -24,6 +24,7 @@ struct ProfRec {
   double bytes;
 };
 static bool g_prof_on = false;
+bool g_prof_is_on() { return g_prof_on; }
 int g_prof_fine_nx = -1;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;

@@ -14,14 +14,21 @@ namespace cm {
 constexpr int kMaxPeers = 8;
 constexpr int kCollMax = 64;  // doubles per all-reduce
 
-// layout of the control block at the start of every rank's workspace (doubles / u64 units)
-//   [0, 8)        halo flags, one per source rank
-//   [8, 16)       collective flags, one per source rank
-//   [16, 16 + 2*8*64)  all-reduce slots [parity][src][kCollMax]
-constexpr size_t kCtlHaloFlags = 0;
-constexpr size_t kCtlCollFlags = 8;
-constexpr size_t kCtlCollBuf = 16;
-constexpr size_t kCtlDoubles = 16 + 2 * kMaxPeers * kCollMax + 16;
+// layout of the control block at the start of every rank's workspace (u64 / double units).  All
+// sequence counters live on the DEVICE (each kernel bumps its own), so launches carry no changing
+// arguments and whole preconditioner applications can be replayed as CUDA graphs.
+//   [0]  flag written by the lower neighbour      [1]  flag written by the upper neighbour
+//   [2]  my exchange counter towards below        [3]  towards above
+//   [4]  all-gather counter  [5] all-reduce counter  [6] all-reduce local reader count
+//   [8, 16)   all-gather flags, one per source rank
+//   [16, 24)  all-reduce flags, one per source rank
+//   [32, 32 + 2*8*64)  all-reduce slots [parity][src][kCollMax]
+constexpr size_t kFlagFromBelow = 0, kFlagFromAbove = 1, kCntDn = 2, kCntUp = 3, kCntAg = 4, kCntAr = 5,
+                 kArReaders = 6;
+constexpr size_t kCtlAgFlags = 8;
+constexpr size_t kCtlCollFlags = 16;
+constexpr size_t kCtlCollBuf = 32;
+constexpr size_t kCtlDoubles = 32 + 2 * kMaxPeers * kCollMax + 16;
 
 size_t dist_ctl_doubles() { return kCtlDoubles; }
 
@@ -45,45 +52,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// grid = number of destination peers; CTA k copies every segment from my workspace to peer
-// dst[k]'s workspace at the same offsets, then publishes `seq` in that peer's flag slot [my_rank].
+// halo exchange in ONE launch: CTA 0 serves the lower neighbour, CTA 1 the upper one.  Each CTA takes
+// the next sequence number of its direction, pushes its segments into the neighbour's workspace,
+// publishes the number there, then waits until the same neighbour has published it here.
 __global__ void __launch_bounds__(1024)
-push_kernel(const double* __restrict__ my_base, const Peers peers, const int my_rank,
-            const int dst0, const int dst1, const int dst_all, const int world, const PushSegs segs,
-            const size_t flag_off, const unsigned long long seq) {
-  int dst;
-  if (dst_all) {
-    dst = blockIdx.x + (blockIdx.x >= my_rank ? 1 : 0);
-    if (dst >= world) return;
-  } else {
-    dst = blockIdx.x == 0 ? dst0 : dst1;
-    if (dst < 0) {  // only one neighbour
-      dst = dst1;
-      if (blockIdx.x == 1 || dst < 0) return;
-    }
-  }
-  double* __restrict__ pb = peers.base[dst];
-  for (int s = 0; s < segs.nseg; ++s) {
-    const double* src = my_base + segs.off[s];
-    double* d = pb + segs.off[s];
-    for (int i = threadIdx.x; i < segs.n[s]; i += blockDim.x) d[i] = src[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0)
-    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + flag_off + my_rank, seq);
-}
-
-// halo exchange in ONE launch: CTA 0 serves the lower neighbour, CTA 1 the upper one.  Each CTA
-// pushes its segments into the neighbour's workspace, publishes `seq` there, then waits until the
-// same neighbour has published `seq` here.
-__global__ void __launch_bounds__(1024)
-exchange_kernel(const double* __restrict__ my_base, const Peers peers, const int my_rank, const int dn,
-                const int up, const PushSegs segs_dn, const PushSegs segs_up, const size_t flag_off,
-                const unsigned long long seq) {
-  const int dst = blockIdx.x == 0 ? dn : up;
+exchange_kernel(double* __restrict__ my_base, const Peers peers, const int dn, const int up,
+                const PushSegs segs_dn, const PushSegs segs_up) {
+  __shared__ unsigned long long s_seq;
+  const bool down = blockIdx.x == 0;
+  const int dst = down ? dn : up;
   if (dst < 0) return;
-  const PushSegs& segs = blockIdx.x == 0 ? segs_dn : segs_up;
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(my_base);
+  if (threadIdx.x == 0) s_seq = ++ctl[down ? kCntDn : kCntUp];
+  const PushSegs& segs = down ? segs_dn : segs_up;
   double* __restrict__ pb = peers.base[dst];
   for (int s = 0; s < segs.nseg; ++s) {
     const double* src = my_base + segs.off[s];
@@ -93,34 +74,65 @@ exchange_kernel(const double* __restrict__ my_base, const Peers peers, const int
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + flag_off + my_rank, seq);
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(my_base) + flag_off + dst;
+    const unsigned long long seq = s_seq;
+    // I am the neighbour's upper (resp. lower) side
+    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + (down ? kFlagFromAbove : kFlagFromBelow), seq);
+    const unsigned long long* f = ctl + (down ? kFlagFromBelow : kFlagFromAbove);
     while (ld_acquire_sys(f) < seq) __nanosleep(40);
   }
 }
 
-// one warp: lane s waits until flag[s] >= seq for every source in the mask
-__global__ void wait_kernel(const double* my_base, const size_t flag_off, const unsigned mask,
-                            const unsigned long long seq) {
-  const int s = threadIdx.x;
-  if (s < kMaxPeers && (mask & (1u << s))) {
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(my_base) + flag_off + s;
-    while (ld_acquire_sys(f) < seq) __nanosleep(100);
+// all-gather of same-offset segments: CTA k pushes to the k-th other rank; CTA 0 then waits for all
+__global__ void __launch_bounds__(1024)
+allgather_kernel(double* __restrict__ my_base, const Peers peers, const int my_rank, const int world,
+                 const PushSegs segs) {
+  __shared__ unsigned long long s_seq;
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(my_base);
+  const int dst = blockIdx.x + (blockIdx.x >= my_rank ? 1 : 0);
+  if (dst >= world) return;
+  // every CTA needs the same number: CTA 0 bumps the counter, the others read counter + 1 ... avoid the
+  // race by deriving it from a value only CTA 0 modifies AFTER all pushes: use a per-launch snapshot
+  if (threadIdx.x == 0) s_seq = ld_acquire_sys(ctl + kCntAg) + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  double* __restrict__ pb = peers.base[dst];
+  for (int s = 0; s < segs.nseg; ++s) {
+    const double* src = my_base + segs.off[s];
+    double* d = pb + segs.off[s];
+    for (int i = threadIdx.x; i < segs.n[s]; i += blockDim.x) d[i] = src[i];
   }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + kCtlAgFlags + my_rank, seq);
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < world && threadIdx.x != my_rank) {
+    const unsigned long long* f = ctl + kCtlAgFlags + threadIdx.x;
+    while (ld_acquire_sys(f) < seq) __nanosleep(40);
+  }
+}
+// the counter is advanced by a trailing one-thread kernel (stream order: after every CTA of the
+// all-gather launch has taken its snapshot and finished)
+__global__ void bump_kernel(double* my_base, const size_t idx) {
+  ++reinterpret_cast<unsigned long long*>(my_base)[idx];
 }
 
 // all-reduce (sum) of n <= 64 doubles in ONE launch: CTA d publishes my values in rank d's slot
 // (CTA my_rank writes the local slot); CTA 0 then waits for every rank's flag and sums in rank order.
 __global__ void __launch_bounds__(64)
 allreduce_kernel(double* __restrict__ my_base, const Peers peers, const int my_rank, const int world,
-                 double* __restrict__ vals, const int n, const int parity, const unsigned long long seq) {
+                 double* __restrict__ vals, const int n) {
   __shared__ double mine[kCollMax];
+  __shared__ unsigned long long s_seq;
+  unsigned long long* ctl = reinterpret_cast<unsigned long long*>(my_base);
   const int dst = blockIdx.x;
+  if (threadIdx.x == 0) s_seq = ld_acquire_sys(ctl + kCntAr) + 1ull;
   if (threadIdx.x < n) mine[threadIdx.x] = vals[threadIdx.x];
   __syncthreads();
-  // CTA 0 overwrites vals with the sum: it may do so only after every CTA of this launch has read it
-  unsigned long long* readers = reinterpret_cast<unsigned long long*>(my_base) + (kCtlDoubles - 8);
-  if (threadIdx.x == 0) atomicAdd(readers, 1ull);
+  const unsigned long long seq = s_seq;
+  const int parity = (int)(seq & 1ull);
+  // CTA 0 overwrites vals with the sum: only after every CTA of this launch has read it
+  if (threadIdx.x == 0) atomicAdd(ctl + kArReaders, 1ull);
   double* pb = (dst == my_rank) ? my_base : peers.base[dst];
   double* slot = pb + kCtlCollBuf + ((size_t)parity * kMaxPeers + my_rank) * kCollMax;
   if (threadIdx.x < n) slot[threadIdx.x] = mine[threadIdx.x];
@@ -130,12 +142,11 @@ allreduce_kernel(double* __restrict__ my_base, const Peers peers, const int my_r
     st_release_sys(reinterpret_cast<unsigned long long*>(pb) + kCtlCollFlags + my_rank, seq);
   if (dst != 0) return;
   if (threadIdx.x < world) {
-    const unsigned long long* f =
-        reinterpret_cast<const unsigned long long*>(my_base) + kCtlCollFlags + threadIdx.x;
+    const unsigned long long* f = ctl + kCtlCollFlags + threadIdx.x;
     while (ld_acquire_sys(f) < seq) __nanosleep(40);
   }
   if (threadIdx.x == 0)
-    while (atomicAdd(readers, 0ull) < seq * (unsigned long long)world) __nanosleep(20);
+    while (atomicAdd(ctl + kArReaders, 0ull) < seq * (unsigned long long)world) __nanosleep(20);
   __syncthreads();
   if (threadIdx.x < n) {
     double s = 0.0;
@@ -154,43 +165,24 @@ static Peers make_peers(const cm_dist* D) {
   return p;
 }
 
-// copy the given segments to the row neighbours (rank-1 and rank+1) and wait for theirs
-int dist_halo(cm_dist* D, const unsigned long long* offs, const int* ns, int nseg, cudaStream_t st) {
-  if (D == nullptr || D->world <= 1) return CM_OK;
-  PushSegs segs_dn{}, segs_up{};
-  (void)segs_up;
-  if (nseg > 8) return CM_E_INVALID;
-  segs_dn.nseg = nseg;
-  for (int i = 0; i < nseg; ++i) { segs_dn.off[i] = offs[i]; segs_dn.n[i] = ns[i]; }
-  const unsigned long long seq = ++D->halo_seq;
-  const int dn = D->rank > 0 ? D->rank - 1 : -1, up = D->rank + 1 < D->world ? D->rank + 1 : -1;
-  push_kernel<<<2, 1024, 0, st>>>((const double*)D->peer_base[D->rank], make_peers(D), D->rank, dn, up,
-                                  0, D->world, segs_dn, kCtlHaloFlags, seq);
-  unsigned mask = 0;
-  if (dn >= 0) mask |= 1u << dn;
-  if (up >= 0) mask |= 1u << up;
-  wait_kernel<<<1, 32, 0, st>>>((const double*)D->peer_base[D->rank], kCtlHaloFlags, mask, seq);
-  g_launches += 1;
-  CM_LAUNCH_CHECK();
-  return CM_OK;
-}
-
-// halo exchange where the segments sent downwards and upwards differ (my first / my last rows)
+// halo exchange: segments sent downwards / upwards (my first / my last rows), wait for the neighbours'
 int dist_halo2(cm_dist* D, const unsigned long long* offs_dn, const int* ns_dn, int nseg_dn,
                const unsigned long long* offs_up, const int* ns_up, int nseg_up, cudaStream_t st) {
   if (D == nullptr || D->world <= 1) return CM_OK;
   if (nseg_dn > 8 || nseg_up > 8) return CM_E_INVALID;
-  const unsigned long long seq = ++D->halo_seq;
   const int dn = D->rank > 0 ? D->rank - 1 : -1, up = D->rank + 1 < D->world ? D->rank + 1 : -1;
   PushSegs sd{}, su{};
   sd.nseg = nseg_dn;
   for (int i = 0; i < nseg_dn; ++i) { sd.off[i] = offs_dn[i]; sd.n[i] = ns_dn[i]; }
   su.nseg = nseg_up;
   for (int i = 0; i < nseg_up; ++i) { su.off[i] = offs_up[i]; su.n[i] = ns_up[i]; }
-  exchange_kernel<<<2, 1024, 0, st>>>((const double*)D->peer_base[D->rank], make_peers(D), D->rank, dn, up,
-                                      sd, su, kCtlHaloFlags, seq);
+  exchange_kernel<<<2, 1024, 0, st>>>((double*)D->peer_base[D->rank], make_peers(D), dn, up, sd, su);
   CM_LAUNCH_CHECK();
   return CM_OK;
+}
+
+int dist_halo(cm_dist* D, const unsigned long long* offs, const int* ns, int nseg, cudaStream_t st) {
+  return dist_halo2(D, offs, ns, nseg, offs, ns, nseg, st);
 }
 
 // every rank sends the same-offset segments to ALL peers (all-gather of owned rows)
@@ -201,12 +193,9 @@ int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, in
   PushSegs s{};
   s.nseg = nseg;
   for (int i = 0; i < nseg; ++i) { s.off[i] = offs[i]; s.n[i] = ns[i]; }
-  const unsigned long long seq = ++D->halo_seq;
-  const double* mb = (const double*)D->peer_base[D->rank];
-  push_kernel<<<D->world - 1, 1024, 0, st>>>(mb, make_peers(D), D->rank, -1, -1, 1, D->world, s,
-                                             kCtlHaloFlags, seq);
-  const unsigned mask = ((1u << D->world) - 1u) & ~(1u << D->rank);
-  wait_kernel<<<1, 32, 0, st>>>(mb, kCtlHaloFlags, mask, seq);
+  double* mb = (double*)D->peer_base[D->rank];
+  allgather_kernel<<<D->world - 1, 1024, 0, st>>>(mb, make_peers(D), D->rank, D->world, s);
+  bump_kernel<<<1, 1, 0, st>>>(mb, kCntAg);
   ++g_launches;
   CM_LAUNCH_CHECK();
   return CM_OK;
@@ -216,10 +205,10 @@ int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, in
 int dist_allreduce(cm_dist* D, double* vals, int n, cudaStream_t st) {
   if (D == nullptr || D->world <= 1) return CM_OK;
   if (n > kCollMax) return CM_E_INVALID;
-  const unsigned long long seq = ++D->coll_seq;
-  const int parity = (int)(seq & 1ull);
   double* mb = (double*)D->peer_base[D->rank];
-  allreduce_kernel<<<D->world, 64, 0, st>>>(mb, make_peers(D), D->rank, D->world, vals, n, parity, seq);
+  allreduce_kernel<<<D->world, 64, 0, st>>>(mb, make_peers(D), D->rank, D->world, vals, n);
+  bump_kernel<<<1, 1, 0, st>>>(mb, kCntAr);
+  ++g_launches;
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

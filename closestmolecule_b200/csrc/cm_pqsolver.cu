@@ -7,6 +7,8 @@
 // workspace content written by cm_pqs_setup.  Replaces the sparse LU the reference requests with
 // linear_solver='mumps'|'umfpack' (advection_diffusion_convergence.py:212,
 // …MixedPrimal_convergence_SUPG.py:137).  The generic Jacobi-GMRES for CSR matrices is here too.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "cm_common.cuh"
@@ -146,6 +148,67 @@ static int vcycle(PQSolver& S, int l, const double* b, double* x, cudaStream_t s
   return zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
 }
 
+// Replays a fixed kernel sequence (one preconditioner application) as a CUDA graph: captured on a
+// private stream at the second call (the first call runs directly so that one-time function
+// attributes are set outside the capture), launched on the caller's stream afterwards.  At small
+// per-GPU sizes the sequence is launch-latency bound; the graph removes the CPU launch cost.
+struct GraphReplayer {
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t cap = nullptr;
+  const void* key = nullptr;
+  int calls = 0;
+  long long launches = 0;
+  double bytes = 0.0;
+  bool enabled = true;
+  GraphReplayer() {
+    const char* e = getenv("CM_GRAPH");
+    enabled = !(e && atoi(e) == 0);
+  }
+  ~GraphReplayer() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (cap) cudaStreamDestroy(cap);
+  }
+  template <class F>
+  int run(const void* k, cudaStream_t st, F&& body) {
+    if (!enabled || g_prof_is_on()) return body(st);
+    if (exec && key == k) {
+      g_launches += launches;
+      g_alg_bytes += bytes;
+      return cudaGraphLaunch(exec, st) == cudaSuccess ? CM_OK : (int)CM_E_CUDA;
+    }
+    if (calls++ < 1 || exec) return body(st);
+    if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return body(st);
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      enabled = false;
+      return body(st);
+    }
+    const long long l0 = g_launches;
+    const double b0 = g_alg_bytes;
+    const int rc = body(cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+    launches = g_launches - l0;
+    bytes = g_alg_bytes - b0;
+    if (rc != CM_OK || ce != cudaSuccess || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      enabled = false;
+      return rc != CM_OK ? rc : body(st);
+    }
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaGraphDestroy(graph);
+      exec = nullptr;
+      enabled = false;
+      return body(st);
+    }
+    cudaGraphDestroy(graph);
+    key = k;
+    return cudaGraphLaunch(exec, st) == cudaSuccess ? CM_OK : (int)CM_E_CUDA;
+  }
+};
+
 size_t pqs_workspace_bytes(int nx, int ny, int restart) {
   PQSolver S;
   if (pqs_layout(S, nx, ny, restart, nullptr)) return 0;
@@ -200,22 +263,26 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
   };
   // M^{-1} = [[App,0],[Aqp,Aqq]]^{-1} (approximately) on the UNSCALED operator, composed with the
   // inverse row scaling: multigrid needs the true (variational) FE operator to be mesh independent
+  GraphReplayer replay;
   LinOp Minv = [&](const double* r, double* z) {
     int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st);
     if (e) return e;
-    if ((e = vcycle(S, 0, S.ru, z, st))) return e;
-    if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st))) return e;
-    // with the wide pattern a colour also couples to lines of its own colour (two rows away): the
-    // iterate must start from zero there too, or M^{-1} would depend on the previous application
-    if (wide && cudaMemsetAsync(z + V, 0, sizeof(double) * V, st) != cudaSuccess) return (int)CM_E_CUDA;
-    for (int s = 0; s < S.q_sweeps && !e; ++s) {
-      e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, (s == 0 && !wide) ? 1 : 0, st, 0, -1,
-                   S.lev[0].r, wide ? S.QQx : nullptr, S.has_extra);
-      if (!e)
-        e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, 0, -1, S.lev[0].r,
-                     wide ? S.QQx : nullptr, S.has_extra);
-    }
-    return e;
+    return replay.run(z, st, [&](cudaStream_t s_) -> int {
+      int e2 = vcycle(S, 0, S.ru, z, s_);
+      if (e2) return e2;
+      if ((e2 = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, s_))) return e2;
+      // with the wide pattern a colour also couples to lines of its own colour (two rows away): the
+      // iterate must start from zero there too, or M^{-1} would depend on the previous application
+      if (wide && cudaMemsetAsync(z + V, 0, sizeof(double) * V, s_) != cudaSuccess) return (int)CM_E_CUDA;
+      for (int sw = 0; sw < S.q_sweeps && !e2; ++sw) {
+        e2 = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, (sw == 0 && !wide) ? 1 : 0, s_, 0, -1,
+                      S.lev[0].r, wide ? S.QQx : nullptr, S.has_extra);
+        if (!e2)
+          e2 = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, s_, 0, -1, S.lev[0].r,
+                        wide ? S.QQx : nullptr, S.has_extra);
+      }
+      return e2;
+    });
   };
   double bnorm = 0.0;
   rc = gmres_solve(2LL * V, A, Minv, S.bs, S.xs, rtol, atol, maxit, restart, 0, S.gm, iters, resid,
@@ -384,22 +451,28 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
     if (e) return e;
     return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, st, rb, re);
   };
+  GraphReplayer replay;
   LinOp Minv = [&](const double* r, double* z) {
     int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st, rb, re);
     if (e) return e;
-    if ((e = vcycle_dist(S, I, 0, S.ru, z, st))) return e;
-    double* zp[1] = {z};
-    if ((e = halo_rows(I, zp, 1, n1, rb, re, st))) return e;
-    if ((e = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, st, rb, re))) return e;
-    double* zq[1] = {z + V};
-    for (int s = 0; s < S.q_sweeps; ++s) {
-      if ((e = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, s == 0 ? 1 : 0, st, rb, re, S.lev[0].r)))
-        return e;
-      if ((e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
-      if ((e = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, st, rb, re, S.lev[0].r))) return e;
-      if (s + 1 < S.q_sweeps && (e = halo_rows(I, zq, 1, n1, rb, re, st))) return e;
-    }
-    return e;
+    return replay.run(z, st, [&](cudaStream_t s_) -> int {
+      int e2 = vcycle_dist(S, I, 0, S.ru, z, s_);
+      if (e2) return e2;
+      double* zp[1] = {z};
+      if ((e2 = halo_rows(I, zp, 1, n1, rb, re, s_))) return e2;
+      if ((e2 = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, s_, rb, re))) return e2;
+      double* zq[1] = {z + V};
+      for (int sw = 0; sw < S.q_sweeps; ++sw) {
+        if ((e2 = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, sw == 0 ? 1 : 0, s_, rb, re,
+                           S.lev[0].r)))
+          return e2;
+        if ((e2 = halo_rows(I, zq, 1, n1, rb, re, s_))) return e2;
+        if ((e2 = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, S.tq, z + V, 0, s_, rb, re, S.lev[0].r)))
+          return e2;
+        if (sw + 1 < S.q_sweeps && (e2 = halo_rows(I, zq, 1, n1, rb, re, s_))) return e2;
+      }
+      return e2;
+    });
   };
   VecSlice sl{(long long)vb, (long long)V + vb, (long long)(ve - vb)};
   double bnorm = 0.0;
