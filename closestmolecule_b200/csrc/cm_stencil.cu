@@ -471,7 +471,6 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
   const size_t nv = (size_t)n1 * (ny + 1);
   const size_t base = (size_t)j * n1;
   const int T = blockDim.x, tid = threadIdx.x;
-  if ((dbg & 64) && blockIdx.x >= 148 && blockIdx.x < 296) __nanosleep(dbg >> 8);
   ZT(0);
   // right-hand side: b minus the couplings to the neighbouring lines.  Branch-free: stencil entries
   // that point outside the grid are stored as zeros, so the neighbour index is only clamped -- every
@@ -483,35 +482,6 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
     const double* __restrict__ A1 = A + nv + base;
     const double* __restrict__ A5 = A + 5 * nv + base;
     const double* __restrict__ A6 = A + 6 * nv + base;
-    if (XZERO && (dbg & 16)) {
-      // all loads of the line in flight at once
-      double rb[kZebraPrefetch], rl[kZebraPrefetch];
-#pragma unroll
-      for (int k = 0; k < kZebraPrefetch; ++k) {
-        const int i = tid + k * T;
-        if (i < n1) { rb[k] = b[base + i]; rl[k] = lf[base + i]; }
-      }
-      double piu2[kZebraPrefetch], pcu2[kZebraPrefetch];
-#pragma unroll
-      for (int k = 0; k < kZebraPrefetch; ++k) {
-        const int i = tid + k * T;
-        if (i < n1) { piu2[k] = iu[base + i]; pcu2[k] = cu[base + i]; }
-      }
-#pragma unroll
-      for (int k = 0; k < kZebraPrefetch; ++k) {
-        const int i = tid + k * T;
-        if (i < n1) { s_z[i] = rb[k]; s_c[i] = rl[k]; }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kZebraPrefetch; ++k) {
-        const int i = tid + k * T;
-        if (i < n1) { s_z[i] *= piu2[k]; s_c[i] = pcu2[k]; }
-      }
-      __syncthreads();
-      for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
-      return;
-    }
 #pragma unroll 3
     for (int i = tid; i < n1; i += T) {
       double r = b[base + i];
@@ -537,7 +507,7 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
   __syncthreads();
   ZT(1);
   // forward: z_i = r_i - l_i z_{i-1}
-  if (!(dbg & 1)) {
+  {
     const int i0 = tid * E, i1 = min(i0 + E, n1);
     Affine m{1.0, 0.0};
     for (int i = i0; i < i1; ++i) {
@@ -565,7 +535,7 @@ zebra_line_kernel(const int nx, const int ny, const int colour, const int E,
   __syncthreads();
   ZT(3);
   // backward: x_i = w_i - cu_i x_{i+1}; thread t takes segment T-1-t so scan order = thread order
-  if (!(dbg & 2)) {
+  {
     const int seg = T - 1 - tid;
     const int i0 = seg * E, i1 = min(i0 + E, n1);
     Affine m{1.0, 0.0};
