@@ -136,13 +136,13 @@ def test_scalar_newton_reproduces_readme_rows():
 
 
 def test_ported_convergence_script_prints_readme_table():
-    """scripts/SphericalAdvectionDiffusionReaction_convergence.py (the reference driver on the GPU
+    """scripts/run_scalar_adr_convergence.py (the reference driver on the GPU
     path) reproduces README.md:109-115 digit for digit."""
     import importlib.util
     import os
     from test_oracle_golden import README_TABLE
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
-                        "SphericalAdvectionDiffusionReaction_convergence.py")
+                        "run_scalar_adr_convergence.py")
     spec = importlib.util.spec_from_file_location("sadr_conv", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -197,12 +197,12 @@ def test_zebra_line_relaxation_building_blocks():
 
 
 def test_pq_supg_convergence_rates_on_gpu():
-    """scripts/pq_supg_convergence.py: expected orders of the P1 x P1 SUPG system (2 in L2(p), 1 in
+    """scripts/run_pq_supg_convergence.py: expected orders of the P1 x P1 SUPG system (2 in L2(p), 1 in
     H1(p) and H1(q)) with mesh-independent GMRES iteration counts."""
     import importlib.util
     import os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
-                        "pq_supg_convergence.py")
+                        "run_pq_supg_convergence.py")
     spec = importlib.util.spec_from_file_location("pq_supg_conv", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -297,7 +297,7 @@ def test_production_constants_fail_loudly():
     import importlib.util
     import os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
-                        "production_instance.py")
+                        "run_production_instance.py")
     spec = importlib.util.spec_from_file_location("prod_inst", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
