@@ -144,7 +144,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -259,12 +259,12 @@ def gpu_arm(args):
         uvec[own] = u0[own]
         return solver.newton_step(compute_residual=True)
 
+    sampler = ClockSampler(local)
+    if rank == 0:       # started before the warm-up so that nvidia-smi is already streaming samples
+        sampler.start()  # when the timed region begins; the samples cover warm-up + timed steps
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = int(lib.cm_launch_count())
     by0 = float(lib.cm_algorithmic_bytes())
     lib.cm_profile_reset()
