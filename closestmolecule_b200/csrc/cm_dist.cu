@@ -51,6 +51,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *flag >= seq; a peer that never arrives (crashed rank) must not hang the GPU for ever:
+// after 60 s the kernel traps, which surfaces as a CUDA error in the host call chain
+__device__ __forceinline__ void spin_until(const unsigned long long* flag, const unsigned long long seq) {
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    __nanosleep(40);
+    if (global_ns() - t0 > 60000000000ull) asm volatile("trap;");
+  }
+}
 
 // halo exchange in ONE launch: CTA 0 serves the lower neighbour, CTA 1 the upper one.  Each CTA takes
 // the next sequence number of its direction, pushes its segments into the neighbour's workspace,
@@ -78,7 +92,7 @@ exchange_kernel(double* __restrict__ my_base, const Peers peers, const int dn, c
     // I am the neighbour's upper (resp. lower) side
     st_release_sys(reinterpret_cast<unsigned long long*>(pb) + (down ? kFlagFromAbove : kFlagFromBelow), seq);
     const unsigned long long* f = ctl + (down ? kFlagFromBelow : kFlagFromAbove);
-    while (ld_acquire_sys(f) < seq) __nanosleep(40);
+    spin_until(f, seq);
   }
 }
 
@@ -108,7 +122,7 @@ allgather_kernel(double* __restrict__ my_base, const Peers peers, const int my_r
   if (blockIdx.x != 0) return;
   if (threadIdx.x < world && threadIdx.x != my_rank) {
     const unsigned long long* f = ctl + kCtlAgFlags + threadIdx.x;
-    while (ld_acquire_sys(f) < seq) __nanosleep(40);
+    spin_until(f, seq);
   }
 }
 // the counter is advanced by a trailing one-thread kernel (stream order: after every CTA of the
@@ -143,7 +157,7 @@ allreduce_kernel(double* __restrict__ my_base, const Peers peers, const int my_r
   if (dst != 0) return;
   if (threadIdx.x < world) {
     const unsigned long long* f = ctl + kCtlCollFlags + threadIdx.x;
-    while (ld_acquire_sys(f) < seq) __nanosleep(40);
+    spin_until(f, seq);
   }
   if (threadIdx.x == 0)
     while (atomicAdd(ctl + kArReaders, 0ull) < seq * (unsigned long long)world) __nanosleep(20);

@@ -895,25 +895,37 @@ line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nl
   }
   __syncthreads();
   unsigned parity = 0;
+  // per array: is the first element of the line on a 16-byte boundary? (the arrays themselves may
+  // start on odd 8-byte offsets, e.g. the q-part of a split vector with an odd vertex count)
+  auto shift_of = [&](int a, size_t base) -> int {
+    return (int)((reinterpret_cast<unsigned long long>(src[a] + base) >> 3) & 1ull);
+  };
   auto issue = [&](int line) {
     const size_t base = (size_t)(jfirst + 2 * line) * n1;
-    const int shf = (int)(base & 1);
-    const size_t a0 = base - shf;
-    const int cnt = (n1 + shf) & ~1;  // even number of elements copied by TMA
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const unsigned bytes = (unsigned)cnt * 8u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(4u * bytes) : "memory");
+      unsigned total = 0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) tma_bulk_g2s(buf[a], src[a] + a0, bytes, &mbar);
+      for (int a = 0; a < 4; ++a) total += (unsigned)((n1 + shift_of(a, base)) & ~1) * 8u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int shf = shift_of(a, base);
+        const int cnt = (n1 + shf) & ~1;  // even number of elements copied by TMA
+        tma_bulk_g2s(buf[a], src[a] + base - shf, (unsigned)cnt * 8u, &mbar);
+      }
     }
-    if (tid >= 32 && tid < 36 && cnt < n1 + shf)  // odd trailing element
-      buf[tid - 32][cnt] = src[tid - 32][a0 + cnt];
+    if (tid >= 32 && tid < 36) {  // odd trailing element
+      const int a = tid - 32;
+      const int shf = shift_of(a, base);
+      const int cnt = (n1 + shf) & ~1;
+      if (cnt < n1 + shf) buf[a][cnt] = src[a][base - shf + cnt];
+    }
   };
   issue(l);
   for (; l < nlines; l += gridDim.x) {
     const size_t lbase = (size_t)(jfirst + 2 * l) * n1;
-    const int shf = (int)(lbase & 1);
+    const int sh0 = shift_of(0, lbase), sh1 = shift_of(1, lbase), sh2 = shift_of(2, lbase), sh3 = shift_of(3, lbase);
     HT(0);
     {  // wait for the bulk copies of this line
       unsigned done = 0;
@@ -929,8 +941,8 @@ line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nl
 #pragma unroll
     for (int e = 0; e < E; ++e)
       if (e < ne) {
-        r[e] = buf[0][shf + i0 + e]; lv[e] = buf[1][shf + i0 + e];
-        iv[e] = buf[2][shf + i0 + e]; cv[e] = buf[3][shf + i0 + e];
+        r[e] = buf[0][sh0 + i0 + e]; lv[e] = buf[1][sh1 + i0 + e];
+        iv[e] = buf[2][sh2 + i0 + e]; cv[e] = buf[3][sh3 + i0 + e];
       }
     __syncthreads();
     if (l + gridDim.x < nlines) issue(l + gridDim.x);
