@@ -236,6 +236,7 @@ def gpu_arm(args):
     else:
         u = cm.Function(V)
         solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+        solver.parameters["newton_solver"]["linear_solver"] = "gmres"
         solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
         if args.variant != "supg":
             solver.parameters["newton_solver"]["krylov_solver"]["restart"] = 100

@@ -89,6 +89,11 @@ _PROTOS = {
     "cm_stencil_line_factor": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
     "cm_stencil_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P, _P], C.c_int),
     "cm_stencil_residual": ([_I, _I] + [_P] * 4 + [_P], C.c_int),
+    "cm_blu_workspace_bytes": ([_I, _I, _I], C.c_int64),
+    "cm_blu_create": ([], C.c_void_p),
+    "cm_blu_destroy": ([_P], C.c_int),
+    "cm_blu_factor": ([_P, _I, _I, _I] + [_P] * 6 + [C.c_int64, C.POINTER(C.c_int32), _P], C.c_int),
+    "cm_blu_solve": ([_P, _I, _I, _I] + [_P] * 4 + [C.c_int64, _P], C.c_int),
     "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,
                          C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),

@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(log))
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lcudart"]
+           "-lcudart", "-lcusolver", "-lcublas"]
     subprocess.check_call(cmd)
     return LIB
 

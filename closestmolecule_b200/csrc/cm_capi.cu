@@ -372,4 +372,39 @@ int cm_profile_reset(void) {
   return CM_OK;
 }
 
+int64_t cm_blu_workspace_bytes(int32_t bs, int32_t nv, int32_t nbn) {
+  if ((bs != 1 && bs != 2) || nv < 1 || nbn < 1) {
+    set_error("cm_blu_workspace_bytes: bad argument");
+    return CM_E_INVALID;
+  }
+  return (int64_t)blu_workspace_bytes(bs, nv, nbn);
+}
+
+void* cm_blu_create(void) { return blu_create(); }
+
+int cm_blu_destroy(void* ctx) { return blu_destroy(ctx); }
+
+int cm_blu_factor(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* perm,
+                  const int32_t* iperm, const int32_t* nrowptr, const int32_t* ncol,
+                  const double* vals, void* workspace, int64_t workspace_bytes, int32_t* info_host,
+                  void* stream) {
+  CM_CHECK_ARG(ctx != nullptr, "null context (cm_blu_create)");
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nv >= 1 && nbn >= 1, "bad size");
+  CM_CHECK_ARG((int64_t)bs * nbn <= 16384, "block size above 16384 dofs");
+  CM_CHECK_ARG(perm && iperm && nrowptr && ncol && vals && workspace, "null pointer");
+  return blu_factor(ctx, bs, nv, nbn, perm, iperm, nrowptr, ncol, vals, workspace,
+                    (size_t)workspace_bytes, info_host, (cudaStream_t)stream);
+}
+
+int cm_blu_solve(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* perm, const double* b,
+                 double* x, void* workspace, int64_t workspace_bytes, void* stream) {
+  CM_CHECK_ARG(ctx != nullptr, "null context (cm_blu_create)");
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nv >= 1 && nbn >= 1, "bad size");
+  CM_CHECK_ARG(perm && b && x && workspace, "null pointer");
+  return blu_solve(ctx, bs, nv, nbn, perm, b, x, workspace, (size_t)workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
 }  // extern "C"

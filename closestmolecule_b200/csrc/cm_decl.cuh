@@ -121,4 +121,14 @@ size_t krylov_workspace_bytes(int bs, int nv, int restart);
 int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
                  const double* vals, const double* b, double* x, double rtol, double atol, int maxit,
                  int restart, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
+
+// cm_blu.cu
+size_t blu_workspace_bytes(int bs, int nv, int nbn);
+void* blu_create();
+int blu_destroy(void* ctx);
+int blu_factor(void* ctx, int bs, int nv, int nbn, const int* perm, const int* iperm,
+               const int* nrowptr, const int* ncol, const double* vals, void* ws, size_t ws_bytes,
+               int* info_host, cudaStream_t st);
+int blu_solve(void* ctx, int bs, int nv, int nbn, const int* perm, const double* b, double* x, void* ws,
+              size_t ws_bytes, cudaStream_t st);
 }  // namespace cm

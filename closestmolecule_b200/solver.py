@@ -4,8 +4,10 @@ advection_diffusion_mixed.py:219-226, …MixedPrimal_convergence.py:132-140), wi
 NewtonSolver semantics: start from the current u, residual convergence test
 ||F|| < atol or ||F||/||F0|| < rtol, full steps x <- x - relaxation*dx, RuntimeError on failure.
 
-There is no sparse LU on the GPU path: linear_solver 'mumps' / 'umfpack' / 'lu' / 'default' are
-aliased to the tightest-tolerance Krylov path ('gmres').
+linear_solver 'mumps' / 'umfpack' / 'lu' / 'default' select the direct path (banded LU with partial
+pivoting on the GPU, cm_blu_*) whenever its factors fit the memory budget
+parameters['newton_solver']['lu_solver']['max_bytes'] (default: 80 % of the free device memory);
+beyond that size (the 16 Mi-cell meshes) they fall back to the Krylov path, like 'gmres' / 'bicgstab'.
 """
 from __future__ import annotations
 
@@ -55,6 +57,105 @@ class StructuredPQLinearSolver:
         if rc < 0:
             _capi.check(rc)
         return rc == 0
+
+
+class BandedLULinearSolver:
+    """Sparse LU stand-in for PETScLUSolver('mumps'|'umfpack') (advection_diffusion_convergence.py:212,
+    ...MixedPrimal_convergence.py:136): banded LU with partial pivoting, block-tridiagonal organisation
+    (cm_blu_factor / cm_blu_solve) + iterative refinement on the assembled CSR.  Works for any
+    nonsingular Jacobian (zero q-q diagonal of the Galerkin form included) on any mesh; memory is
+    32*(bs*nbn)^2 bytes per block of nbn nodes, nbn = node bandwidth of the renumbered pattern."""
+
+    def __init__(self, asm, max_bytes=None, refinement_steps=1):
+        self.asm = asm
+        self.lib = _capi.lib()
+        self.bs = asm.bs
+        t = asm.topo
+        self.perm, self.iperm, self.nbn = self.ordering(asm.mesh, t)
+        self.nbytes = int(self.lib.cm_blu_workspace_bytes(self.bs, t.nv, self.nbn))
+        if self.nbytes <= 0:
+            raise LinearSolveError("cm_blu_workspace_bytes failed")
+        if max_bytes is None:
+            max_bytes = int(0.8 * torch.cuda.mem_get_info(asm.mesh.device)[0])
+        if self.nbytes > max_bytes:
+            raise LinearSolveError(
+                f"the LU factors need {self.nbytes / 2**30:.1f} GiB (node bandwidth {self.nbn}), more than "
+                f"the budget of {max_bytes / 2**30:.1f} GiB: use linear_solver='gmres'")
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=asm.mesh.device)
+        self.ctx = self.lib.cm_blu_create()
+        if not self.ctx:
+            raise LinearSolveError("cm_blu_create failed: " + self.lib.cm_last_error().decode())
+        self.refinement_steps = int(refinement_steps)
+        self._r = torch.empty_like(asm.b)
+        self._d = torch.empty_like(asm.b)
+        self.last_iterations = 0
+        self.last_residual = 0.0
+
+    def __del__(self):
+        ctx, self.ctx = getattr(self, "ctx", None), None
+        if ctx:
+            self.lib.cm_blu_destroy(ctx)
+
+    @staticmethod
+    def ordering(mesh, topo):
+        """(perm, iperm, nbn): node renumbering with a small bandwidth.  RectangleMesh numbering: the
+        grid lines along the shorter direction; anything else: reverse Cuthill-McKee of the node pattern
+        (host-side setup, once per mesh)."""
+        dev, V = topo.nrowptr.device, topo.nv
+        if mesh.structured and mesh.nx > mesh.ny:
+            v = torch.arange(V, device=dev)
+            perm = (v % (mesh.nx + 1)) * (mesh.ny + 1) + v // (mesh.nx + 1)
+        elif mesh.structured:
+            perm = torch.arange(V, device=dev)
+        else:
+            import numpy as np
+            import scipy.sparse as sp
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            rp, col = topo.nrowptr.cpu().numpy(), topo.ncol.cpu().numpy()
+            G = sp.csr_matrix((np.ones(col.size, dtype=np.int8), col, rp), shape=(V, V))
+            order = reverse_cuthill_mckee(G, symmetric_mode=True).astype(np.int64)   # order[pos] = node
+            perm = torch.empty(V, dtype=torch.int64, device=dev)
+            perm[torch.as_tensor(order, device=dev)] = torch.arange(V, device=dev)
+        iperm = torch.empty_like(perm)
+        iperm[perm] = torch.arange(V, device=dev)
+        deg = (topo.nrowptr[1:] - topo.nrowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(V, device=dev), deg)
+        bw = int((perm[rows] - perm[topo.ncol.long()]).abs().max())
+        nbn = max(8, -(-bw // 8) * 8)
+        return perm.to(torch.int32).contiguous(), iperm.to(torch.int32).contiguous(), nbn
+
+    def setup(self):
+        t = self.asm.topo
+        info = C.c_int32(0)
+        _capi.check(self.lib.cm_blu_factor(
+            self.ctx, self.bs, t.nv, self.nbn, _capi.ptr(self.perm), _capi.ptr(self.iperm),
+            _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(self.asm.vals), _capi.ptr(self.ws),
+            self.nbytes, C.byref(info), _capi.stream_ptr()))
+
+    def _solve(self, b, x):
+        _capi.check(self.lib.cm_blu_solve(self.ctx, self.bs, self.asm.topo.nv, self.nbn,
+                                          _capi.ptr(self.perm), _capi.ptr(b), _capi.ptr(x),
+                                          _capi.ptr(self.ws), self.nbytes, _capi.stream_ptr()))
+
+    def _residual(self, b, x):
+        t = self.asm.topo
+        _capi.check(self.lib.cm_spmv(self.bs, t.nv, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
+                                     _capi.ptr(self.asm.vals), _capi.ptr(x), _capi.ptr(self._r),
+                                     _capi.stream_ptr()))
+        torch.sub(b, self._r, out=self._r)
+        return self._r
+
+    def solve(self, b, x, rtol=0.0, atol=0.0, maxit=0):
+        self._solve(b, x)
+        for _ in range(self.refinement_steps):
+            self._solve(self._residual(b, x), self._d)
+            x.add_(self._d)
+        bn = float(torch.linalg.vector_norm(b))
+        self.last_residual = float(torch.linalg.vector_norm(self._residual(b, x))) / (bn if bn > 0 else 1.0)
+        self.last_iterations = 0
+        if not (self.last_residual == self.last_residual):
+            raise LinearSolveError("LU solve produced NaN (numerically singular Jacobian)")
+        return True
 
 
 class JacobiKrylovLinearSolver:
@@ -117,15 +218,21 @@ class NonlinearVariationalSolver:
         return {"linear_solver": "default", "absolute_tolerance": 1e-10, "relative_tolerance": 1e-9,
                 "maximum_iterations": 50, "relaxation_parameter": 1.0, "error_on_nonconvergence": True,
                 "report": False,
+                "lu_solver": {"max_bytes": None, "refinement_steps": 1},
                 "krylov_solver": {"relative_tolerance": 1e-11, "absolute_tolerance": 0.0,
                                   "maximum_iterations": 400, "restart": 40}}
 
     def _linear_solver(self, prm):
         if self._linear is None:
             name = prm["linear_solver"]
-            if name in _LU_ALIASES or name in ("gmres", "bicgstab"):
-                pass
-            else:
+            if name in _LU_ALIASES:
+                try:
+                    self._linear = BandedLULinearSolver(self.asm, prm["lu_solver"]["max_bytes"],
+                                                        prm["lu_solver"]["refinement_steps"])
+                    return self._linear
+                except LinearSolveError as e:
+                    self.lu_fallback_reason = str(e)      # too large for a direct solve: Krylov path
+            elif name not in ("gmres", "bicgstab"):
                 raise ValueError(f"unknown linear_solver '{name}'")
             restart = prm["krylov_solver"]["restart"]
             if isinstance(self.problem.form, PQPrimalForm):

@@ -279,6 +279,32 @@ int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_
                     double rtol, double atol, int32_t maxit, int32_t restart, void* workspace,
                     int64_t workspace_bytes, int32_t* iters_host, double* resid_host, void* stream);
 
+/* ---- a11, direct path: banded LU with partial pivoting (block-tridiagonal organisation) ----------
+ * Replaces PETScLUSolver('mumps'|'umfpack'|default LU): advection_diffusion_convergence.py:212,
+ * advection_diffusion_mixed.py:223, ...MixedPrimal_convergence.py:136, SphericalLaplace_convergence.py:135
+ * -- the exact (to rounding) solve the reference relies on for the unstabilised Galerkin q-equation
+ * (zero q-q diagonal, advection_diffusion_convergence.py:203) and on unstructured meshes, where the
+ * multigrid-preconditioned Krylov path does not apply.
+ *   perm[nv]  : new position of every node; iperm its inverse.  Coupled nodes must end up at most nbn
+ *               positions apart (RectangleMesh numbering: nbn = nx+2, or ny+2 after transposing).
+ *   bs        : 1 scalar node CSR, 2 the interleaved P-Q value layout described at the top.
+ *   workspace : cm_blu_workspace_bytes(bs,nv,nbn) bytes = 32*bs^2*nbn^2 per block of nbn nodes
+ *               (L, U with fill and the pivot permutations); carries the factors to cm_blu_solve.
+ *   ctx       : host object owning the cuSOLVER/cuBLAS handles and the getrf scratch (dense panel LU,
+ *               triangular solves and Schur updates are library calls; scatter / pivot / gather /
+ *               permutation kernels are this library's).
+ * cm_blu_factor synchronises the stream once at the end and reports info_host = 0, or 1 + the
+ * renumbered dof of an exactly zero pivot (returns CM_E_BREAKDOWN). */
+int64_t cm_blu_workspace_bytes(int32_t bs, int32_t nv, int32_t nbn);
+void* cm_blu_create(void);
+int cm_blu_destroy(void* ctx);
+int cm_blu_factor(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* perm,
+                  const int32_t* iperm, const int32_t* nrowptr, const int32_t* ncol,
+                  const double* vals, void* workspace, int64_t workspace_bytes, int32_t* info_host,
+                  void* stream);
+int cm_blu_solve(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* perm, const double* b,
+                 double* x, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ def grad_q(x, y):
     return -pi * y * torch.sin(pi * x * y), -pi * x * torch.sin(pi * x * y)
 
 
-def main(nkmax=8, report=False):
+def main(nkmax=8, report=False, linear_solver='umfpack'):
     hh, nn, ep, rp, e1p, r1p, eq, rq, its = [], [], [], [0.0], [], [0.0], [], [0.0], []
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
@@ -43,7 +43,7 @@ def main(nkmax=8, report=False):
         FF = PQPrimalForm.manufactured(Vh, "supg", D1=1e-3, D2=1.5e-3, stab=1.0)
         solver = NonlinearVariationalSolver(NonlinearVariationalProblem(FF, u, bcs=bcs))
         solver.parameters['nonlinear_solver'] = 'newton'
-        solver.parameters['newton_solver']['linear_solver'] = 'umfpack'
+        solver.parameters['newton_solver']['linear_solver'] = linear_solver   # 'umfpack' at …_SUPG.py:137
         solver.parameters['newton_solver']['absolute_tolerance'] = 1e-8
         solver.parameters['newton_solver']['relative_tolerance'] = 1e-8
         solver.parameters['newton_solver']['report'] = report

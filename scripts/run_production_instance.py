@@ -4,10 +4,11 @@ for the CG1 x CG1 primal formulation: same mesh labels (right=21, top=22, left=2
 Dirichlet list and order (:174-183), same data formulas (PInitial/QInitial :40-44,79-80), same Newton
 parameters (:207-215), steady state or backward-Euler time loop (:196-204,219-226).
 
-The reference's unstabilised Galerkin q-equation needs a pivoting sparse LU; on the GPU
-path the q-equation takes the SUPG test function of …MixedPrimal_convergence_SUPG.py:118-129
-(`supg_stab`, default 1) -- set supg_stab=0 to get the reference's form (assembly works, the
-structured solver then reports a zero pivot).
+supg_stab=0 (default) is the reference's unstabilised Galerkin q-equation; it needs a pivoting sparse
+LU, which linear_solver='mumps' provides on the GPU (banded LU with partial pivoting,
+cm_blu_*) for meshes whose factors fit in HBM.  Beyond that size use linear_solver='gmres' together
+with the SUPG test function of …MixedPrimal_convergence_SUPG.py:118-129 (supg_stab=1); note that the
+multigrid-preconditioned Krylov path still stalls on the production constants.
 """
 import math
 import os
@@ -20,7 +21,8 @@ from closestmolecule_b200 import *  # noqa: E402,F401,F403
 
 
 def solve_problem_instance(concentration, t_final, dt, mesh, bdry, sigma, deg=1, steady_state=False,
-                           D1=2.0, D2=1.5, r1_max=5.0, supg_stab=1.0, report=False, sigma_fn=None):
+                           D1=2.0, D2=1.5, r1_max=5.0, supg_stab=0.0, report=False, sigma_fn=None,
+                           linear_solver='mumps'):
     assert deg == 1, "the GPU hot path is CG1 x CG1"
     right, top, left, bottom = 21, 22, 23, 24
     V1 = 4 * math.pi * (r1_max - sigma) ** 3 / 3
@@ -54,7 +56,7 @@ def solve_problem_instance(concentration, t_final, dt, mesh, bdry, sigma, deg=1,
     problem = NonlinearVariationalProblem(FF, u, bcs=bc)
     solver = NonlinearVariationalSolver(problem)
     solver.parameters['nonlinear_solver'] = 'newton'
-    solver.parameters['newton_solver']['linear_solver'] = 'mumps'
+    solver.parameters['newton_solver']['linear_solver'] = linear_solver   # 'mumps' at :212
     solver.parameters['newton_solver']['absolute_tolerance'] = 1e-9
     solver.parameters['newton_solver']['relative_tolerance'] = 1e-9
     solver.parameters['newton_solver']['maximum_iterations'] = 10
@@ -67,6 +69,7 @@ def solve_problem_instance(concentration, t_final, dt, mesh, bdry, sigma, deg=1,
         p_h, q_h = u.split()
         p_old.vector().copy_(p_h)          # assign(p_old, p_h)
         t += dt
+    solve_problem_instance.last_solver = solver      # for the parity tests
     return u, log
 
 

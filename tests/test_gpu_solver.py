@@ -19,6 +19,19 @@ pytestmark = pytest.mark.gpu
 P1 = cm.FiniteElement("CG", "triangle", 1)
 
 
+@pytest.fixture(autouse=True)
+def _krylov_by_default(monkeypatch):
+    """This file tests the multigrid / Jacobi preconditioned Krylov paths: 'default' (which now selects
+    the direct LU whenever its factors fit, tests/test_gpu_direct.py) is mapped to 'gmres' here."""
+    orig = cm.NonlinearVariationalSolver._defaults
+
+    def defaults():
+        d = orig()
+        d["linear_solver"] = "gmres"
+        return d
+    monkeypatch.setattr(cm.NonlinearVariationalSolver, "_defaults", staticmethod(defaults))
+
+
 def _supg_problem(nx, ny):
     mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny)
     V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
@@ -69,7 +82,7 @@ def test_newton_supg_matches_oracle(nx, ny):
     mesh, V, form, bcs = _supg_problem(nx, ny)
     u = cm.Function(V)
     s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
-    s.parameters["newton_solver"]["linear_solver"] = "umfpack"       # …_SUPG.py:137 (aliased)
+    s.parameters["newton_solver"]["linear_solver"] = "gmres"
     s.parameters["newton_solver"]["absolute_tolerance"] = 1e-8
     s.parameters["newton_solver"]["relative_tolerance"] = 1e-8
     it, conv = s.solve()
@@ -206,7 +219,7 @@ def test_pq_supg_convergence_rates_on_gpu():
     spec = importlib.util.spec_from_file_location("pq_supg_conv", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    r = mod.main(8)
+    r = mod.main(8, linear_solver="gmres")
     assert 1.9 < r["rp"][-1] < 2.1 and 0.95 < r["r1p"][-1] < 1.05 and 0.9 < r["rq"][-1] < 1.3
     assert max(max(l) for _, l in r["its"][3:]) <= 20
 
@@ -293,7 +306,8 @@ def test_transient_backward_euler_steps_match_oracle():
 
 def test_production_constants_fail_loudly():
     """The reference's production form (unstabilised Galerkin q-equation, advection-dominated p-block)
-    needs a pivoting sparse LU: the GPU solver must raise, never return garbage."""
+    needs a pivoting sparse LU (tests/test_gpu_direct.py): the Krylov path must raise,
+    never return garbage."""
     import importlib.util
     import os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
@@ -304,7 +318,8 @@ def test_production_constants_fail_loudly():
     mesh = cm.RectangleMesh(cm.Point(0, 0.1), cm.Point(5, 5), 64, 64)
     bdry = cm.structured_boundary_markers(mesh)
     with pytest.raises(RuntimeError):
-        mod.solve_problem_instance(1, 0.1, 0.1, mesh, bdry, 0.1, steady_state=True, supg_stab=0.0)
+        mod.solve_problem_instance(1, 0.1, 0.1, mesh, bdry, 0.1, steady_state=True, supg_stab=0.0,
+                                   linear_solver="gmres")
 
 
 def test_unstructured_xml_mesh_scalar_newton(tmp_path):
