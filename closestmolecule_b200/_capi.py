@@ -94,6 +94,10 @@ _PROTOS = {
     "cm_blu_destroy": ([_P], C.c_int),
     "cm_blu_factor": ([_P, _I, _I, _I] + [_P] * 6 + [C.c_int64, C.POINTER(C.c_int32), _P], C.c_int),
     "cm_blu_solve": ([_P, _I, _I, _I] + [_P] * 4 + [C.c_int64, _P], C.c_int),
+    "cm_functional_workspace_doubles": ([], C.c_int64),
+    "cm_functional_error_norms": ([_I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
+    "cm_project_flux_dg0": ([_I, _P, _D, _D, _I, _P, _P, _P, _P, _P], C.c_int),
+    "cm_functional_boundary_flux": ([_I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,
                          C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),

@@ -407,4 +407,32 @@ int cm_blu_solve(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* 
                    (cudaStream_t)stream);
 }
 
+int64_t cm_functional_workspace_doubles(void) { return (int64_t)functional_workspace_doubles(); }
+
+int cm_functional_error_norms(int32_t nq, const double* rule_host, int32_t weighted,
+                              int32_t x_derivative_only, int32_t ncells, const int32_t* cells,
+                              const double* coords, const double* uh, int32_t uh_stride,
+                              const double* exact_q, const double* grad_q, double* work, void* stream) {
+  CM_CHECK_ARG(ncells >= 1 && uh_stride >= 1, "bad size");
+  CM_CHECK_ARG(rule_host && cells && coords && uh && exact_q && grad_q && work, "null pointer");
+  return functional_error_norms(nq, rule_host, weighted, x_derivative_only, ncells, cells, coords, uh,
+                                uh_stride, exact_q, grad_q, work, (cudaStream_t)stream);
+}
+
+int cm_project_flux_dg0(int32_t nq, const double* rule_host, double D1, double D2, int32_t ncells,
+                        const int32_t* cells, const double* coords, const double* u, double* flux,
+                        void* stream) {
+  CM_CHECK_ARG(ncells >= 1, "bad size");
+  CM_CHECK_ARG(rule_host && cells && coords && u && flux, "null pointer");
+  return project_flux_dg0(nq, rule_host, D1, D2, ncells, cells, coords, u, flux, (cudaStream_t)stream);
+}
+
+int cm_functional_boundary_flux(int32_t nfe, const int32_t* efverts, const int32_t* efopp,
+                                const int32_t* efcell, const double* coords, const double* flux,
+                                double* out3, void* stream) {
+  CM_CHECK_ARG(nfe >= 0, "bad size");
+  CM_CHECK_ARG(coords && flux && out3 && (nfe == 0 || (efverts && efopp && efcell)), "null pointer");
+  return functional_boundary_flux(nfe, efverts, efopp, efcell, coords, flux, out3, (cudaStream_t)stream);
+}
+
 }  // extern "C"

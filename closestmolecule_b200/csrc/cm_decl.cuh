@@ -131,4 +131,14 @@ int blu_factor(void* ctx, int bs, int nv, int nbn, const int* perm, const int* i
                int* info_host, cudaStream_t st);
 int blu_solve(void* ctx, int bs, int nv, int nbn, const int* perm, const double* b, double* x, void* ws,
               size_t ws_bytes, cudaStream_t st);
+
+// cm_functional.cu
+size_t functional_workspace_doubles();
+int functional_error_norms(int nq, const double* rule_host, int weighted, int xonly, int ncells,
+                           const int* cells, const double* coords, const double* uh, int stride,
+                           const double* exq, const double* grq, double* work, cudaStream_t st);
+int project_flux_dg0(int nq, const double* rule_host, double D1, double D2, int ncells, const int* cells,
+                     const double* coords, const double* u, double* flux, cudaStream_t st);
+int functional_boundary_flux(int nfe, const int* efverts, const int* efopp, const int* efcell,
+                             const double* coords, const double* flux, double* out3, cudaStream_t st);
 }  // namespace cm

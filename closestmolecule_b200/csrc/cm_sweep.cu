@@ -273,11 +273,24 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
   const int nrows = row_end - row_begin;
   if (nrows <= 0) return CM_OK;
   const int strips = (nx + 1 + kTX - 2) / (kTX - 1);
-  // enough y-segments to fill the machine several times over, at least 32 rows each
-  int segs = (148 * 8 + strips - 1) / strips;
-  int rows = (nrows + segs - 1) / segs;
-  if (rows < 32) rows = 32;
-  segs = (nrows + rows - 1) / rows;
+  // y-segments of at least 32 rows each (every segment recomputes the quad row below its first
+  // vertex row); their number is chosen so that the grid fills a whole number of waves of
+  // 148 SMs x 2 resident CTAs as exactly as possible (no nearly empty last wave)
+  int rows = 32, segs = (nrows + rows - 1) / rows;
+  {
+    const int slots = 148 * 2;
+    double best = 1e300;
+    int best_rows = rows;
+    for (int r = 32; r <= 96 && r <= (nrows > 32 ? nrows : 32); ++r) {
+      const int sg = (nrows + r - 1) / r;
+      const long long ctas = (long long)sg * strips;
+      const long long waves = (ctas + slots - 1) / slots;
+      const double cost = (double)waves * (r + 1);  // time ~ waves x (rows + redundant start row)
+      if (cost < best) { best = cost; best_rows = r; }
+    }
+    rows = best_rows;
+    segs = (nrows + rows - 1) / rows;
+  }
   const size_t smem = (size_t)2 * kAccPerVertex * kTX * sizeof(double);
   dim3 grid(strips, segs);
   // algorithmic bytes: 148.05 B per cell of the assembled rows

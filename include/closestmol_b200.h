@@ -305,6 +305,35 @@ int cm_blu_factor(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t*
 int cm_blu_solve(void* ctx, int32_t bs, int32_t nv, int32_t nbn, const int32_t* perm, const double* b,
                  double* x, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- a12: scalar functionals and the flux post-processing of the drivers --------------------------
+ * rule_host[3*nq] = (xi, eta, weight) of the triangle rule (weights sum to 1/2; FIAT default rules).
+ * All reductions use a fixed grid and summation order (bit-reproducible).
+ *   cm_functional_error_norms: work[0] = sum a (u_ex - u_h)^2, work[1] = sum a |grad u_ex - grad u_h|^2
+ *     (x derivative only when x_derivative_only), a = w |det| [* (4 pi x y)^2 when weighted]; take the
+ *     square roots on the host.  Replaces assemble((u_ex-u_h)**2*dx) etc. at
+ *     SphericalAdvectionDiffusionReaction_convergence.py:117-118 and ...MixedPrimal_convergence.py:148-150.
+ *     uh: nodal values with stride uh_stride (2 for a component of the interleaved P-Q vector);
+ *     exact_q[ncells*nq], grad_q[ncells*nq*2]: exact data at the quadrature points;
+ *     work: cm_functional_workspace_doubles() device doubles.
+ *   cm_project_flux_dg0: flux[ncells*2] = cell means of (D2*(dp/dx + x^2 p^2/q), D1*dp/dy) = the
+ *     project(dMatrix*grad(p_h) + D2*r2*r2*p_h/q_h*p_h*r2_vec, VectorFunctionSpace(mesh,"DG",0)) of
+ *     convergence/advection_diffusion_convergence.py:222-223.
+ *   cm_functional_boundary_flux: out3 = (r2 part, r1 part, total) of
+ *     assemble(dot(flux,n)*4*pi*r1**2*ds(marker)) (advection_diffusion_mixed.py:261-263) over the listed
+ *     exterior facets: efverts[nfe*2], efopp[nfe] (vertex of the attached cell opposite the facet),
+ *     efcell[nfe] (the attached cell). */
+int64_t cm_functional_workspace_doubles(void);
+int cm_functional_error_norms(int32_t nq, const double* rule_host, int32_t weighted,
+                              int32_t x_derivative_only, int32_t ncells, const int32_t* cells,
+                              const double* coords, const double* uh, int32_t uh_stride,
+                              const double* exact_q, const double* grad_q, double* work, void* stream);
+int cm_project_flux_dg0(int32_t nq, const double* rule_host, double D1, double D2, int32_t ncells,
+                        const int32_t* cells, const double* coords, const double* u, double* flux,
+                        void* stream);
+int cm_functional_boundary_flux(int32_t nfe, const int32_t* efverts, const int32_t* efopp,
+                                const int32_t* efcell, const double* coords, const double* flux,
+                                double* out3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
