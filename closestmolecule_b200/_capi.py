@@ -98,6 +98,11 @@ _PROTOS = {
     "cm_functional_error_norms": ([_I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
     "cm_project_flux_dg0": ([_I, _P, _D, _D, _I, _P, _P, _P, _P, _P], C.c_int),
     "cm_functional_boundary_flux": ([_I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cm_mixed_m0_cells": ([_I, _P, _D, _D, _D, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cm_csr_gather": ([_I, _P, _P, _P, _P, _I, _P], C.c_int),
+    "cm_csr_add_mapped": ([_I, _P, _P, _P, _P], C.c_int),
+    "cm_mixed_workspace_doubles": ([], C.c_int64),
+    "cm_mixed_m0_errors": ([_I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
     "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,
                          C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),

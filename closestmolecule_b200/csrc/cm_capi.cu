@@ -435,4 +435,38 @@ int cm_functional_boundary_flux(int32_t nfe, const int32_t* efverts, const int32
   return functional_boundary_flux(nfe, efverts, efopp, efcell, coords, flux, out3, (cudaStream_t)stream);
 }
 
+int cm_mixed_m0_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps,
+                      int32_t ncells, const int32_t* cells, const double* coords,
+                      const int32_t* cell_edges, const double* sign, int32_t nedges, const double* u,
+                      const double* f2q, const double* f3q, double* Je, double* Fe, void* stream) {
+  CM_CHECK_ARG(ncells >= 1 && nedges >= 3, "bad size");
+  CM_CHECK_ARG(rule_host && cells && coords && cell_edges && sign && u && f2q && f3q && Fe, "null pointer");
+  return mixed_m0_cells(nq, rule_host, D1, D2, geps, ncells, cells, coords, cell_edges, sign, nedges, u,
+                        f2q, f3q, Je, Fe, (cudaStream_t)stream);
+}
+
+int cm_csr_gather(int32_t nslots, const int32_t* ptr, const int32_t* idx, const double* src, double* out,
+                  int32_t accumulate, void* stream) {
+  CM_CHECK_ARG(nslots >= 0, "bad size");
+  CM_CHECK_ARG(nslots == 0 || (ptr && idx && src && out), "null pointer");
+  return csr_gather(nslots, ptr, idx, src, out, accumulate, (cudaStream_t)stream);
+}
+
+int cm_csr_add_mapped(int32_t n, const int32_t* map, const double* src, double* dst, void* stream) {
+  CM_CHECK_ARG(n >= 0, "bad size");
+  CM_CHECK_ARG(n == 0 || (map && src && dst), "null pointer");
+  return add_mapped(n, map, src, dst, (cudaStream_t)stream);
+}
+
+int64_t cm_mixed_workspace_doubles(void) { return (int64_t)mixed_workspace_doubles(); }
+
+int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, const int32_t* cells,
+                       const double* coords, const int32_t* cell_edges, const double* sign,
+                       int32_t nedges, const double* u, const double* exact_q, double* work, void* stream) {
+  CM_CHECK_ARG(ncells >= 1 && nedges >= 3, "bad size");
+  CM_CHECK_ARG(rule_host && cells && coords && cell_edges && sign && u && exact_q && work, "null pointer");
+  return mixed_m0_errors(nq, rule_host, ncells, cells, coords, cell_edges, sign, nedges, u, exact_q, work,
+                         (cudaStream_t)stream);
+}
+
 }  // extern "C"

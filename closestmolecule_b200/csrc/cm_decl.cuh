@@ -141,4 +141,17 @@ int project_flux_dg0(int nq, const double* rule_host, double D1, double D2, int 
                      const double* coords, const double* u, double* flux, cudaStream_t st);
 int functional_boundary_flux(int nfe, const int* efverts, const int* efopp, const int* efcell,
                              const double* coords, const double* flux, double* out3, cudaStream_t st);
+
+// cm_mixed.cu
+int mixed_m0_cells(int nq, const double* rule_host, double D1, double D2, double geps, int ncells,
+                   const int* cells, const double* coords, const int* cell_edges, const double* sign,
+                   int nE, const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
+                   cudaStream_t st);
+int csr_gather(int nslots, const int* ptr, const int* idx, const double* src, double* out, int accumulate,
+               cudaStream_t st);
+int add_mapped(int n, const int* map, const double* src, double* dst, cudaStream_t st);
+size_t mixed_workspace_doubles();
+int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cells, const double* coords,
+                    const int* cell_edges, const double* sign, int nE, const double* u, const double* exq,
+                    double* work, cudaStream_t st);
 }  // namespace cm

@@ -1,0 +1,308 @@
+"""Lowest-order mixed-primal system RT1 x DG0 x CG1 (deg = 0) of
+convergence/test_for_paper_convergence.py:68,108-167 on the GPU.
+
+Host side = topology tables (edge numbering, orientation signs, the scalar CSR pattern and the per-slot
+gather lists that make the scatter-add deterministic) built once per mesh with torch; per Newton step
+the work is in the CUDA library: cm_mixed_m0_cells (element tensors), cm_csr_gather (assembly),
+cm_assemble_c0ip_facets / cm_assemble_exterior_facets (q-q facet operator, shared with the P-Q path),
+cm_apply_dirichlet, and the pivoting banded LU cm_blu_* ('mumps' at :162).  Global dofs
+[edges | cells | vertices] (DOLFIN's own numbering of this mixed space is not reproducible without
+DOLFIN; the results are numbering independent).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from .assembler import PQAssembler
+from .forms import EF_ADV, EF_DATA, EF_PENALTY, PQPrimalForm
+from .manufactured import _torchify, p_exact, q_exact
+from .mesh import DOLFIN_EPS
+from .quadrature import facet_rule, triangle_rule
+from .solver import BandedLULinearSolver
+from .space import FiniteElement, FunctionSpace, MixedElement
+
+
+def paper_data(D1, D2):
+    """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = dq_ex/dx + r2^2 p_ex
+    (:124-128), div_rad(sig_ex) and dq_ex/dx for the error norms, as torch callables."""
+    import sympy as sm
+    x, y = sm.symbols("x y", positive=True)
+    pe = sm.sin(sm.pi * x) * sm.sin(sm.pi * y)
+    qe = sm.Rational(3, 2) + sm.cos(sm.pi * x * y)
+    G = x ** 2 * pe ** 2 / (qe + DOLFIN_EPS)
+    sx = -sm.diff(pe, x) - G
+    sy = -sm.diff(pe, y)
+    f2 = sm.diff(x ** 2 * D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * D1 * sy, y) / y ** 2
+    f3 = sm.diff(qe, x) + x ** 2 * pe
+    drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
+    T = lambda e: _torchify(e, (x, y))
+    return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)))
+
+
+class _Holder:
+    """What BandedLULinearSolver needs from an assembler: mesh.device / .structured, topo, vals, b, bs."""
+
+    class _M:
+        structured = False
+
+    class _T:
+        pass
+
+    def __init__(self, device, rowptr, col, n, vals, b):
+        self.mesh = self._M()
+        self.mesh.device = device
+        self.topo = self._T()
+        self.topo.nrowptr, self.topo.ncol, self.topo.nv = rowptr, col, n
+        self.vals, self.b, self.bs = vals, b, 1
+
+
+def _csr_from_pairs(rows, cols, n):
+    key = torch.unique(rows * n + cols)
+    r = key // n
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=rows.device)
+    rp[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
+    return key, rp.to(torch.int32).contiguous(), (key % n).to(torch.int32).contiguous()
+
+
+def _gather_lists(slot, nslots):
+    """Per-slot lists of the contributing entries, ascending entry index (= ascending cell)."""
+    _, order = torch.sort(slot, stable=True)
+    ptr = torch.zeros(nslots + 1, dtype=torch.int64, device=slot.device)
+    ptr[1:] = torch.cumsum(torch.bincount(slot, minlength=nslots), 0)
+    return ptr.to(torch.int32).contiguous(), order
+
+
+class PaperMixedSystem:
+    """Assembly + Newton solve of the k=0 'paper' system on UnitSquareMesh-like meshes with the facet
+    markers left=30, right=31, rest=32 (:90-94)."""
+
+    def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.05, stab2=1.0, degree=6, tables_only=False):
+        if not tables_only:
+            _capi.require_cuda(mesh.coords)
+            self.lib = _capi.lib()
+        self.mesh, self.bdry = mesh, bdry
+        self.D1, self.D2 = float(D1), float(D2)
+        dev = mesh.device
+        fc = mesh.facets()
+        V, C, E = mesh.num_vertices(), mesh.num_cells(), fc.num
+        self.V, self.C, self.E, self.N = V, C, E, E + C + V
+        cells = mesh.cells.long()
+        X = mesh.coords
+        # cell -> edges (local facet i opposite local vertex i) and orientation signs
+        fa = torch.stack([cells[:, 1], cells[:, 0], cells[:, 0]], 1)
+        fb = torch.stack([cells[:, 2], cells[:, 2], cells[:, 1]], 1)
+        key = torch.minimum(fa, fb) * V + torch.maximum(fa, fb)
+        allkey = fc.verts[:, 0].long() * V + fc.verts[:, 1].long()
+        ce = torch.searchsorted(allkey, key)
+        A, B = X[fc.verts[:, 0].long()], X[fc.verts[:, 1].long()]
+        t = B - A
+        self.elen = t.pow(2).sum(1).sqrt()
+        self.enorm = torch.stack([t[:, 1], -t[:, 0]], 1) / self.elen[:, None]
+        mid = 0.5 * (A + B)[ce]
+        sign = torch.sign(((mid - X[cells]) * self.enorm[ce]).sum(-1))
+        self.cell_edges = ce.to(torch.int32).contiguous()
+        self.sign = sign.to(torch.float64).contiguous()
+        # quadrature rule and forcing at the cell points
+        pts, wts = triangle_rule(degree)
+        self.rule = np.ascontiguousarray(np.concatenate([pts, wts[:, None]], 1), dtype=np.float64)
+        self.nq = self.rule.shape[0]
+        phi = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
+        P = torch.einsum("qi,cid->cqd", phi, X[cells])
+        self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
+        self.data = paper_data(D1, D2)
+        self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
+        self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
+        # q-q facet operator: the C0IP 'paper' q-equation on the CG1 x CG1 machinery (same kernels)
+        self.qtopo = mesh.topology(True)
+        if not tables_only:
+            P1 = FiniteElement("CG", "triangle", 1)
+            W = FunctionSpace(mesh, MixedElement([P1, P1]))
+            form = PQPrimalForm(W, D1, D2, G=("power", 1.0), q_adv=0.0, q_divr=1.0, q_ibp=1.0,
+                                c0ip_gamma=stab / 1.0 ** 3.5, c0ip_h="facet", pen_stab2=stab2, degree=degree,
+                                ext_terms=[(bdry, 30, EF_ADV), (bdry, 32, EF_ADV), (bdry, 31, EF_DATA),
+                                           (bdry, "on_boundary", EF_PENALTY)], q_data=q_exact)
+            qasm = PQAssembler(form)
+            assert qasm.topo is self.qtopo
+            self.Kq, self.cq = qasm.Kq, qasm.cq
+        # scalar CSR pattern: cell blocks + the (vertex x vertex) facet pattern
+        cid = torch.arange(C, device=dev)[:, None]
+        cd = torch.cat([ce, E + cid, E + C + cells], 1)                               # [C,7]
+        self.cell_dofs = cd
+        rows_c = cd.repeat_interleave(7, dim=1).flatten()
+        cols_c = cd.repeat(1, 7).flatten()
+        qdeg = (self.qtopo.nrowptr[1:] - self.qtopo.nrowptr[:-1]).long()
+        qrows = E + C + torch.repeat_interleave(torch.arange(V, device=dev), qdeg)
+        qcols = E + C + self.qtopo.ncol.long()
+        N = self.N
+        self._key, self.rowptr, self.col = _csr_from_pairs(torch.cat([rows_c, qrows]), torch.cat([cols_c, qcols]), N)
+        self.nnz = int(self.col.numel())
+        slot_c = torch.searchsorted(self._key, rows_c * N + cols_c)                     # cell-major, (i,j) inside
+        # element storage is entry-major ([49][C]): entry index of (c, e) is e*C + c
+        ent = (torch.arange(49, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.mat_ptr, order = _gather_lists(slot_c, self.nnz)
+        self.mat_idx = ent[order].to(torch.int32).contiguous()
+        entv = (torch.arange(7, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.vec_ptr, order = _gather_lists(cd.flatten(), N)
+        self.vec_idx = entv[order].to(torch.int32).contiguous()
+        self.kq_map = torch.searchsorted(self._key, qrows * N + qcols).to(torch.int32).contiguous()
+        self.diag_slot_all = (torch.searchsorted(self._key, torch.arange(N, device=dev) * (N + 1))
+                              - self.rowptr[:-1].long()).to(torch.int32)
+        if tables_only:
+            return
+        # buffers
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.Je = torch.empty(49 * C, **f64)
+        self.Fe = torch.empty(7 * C, **f64)
+        self.vals = torch.zeros(self.nnz, **f64)
+        self.b = torch.zeros(N, **f64)
+        self._kqq = torch.empty(V, **f64)
+        self.bnat = self._natural_data(degree)
+        self._lin = None
+        self.newton_its = 0
+
+    # -- state-independent pieces ----------------------------------------------------------------
+    def _natural_data(self, degree):
+        """+ p_ex (tau.n) W ds(right), ds(rest) on the s-rows (:148-149): RT0 normal trace = 1/|F| on its
+        own facet, so only the facet's own dof is touched."""
+        mesh, fc = self.mesh, self.mesh.facets()
+        dev = mesh.device
+        sel = torch.nonzero((fc.cell1 < 0) & ((self.bdry.values == 31) | (self.bdry.values == 32))).flatten()
+        A = mesh.coords[fc.verts[sel, 0].long()]
+        B = mesh.coords[fc.verts[sel, 1].long()]
+        t = B - A
+        L = t.pow(2).sum(1).sqrt()
+        nrm = torch.stack([t[:, 1], -t[:, 0]], 1) / L[:, None]
+        opp = mesh.coords[mesh.cells.long()[fc.cell0[sel].long(), fc.loc0[sel].long()]]
+        flip = ((opp - A) * nrm).sum(1) > 0
+        nrm = torch.where(flip[:, None], -nrm, nrm)
+        m = (degree + 2) // 2
+        p, w = np.polynomial.legendre.leggauss(m)
+        s = torch.tensor(0.5 * (p + 1.0), device=dev)
+        wq = torch.tensor(0.5 * w, device=dev)
+        Pq = A[:, None, :] + s[None, :, None] * t[:, None, :]
+        Wf = (4.0 * math.pi * Pq[:, :, 0] * Pq[:, :, 1]) ** 2
+        sgn = torch.sign((nrm * self.enorm[sel]).sum(1))
+        out = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        out[sel] = (wq[None, :] * Wf * p_exact(Pq[:, :, 0], Pq[:, :, 1])).sum(1) * sgn
+        return out
+
+    def sigD(self):
+        """project(sig_ex, RT) (:132): unweighted L2 projection; RT mass matrix assembled with the same
+        gather machinery and solved with the banded LU."""
+        dev = self.mesh.device
+        C, E = self.C, self.E
+        cells = self.mesh.cells.long()
+        Xc = self.mesh.coords[cells]
+        det = ((Xc[:, 1, 0] - Xc[:, 0, 0]) * (Xc[:, 2, 1] - Xc[:, 0, 1])
+               - (Xc[:, 2, 0] - Xc[:, 0, 0]) * (Xc[:, 1, 1] - Xc[:, 0, 1]))
+        area = 0.5 * det.abs()
+        wts = torch.tensor(self.rule[:, 2], device=dev)
+        a = wts[None, :] * (2 * area)[:, None]
+        P = torch.stack([self.xq, self.yq], -1)
+        R = (P[:, :, None, :] - Xc[:, None, :, :]) * (self.sign / (2 * area[:, None]))[:, None, :, None]
+        sex = torch.stack([self.data["sx"](self.xq, self.yq), self.data["sy"](self.xq, self.yq)], -1)
+        Me = torch.einsum("cq,cqid,cqjd->cij", a, R, R)                                # [C,3,3]
+        be = torch.einsum("cq,cqid,cqd->ci", a, R, sex)
+        ce = self.cell_edges.long()
+        rows = ce.repeat_interleave(3, dim=1).flatten()
+        cols = ce.repeat(1, 3).flatten()
+        key, rp, col = _csr_from_pairs(rows, cols, E)
+        slot = torch.searchsorted(key, rows * E + cols)
+        ptr, order = _gather_lists(slot, key.numel())
+        vals = torch.empty(key.numel(), dtype=torch.float64, device=dev)
+        st = _capi.stream_ptr()
+        src = Me.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(key.numel(), _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
+                                           _capi.ptr(src), _capi.ptr(vals), 0, st))
+        ptr2, order2 = _gather_lists(ce.flatten(), E)
+        rhs = torch.empty(E, dtype=torch.float64, device=dev)
+        src2 = be.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(E, _capi.ptr(ptr2), _capi.ptr(order2.to(torch.int32).contiguous()),
+                                           _capi.ptr(src2), _capi.ptr(rhs), 0, st))
+        lin = BandedLULinearSolver(_Holder(dev, rp, col, E, vals, rhs))
+        lin.setup()
+        x = torch.empty_like(rhs)
+        lin.solve(rhs, x)
+        return x
+
+    # -- per Newton step ----------------------------------------------------------------------------
+    def assemble(self, u, want_jac=True):
+        """F(u) -> self.b and (optionally) J(u) -> self.vals on the scalar CSR (rowptr, col)."""
+        lib, st, mesh = self.lib, _capi.stream_ptr(), self.mesh
+        _capi.check(lib.cm_mixed_m0_cells(
+            self.nq, self.rule.ctypes.data, self.D1, self.D2, DOLFIN_EPS, self.C, _capi.ptr(mesh.cells),
+            _capi.ptr(mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), self.E, _capi.ptr(u),
+            _capi.ptr(self.f2q), _capi.ptr(self.f3q), _capi.ptr(self.Je) if want_jac else None,
+            _capi.ptr(self.Fe), st))
+        _capi.check(lib.cm_csr_gather(self.N, _capi.ptr(self.vec_ptr), _capi.ptr(self.vec_idx),
+                                      _capi.ptr(self.Fe), _capi.ptr(self.b), 0, st))
+        # q-rows: + Kq q + cq (facet terms), s-rows: + natural p data
+        uq = u[self.E + self.C:]
+        t = self.qtopo
+        _capi.check(lib.cm_spmv(1, self.V, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(self.Kq),
+                                uq.data_ptr(), _capi.ptr(self._kqq), st))
+        self.b[self.E + self.C:] += self._kqq + self.cq
+        self.b += self.bnat
+        if want_jac:
+            _capi.check(lib.cm_csr_gather(self.nnz, _capi.ptr(self.mat_ptr), _capi.ptr(self.mat_idx),
+                                          _capi.ptr(self.Je), _capi.ptr(self.vals), 0, st))
+            _capi.check(lib.cm_csr_add_mapped(self.kq_map.numel(), _capi.ptr(self.kq_map), _capi.ptr(self.Kq),
+                                              _capi.ptr(self.vals), st))
+        return (self.vals if want_jac else None), self.b
+
+    def _apply_bc(self, u, with_matrix):
+        _capi.check(self.lib.cm_apply_dirichlet(
+            1, self.bc_dofs.numel(), _capi.ptr(self.bc_dofs), _capi.ptr(self.bc_diag), _capi.ptr(self.bc_vals),
+            _capi.ptr(u), _capi.ptr(self.rowptr), _capi.ptr(self.vals) if with_matrix else None,
+            _capi.ptr(self.b), _capi.stream_ptr()))
+
+    def solve(self, tol=1e-7, maxit=50):
+        """SNES 'basic' Newton from u = 0 with 'mumps' (:159-165): abs / rel tolerance 1e-7."""
+        dev = self.mesh.device
+        fc = self.mesh.facets()
+        bc = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 30)).flatten()          # left edges (:133)
+        self.bc_dofs = bc.to(torch.int32).contiguous()
+        self.bc_vals = self.sigD()[bc].contiguous()
+        self.bc_diag = self.diag_slot_all[bc].contiguous()
+        u = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        self.assemble(u, False)
+        self._apply_bc(u, False)
+        r0 = r = float(torch.linalg.vector_norm(self.b))
+        if self._lin is None:
+            self._lin = BandedLULinearSolver(_Holder(dev, self.rowptr, self.col, self.N, self.vals, self.b))
+        dx = torch.empty_like(u)
+        it = 0
+        while not (r < tol or r / r0 < tol) and it < maxit:
+            self.assemble(u, True)
+            self._apply_bc(u, True)
+            self._lin.setup()
+            self._lin.solve(self.b, dx)
+            u -= dx
+            it += 1
+            self.assemble(u, False)
+            self._apply_bc(u, False)
+            r = float(torch.linalg.vector_norm(self.b))
+            if r != r:
+                raise RuntimeError("Newton solver diverged (NaN residual)")
+        if not (r < tol or r / r0 < tol):
+            raise RuntimeError("Newton solver did not converge because maximum number of iterations reached")
+        self.newton_its = it
+        return u
+
+    def errors(self, u):
+        """(e_div(s), e_0(p), e_1(q)) of :175-177 (weighted norms, degree-6 rule)."""
+        d, x, y = self.data, self.xq, self.yq
+        exq = torch.stack([d["sx"](x, y), d["sy"](x, y), d["drs"](x, y), p_exact(x, y), q_exact(x, y),
+                           d["qx"](x, y)], -1).to(torch.float64).contiguous()
+        work = torch.empty(int(self.lib.cm_mixed_workspace_doubles()), dtype=torch.float64,
+                           device=self.mesh.device)
+        _capi.check(self.lib.cm_mixed_m0_errors(
+            self.nq, self.rule.ctypes.data, self.C, _capi.ptr(self.mesh.cells), _capi.ptr(self.mesh.coords),
+            _capi.ptr(self.cell_edges), _capi.ptr(self.sign), self.E, _capi.ptr(u), _capi.ptr(exq),
+            _capi.ptr(work), _capi.stream_ptr()))
+        s = work[:3].cpu()
+        return tuple(math.sqrt(float(v)) for v in s)

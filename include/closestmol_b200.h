@@ -334,6 +334,33 @@ int cm_functional_boundary_flux(int32_t nfe, const int32_t* efverts, const int32
                                 const int32_t* efcell, const double* coords, const double* flux,
                                 double* out3, void* stream);
 
+/* ---- section 8f row 1: lowest-order mixed-primal system RT1 x DG0 x CG1 (deg = 0) ------------------
+ * convergence/test_for_paper_convergence.py:68,108-167; its recorded k=0 table (:200-207) is the
+ * known-answer test.  Global dofs [edges | cells | vertices]; per cell 7 local dofs (3 edge fluxes on the
+ * facets opposite local vertices 0,1,2, the cell value of p, 3 vertex values of q).
+ *   cm_mixed_m0_cells : element residual Fe[7][ncells] and Jacobian Je[49][ncells] (entry-major; Je may be
+ *     NULL) of the cell integrals (:137-141,150-151).  cell_edges[ncells*3], sign[ncells*3] (+-1: outward
+ *     normal of the cell vs the global edge normal), f2q/f3q[ncells*nq] forcing at the quadrature points.
+ *   cm_csr_gather     : out[s] (+)= sum of src[idx[k]], k in [ptr[s],ptr[s+1]) in list order -- the
+ *     deterministic replacement of GenericTensor::add_local [ext] through a precomputed cell->nnz map
+ *     (lists sorted by cell = DOLFIN's serial insertion order); works for matrices and vectors.
+ *   cm_csr_add_mapped : dst[map[k]] += src[k] (injective map; adds the q-q facet operator of
+ *     cm_assemble_c0ip_facets / cm_assemble_exterior_facets into the mixed CSR).
+ *   cm_mixed_m0_errors: work[0..2] = squares of e_div(s), e_0(p), e_1(q) (:175-177);
+ *     exact_q[ncells*nq*6] = (s_x, s_y, div_rad s, p, q, dq/dx) at the quadrature points;
+ *     work: cm_mixed_workspace_doubles() device doubles. */
+int cm_mixed_m0_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps,
+                      int32_t ncells, const int32_t* cells, const double* coords,
+                      const int32_t* cell_edges, const double* sign, int32_t nedges, const double* u,
+                      const double* f2q, const double* f3q, double* Je, double* Fe, void* stream);
+int cm_csr_gather(int32_t nslots, const int32_t* ptr, const int32_t* idx, const double* src, double* out,
+                  int32_t accumulate, void* stream);
+int cm_csr_add_mapped(int32_t n, const int32_t* map, const double* src, double* dst, void* stream);
+int64_t cm_mixed_workspace_doubles(void);
+int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, const int32_t* cells,
+                       const double* coords, const int32_t* cell_edges, const double* sign,
+                       int32_t nedges, const double* u, const double* exact_q, double* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,74 @@
+"""SURVEY §8f row 1 on the GPU: the RT1 x DG0 x CG1 'paper' system (test_for_paper_convergence.py, deg=0).
+Element tensors + deterministic gather vs the oracle's assembly, Newton solution vs the oracle's, and the
+recorded k=0 table (:200-207) reproduced through the GPU path."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import closestmolecule_b200 as cm
+from closestmolecule_b200.mixed import PaperMixedSystem
+from oracle import paper_m0
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _system(n):
+    mesh = cm.UnitSquareMesh(n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    return PaperMixedSystem(mesh, bd)
+
+
+@pytest.mark.parametrize("n", [4, 12])
+def test_assembly_matches_oracle(n):
+    S, O = _system(n), paper_m0.PaperM0(n)
+    rng = np.random.default_rng(1)
+    un = np.concatenate([rng.standard_normal(O.E), 0.5 + rng.random(O.C), 1.0 + rng.random(O.V)])
+    u = torch.tensor(un, device=S.mesh.device)
+    vals, b = S.assemble(u, True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    scale = abs(J).max()
+    assert abs(got - J).max() < 1e-12 * scale, abs(got - J).max() / scale
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    # residual-only pass gives the same vector
+    _, b2 = S.assemble(u, False)
+    assert torch.equal(b2, b)
+
+
+def test_newton_solution_and_errors_match_oracle():
+    n = 8
+    S, O = _system(n), paper_m0.PaperM0(n)
+    u = S.solve()
+    uo = O.solve()
+    assert S.newton_its == O.newton_its
+    assert np.linalg.norm(u.cpu().numpy() - uo) / np.linalg.norm(uo) < 1e-8
+    assert np.allclose(S.errors(u), O.errors(uo), rtol=1e-8)
+    assert np.allclose(S.sigD().cpu().numpy(), O.sigD(), rtol=1e-9, atol=1e-11)
+
+
+def test_recorded_k0_table_through_the_gpu_path():
+    """scripts/run_paper_mixed_convergence.py prints the table recorded at test_for_paper_convergence.py:200-207:
+    levels 3-6 digit for digit, the two coarsest to the last printed digit (analytic data instead of
+    degree-5/6 interpolants) -- exactly as the oracle does (tests/test_oracle_golden.py)."""
+    from test_oracle_golden import PAPER_K0
+    spec = importlib.util.spec_from_file_location("paper_conv", os.path.join(ROOT, "scripts",
+                                                                             "run_paper_mixed_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows, its = mod.main(6)
+    got = [[float(t) for t in r.replace("&", " ").split()] for r in rows]
+    ref = [[float(t) for t in r.replace("&", " ").split()] for r in PAPER_K0[:6]]
+    for k in range(2, 6):
+        assert rows[k].split() == PAPER_K0[k].split(), (rows[k], PAPER_K0[k])
+    for k in range(2):
+        assert got[k][0] == ref[k][0] and got[k][1] == ref[k][1]
+        for a, b in zip(got[k][2::2], ref[k][2::2]):
+            assert abs(a - b) <= 0.011 * 10 ** np.floor(np.log10(b)), (a, b)

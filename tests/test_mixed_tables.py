@@ -1,0 +1,62 @@
+"""Host tables of the RT1 x DG0 x CG1 path (closestmolecule_b200/mixed.py) against the oracle
+(oracle/paper_m0.py): edge numbering, orientation signs, CSR pattern, and the per-slot gather lists that
+replace DOLFIN's serial add_local (checked by emulating cm_csr_gather with torch)."""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+import closestmolecule_b200 as cm
+from closestmolecule_b200.mixed import PaperMixedSystem
+from oracle import paper_m0
+
+
+def _system(n):
+    mesh = cm.UnitSquareMesh(n, n, device="cpu")
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    return PaperMixedSystem(mesh, bd, tables_only=True)
+
+
+def _emulate_gather(ptr, idx, src):
+    out = torch.zeros(ptr.numel() - 1, dtype=torch.float64)
+    seg = torch.repeat_interleave(torch.arange(ptr.numel() - 1), (ptr[1:] - ptr[:-1]).long())
+    out.index_add_(0, seg, src[idx.long()])
+    return out
+
+
+def test_tables_match_oracle_and_gather_lists_assemble():
+    n = 6
+    S, O = _system(n), paper_m0.PaperM0(n)
+    assert (S.E, S.C, S.V, S.N) == (O.E, O.C, O.V, O.N)
+    assert np.array_equal(S.cell_edges.numpy(), O.cell_edges)
+    assert np.array_equal(S.sign.numpy(), O.sign)
+    assert np.array_equal(S.cell_dofs.numpy(), O.cell_dofs)
+    assert np.array_equal(np.sort((S.bdry.values.numpy() == 30).nonzero()[0]), np.sort((O.markers == 30).nonzero()[0]))
+    # the oracle's Jacobian pattern (cells + facet terms) is contained in ours, slot for slot
+    J, _ = O.assemble(np.linspace(0.5, 1.5, O.N), True)
+    A = sp.csr_matrix((np.ones(S.nnz), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N))
+    assert (abs(J) > 0).multiply(A == 0).nnz == 0
+    # gather lists: random element tensors, entry-major storage like the kernel writes them
+    rng = np.random.default_rng(0)
+    Je = rng.standard_normal((S.C, 49))
+    Fe = rng.standard_normal((S.C, 7))
+    vals = _emulate_gather(S.mat_ptr, S.mat_idx, torch.tensor(Je.T.copy().ravel()))
+    cd = S.cell_dofs.numpy()
+    ref = sp.coo_matrix((Je.ravel(), (np.repeat(cd, 7, axis=1).ravel(), np.tile(cd, (1, 7)).ravel())),
+                        shape=(S.N, S.N)).tocsr()
+    got = sp.csr_matrix((vals.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N))
+    assert abs(got - ref).max() < 1e-13
+    b = _emulate_gather(S.vec_ptr, S.vec_idx, torch.tensor(Fe.T.copy().ravel()))
+    bref = np.zeros(S.N)
+    np.add.at(bref, cd.ravel(), Fe.ravel())
+    assert np.max(np.abs(b.numpy() - bref)) < 1e-13
+    # q-q facet operator map and diagonal slots
+    rp, col = S.rowptr.numpy(), S.col.numpy()
+    assert all(col[rp[i] + S.diag_slot_all[i]] == i for i in range(S.N))
+    t = S.qtopo
+    qrows = np.repeat(np.arange(S.V), np.diff(t.nrowptr.numpy()))
+    rows_of_slot = np.repeat(np.arange(S.N), np.diff(rp))
+    assert np.array_equal(rows_of_slot[S.kq_map.numpy()], S.E + S.C + qrows)
+    assert np.array_equal(col[S.kq_map.numpy()], S.E + S.C + t.ncol.numpy())
