@@ -1,7 +1,7 @@
 // Newton linear solve J dx = F on structured meshes: GMRES on the row-equilibrated system,
 // right-preconditioned by the field split diag(App, Aqq) (optionally block-lower-triangular
 // [[App, 0], [Aqp, Aqq]], CM_PRECOND_LOWER=1):
-//   p-block: one geometric-multigrid V(1,1) cycle with zebra x-line relaxation (Galerkin coarse
+//   p-block: one geometric-multigrid V(1,2) cycle with zebra x-line relaxation (Galerkin coarse
 //            operators in stencil form, dense inverse on the coarsest grid);
 //   q-block: two zebra x-line relaxation sweeps (the q-equation is transport along r2).
 // All of it is caller-provided workspace + kernels; nothing is kept between calls except the
@@ -29,6 +29,8 @@ struct PQSLevel {
 struct PQSolver {
   int nx, ny, nv, nlev, restart;
   int q_sweeps = 2;  // zebra sweeps on the q-block per application
+  int pre_smooth = 1, post_smooth = 2;  // zebra sweeps before / after the coarse-grid correction
+  int dist_ld = 3;      // multi-GPU: first replicated level
   // block-diagonal instead of block-lower-triangular field split: the q-sweeps take r_q directly
   // (no Aqp z_p correction).  Same GMRES iteration counts on the SUPG problems (the triangular
   // coupling costs GMRES nothing here), one residual pass and one halo exchange less per iteration.
@@ -53,6 +55,17 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CM_PRECOND_LOWER"); mode = (e && atoi(e) != 0) ? 1 : 0; }
     S.diag_split = mode == 0;
+    // tuning knobs; defaults 2 q-sweeps and V(1,2): measured at 16 Mi cells (profiles/README.md)
+    // V(1,1) 13 its / 33.9 ms, V(1,2) 11 / 32.9, V(2,2) 10 / 33.9, V(1,0) 19 / 42.4; q-sweeps 1: +1 it
+    static int qs = -1, pre = -1, post = -1, ld = -1;
+    if (qs < 0) { const char* e = getenv("CM_Q_SWEEPS"); qs = (e && atoi(e) > 0) ? atoi(e) : 2; }
+    if (pre < 0) { const char* e = getenv("CM_MG_PRE"); pre = (e && atoi(e) > 0) ? atoi(e) : 1; }
+    if (post < 0) { const char* e = getenv("CM_MG_POST"); post = e ? atoi(e) : 2; }
+    if (ld < 0) { const char* e = getenv("CM_DIST_LD"); ld = (e && atoi(e) > 0) ? atoi(e) : 3; }
+    S.q_sweeps = qs;
+    S.pre_smooth = pre;
+    S.post_smooth = post;
+    S.dist_ld = ld;
   }
   S.nx = nx;
   S.ny = ny;
@@ -150,12 +163,14 @@ static int vcycle(PQSolver& S, int l, const double* b, double* x, cudaStream_t s
     return rc;
   }
   PQSLevel& C = S.lev[l + 1];
-  if ((rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, true, st))) return rc;
+  for (int s = 0; s < S.pre_smooth; ++s)
+    if ((rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, s == 0, st))) return rc;
   if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st))) return rc;
   if ((rc = st_restrict(C.nx, C.ny, L.r, C.b, st))) return rc;
   if ((rc = vcycle(S, l + 1, C.b, C.x, st))) return rc;
   if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st))) return rc;
-  return zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
+  for (int s = 0; s < S.post_smooth && !rc; ++s) rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
+  return rc;
 }
 
 // Replays a fixed kernel sequence (one preconditioner application) as a CUDA graph: captured on a
@@ -327,7 +342,7 @@ struct DistInfo {
 static void dist_info(const PQSolver& S, cm_dist* D, double* base, DistInfo& I) {
   I.D = D;
   I.base = base;
-  I.Ld = S.nlev - 1 < 3 ? S.nlev - 1 : 3;
+  I.Ld = S.nlev - 1 < S.dist_ld ? S.nlev - 1 : S.dist_ld;
   for (int l = 0; l <= I.Ld; ++l) {
     I.rb[l] = D->row_begin[D->rank] >> l;
     I.re[l] = (D->rank + 1 == D->world) ? S.lev[l].ny + 1 : (D->row_begin[D->rank + 1] >> l);
@@ -362,10 +377,12 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
   PQSLevel& C = S.lev[l + 1];
   const int n1 = L.nx + 1, rb = I.rb[l], re = I.re[l];
   double* xa[1] = {x};
-  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 1, st, rb, re, L.r))) return rc;
-  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
-  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  for (int s = 0; s < S.pre_smooth; ++s) {
+    if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0 ? 1 : 0, st, rb, re, L.r))) return rc;
+    if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+    if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
+    if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+  }
   if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st, rb, re))) return rc;
   double* ra[1] = {L.r};
   if ((rc = halo_rows(I, ra, 1, n1, rb, re, st))) return rc;
@@ -376,10 +393,13 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
     if ((rc = halo_rows(I, ca, 1, C.nx + 1, I.rb[l + 1], I.re[l + 1], st))) return rc;
   }
   if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st, rb, re))) return rc;
-  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
-  if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
-  return st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r);
+  for (int s = 0; s < S.post_smooth; ++s) {
+    if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+    if ((rc = st_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
+    if ((rc = halo_rows(I, xa, 1, n1, rb, re, st))) return rc;
+    if ((rc = st_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, st, rb, re, L.r))) return rc;
+  }
+  return CM_OK;
 }
 
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,

@@ -1060,9 +1060,15 @@ int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const
   const int nv = (nx + 1) * (ny + 1);
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
+  // interior-facet couples present?  (one 4-byte read of the total entry count, once per Jacobian):
+  // without them the 6 extra q-q diagonals are neither zero-filled here nor read anywhere (has_extra = 0)
+  int nnz = 0;
+  CM_CUDA(cudaMemcpyAsync(&nnz, nrowptr + nv, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CM_CUDA(cudaStreamSynchronize(st));
+  const long long nnz7 = (long long)nv + 2LL * ((long long)nx * (ny + 1) + (long long)ny * (nx + 1) + (long long)nx * ny);
   extract_blocks_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
-                                                           PP, PQ, QP, QQ, sp, sq, err, vb, ve, QQx,
-                                                           has_extra);
+                                                           PP, PQ, QP, QQ, sp, sq, err, vb, ve,
+                                                           nnz != nnz7 ? QQx : nullptr, has_extra);
   CM_BYTES((double)(ve - vb) * (2 * 28 * 8.0 + 16.0));  // CSR values in, 4 stencil blocks + scalings out
   CM_LAUNCH_CHECK();
   return CM_OK;

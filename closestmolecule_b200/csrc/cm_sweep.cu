@@ -72,6 +72,65 @@ __device__ __forceinline__ void cell_sums(const cm_pq_params& P, const TriGeom& 
   (void)trans;
 }
 
+// Residual only (the convergence test of every Newton iteration): the three element rows of F straight
+// from the quadrature points, without the mass-type matrices the Jacobian needs:
+//   Fp_I = S0 (D2 gx_I p_x + D1 gy_I p_y) + D2 gx_I SG + inv_dt sum_k a dp_k l_I
+//   Fq_I = sum_k a rho_k (l_I + tau gx_I) - q_ibp gx_I sum_k a q_k,
+//   rho = q_react q + q_adv q_x + x^2 (q_x2p p + q_x2q q) - q_divr (2/x) q.
+template <int NQ, int GKIND, bool QGEN>
+__device__ __forceinline__ void cell_resid(const cm_pq_params& P, const TriGeom& g, const double* pe,
+                                           const double* qe, const double* po, const bool trans,
+                                           const double tau, double* Fp, double* Fq) {
+  const double gx[3] = {g.gx0, g.gx1, g.gx2}, gy[3] = {g.gy0, g.gy1, g.gy2};
+  const double px = pe[0] * gx[0] + pe[1] * gx[1] + pe[2] * gx[2];
+  const double py = pe[0] * gy[0] + pe[1] * gy[1] + pe[2] * gy[2];
+  const double qx = qe[0] * gx[0] + qe[1] * gx[1] + qe[2] * gx[2];
+  const double dp[3] = {pe[0] - po[0], pe[1] - po[1], pe[2] - po[2]};
+  double S0 = 0.0, SG = 0.0, R0 = 0.0, Q0 = 0.0;
+  double Rq[3] = {0.0, 0.0, 0.0}, T[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    double l[3], w;
+    TriRule<NQ>::get(k, l[0], l[1], l[2], w);
+    const double x = l[0] * g.x0 + l[1] * g.x1 + l[2] * g.x2;
+    const double y = l[0] * g.y0 + l[1] * g.y1 + l[2] * g.y2;
+    const double t = kFourPi * x * y;
+    const double a = w * g.adet * (t * t);
+    const double p = l[0] * pe[0] + l[1] * pe[1] + l[2] * pe[2];
+    const double q = l[0] * qe[0] + l[1] * qe[1] + l[2] * qe[2];
+    const double x2 = x * x;
+    double G, Gp, Gq;
+    eval_G<GKIND>(P, x2, p, q, G, Gp, Gq);
+    S0 += a;
+    SG += a * G;
+    double rho;
+    if (QGEN) {
+      rho = P.q_react * q + P.q_adv * qx + x2 * (P.q_x2p * p + P.q_x2q * q);
+      if (P.q_divr != 0.0) rho -= P.q_divr * (2.0 / x) * q;
+      if (P.q_ibp != 0.0) Q0 += a * q;
+    } else {
+      rho = qx + x2 * p;
+    }
+    const double ar = a * rho;
+    R0 += ar;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Rq[i] += ar * l[i];
+    if (trans) {
+      const double ad = a * (l[0] * dp[0] + l[1] * dp[1] + l[2] * dp[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) T[i] += ad * l[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double dg = P.D2 * gx[i];
+    Fp[i] = S0 * (dg * px + P.D1 * gy[i] * py) + dg * SG;
+    if (trans) Fp[i] += P.inv_dt * T[i];
+    Fq[i] = Rq[i];
+    if (QGEN) Fq[i] += tau * gx[i] * R0 - P.q_ibp * gx[i] * Q0;
+  }
+}
+
 // element rows of local vertex I: 3 column blocks (pp,pq,qp,qq) + (Fp,Fq)
 template <int I, bool QGEN>
 __device__ __forceinline__ void cell_row(const cm_pq_params& P, const TriGeom& g, const CellSums& S,
@@ -126,16 +185,20 @@ template <int I, bool QGEN, bool WANTJ>
 __device__ __forceinline__ void add_row(const cm_pq_params& P, const TriGeom& g, const CellSums& S,
                                         const double* pe, const double* qe, const double* po,
                                         const bool trans, const double tau, double* acc, const int col,
-                                        const int s0, const int s1, const int s2) {
-  double J[3][4], Fp, Fq;
-  cell_row<I, QGEN>(P, g, S, pe, qe, po, trans, tau, J, Fp, Fq);
+                                        const int s0, const int s1, const int s2, const double* Fpr,
+                                        const double* Fqr) {
   if (WANTJ) {
+    double J[3][4], Fp, Fq;
+    cell_row<I, QGEN>(P, g, S, pe, qe, po, trans, tau, J, Fp, Fq);
     acc_add(acc, col, s0, J[0]);
     acc_add(acc, col, s1, J[1]);
     acc_add(acc, col, s2, J[2]);
+    acc[28 * kTX + col] += Fp;
+    acc[29 * kTX + col] += Fq;
+  } else {  // residual only: the rows were computed by cell_resid
+    acc[28 * kTX + col] += Fpr[I];
+    acc[29 * kTX + col] += Fqr[I];
   }
-  acc[28 * kTX + col] += Fp;
-  acc[29 * kTX + col] += Fq;
 }
 
 // 2*kTX threads: thread t < kTX owns cell A = (v0,v1,v3) of quad (ix0-1+t, jq), thread kTX+t owns
@@ -188,6 +251,7 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
     CellSums S;
     double tau = 0.0;
     double pe[3], qe[3], po[3] = {0.0, 0.0, 0.0};
+    double Fpr[3], Fqr[3];  // residual-only pass: element rows of F
     const bool active = quad_ok && row_ok;
     if (active) {
       const int v0 = jq * n1 + qx;
@@ -200,34 +264,37 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
       pe[0] = U0.x; pe[1] = U1.x; pe[2] = U2.x;
       qe[0] = U0.y; qe[1] = U1.y; qe[2] = U2.y;
       if (trans) { po[0] = p_old[v0]; po[1] = p_old[vm]; po[2] = p_old[v3]; }
-      cell_sums<NQ, GKIND, QGEN>(P, g, pe[0], pe[1], pe[2], qe[0], qe[1], qe[2], trans, S);
       if (QGEN && P.supg_stab != 0.0) tau = 0.5 * P.supg_stab * g.hmax();
+      if (WANTJ)
+        cell_sums<NQ, GKIND, QGEN>(P, g, pe[0], pe[1], pe[2], qe[0], qe[1], qe[2], trans, S);
+      else
+        cell_resid<NQ, GKIND, QGEN>(P, g, pe, qe, po, trans, tau, Fpr, Fqr);
     }
     __syncthreads();  // previous write-out (which re-zeroed its buffer) done
     // ---- phase 1: A row 1 -> (row jq, right vertex); B row 1 -> (row jq+1, left vertex) ----------
     if (active) {
       if (!isB) {
-        if (do_lo && ownR) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colR, 2, 3, 5);
+        if (do_lo && ownR) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colR, 2, 3, 5, Fpr, Fqr);
       } else {
-        if (do_up && ownL) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colL, 1, 3, 4);
+        if (do_up && ownL) add_row<1, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colL, 1, 3, 4, Fpr, Fqr);
       }
     }
     __syncthreads();
     // ---- phase 2: A row 0 -> (row jq, left vertex); B row 2 -> (row jq+1, right vertex) ----------
     if (active) {
       if (!isB) {
-        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 4, 6);
+        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 4, 6, Fpr, Fqr);
       } else {
-        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 2, 3);
+        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 2, 3, Fpr, Fqr);
       }
     }
     __syncthreads();
     // ---- phase 3: A row 2 -> (row jq+1, right vertex); B row 0 -> (row jq, left vertex) ----------
     if (active) {
       if (!isB) {
-        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 1, 3);
+        if (do_up && ownR) add_row<2, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accUp, colR, 0, 1, 3, Fpr, Fqr);
       } else {
-        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 5, 6);
+        if (do_lo && ownL) add_row<0, QGEN, WANTJ>(P, g, S, pe, qe, po, trans, tau, accLo, colL, 3, 5, 6, Fpr, Fqr);
       }
     }
     __syncthreads();

@@ -198,7 +198,7 @@ int cm_spmv(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
 
 /* Newton linear solve on structured (RectangleMesh-numbered) meshes: right-preconditioned
  * GMRES(restart) on the row-equilibrated Jacobian with the block-lower-triangular field split
- * [[App,0],[Aqp,Aqq]]: p-block = one geometric-multigrid V(1,1) cycle (zebra x-line relaxation,
+ * [[App,0],[Aqp,Aqq]]: p-block = one geometric-multigrid V(1,2) cycle (zebra x-line relaxation,
  * Galerkin coarse operators, dense coarsest solve), q-block = one zebra x-line sweep.
  *   cm_pqs_setup : once per Jacobian (vals = assembled J with Dirichlet rows applied): extracts and
  *                  scales the four stencil blocks, builds the hierarchy and the line factors.
