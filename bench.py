@@ -124,6 +124,8 @@ def workload_config(args, nx, ny):
                             or args.gpus == 1 else f"one mesh strip-partitioned by vertex rows over {args.gpus} GPUs "
                             "(P2P halo / all-gather / all-reduce kernels over NVLink)"),
             "l2_policy": "inputs larger than L2 (Jacobian 1.9 GB, Krylov basis > 1 GB)",
+            "linear_solver": ("pivoting banded LU (cm_blu_*) + 1 refinement step" if getattr(args, "linear_solver", "gmres") == "lu"
+                              else "GMRES(40) + field split + V(1,2) multigrid / zebra line relaxation"),
             "linear_rtol": LIN_RTOL}
 
 
@@ -212,6 +214,11 @@ def gpu_arm(args):
     if args.variant == "supg":
         form = cm.PQPrimalForm.manufactured(V, "supg")
         bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    elif args.variant == "galerkin":   # BASELINE config 2 (…MixedPrimal_convergence.py:108-131): needs the LU path
+        bd.set_all(0)
+        cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+        form = cm.PQPrimalForm.manufactured(V, "galerkin")
+        bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
     else:   # C0IP variants of BASELINE config 3 (…_C0IP.py:141-147 / test_for_paper_convergence.py:140-153)
         cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
         cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
@@ -236,7 +243,7 @@ def gpu_arm(args):
     else:
         u = cm.Function(V)
         solver = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
-        solver.parameters["newton_solver"]["linear_solver"] = "gmres"
+        solver.parameters["newton_solver"]["linear_solver"] = "mumps" if args.linear_solver == "lu" else "gmres"
         solver.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
         if args.variant != "supg":
             solver.parameters["newton_solver"]["krylov_solver"]["restart"] = 100
@@ -413,7 +420,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096, help="mesh is nx x nx/2 (default: the 16 Mi-cell mesh)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", default="supg", choices=["supg", "c0ip_minus", "c0ip_paper"],
+    ap.add_argument("--linear-solver", default="gmres", choices=["gmres", "lu"],
+                    help="gmres: multigrid-preconditioned Krylov path (default, the 16 Mi-cell hot path); "
+                         "lu: pivoting banded LU on the GPU (needed by --variant galerkin)")
+    ap.add_argument("--variant", default="supg", choices=["supg", "galerkin", "c0ip_minus", "c0ip_paper"],
                     help="q-equation variant (default: the SUPG headline workload)")
     ap.add_argument("--instances", action="store_true",
                     help="N>1: independent problem instance per GPU (weak scaling) instead of strip partitioning")

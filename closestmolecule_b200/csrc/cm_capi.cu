@@ -6,8 +6,9 @@
 
 namespace cm {
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 double g_alg_bytes = 0.0;
+const char* last_error_text() { return g_err; }
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -60,7 +61,7 @@ int cm_version(void) { return 100; }
 
 const char* cm_last_error(void) { return g_err; }
 
-int64_t cm_launch_count(void) { return (int64_t)g_launches; }
+int64_t cm_launch_count(void) { return (int64_t)g_launches.load(); }
 
 double cm_algorithmic_bytes(void) { return g_alg_bytes; }
 

@@ -1,6 +1,8 @@
 // Shared device helpers: error handling, FIAT quadrature tables, P1 geometry, the G nonlinearity.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -29,7 +31,8 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<long long> g_launches;  // kernels launched by this library (bench.py's gpu_launches);
+                                           // atomic: the two chains of the direct solver launch from two threads
 extern double g_alg_bytes;    // algorithmic (compulsory) bytes of the kernels launched so far (Newton-step roofline)
 #define CM_BYTES(x) (cm::g_alg_bytes += (double)(x))
 #define CM_LAUNCH_CHECK()      \

@@ -70,11 +70,10 @@ def run(nx, cpu):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    cpu_max = 512
-    if "--cpu-max" in sys.argv:
-        cpu_max = int(sys.argv[sys.argv.index("--cpu-max") + 1])
-        args = [a for a in args if a != str(cpu_max)] if False else [a for a in sys.argv[1:] if not a.startswith("--")]
-        args.remove(str(cpu_max))
-    for a in args:
-        run(int(a), int(a) <= cpu_max)
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("nx", type=int, nargs="+", help="mesh is nx x nx/2")
+    ap.add_argument("--cpu-max", type=int, default=512, help="largest nx that is also solved by SuperLU on the host")
+    a = ap.parse_args()
+    for n in a.nx:
+        run(n, n <= a.cpu_max)
