@@ -26,6 +26,7 @@ bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1)
 # single-GPU reference
 u = cm.Function(V)
 s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, u, bcs))
+s.parameters["newton_solver"]["linear_solver"] = "gmres"   # the same Krylov path as the distributed solver
 s.parameters["newton_solver"]["absolute_tolerance"] = 1e-8
 s.parameters["newton_solver"]["relative_tolerance"] = 1e-8
 it1, _ = s.solve()
