@@ -317,7 +317,7 @@ def gpu_arm(args):
     # ---- e2e: host buffers in, host buffers out, through the public Newton-step call ------------
     h_in = torch.empty(u0[own].numel(), dtype=torch.float64, pin_memory=True)
     h_in.copy_(u0[own])
-    h_out = torch.empty_like(h_in)
+    h_out = torch.empty(h_in.numel(), dtype=torch.float64, pin_memory=True)   # empty_like would not be pinned
     e2e_steps = max(1, min(args.steps, 3))
     dst = uvec[own]
     for _ in range(1):              # untimed warm-up of the copy path
