@@ -75,7 +75,8 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
                       int* err, cudaStream_t st, int r0 = 0, int r1 = -1, double* QQx = nullptr,
-                      int* has_extra = nullptr);
+                      int* has_extra = nullptr, int* wide_host = nullptr);
+int st_lump_extras(int nx, int ny, const double* QQ, const double* QQx, double* QQl, cudaStream_t st);
 int st_split_scale(int nv, const double* b, const double* sp, const double* sq, double* out,
                    cudaStream_t st, int vb = 0, int ve = -1);
 int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb = 0, int ve = -1);

@@ -35,10 +35,16 @@ struct PQSolver {
   // (no Aqp z_p correction).  Same GMRES iteration counts on the SUPG problems (the triangular
   // coupling costs GMRES nothing here), one residual pass and one halo exchange less per iteration.
   bool diag_split = true;
+  bool upper_split = false;  // block-upper-triangular [[App, Apq], [0, Aqq]]: q first, then p with r_p - Apq z_q
   bool dense_coarse;
   PQSLevel lev[kMaxLevels];
+  PQSLevel qlev[kMaxLevels];  // hierarchy of the 7-point stand-in of the C0IP q-block (same grids as lev)
+  double* qAinv;              // its coarsest-grid inverse
+  bool q_mg = false;          // C0IP: one V-cycle on the q-block instead of plain line sweeps (CM_Q_MG=1)
+  int q_sweeps_wide = 6;      // C0IP: line sweeps on the 7-point stand-in of the q-block
   double *PP, *PQ, *QP, *QQ, *sp, *sq;
   double* QQx;      // 6 extra q-q diagonals of the C0IP interior-facet pattern
+  double* QQl;      // 7-point stand-in of the 13-point q-block for the line relaxation (st_lump_extras)
   int* has_extra;   // device flag: any of them non-zero
   double *qlf, *qiu, *qcu;
   double *Ainv, *Mwork;
@@ -55,6 +61,9 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CM_PRECOND_LOWER"); mode = (e && atoi(e) != 0) ? 1 : 0; }
     S.diag_split = mode == 0;
+    static int upper = -1;
+    if (upper < 0) { const char* e = getenv("CM_PRECOND_UPPER"); upper = (e && atoi(e) != 0) ? 1 : 0; }
+    S.upper_split = upper != 0;
     // tuning knobs; defaults 2 q-sweeps and V(1,2): measured at 16 Mi cells (profiles/README.md)
     // V(1,1) 13 its / 33.9 ms, V(1,2) 11 / 32.9, V(2,2) 10 / 33.9, V(1,0) 19 / 42.4; q-sweeps 1: +1 it
     static int qs = -1, pre = -1, post = -1, ld = -1;
@@ -86,6 +95,7 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
   S.QP = take(7 * V);
   S.QQ = take(7 * V);
   S.QQx = take(6 * V);
+  S.QQl = take(7 * V);
   S.has_extra = (int*)take(2);
   S.sp = take(V);
   S.sq = take(V);
@@ -120,6 +130,33 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
   S.dense_coarse = nc <= (size_t)kCoarseDenseMax;
   S.Ainv = take(S.dense_coarse ? nc * nc : 2);
   S.Mwork = take(S.dense_coarse ? 2 * nc * nc : 2);
+  for (int k = 0; k < S.nlev; ++k) {
+    PQSLevel& Q = S.qlev[k];
+    const PQSLevel& L = S.lev[k];
+    Q.nx = L.nx;
+    Q.ny = L.ny;
+    Q.n = L.n;
+    Q.A = (k == 0) ? S.QQl : take(7 * Q.n);
+    Q.lf = (k == 0) ? S.qlf : take(Q.n);
+    Q.iu = (k == 0) ? S.qiu : take(Q.n);
+    Q.cu = (k == 0) ? S.qcu : take(Q.n);
+    Q.r = (k == 0) ? L.r : take(Q.n);   // level-0 scratch is shared: the two cycles run one after the other
+    Q.x = (k == 0) ? nullptr : take(Q.n);
+    Q.b = (k == 0) ? nullptr : take(Q.n);
+  }
+  S.qAinv = take(S.dense_coarse ? nc * nc : 2);
+  {
+    static int qmg = -1;
+    // 4 Mi cells (profiles/README.md): the V-cycle on the q-block helps the minus-sign variant (114 GMRES
+    // iterations) but diverges on the "paper" variant (Galerkin coarse operators of the transport part): off
+    // by default; line sweeps on the 7-point stand-in instead: 3 sweeps 94 / 222 iterations ("paper" /
+    // minus-sign variant), 6 sweeps 89 / 123
+    if (qmg < 0) { const char* e = getenv("CM_Q_MG"); qmg = e ? atoi(e) : 0; }
+    S.q_mg = qmg != 0;
+    static int qsw = -1;
+    if (qsw < 0) { const char* e = getenv("CM_Q_SWEEPS_WIDE"); qsw = (e && atoi(e) > 0) ? atoi(e) : 6; }
+    S.q_sweeps_wide = qsw;
+  }
   S.err = (int*)take(4);
   S.gm = take(gmres_workspace_doubles(2 * (long long)V, restart));
   S.total_doubles = off;
@@ -154,24 +191,29 @@ static int zebra_sweep(const PQSLevel& L, const double* A, const double* lf, con
   return st_zebra(L.nx, L.ny, 1, A, lf, iu, cu, b, x, 0, st, 0, -1, L.r);
 }
 
-static int vcycle(PQSolver& S, int l, const double* b, double* x, cudaStream_t st) {
-  PQSLevel& L = S.lev[l];
+static int vcycle_on(PQSolver& S, PQSLevel* lev, const double* Ainv, int l, const double* b, double* x,
+                     cudaStream_t st) {
+  PQSLevel& L = lev[l];
   int rc;
   if (l == S.nlev - 1) {
-    if (S.dense_coarse) return st_coarse_apply((int)L.n, S.Ainv, b, x, st);
+    if (S.dense_coarse) return st_coarse_apply((int)L.n, Ainv, b, x, st);
     rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, true, st);
     for (int s = 1; s < 30 && !rc; ++s) rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
     return rc;
   }
-  PQSLevel& C = S.lev[l + 1];
+  PQSLevel& C = lev[l + 1];
   for (int s = 0; s < S.pre_smooth; ++s)
     if ((rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, s == 0, st))) return rc;
   if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st))) return rc;
   if ((rc = st_restrict(C.nx, C.ny, L.r, C.b, st))) return rc;
-  if ((rc = vcycle(S, l + 1, C.b, C.x, st))) return rc;
+  if ((rc = vcycle_on(S, lev, Ainv, l + 1, C.b, C.x, st))) return rc;
   if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st))) return rc;
   for (int s = 0; s < S.post_smooth && !rc; ++s) rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
   return rc;
+}
+
+static int vcycle(PQSolver& S, int l, const double* b, double* x, cudaStream_t st) {
+  return vcycle_on(S, S.lev, S.Ainv, l, b, x, st);
 }
 
 // Replays a fixed kernel sequence (one preconditioner application) as a CUDA graph: captured on a
@@ -254,9 +296,11 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
   }
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
   CM_CUDA(cudaMemsetAsync(S.has_extra, 0, sizeof(int), st));
+  int wide = 0;
   if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err, st, 0,
-                              -1, S.QQx, S.has_extra)))
+                              -1, S.QQx, S.has_extra, &wide)))
     return rc;
+  if (wide && (rc = st_lump_extras(nx, ny, S.QQ, S.QQx, S.QQl, st))) return rc;
   for (int l = 0; l < S.nlev; ++l) {
     PQSLevel& L = S.lev[l];
     if ((rc = st_line_factor(L.nx, L.ny, L.A, L.lf, L.iu, L.cu, S.err, st))) return rc;
@@ -265,7 +309,17 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
   }
   PQSLevel& C = S.lev[S.nlev - 1];
   if (S.dense_coarse && (rc = st_coarse_invert(C.nx, C.ny, C.A, S.Mwork, S.Ainv, S.err, st))) return rc;
-  if ((rc = st_line_factor(nx, ny, S.QQ, S.qlf, S.qiu, S.qcu, S.err, st))) return rc;
+  if ((rc = st_line_factor(nx, ny, wide ? S.QQl : S.QQ, S.qlf, S.qiu, S.qcu, S.err, st))) return rc;
+  if (wide && S.q_mg) {  // Galerkin hierarchy of the 7-point stand-in of the C0IP q-block
+    for (int l = 0; l < S.nlev; ++l) {
+      PQSLevel& Q = S.qlev[l];
+      if (l > 0 && (rc = st_line_factor(Q.nx, Q.ny, Q.A, Q.lf, Q.iu, Q.cu, S.err, st))) return rc;
+      if (l + 1 < S.nlev && (rc = st_rap(S.qlev[l + 1].nx, S.qlev[l + 1].ny, Q.A, S.qlev[l + 1].A, st)))
+        return rc;
+    }
+    PQSLevel& QC = S.qlev[S.nlev - 1];
+    if (S.dense_coarse && (rc = st_coarse_invert(QC.nx, QC.ny, QC.A, S.Mwork, S.qAinv, S.err, st))) return rc;
+  }
   return check_err_flag(S, st, "cm_pqs_setup");
 }
 
@@ -294,23 +348,32 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
     int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st);
     if (e) return e;
     return replay.run(z, st, [&](cudaStream_t s_) -> int {
-      int e2 = vcycle(S, 0, S.ru, z, s_);
-      if (e2) return e2;
+      // 13-point (C0IP) q-block: the relaxation runs on its 7-point stand-in (st_lump_extras); the outer
+      // Krylov operator keeps the full stencil
+      const double* Aq = wide ? S.QQl : S.QQ;
+      auto q_sweeps = [&](const double* bq) -> int {
+        if (wide && S.q_mg) return vcycle_on(S, S.qlev, S.qAinv, 0, bq, z + V, s_);
+        int e3 = CM_OK;
+        const int nsw = wide ? S.q_sweeps_wide : S.q_sweeps;
+        for (int sw = 0; sw < nsw && !e3; ++sw) {
+          e3 = st_zebra(nx, ny, 0, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, sw == 0 ? 1 : 0, s_, 0, -1, S.lev[0].r);
+          if (!e3) e3 = st_zebra(nx, ny, 1, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, 0, s_, 0, -1, S.lev[0].r);
+        }
+        return e3;
+      };
+      int e2;
+      if (S.upper_split) {  // z_q = Mq^{-1} r_q, then z_p = Mp^{-1} (r_p - Apq z_q)
+        if ((e2 = q_sweeps(S.ru + V))) return e2;
+        if ((e2 = st_residual(nx, ny, S.PQ, S.ru, z + V, S.tq, s_))) return e2;
+        return vcycle(S, 0, S.tq, z, s_);
+      }
+      if ((e2 = vcycle(S, 0, S.ru, z, s_))) return e2;
       const double* bq = S.ru + V;
       if (!S.diag_split) {
         if ((e2 = st_residual(nx, ny, S.QP, S.ru + V, z, S.tq, s_))) return e2;
         bq = S.tq;
       }
-      // with the wide pattern a colour also couples to lines of its own colour (two rows away): the
-      // iterate must start from zero there too, or M^{-1} would depend on the previous application
-      if (wide && cudaMemsetAsync(z + V, 0, sizeof(double) * V, s_) != cudaSuccess) return (int)CM_E_CUDA;
-      for (int sw = 0; sw < S.q_sweeps && !e2; ++sw) {
-        e2 = st_zebra(nx, ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, bq, z + V, (sw == 0 && !wide) ? 1 : 0, s_, 0, -1,
-                      S.lev[0].r, wide ? S.QQx : nullptr, S.has_extra);
-        if (!e2)
-          e2 = st_zebra(nx, ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, bq, z + V, 0, s_, 0, -1, S.lev[0].r,
-                        wide ? S.QQx : nullptr, S.has_extra);
-      }
+      e2 = q_sweeps(bq);
       return e2;
     });
   };

@@ -89,6 +89,35 @@ extract_blocks_kernel(const int nx, const int nv, const int* __restrict__ nrowpt
   }
 }
 
+// 7-point stand-in for the 13-point C0IP q-block, used by the line relaxation only: every interior-facet
+// couple is replaced by the linear extrapolation of its end point through stencil neighbours,
+//   q(-1,+1) ~ q(-1,0)+q(0,+1)-q(0,0),  q(+1,-1) ~ q(+1,0)+q(0,-1)-q(0,0),  q(+1,+2) ~ q(+1,+1)+q(0,+1)-q(0,0),
+//   q(-1,-2) ~ q(-1,-1)+q(0,-1)-q(0,0), q(+2,+1) ~ q(+1,+1)+q(+1,0)-q(0,0), q(-2,-1) ~ q(-1,-1)+q(-1,0)-q(0,0),
+// so that the lumped operator acts like the full one on affine functions (which the gradient-jump penalty
+// of ..._C0IP.py:147 annihilates) and stays within a factor of two of it on the roughest modes
+// (1-D analogue: [1,-4,6,-4,1] -> [-2,4,-2]).  Lagging the six diagonals inside the relaxation instead
+// is not a convergent splitting.
+__global__ void __launch_bounds__(kSB)
+lump_extras_kernel(const int nv, const double* __restrict__ QQ, const double* __restrict__ QQx,
+                   double* __restrict__ QQl) {
+  const int v = blockIdx.x * kSB + threadIdx.x;
+  if (v >= nv) return;
+  double a[7], x[6];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) a[k] = QQ[(size_t)k * nv + v];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) x[e] = QQx[(size_t)e * nv + v];
+  a[2] += x[0] + x[5];
+  a[5] += x[0] + x[2];
+  a[4] += x[1] + x[4];
+  a[1] += x[1] + x[3];
+  a[6] += x[2] + x[4];
+  a[0] += x[3] + x[5];
+  a[3] -= x[0] + x[1] + x[2] + x[3] + x[4] + x[5];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) QQl[(size_t)k * nv + v] = a[k];
+}
+
 // interleaved b -> split, scaled:  out[v] = sp*b[2v], out[nv+v] = sq*b[2v+1]
 __global__ void __launch_bounds__(kSB)
 split_scale_kernel(const int nv, const double2* __restrict__ b, const double* __restrict__ sp,
@@ -1054,9 +1083,18 @@ static inline void row_range(int ny, int n1, int r0, int r1, int& vb, int& ve) {
   ve = r1 * n1;
 }
 
+int st_lump_extras(int nx, int ny, const double* QQ, const double* QQx, double* QQl, cudaStream_t st) {
+  const int nv = (nx + 1) * (ny + 1);
+  lump_extras_kernel<<<grid_for(nv), kSB, 0, st>>>(nv, QQ, QQx, QQl);
+  CM_BYTES((double)nv * 20 * 8.0);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
-                      int* err, cudaStream_t st, int r0, int r1, double* QQx, int* has_extra) {
+                      int* err, cudaStream_t st, int r0, int r1, double* QQx, int* has_extra,
+                      int* wide_host) {
   const int nv = (nx + 1) * (ny + 1);
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
@@ -1069,6 +1107,7 @@ int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const
   extract_blocks_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, nv, nrowptr, ncol, (const double2*)vals,
                                                            PP, PQ, QP, QQ, sp, sq, err, vb, ve,
                                                            nnz != nnz7 ? QQx : nullptr, has_extra);
+  if (wide_host) *wide_host = (nnz != nnz7 && QQx != nullptr) ? 1 : 0;
   CM_BYTES((double)(ve - vb) * (2 * 28 * 8.0 + 16.0));  // CSR values in, 4 stencil blocks + scalings out
   CM_LAUNCH_CHECK();
   return CM_OK;
