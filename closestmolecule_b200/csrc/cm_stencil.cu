@@ -900,7 +900,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 }
 
 template <int E>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(896, 1)
 line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nlines,
                       const double* __restrict__ lf, const double* __restrict__ iu,
                       const double* __restrict__ cu, const double* __restrict__ rhs,
@@ -919,7 +919,8 @@ line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nl
   int l = blockIdx.x;
   if (l >= nlines) return;
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    // one phase = the four arrays of one line: four arrive.expect_tx (one per array) complete it
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -929,52 +930,61 @@ line_solve_tma_kernel(const int nx, const int ny, const int jfirst, const int nl
   auto shift_of = [&](int a, size_t base) -> int {
     return (int)((reinterpret_cast<unsigned long long>(src[a] + base) >> 3) & 1ull);
   };
-  auto issue = [&](int line) {
+  // array a of `line` -> buf[a]; called by all threads after a barrier that ended the reads of buf[a]
+  auto issue_one = [&](int a, int line) {
     const size_t base = (size_t)(jfirst + 2 * line) * n1;
+    const int shf = shift_of(a, base);
+    const int cnt = (n1 + shf) & ~1;  // even number of elements copied by TMA
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      unsigned total = 0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) total += (unsigned)((n1 + shift_of(a, base)) & ~1) * 8u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int shf = shift_of(a, base);
-        const int cnt = (n1 + shf) & ~1;  // even number of elements copied by TMA
-        tma_bulk_g2s(buf[a], src[a] + base - shf, (unsigned)cnt * 8u, &mbar);
-      }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"((unsigned)cnt * 8u) : "memory");
+      tma_bulk_g2s(buf[a], src[a] + base - shf, (unsigned)cnt * 8u, &mbar);
     }
-    if (tid >= 32 && tid < 36) {  // odd trailing element
-      const int a = tid - 32;
-      const int shf = shift_of(a, base);
-      const int cnt = (n1 + shf) & ~1;
-      if (cnt < n1 + shf) buf[a][cnt] = src[a][base - shf + cnt];
-    }
+    if (tid == 32 && cnt < n1 + shf) buf[a][cnt] = src[a][base - shf + cnt];  // odd trailing element
   };
-  issue(l);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) issue_one(a, l);
   for (; l < nlines; l += gridDim.x) {
     const size_t lbase = (size_t)(jfirst + 2 * l) * n1;
     const int sh0 = shift_of(0, lbase), sh1 = shift_of(1, lbase), sh2 = shift_of(2, lbase), sh3 = shift_of(3, lbase);
+    const bool more = l + gridDim.x < nlines;
+    const int lnext = l + gridDim.x;
     HT(0);
-    {  // wait for the bulk copies of this line
+    {  // wait for the bulk copies of this line (bounded: a lost copy must not hang the GPU)
       unsigned done = 0;
+      long long spins = 0;
       while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1ll << 26)) __trap();
       }
       parity ^= 1u;
     }
-    __syncthreads();  // the plain-load tail element is visible too
+    __syncthreads();  // the plain-load tail elements are visible too
     HT(1);
+    // shared -> registers array by array; each buffer is refilled for the CTA's next line as soon as it
+    // has been read, so the copies of the next line are in flight during the rest of this phase and the scans
     double r[E], lv[E], iv[E], cv[E];
 #pragma unroll
     for (int e = 0; e < E; ++e)
-      if (e < ne) {
-        r[e] = buf[0][sh0 + i0 + e]; lv[e] = buf[1][sh1 + i0 + e];
-        iv[e] = buf[2][sh2 + i0 + e]; cv[e] = buf[3][sh3 + i0 + e];
-      }
+      if (e < ne) r[e] = buf[0][sh0 + i0 + e];
     __syncthreads();
-    if (l + gridDim.x < nlines) issue(l + gridDim.x);
+    if (more) issue_one(0, lnext);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) lv[e] = buf[1][sh1 + i0 + e];
+    __syncthreads();
+    if (more) issue_one(1, lnext);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) iv[e] = buf[2][sh2 + i0 + e];
+    __syncthreads();
+    if (more) issue_one(2, lnext);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (e < ne) cv[e] = buf[3][sh3 + i0 + e];
+    __syncthreads();
+    if (more) issue_one(3, lnext);
     HT(2);
     Affine m{1.0, 0.0};
 #pragma unroll
@@ -1250,7 +1260,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
     static int dbg2 = -1;
     if (dbg2 < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg2 = e ? atoi(e) : 0; }
     const int grid = nlines < 148 ? nlines : 148;
-    if (pipe_mode >= 4 && n1 <= 5 * 1024 && (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
+    if (pipe_mode >= 4 && n1 <= 5 * 896 && (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
       static bool attr4 = false;
       if (!attr4) {
         CM_CUDA(cudaFuncSetAttribute(line_solve_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
