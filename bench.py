@@ -117,6 +117,13 @@ UNIT = "cells/s"
 
 
 def workload_config(args, nx, ny):
+    if getattr(args, "weak", False) and args.gpus > 1:
+        return {"workload": f"P-Q CG1xCG1 manufactured {getattr(args, 'variant', 'supg').upper()} Newton step on ONE "
+                            f"RectangleMesh {nx}x{ny} ({2 * nx * ny} cells) strip-partitioned over {args.gpus} GPUs "
+                            f"({2 * nx * ny // args.gpus} cells per GPU: weak scaling)",
+                "nx": nx, "ny": ny, "cells": 2 * nx * ny, "cells_per_gpu": 2 * nx * ny // args.gpus,
+                "parallelism": "one mesh strip-partitioned by vertex rows (P2P halo / all-gather / all-reduce kernels over NVLink)",
+                "l2_policy": "inputs larger than L2", "linear_rtol": LIN_RTOL}
     return {"workload": f"P-Q CG1xCG1 manufactured {getattr(args, 'variant', 'supg').upper()} Newton step on RectangleMesh {nx}x{ny} "
                         f"({2 * nx * ny} cells) per GPU",
             "nx": nx, "ny": ny, "cells_per_gpu": 2 * nx * ny, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
@@ -204,9 +211,13 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
     nx = args.nx
     ny = nx // 2
+    if args.weak and world > 1:      # weak scaling: the strip-partitioned mesh grows with the GPUs (nx x nx/2 cells x 2 per GPU)
+        ny = ny * world
     lib = _capi.lib()
 
-    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny, device=dev)
+    # weak scaling keeps the cell shape: the domain grows in r1 with the number of GPUs
+    top = float(world) if (args.weak and world > 1) else 1.0
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, top), nx, ny, device=dev)
     P1 = cm.FiniteElement("CG", mesh.ufl_cell(), 1)
     V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
     bd = cm.MeshFunction("size_t", mesh, 1, 0)
@@ -362,7 +373,7 @@ def gpu_arm(args):
             "metric": METRIC, "value": (1 if strong else world) * cells / (ms_step * 1e-3), "unit": UNIT,
             "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if (strong and not args.weak) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, nx, ny),
             "newton_step_ms": ms_step, "linear_iterations_per_step": lin_its,
             "assembly_ms": asm_ms, "assembly_cells_per_s": cells / (asm_ms * 1e-3),
@@ -425,6 +436,9 @@ def main():
                          "lu: pivoting banded LU on the GPU (needed by --variant galerkin)")
     ap.add_argument("--variant", default="supg", choices=["supg", "galerkin", "c0ip_minus", "c0ip_paper"],
                     help="q-equation variant (default: the SUPG headline workload)")
+    ap.add_argument("--weak", action="store_true",
+                    help="N > 1: strip-partition a mesh of N x (nx x nx/2 x 2) cells (fixed work per GPU) "
+                         "instead of the same 16 Mi-cell mesh")
     ap.add_argument("--instances", action="store_true",
                     help="N>1: independent problem instance per GPU (weak scaling) instead of strip partitioning")
     args = ap.parse_args()
