@@ -1,0 +1,300 @@
+"""Oracle for the k=1 "paper" system RT2 x DG1 x CG2 of convergence/test_for_paper_convergence.py (deg=1),
+whose two recorded error tables are at :209-225 (test infrastructure; SURVEY section 8f row 1, second half).
+
+Same weak form as oracle/paper_m0.py (:137-153) on the next element family:
+  s in RT2 (FEniCS numbering of the degree: P1^2 + x P1~, 8 per cell), p in DG1 (3 per cell), q in CG2 (6 per cell).
+Bases (any basis of the same spaces gives the same discrete solution; FIAT's nodal bases are not needed):
+  RT2: for the facet i opposite local vertex i with end points j < k: lambda_j N_i, lambda_k N_i with the RT0
+       function N_i = sigma_i (x - X_i) / (2|K|) (normal trace lambda/|F| on its own facet, zero on the others:
+       H(div)-conforming with one dof per (facet, end point)); interior: lambda_1 N_1, lambda_2 N_2 (unsigned).
+  DG1: the barycentric coordinates.   CG2: lambda_i (2 lambda_i - 1) at the vertices, 4 lambda_j lambda_k on the edges.
+Global dofs [2 per edge | 2 per cell | 3 per cell | vertices | edges]: 3E + 5C + V, the DoF column of the table.
+Quadrature degree 6 everywhere (:38), stab2 = 1.0*(deg+1) = 2 (:71), stab = 0.1 as the comment at :70 says
+("0.05 for k=0 // 0.1 for k=1"; the first recorded k=1 table is reproduced with it), hK = FacetArea (:97).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import fem
+from .fem import DOLFIN_EPS
+from .paper_m0 import D1, D2, _sym, p_ex, q_ex
+
+DEG = 1
+OTHER = ((1, 2), (0, 2), (0, 1))          # end points (local vertices, ascending) of the facet opposite vertex i
+
+
+def p2_basis(lam, g):
+    """lam [..., 3] barycentric coordinates, g [C, 3, 2] their gradients -> values [..., 6], gradients [..., 6, 2]
+    (leading dims of lam must broadcast against [C, nq])."""
+    val = np.concatenate([lam * (2 * lam - 1),
+                          np.stack([4 * lam[..., j] * lam[..., k] for j, k in OTHER], -1)], -1)
+    gv = (4 * lam - 1)[..., None] * g[:, None, :, :]
+    ge = np.stack([4 * (lam[..., j, None] * g[:, None, k, :] + lam[..., k, None] * g[:, None, j, :])
+                   for j, k in OTHER], -2)
+    return val, np.concatenate([gv, ge], -2)
+
+
+class PaperM1:
+    def __init__(self, n, stab=0.1, stab2=1.0 * (DEG + 1)):
+        self.mesh = mesh = fem.unit_square_mesh(n, n)
+        self.fc = fc = mesh.facets()
+        self.E, self.C, self.V = fc.verts.shape[0], mesh.num_cells, mesh.num_vertices
+        E, C, V = self.E, self.C, self.V
+        self.N = 3 * E + 5 * C + V
+        self.stab, self.stab2 = stab, stab2
+        self.gamma = stab / (DEG + 1) ** 3.5                                          # :144
+        self.sym = _sym()
+        X = mesh.coords
+        left = lambda P: fem.near(P[..., 0], 0.0)
+        right = lambda P: fem.near(P[..., 0], 1.0)
+        rest = lambda P: fem.near(P[..., 1], 0.0) | fem.near(P[..., 1], 1.0)
+        self.markers = fem.mark_facets(mesh, [(left, 30), (right, 31), (rest, 32)])
+        cells = mesh.cells.astype(np.int64)
+        fa = np.stack([cells[:, 1], cells[:, 0], cells[:, 0]], 1)
+        fb = np.stack([cells[:, 2], cells[:, 2], cells[:, 1]], 1)
+        key = np.minimum(fa, fb) * V + np.maximum(fa, fb)
+        allkey = fc.verts[:, 0].astype(np.int64) * V + fc.verts[:, 1]
+        self.cell_edges = ce = np.searchsorted(allkey, key)                           # [C,3]
+        A, B = X[fc.verts[:, 0]], X[fc.verts[:, 1]]
+        t = B - A
+        self.elen = np.sqrt((t ** 2).sum(1))
+        self.enorm = np.stack([t[:, 1], -t[:, 0]], 1) / self.elen[:, None]
+        det, grads, Xc = fem.cell_geometry(mesh)
+        self.area, self.Xc, self.grads = 0.5 * np.abs(det), Xc, grads
+        mid = 0.5 * (A + B)[ce]
+        self.sign = np.sign(((mid - Xc) * self.enorm[ce]).sum(-1))                    # [C,3]
+        self.pts, self.wts = fem.triangle_rule(6)
+        self.lam = np.stack([1 - self.pts[:, 0] - self.pts[:, 1], self.pts[:, 0], self.pts[:, 1]], 1)   # [nq,3]
+        self.P = np.einsum("qi,cid->cqd", self.lam, Xc)
+        # global dof numbers of the 17 local dofs
+        cid = np.arange(C)[:, None]
+        sd = np.concatenate([np.stack([2 * ce[:, i], 2 * ce[:, i] + 1], 1) for i in range(3)]
+                            + [2 * E + 2 * cid, 2 * E + 2 * cid + 1], 1)                 # [C,8]
+        pd = 2 * E + 2 * C + 3 * cid + np.arange(3)[None, :]
+        self.q0 = 2 * E + 5 * C
+        qd = np.concatenate([self.q0 + cells, self.q0 + V + ce], 1)                    # [C,6]
+        self.sd, self.pd, self.qd = sd, pd, qd
+        self.cell_dofs = np.concatenate([sd, pd, qd], 1)                              # [C,17]
+        ext = fc.exterior
+        m = self.markers[ext]
+        self.ext = ext
+        self.k_adv = ((m == 30) | (m == 32)).astype(float)
+        self.k_dat = (m == 31).astype(float)
+
+    # -- bases at points given by barycentric coordinates lam [C, nq, 3] (or [nq, 3]) ------------------
+    def rt_basis(self, lam, P, cells=None):
+        """values R [C,nq,8,2], d/dx of the x component and d/dy of the y component [C,nq,8]."""
+        idx = slice(None) if cells is None else cells
+        Xc, g, area, sign = self.Xc[idx], self.grads[idx], self.area[idx], self.sign[idx]
+        if lam.ndim == 2:
+            lam = np.broadcast_to(lam[None], (Xc.shape[0],) + lam.shape)
+        R, dxx, dyy = [], [], []
+        funcs = [(i, a, sign[:, i]) for i in range(3) for a in OTHER[i]] + [(1, 1, None), (2, 2, None)]
+        for i, a, sg in funcs:
+            c = (1.0 if sg is None else sg) / (2 * area)                                # [C]
+            d = P - Xc[:, None, i, :]                                                  # [C,nq,2]
+            la = lam[..., a]
+            R.append(la[..., None] * d * c[:, None, None])
+            dxx.append(c[:, None] * (g[:, None, a, 0] * d[..., 0] + la))
+            dyy.append(c[:, None] * (g[:, None, a, 1] * d[..., 1] + la))
+        return np.stack(R, 2), np.stack(dxx, 2), np.stack(dyy, 2)
+
+    def assemble(self, u, want_jac=True):
+        mesh, C = self.mesh, self.C
+        lam, P = self.lam, self.P
+        x, y = P[:, :, 0], P[:, :, 1]
+        W = (4 * np.pi * x * y) ** 2
+        a = self.wts[None, :] * (2 * self.area)[:, None] * W
+        R, dxx, dyy = self.rt_basis(lam, P)
+        Rx, Ry = R[..., 0], R[..., 1]
+        dr = dxx + dyy + 2 * Rx / x[..., None] + 2 * Ry / y[..., None]                # div_rad(Psi)
+        drD = D2 * (dxx + 2 * Rx / x[..., None]) + D1 * (dyy + 2 * Ry / y[..., None])  # div_rad(D Psi)
+        chi = np.broadcast_to(lam[None], (C,) + lam.shape)                             # DG1
+        lamc = chi
+        phi, gphi = p2_basis(lamc, self.grads)
+        se, pe, qe = u[self.sd], u[self.pd], u[self.qd]
+        s = np.einsum("cqad,ca->cqd", R, se)
+        p = np.einsum("cqb,cb->cq", chi, pe)
+        q = np.einsum("cqk,ck->cq", phi, qe)
+        x2 = x * x
+        iq = 1.0 / (q + DOLFIN_EPS)
+        G, Gp, Gq = x2 * p * p * iq, 2 * x2 * p * iq, -x2 * p * p * iq * iq
+        f2, f3 = self.sym["f2"](x, y), self.sym["f3"](x, y)
+        Fe = np.zeros((C, 17))
+        Fe[:, :8] = np.einsum("cq,cqa->ca", a, np.einsum("cqd,cqad->cqa", s, R) + G[..., None] * Rx
+                              - p[..., None] * dr)
+        Fe[:, 8:11] = np.einsum("cq,cqb->cb", a * (-np.einsum("cqa,ca->cq", drD, se) + f2), chi)
+        Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * (-(2 / x) * q + x2 * p - f3), phi)
+                      - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
+        b = np.zeros(self.N)
+        np.add.at(b, self.cell_dofs.ravel(), Fe.ravel())
+        rows, cols, vals = [], [], []
+        if want_jac:
+            Je = np.zeros((C, 17, 17))
+            Je[:, :8, :8] = np.einsum("cq,cqad,cqbd->cab", a, R, R)
+            Je[:, :8, 8:11] = np.einsum("cq,cqa,cqb->cab", a, Gp[..., None] * Rx - dr, chi)
+            Je[:, :8, 11:] = np.einsum("cq,cqa,cqk->cak", a * Gq, Rx, phi)
+            Je[:, 8:11, :8] = -np.einsum("cq,cqb,cqa->cba", a, chi, drD)
+            Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2, phi, chi)
+            Je[:, 11:, 11:] = (-np.einsum("cq,cqk,cql->ckl", a * (2 / x), phi, phi)
+                               - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
+            rows.append(np.repeat(self.cell_dofs, 17, axis=1).ravel())
+            cols.append(np.tile(self.cell_dofs, (1, 17)).ravel())
+            vals.append(Je.ravel())
+        self._exterior(u, b, rows, cols, vals, want_jac)
+        self._interior(u, b, rows, cols, vals, want_jac)
+        J = None
+        if want_jac:
+            J = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                              shape=(self.N, self.N)).tocsr()
+        return J, b
+
+    def _facet_lam(self, fidx, cell, s):
+        """barycentric coordinates [n,nq,3] in `cell` of the points A + s (B - A) of facets fidx."""
+        fc, cv = self.fc, self.mesh.cells[cell]
+        va = fc.verts[fidx, 0][:, None] == cv
+        vb = fc.verts[fidx, 1][:, None] == cv
+        return va[:, None, :] * (1.0 - s)[None, :, None] + vb[:, None, :] * s[None, :, None]
+
+    def _exterior(self, u, b, rows, cols, vals, want_jac):
+        """q-rows: (r2vec.n) q w W ds(left,rest) + (r2vec.n) q_ex w W ds(right) + stab2 (hK neg(r2vec.n)^2 + 8/hK)
+        (q - q_ex) w ds (:142-145,152-153); s-rows: + p_ex (tau.n) W ds(right,rest) (:148-149)."""
+        mesh, fc, ext = self.mesh, self.fc, self.ext
+        L, nrm, A, B = fem.facet_geometry(mesh, ext)
+        s, w = fem.facet_rule(6)
+        cell = fc.cell0[ext]
+        lam = self._facet_lam(ext, cell, s)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        x, y = Pq[..., 0], Pq[..., 1]
+        W = (4 * np.pi * x * y) ** 2
+        phi, _ = p2_basis(lam, self.grads[cell])
+        qd = self.qd[cell]
+        qh = np.einsum("nqk,nk->nq", phi, u[qd])
+        bn = nrm[:, 0]                                                               # r2vec = (1,0)
+        neg = 0.5 * (np.abs(bn) - bn)
+        pen = self.stab2 * (L * neg ** 2 + 8.0 / L)
+        ds = w[None, :] * L[:, None]
+        cq = (self.k_adv * bn)[:, None] * W + pen[:, None]
+        cd = (self.k_dat * bn)[:, None] * W - pen[:, None]
+        Fx = np.einsum("nq,nqk->nk", ds * (cq * qh + cd * q_ex(x, y)), phi)
+        np.add.at(b, qd.ravel(), Fx.ravel())
+        if want_jac:
+            Jx = np.einsum("nq,nqk,nql->nkl", ds * cq, phi, phi)
+            rows.append(np.repeat(qd, 6, axis=1).ravel())
+            cols.append(np.tile(qd, (1, 6)).ravel())
+            vals.append(Jx.ravel())
+        # natural p data on the s-rows of the right / rest facets: only the two functions of the facet itself
+        # have a normal trace there, lambda_end / |F| * sign_out
+        sel = (self.markers[ext] == 31) | (self.markers[ext] == 32)
+        sgn = np.sign((nrm * self.enorm[ext]).sum(1))
+        pw = ds * W * p_ex(x, y)                                                     # [n,nq]
+        for slot, lamend in ((0, 1.0 - s), (1, s)):
+            val = (pw * lamend[None, :]).sum(1) * sgn / L
+            np.add.at(b, 2 * ext[sel] + slot, val[sel])
+
+    def _interior(self, u, b, rows, cols, vals, want_jac):
+        """gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS, hK = FacetArea (:144)."""
+        mesh, fc = self.mesh, self.fc
+        fi = fc.interior
+        L, nrm, A, B = fem.facet_geometry(mesh, fi)
+        s, w = fem.facet_rule(6)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        W = (4 * np.pi * Pq[..., 0] * Pq[..., 1]) ** 2
+        c0, c1 = fc.cell0[fi], fc.cell1[fi]
+        d = []
+        for cell, sg in ((c0, 1.0), (c1, -1.0)):
+            lam = self._facet_lam(fi, cell, s)
+            _, gphi = p2_basis(lam, self.grads[cell])
+            d.append(sg * np.einsum("nqkd,nd->nqk", gphi, nrm))
+        d = np.concatenate(d, 2)                                                     # [Fi,nq,12]
+        md = np.concatenate([self.qd[c0], self.qd[c1]], 1)
+        coef = self.gamma * (L ** 2)[:, None] * w[None, :] * L[:, None] * W
+        jq = np.einsum("nqk,nk->nq", d, u[md])
+        np.add.at(b, md.ravel(), np.einsum("nq,nqk->nk", coef * jq, d).ravel())
+        if want_jac:
+            Ji = np.einsum("nq,nqk,nql->nkl", coef, d, d)
+            rows.append(np.repeat(md, 12, axis=1).ravel())
+            cols.append(np.tile(md, (1, 12)).ravel())
+            vals.append(Ji.ravel())
+
+    def sigD(self):
+        """project(sig_ex, RT2) (:132): unweighted L2 projection with the degree-6 rule."""
+        R, _, _ = self.rt_basis(self.lam, self.P)
+        a = self.wts[None, :] * (2 * self.area)[:, None]
+        x, y = self.P[:, :, 0], self.P[:, :, 1]
+        sex = np.stack([self.sym["sx"](x, y), self.sym["sy"](x, y)], -1)
+        Me = np.einsum("cq,cqad,cqbd->cab", a, R, R)
+        be = np.einsum("cq,cqad,cqd->ca", a, R, sex)
+        ns = 2 * self.E + 2 * self.C
+        M = sp.coo_matrix((Me.ravel(), (np.repeat(self.sd, 8, axis=1).ravel(), np.tile(self.sd, (1, 8)).ravel())),
+                          shape=(ns, ns)).tocsc()
+        rhs = np.zeros(ns)
+        np.add.at(rhs, self.sd.ravel(), be.ravel())
+        return spla.splu(M).solve(rhs)
+
+    def solve(self, tol=1e-7, maxit=50):
+        le = np.nonzero(self.markers == 30)[0]
+        bc_dofs = np.concatenate([2 * le, 2 * le + 1])                                # both dofs of the left edges (:133)
+        g = self.sigD()[bc_dofs]
+        u = np.zeros(self.N)
+        _, b = self.assemble(u, False)
+        b[bc_dofs] = u[bc_dofs] - g
+        r0 = r = np.linalg.norm(b)
+        it = 0
+        while not (r < tol or r / r0 < tol) and it < maxit:
+            J, _ = self.assemble(u, True)
+            J = J.tolil()
+            J[bc_dofs, :] = 0.0
+            J[bc_dofs, bc_dofs] = 1.0
+            u -= spla.splu(J.tocsc()).solve(b)
+            it += 1
+            _, b = self.assemble(u, False)
+            b[bc_dofs] = u[bc_dofs] - g
+            r = np.linalg.norm(b)
+        self.newton_its = it
+        return u
+
+    def errors(self, u):
+        """(:175-177) e_div(s), e_0(p), e_1(q): weighted norms, degree-6 rule."""
+        lam, P = self.lam, self.P
+        x, y = P[:, :, 0], P[:, :, 1]
+        W = (4 * np.pi * x * y) ** 2
+        a = self.wts[None, :] * (2 * self.area)[:, None] * W
+        R, dxx, dyy = self.rt_basis(lam, P)
+        dr = dxx + dyy + 2 * R[..., 0] / x[..., None] + 2 * R[..., 1] / y[..., None]
+        se = u[self.sd]
+        s = np.einsum("cqad,ca->cqd", R, se)
+        drs = np.einsum("cqa,ca->cq", dr, se)
+        sx, sy = self.sym["sx"](x, y), self.sym["sy"](x, y)
+        es = np.sqrt((a * ((sx - s[..., 0]) ** 2 + (sy - s[..., 1]) ** 2 + (self.sym["drs"](x, y) - drs) ** 2)).sum())
+        ph = np.einsum("qb,cb->cq", lam, u[self.pd])
+        ep = np.sqrt((a * (p_ex(x, y) - ph) ** 2).sum())
+        phi, gphi = p2_basis(np.broadcast_to(lam[None], (self.C,) + lam.shape), self.grads)
+        qh = np.einsum("cqk,ck->cq", phi, u[self.qd])
+        qhx = np.einsum("cqk,ck->cq", gphi[..., 0], u[self.qd])
+        eq = np.sqrt((a * ((q_ex(x, y) - qh) ** 2 + (self.sym["qx"](x, y) - qhx) ** 2)).sum())
+        return float(es), float(ep), float(eq)
+
+
+def table(levels=5, stab=0.1):
+    rows, prev = [], None
+    for nk in range(levels):
+        n = 2 ** (nk + 1)
+        m = PaperM1(n, stab=stab)
+        u = m.solve()
+        h = m.mesh.hmax()
+        e = m.errors(u)
+        r = [0.0, 0.0, 0.0] if prev is None else [np.log(a / b) / np.log(h / prev[0]) for a, b in zip(e, prev[1])]
+        rows.append('{:6d} & {:.4f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} '.format(
+            m.N, h, e[0], r[0], e[1], r[1], e[2], r[2]))
+        prev = (h, e)
+    return rows
+
+
+if __name__ == "__main__":
+    import sys
+    for row in table(int(sys.argv[1]) if len(sys.argv) > 1 else 5, float(sys.argv[2]) if len(sys.argv) > 2 else 0.1):
+        print(row)

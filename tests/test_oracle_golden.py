@@ -170,3 +170,25 @@ def test_paper_k0_table_pins_facet_terms():
         assert got[k][0] == ref[k][0] and got[k][1] == ref[k][1]
         for a, b in zip(got[k][2::2], ref[k][2::2]):          # error columns: <= 1 in the 3rd digit
             assert abs(a - b) <= 0.011 * 10 ** np.floor(np.log10(b)), (a, b)
+
+
+# convergence/test_for_paper_convergence.py:211-217, verbatim (first k=1 table: RT2 x DG1 x CG2)
+PAPER_K1 = _golden("paper_k1_table.txt")
+
+
+def test_paper_k1_table_rt2_dg1_cg2():
+    """oracle/paper_m1.py (RT2 x DG1 x CG2, stab = 0.1 as the comment at :70 says, stab2 = 2) against the first
+    recorded k=1 table: rows from the third level on digit for digit, the two coarsest to the last printed digit
+    of e_1(q) (analytic data instead of degree-5/6 interpolants).  DoF column = 3E + 5C + V.
+    The second recorded k=1 table (:219-225) has the same e_div(s) / e_0(p) columns and a different e_1(q): its
+    stabilisation parameters are not recorded in the script."""
+    from oracle import paper_m1
+    levels = 5
+    rows = paper_m1.table(levels)
+    got = [[float(t) for t in r.replace("&", " ").split()] for r in rows]
+    ref = [[float(t) for t in r.replace("&", " ").split()] for r in PAPER_K1[:levels]]
+    for k in range(2, levels):
+        assert rows[k].split() == PAPER_K1[k].split(), (rows[k], PAPER_K1[k])
+    for k in range(2):
+        assert got[k][:6] == ref[k][:6], (rows[k], PAPER_K1[k])          # DoF, h, e_div(s), r, e_0(p), r exactly
+        assert abs(got[k][6] - ref[k][6]) <= 0.011 * 10 ** np.floor(np.log10(ref[k][6])), (got[k], ref[k])
