@@ -99,6 +99,8 @@ _PROTOS = {
     "cm_project_flux_dg0": ([_I, _P, _D, _D, _I, _P, _P, _P, _P, _P], C.c_int),
     "cm_functional_boundary_flux": ([_I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_mixed_m0_cells": ([_I, _P, _D, _D, _D, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cm_mixed_m1_cells": ([_I, _P, _D, _D, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cm_mixed_m1_errors": ([_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_csr_gather": ([_I, _P, _P, _P, _P, _I, _P], C.c_int),
     "cm_csr_add_mapped": ([_I, _P, _P, _P, _P], C.c_int),
     "cm_mixed_workspace_doubles": ([], C.c_int64),

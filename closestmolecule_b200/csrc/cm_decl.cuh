@@ -155,4 +155,11 @@ size_t mixed_workspace_doubles();
 int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cells, const double* coords,
                     const int* cell_edges, const double* sign, int nE, const double* u, const double* exq,
                     double* work, cudaStream_t st);
+int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, int ncells, int nE,
+                   int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
+                   const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
+                   cudaStream_t st);
+int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV, const int* cells,
+                    const double* coords, const int* cell_edges, const double* sign, const double* u,
+                    const double* exq, double* work, cudaStream_t st);
 }  // namespace cm

@@ -213,6 +213,222 @@ mixed_final_sum_kernel(const int nparts, const double* __restrict__ partial, dou
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k = 1: RT2 x DG1 x CG2 (test_for_paper_convergence.py with deg = 1; recorded table :211-217).
+// Bases: RT2 = { lambda_j N_i, lambda_k N_i : facet i opposite local vertex i with end points j < k }
+// + { lambda_1 N_1, lambda_2 N_2 } (unsigned) with the RT0 functions N_i = sigma_i (x - X_i)/(2|K|);
+// DG1 = barycentric coordinates; CG2 = lambda_i (2 lambda_i - 1), 4 lambda_j lambda_k.  17 local dofs
+// [s:8 | p:3 | q:6]; global dofs [2 per edge | 2 per cell | 3 per cell | vertices | edges].
+// One thread per (test function, cell): it evaluates all bases at the quadrature points and accumulates its
+// row of the 17 x 17 element Jacobian and its residual entry (entry-major storage, coalesced over cells).
+// ------------------------------------------------------------------------------------------------
+struct M1Cell {
+  double X[3], Y[3], gx[3], gy[3], adet, rs[3];  // rs = sigma_i / (2|K|)
+  double se[8], pe[3], qe[6];
+};
+
+struct M1Point {
+  double a, x, y;            // weight * |det| * W, coordinates
+  double Rx[8], Ry[8], dr[8], drD[8], chi[3], phi[6], phix[6];
+};
+
+__device__ __forceinline__ void m1_load_cell(const int c, const int ncells, const int nE, const int nV,
+                                             const int* __restrict__ cells,
+                                             const double2* __restrict__ coords,
+                                             const int* __restrict__ cell_edges,
+                                             const double* __restrict__ sign, const double* __restrict__ u,
+                                             M1Cell& K) {
+  int v[3], e[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    v[i] = cells[3 * (size_t)c + i];
+    e[i] = cell_edges[3 * (size_t)c + i];
+    const double2 P = coords[v[i]];
+    K.X[i] = P.x;
+    K.Y[i] = P.y;
+  }
+  const double j00 = K.X[1] - K.X[0], j01 = K.X[2] - K.X[0], j10 = K.Y[1] - K.Y[0], j11 = K.Y[2] - K.Y[0];
+  const double det = j00 * j11 - j01 * j10, id = 1.0 / det;
+  K.adet = fabs(det);
+  K.gx[1] = j11 * id;  K.gy[1] = -j01 * id;
+  K.gx[2] = -j10 * id; K.gy[2] = j00 * id;
+  K.gx[0] = -(K.gx[1] + K.gx[2]);
+  K.gy[0] = -(K.gy[1] + K.gy[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) K.rs[i] = sign[3 * (size_t)c + i] / K.adet;   // 2|K| = |det|
+  if (u != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      K.se[2 * i] = u[2 * e[i]];
+      K.se[2 * i + 1] = u[2 * e[i] + 1];
+      K.pe[i] = u[2 * nE + 2 * ncells + 3 * c + i];
+    }
+    K.se[6] = u[2 * nE + 2 * c];
+    K.se[7] = u[2 * nE + 2 * c + 1];
+    const int q0 = 2 * nE + 5 * ncells;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      K.qe[i] = u[q0 + v[i]];
+      K.qe[3 + i] = u[q0 + nV + e[i]];
+    }
+  }
+}
+
+__device__ __forceinline__ void m1_eval_point(const M1Cell& K, const double l1, const double l2, const double w,
+                                              const double D1, const double D2, M1Point& Q) {
+  const double lam[3] = {1.0 - l1 - l2, l1, l2};
+  Q.x = lam[0] * K.X[0] + lam[1] * K.X[1] + lam[2] * K.X[2];
+  Q.y = lam[0] * K.Y[0] + lam[1] * K.Y[1] + lam[2] * K.Y[2];
+  const double t = kFourPi * Q.x * Q.y;
+  Q.a = w * K.adet * (t * t);
+  // RT2: (facet i, end point a, scale) for the 6 facet functions, then the two interior ones (unsigned scale)
+  const int fi[8] = {0, 0, 1, 1, 2, 2, 1, 2};
+  const int fa[8] = {1, 2, 0, 2, 0, 1, 1, 2};
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int i = fi[m], a = fa[m];
+    const double c = (m < 6) ? K.rs[i] : 1.0 / K.adet;
+    const double dx = Q.x - K.X[i], dy = Q.y - K.Y[i];
+    Q.Rx[m] = lam[a] * dx * c;
+    Q.Ry[m] = lam[a] * dy * c;
+    const double dxx = c * (K.gx[a] * dx + lam[a]);
+    const double dyy = c * (K.gy[a] * dy + lam[a]);
+    Q.dr[m] = dxx + dyy + 2.0 * Q.Rx[m] / Q.x + 2.0 * Q.Ry[m] / Q.y;
+    Q.drD[m] = D2 * (dxx + 2.0 * Q.Rx[m] / Q.x) + D1 * (dyy + 2.0 * Q.Ry[m] / Q.y);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Q.chi[i] = lam[i];
+    Q.phi[i] = lam[i] * (2.0 * lam[i] - 1.0);
+    Q.phix[i] = (4.0 * lam[i] - 1.0) * K.gx[i];
+  }
+  const int ej[3] = {1, 0, 0}, ek[3] = {2, 2, 1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Q.phi[3 + i] = 4.0 * lam[ej[i]] * lam[ek[i]];
+    Q.phix[3 + i] = 4.0 * (lam[ej[i]] * K.gx[ek[i]] + lam[ek[i]] * K.gx[ej[i]]);
+  }
+}
+
+// Je: [289][ncells] (row-major local (test, trial), entry-major over cells), Fe: [17][ncells]
+__global__ void __launch_bounds__(kMxThreads)
+mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const double geps, const int ncells,
+                      const int nE, const int nV, const int* __restrict__ cells,
+                      const double2* __restrict__ coords, const int* __restrict__ cell_edges,
+                      const double* __restrict__ sign, const double* __restrict__ u,
+                      const double* __restrict__ f2q, const double* __restrict__ f3q,
+                      double* __restrict__ Je, double* __restrict__ Fe) {
+  const long long t = (long long)blockIdx.x * kMxThreads + threadIdx.x;
+  if (t >= 17ll * ncells) return;
+  const int row = (int)(t / ncells), c = (int)(t % ncells);
+  M1Cell K;
+  m1_load_cell(c, ncells, nE, nV, cells, coords, cell_edges, sign, u, K);
+  double J[17], F = 0.0;
+#pragma unroll
+  for (int b = 0; b < 17; ++b) J[b] = 0.0;
+  for (int k = 0; k < R.nq; ++k) {
+    M1Point Q;
+    m1_eval_point(K, R.l1[k], R.l2[k], R.w[k], D1, D2, Q);
+    double sx = 0.0, sy = 0.0, drDs = 0.0, p = 0.0, q = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      sx += K.se[m] * Q.Rx[m];
+      sy += K.se[m] * Q.Ry[m];
+      drDs += K.se[m] * Q.drD[m];
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) p += K.pe[b] * Q.chi[b];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) q += K.qe[m] * Q.phi[m];
+    const double x2 = Q.x * Q.x;
+    const double iq = 1.0 / (q + geps);
+    const double tg = x2 * p * iq;
+    const double G = tg * p, Gp = 2.0 * tg, Gq = -G * iq;
+    const double a = Q.a;
+    if (row < 8) {
+      const double rx = Q.Rx[row], ry = Q.Ry[row], dra = Q.dr[row];
+      F += a * (sx * rx + sy * ry + G * rx - p * dra);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) J[b] += a * (rx * Q.Rx[b] + ry * Q.Ry[b]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) J[8 + b] += a * (Gp * rx - dra) * Q.chi[b];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) J[11 + m] += a * Gq * rx * Q.phi[m];
+    } else if (row < 11) {
+      const double ch = Q.chi[row - 8];
+      F += a * (-drDs + f2q[(size_t)c * R.nq + k]) * ch;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) J[b] -= a * ch * Q.drD[b];
+    } else {
+      const double ph = Q.phi[row - 11], phx = Q.phix[row - 11];
+      F += a * ((-(2.0 / Q.x) * q + x2 * p - f3q[(size_t)c * R.nq + k]) * ph - q * phx);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * Q.chi[b] * ph;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) J[11 + m] -= a * ((2.0 / Q.x) * Q.phi[m] * ph + phx * Q.phi[m]);
+    }
+  }
+  Fe[(size_t)row * ncells + c] = F;
+  if (Je != nullptr) {
+#pragma unroll
+    for (int b = 0; b < 17; ++b) Je[((size_t)row * 17 + b) * ncells + c] = J[b];
+  }
+}
+
+// squares of e_div(s), e_0(p), e_1(q) for k = 1; exq[ncells*nq*6] = (s_x, s_y, div_rad s, p, q, dq/dx)
+__global__ void __launch_bounds__(kMxThreads)
+mixed_m1_errors_kernel(const MxRule R, const int ncells, const int nE, const int nV,
+                       const int* __restrict__ cells, const double2* __restrict__ coords,
+                       const int* __restrict__ cell_edges, const double* __restrict__ sign,
+                       const double* __restrict__ u, const double* __restrict__ exq,
+                       double* __restrict__ partial) {
+  double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+  for (int c = blockIdx.x * kMxThreads + threadIdx.x; c < ncells; c += kMxBlocks * kMxThreads) {
+    M1Cell K;
+    m1_load_cell(c, ncells, nE, nV, cells, coords, cell_edges, sign, u, K);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int k = 0; k < R.nq; ++k) {
+      M1Point Q;
+      m1_eval_point(K, R.l1[k], R.l2[k], R.w[k], 1.0, 1.0, Q);
+      double sx = 0.0, sy = 0.0, drs = 0.0, p = 0.0, q = 0.0, qx = 0.0;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        sx += K.se[m] * Q.Rx[m];
+        sy += K.se[m] * Q.Ry[m];
+        drs += K.se[m] * Q.dr[m];
+      }
+#pragma unroll
+      for (int b = 0; b < 3; ++b) p += K.pe[b] * Q.chi[b];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) {
+        q += K.qe[m] * Q.phi[m];
+        qx += K.qe[m] * Q.phix[m];
+      }
+      const double* ex = exq + ((size_t)c * R.nq + k) * 6;
+      const double d0 = ex[0] - sx, d1 = ex[1] - sy, d2 = ex[2] - drs, dp = ex[3] - p, dq = ex[4] - q,
+                   dqx = ex[5] - qx;
+      c0 += Q.a * (d0 * d0 + d1 * d1 + d2 * d2);
+      c1 += Q.a * (dp * dp);
+      c2 += Q.a * (dq * dq + dqx * dqx);
+    }
+    e0 += c0;
+    e1 += c1;
+    e2 += c2;
+  }
+  __shared__ double sh[3][kMxThreads];
+  sh[0][threadIdx.x] = e0;
+  sh[1][threadIdx.x] = e1;
+  sh[2][threadIdx.x] = e2;
+  __syncthreads();
+  for (int o = kMxThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int m = 0; m < 3; ++m) sh[m][threadIdx.x] += sh[m][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int m = 0; m < 3; ++m) partial[3 * blockIdx.x + m] = sh[m][0];
+}
+
 static int mx_rule(int nq, const double* rule_host, MxRule& R) {
   if (nq < 1 || nq > kMxRule || rule_host == nullptr) return CM_E_INVALID;
   R.nq = nq;
@@ -267,6 +483,39 @@ int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cell
   }
   mixed_m0_errors_kernel<<<kMxBlocks, kMxThreads, 0, st>>>(R, ncells, cells, (const double2*)coords,
                                                           cell_edges, sign, nE, u, exq, work + 4);
+  CM_LAUNCH_CHECK();
+  mixed_final_sum_kernel<<<1, 32, 0, st>>>(kMxBlocks, work + 4, work);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, int ncells, int nE,
+                   int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
+                   const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
+                   cudaStream_t st) {
+  MxRule R;
+  if (mx_rule(nq, rule_host, R)) {
+    set_error("cm_mixed_m1_cells: bad quadrature rule (1..%d points)", kMxRule);
+    return CM_E_INVALID;
+  }
+  const long long nt = 17ll * ncells;
+  mixed_m1_cells_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
+      R, D1, D2, geps, ncells, nE, nV, cells, (const double2*)coords, cell_edges, sign, u, f2q, f3q, Je, Fe);
+  CM_LAUNCH_CHECK();
+  CM_BYTES((double)ncells * (12.0 + 12.0 + 24.0 + 136.0 + 16.0 * nq + 136.0 + (Je ? 2312.0 : 0.0)));
+  return CM_OK;
+}
+
+int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV, const int* cells,
+                    const double* coords, const int* cell_edges, const double* sign, const double* u,
+                    const double* exq, double* work, cudaStream_t st) {
+  MxRule R;
+  if (mx_rule(nq, rule_host, R)) {
+    set_error("cm_mixed_m1_errors: bad quadrature rule (1..%d points)", kMxRule);
+    return CM_E_INVALID;
+  }
+  mixed_m1_errors_kernel<<<kMxBlocks, kMxThreads, 0, st>>>(R, ncells, nE, nV, cells, (const double2*)coords,
+                                                          cell_edges, sign, u, exq, work + 4);
   CM_LAUNCH_CHECK();
   mixed_final_sum_kernel<<<1, 32, 0, st>>>(kMxBlocks, work + 4, work);
   CM_LAUNCH_CHECK();

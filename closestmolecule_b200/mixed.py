@@ -306,3 +306,296 @@ class PaperMixedSystem:
             _capi.ptr(work), _capi.stream_ptr()))
         s = work[:3].cpu()
         return tuple(math.sqrt(float(v)) for v in s)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# k = 1: RT2 x DG1 x CG2 (test_for_paper_convergence.py with deg = 1, recorded table :211-217)
+# ---------------------------------------------------------------------------------------------------------
+_OTHER = ((1, 2), (0, 2), (0, 1))      # end points (local vertices) of the facet opposite local vertex i
+
+
+def _p2_basis(lam, g):
+    """lam [n, nq, 3], g [n, 3, 2] -> CG2 values [n, nq, 6] and gradients [n, nq, 6, 2] (vertices, then facets)."""
+    val = torch.cat([lam * (2 * lam - 1),
+                     torch.stack([4 * lam[..., j] * lam[..., k] for j, k in _OTHER], -1)], -1)
+    gv = (4 * lam - 1)[..., None] * g[:, None, :, :]
+    ge = torch.stack([4 * (lam[..., j, None] * g[:, None, k, :] + lam[..., k, None] * g[:, None, j, :])
+                      for j, k in _OTHER], -2)
+    return val, torch.cat([gv, ge], -2)
+
+
+class PaperMixedSystemK1:
+    """RT2 x DG1 x CG2 'paper' system on the GPU: per Newton step cm_mixed_m1_cells (17 x 17 element tensors),
+    cm_csr_gather, cm_spmv, cm_apply_dirichlet and the pivoting LU (cm_blu_*).  The q-q facet operator (C0IP
+    jump penalty on CG2, weak outflow data, boundary penalty; :142-145,152-153) and the natural p data on the
+    flux rows (:148-149) are state independent: they are tabulated once per mesh with torch on the device
+    (setup, like the forcing at the quadrature points) and enter every step as a constant matrix / vector."""
+
+    def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=2.0, degree=6, tables_only=False):
+        if not tables_only:
+            _capi.require_cuda(mesh.coords)
+            self.lib = _capi.lib()
+        self.mesh, self.bdry = mesh, bdry
+        self.D1, self.D2 = float(D1), float(D2)
+        self.gamma = stab / 2.0 ** 3.5                       # stab/(deg+1)^3.5 (:144)
+        self.stab2 = float(stab2)
+        dev = mesh.device
+        fc = mesh.facets()
+        V, C, E = mesh.num_vertices(), mesh.num_cells(), fc.num
+        self.V, self.C, self.E = V, C, E
+        self.N = N = 3 * E + 5 * C + V
+        cells = mesh.cells.long()
+        X = mesh.coords
+        fa = torch.stack([cells[:, 1], cells[:, 0], cells[:, 0]], 1)
+        fb = torch.stack([cells[:, 2], cells[:, 2], cells[:, 1]], 1)
+        key = torch.minimum(fa, fb) * V + torch.maximum(fa, fb)
+        allkey = fc.verts[:, 0].long() * V + fc.verts[:, 1].long()
+        ce = torch.searchsorted(allkey, key)
+        A, B = X[fc.verts[:, 0].long()], X[fc.verts[:, 1].long()]
+        t = B - A
+        self.elen = t.pow(2).sum(1).sqrt()
+        self.enorm = torch.stack([t[:, 1], -t[:, 0]], 1) / self.elen[:, None]
+        Xc = X[cells]
+        self.sign = torch.sign(((0.5 * (A + B)[ce] - Xc) * self.enorm[ce]).sum(-1)).to(torch.float64).contiguous()
+        self.cell_edges = ce.to(torch.int32).contiguous()
+        det = ((Xc[:, 1, 0] - Xc[:, 0, 0]) * (Xc[:, 2, 1] - Xc[:, 0, 1])
+               - (Xc[:, 2, 0] - Xc[:, 0, 0]) * (Xc[:, 1, 1] - Xc[:, 0, 1]))
+        g1 = torch.stack([Xc[:, 2, 1] - Xc[:, 0, 1], -(Xc[:, 2, 0] - Xc[:, 0, 0])], 1) / det[:, None]
+        g2 = torch.stack([-(Xc[:, 1, 1] - Xc[:, 0, 1]), Xc[:, 1, 0] - Xc[:, 0, 0]], 1) / det[:, None]
+        self.grads = torch.stack([-(g1 + g2), g1, g2], 1)                              # [C,3,2]
+        self.area = 0.5 * det.abs()
+        pts, wts = triangle_rule(degree)
+        self.rule = np.ascontiguousarray(np.concatenate([pts, wts[:, None]], 1), dtype=np.float64)
+        self.nq = self.rule.shape[0]
+        self.lamq = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
+        P = torch.einsum("qi,cid->cqd", self.lamq, Xc)
+        self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
+        self.data = paper_data(D1, D2)
+        self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
+        self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
+        # global dofs of the 17 local ones: [2 per edge | 2 per cell | 3 per cell | vertices | edges]
+        cid = torch.arange(C, device=dev)[:, None]
+        sd = torch.cat([torch.stack([2 * ce[:, i], 2 * ce[:, i] + 1], 1) for i in range(3)]
+                       + [2 * E + 2 * cid, 2 * E + 2 * cid + 1], 1)
+        pd = 2 * E + 2 * C + 3 * cid + torch.arange(3, device=dev)[None, :]
+        self.q0 = q0 = 2 * E + 5 * C
+        qd = torch.cat([q0 + cells, q0 + V + ce], 1)
+        self.sd, self.pd, self.qd = sd, pd, qd
+        self.cell_dofs = cd = torch.cat([sd, pd, qd], 1)                               # [C,17]
+        # constant facet operator (COO) and vectors
+        fr, fcn, fv, self.cvec = self._facet_tables(degree)
+        rows_c = cd.repeat_interleave(17, dim=1).flatten()
+        cols_c = cd.repeat(1, 17).flatten()
+        self._key, self.rowptr, self.col = _csr_from_pairs(torch.cat([rows_c, fr]), torch.cat([cols_c, fcn]), N)
+        self.nnz = int(self.col.numel())
+        slot_c = torch.searchsorted(self._key, rows_c * N + cols_c)
+        ent = (torch.arange(289, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.mat_ptr, order = _gather_lists(slot_c, self.nnz)
+        self.mat_idx = ent[order].to(torch.int32).contiguous()
+        entv = (torch.arange(17, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.vec_ptr, order = _gather_lists(cd.flatten(), N)
+        self.vec_idx = entv[order].to(torch.int32).contiguous()
+        self.Kf = torch.zeros(self.nnz, dtype=torch.float64, device=dev)
+        self.Kf.index_add_(0, torch.searchsorted(self._key, fr * N + fcn), fv)
+        self.diag_slot_all = (torch.searchsorted(self._key, torch.arange(N, device=dev) * (N + 1))
+                              - self.rowptr[:-1].long()).to(torch.int32)
+        if tables_only:
+            return
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.Je = torch.empty(289 * C, **f64)
+        self.Fe = torch.empty(17 * C, **f64)
+        self.vals = torch.zeros(self.nnz, **f64)
+        self.b = torch.zeros(N, **f64)
+        self._ku = torch.empty(N, **f64)
+        self._lin = None
+        self.newton_its = 0
+
+    # -- state-independent facet terms -----------------------------------------------------------------------
+    def _facet_lam(self, fidx, cell, s):
+        fc, cv = self.mesh.facets(), self.mesh.cells.long()[cell]
+        va = (fc.verts[fidx, 0].long()[:, None] == cv).to(torch.float64)
+        vb = (fc.verts[fidx, 1].long()[:, None] == cv).to(torch.float64)
+        return va[:, None, :] * (1.0 - s)[None, :, None] + vb[:, None, :] * s[None, :, None]
+
+    def _facet_geometry(self, fidx):
+        mesh, fc = self.mesh, self.mesh.facets()
+        A = mesh.coords[fc.verts[fidx, 0].long()]
+        B = mesh.coords[fc.verts[fidx, 1].long()]
+        t = B - A
+        L = t.pow(2).sum(1).sqrt()
+        nrm = torch.stack([t[:, 1], -t[:, 0]], 1) / L[:, None]
+        opp = mesh.coords[mesh.cells.long()[fc.cell0[fidx].long(), fc.loc0[fidx].long()]]
+        flip = ((opp - A) * nrm).sum(1) > 0
+        return L, torch.where(flip[:, None], -nrm, nrm), A, B
+
+    def _facet_tables(self, degree):
+        """COO (rows, cols, vals) of the constant q-q facet matrix and the constant vector (q_ex data on the
+        q-rows, natural p data on the flux rows)."""
+        mesh, fc, dev = self.mesh, self.mesh.facets(), self.mesh.device
+        m = (degree + 2) // 2
+        p, w = np.polynomial.legendre.leggauss(m)
+        s = torch.tensor(0.5 * (p + 1.0), device=dev)
+        w = torch.tensor(0.5 * w, device=dev)
+        cvec = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        rows, cols, vals = [], [], []
+        # exterior facets
+        ext = torch.nonzero(fc.cell1 < 0).flatten()
+        L, nrm, A, B = self._facet_geometry(ext)
+        cell = fc.cell0[ext].long()
+        lam = self._facet_lam(ext, cell, s)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        x, y = Pq[..., 0], Pq[..., 1]
+        W = (4.0 * math.pi * x * y) ** 2
+        phi, _ = _p2_basis(lam, self.grads[cell])
+        mk = self.bdry.values[ext]
+        k_adv = ((mk == 30) | (mk == 32)).to(torch.float64)
+        k_dat = (mk == 31).to(torch.float64)
+        bn = nrm[:, 0]
+        neg = 0.5 * (bn.abs() - bn)
+        pen = self.stab2 * (L * neg ** 2 + 8.0 / L)
+        ds = w[None, :] * L[:, None]
+        cq = (k_adv * bn)[:, None] * W + pen[:, None]
+        cdat = (k_dat * bn)[:, None] * W - pen[:, None]
+        qd = self.qd[cell]
+        cvec.index_add_(0, qd.flatten(), torch.einsum("nq,nqk->nk", ds * cdat * q_exact(x, y), phi).flatten())
+        Jx = torch.einsum("nq,nqk,nql->nkl", ds * cq, phi, phi)
+        rows.append(qd.repeat_interleave(6, dim=1).flatten())
+        cols.append(qd.repeat(1, 6).flatten())
+        vals.append(Jx.flatten())
+        sel = (mk == 31) | (mk == 32)
+        sgn = torch.sign((nrm * self.enorm[ext]).sum(1))
+        pw = ds * W * p_exact(x, y)
+        for slot, lamend in ((0, 1.0 - s), (1, s)):
+            val = (pw * lamend[None, :]).sum(1) * sgn / L
+            cvec.index_add_(0, (2 * ext + slot)[sel], val[sel])
+        # interior facets: gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS, hK = FacetArea
+        fi = torch.nonzero(fc.cell1 >= 0).flatten()
+        L, nrm, A, B = self._facet_geometry(fi)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        W = (4.0 * math.pi * Pq[..., 0] * Pq[..., 1]) ** 2
+        c0, c1 = fc.cell0[fi].long(), fc.cell1[fi].long()
+        d = []
+        for cell, sg in ((c0, 1.0), (c1, -1.0)):
+            lam = self._facet_lam(fi, cell, s)
+            _, gphi = _p2_basis(lam, self.grads[cell])
+            d.append(sg * torch.einsum("nqkd,nd->nqk", gphi, nrm))
+        d = torch.cat(d, 2)
+        md = torch.cat([self.qd[c0], self.qd[c1]], 1)
+        coef = self.gamma * (L ** 2)[:, None] * w[None, :] * L[:, None] * W
+        Ji = torch.einsum("nq,nqk,nql->nkl", coef, d, d)
+        rows.append(md.repeat_interleave(12, dim=1).flatten())
+        cols.append(md.repeat(1, 12).flatten())
+        vals.append(Ji.flatten())
+        return torch.cat(rows), torch.cat(cols), torch.cat(vals), cvec
+
+    def _rt_values(self):
+        """RT2 basis values at the cell quadrature points [C,nq,8,2] (setup: the projection of sig_ex)."""
+        Xc = self.mesh.coords[self.mesh.cells.long()]
+        P = torch.stack([self.xq, self.yq], -1)
+        lam = self.lamq[None].expand(self.C, -1, -1)
+        R = []
+        funcs = [(i, a, self.sign[:, i]) for i in range(3) for a in _OTHER[i]] + [(1, 1, None), (2, 2, None)]
+        for i, a, sg in funcs:
+            c = (1.0 if sg is None else sg) / (2 * self.area)
+            R.append(lam[..., a, None] * (P - Xc[:, None, i, :]) * c[:, None, None])
+        return torch.stack(R, 2)
+
+    def sigD(self):
+        """project(sig_ex, RT2) (:132), unweighted; mass matrix through cm_csr_gather, solve through cm_blu_*."""
+        dev, E, C = self.mesh.device, self.E, self.C
+        R = self._rt_values()
+        a = torch.tensor(self.rule[:, 2], device=dev)[None, :] * (2 * self.area)[:, None]
+        sex = torch.stack([self.data["sx"](self.xq, self.yq), self.data["sy"](self.xq, self.yq)], -1)
+        Me = torch.einsum("cq,cqad,cqbd->cab", a, R, R)
+        be = torch.einsum("cq,cqad,cqd->ca", a, R, sex)
+        ns = 2 * E + 2 * C
+        rows = self.sd.repeat_interleave(8, dim=1).flatten()
+        cols = self.sd.repeat(1, 8).flatten()
+        key, rp, col = _csr_from_pairs(rows, cols, ns)
+        ptr, order = _gather_lists(torch.searchsorted(key, rows * ns + cols), key.numel())
+        vals = torch.empty(key.numel(), dtype=torch.float64, device=dev)
+        st = _capi.stream_ptr()
+        src = Me.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(key.numel(), _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
+                                           _capi.ptr(src), _capi.ptr(vals), 0, st))
+        ptr2, order2 = _gather_lists(self.sd.flatten(), ns)
+        rhs = torch.empty(ns, dtype=torch.float64, device=dev)
+        src2 = be.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(ns, _capi.ptr(ptr2), _capi.ptr(order2.to(torch.int32).contiguous()),
+                                           _capi.ptr(src2), _capi.ptr(rhs), 0, st))
+        lin = BandedLULinearSolver(_Holder(dev, rp, col, ns, vals, rhs))
+        lin.setup()
+        x = torch.empty_like(rhs)
+        lin.solve(rhs, x)
+        return x
+
+    # -- per Newton step ---------------------------------------------------------------------------------------
+    def assemble(self, u, want_jac=True):
+        lib, st, mesh = self.lib, _capi.stream_ptr(), self.mesh
+        _capi.check(lib.cm_mixed_m1_cells(
+            self.nq, self.rule.ctypes.data, self.D1, self.D2, DOLFIN_EPS, self.C, self.E, self.V,
+            _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign),
+            _capi.ptr(u), _capi.ptr(self.f2q), _capi.ptr(self.f3q), _capi.ptr(self.Je) if want_jac else None,
+            _capi.ptr(self.Fe), st))
+        _capi.check(lib.cm_csr_gather(self.N, _capi.ptr(self.vec_ptr), _capi.ptr(self.vec_idx),
+                                      _capi.ptr(self.Fe), _capi.ptr(self.b), 0, st))
+        _capi.check(lib.cm_spmv(1, self.N, _capi.ptr(self.rowptr), _capi.ptr(self.col), _capi.ptr(self.Kf),
+                                _capi.ptr(u), _capi.ptr(self._ku), st))
+        self.b += self._ku
+        self.b += self.cvec
+        if want_jac:
+            self.vals.copy_(self.Kf)
+            _capi.check(lib.cm_csr_gather(self.nnz, _capi.ptr(self.mat_ptr), _capi.ptr(self.mat_idx),
+                                          _capi.ptr(self.Je), _capi.ptr(self.vals), 1, st))
+        return (self.vals if want_jac else None), self.b
+
+    def _apply_bc(self, u, with_matrix):
+        _capi.check(self.lib.cm_apply_dirichlet(
+            1, self.bc_dofs.numel(), _capi.ptr(self.bc_dofs), _capi.ptr(self.bc_diag), _capi.ptr(self.bc_vals),
+            _capi.ptr(u), _capi.ptr(self.rowptr), _capi.ptr(self.vals) if with_matrix else None,
+            _capi.ptr(self.b), _capi.stream_ptr()))
+
+    def solve(self, tol=1e-7, maxit=50):
+        dev = self.mesh.device
+        fc = self.mesh.facets()
+        le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 30)).flatten()          # left edges (:133)
+        bc, _ = torch.sort(torch.cat([2 * le, 2 * le + 1]))
+        self.bc_dofs = bc.to(torch.int32).contiguous()
+        self.bc_vals = self.sigD()[bc].contiguous()
+        self.bc_diag = self.diag_slot_all[bc].contiguous()
+        u = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        self.assemble(u, False)
+        self._apply_bc(u, False)
+        r0 = r = float(torch.linalg.vector_norm(self.b))
+        if self._lin is None:
+            self._lin = BandedLULinearSolver(_Holder(dev, self.rowptr, self.col, self.N, self.vals, self.b))
+        dx = torch.empty_like(u)
+        it = 0
+        while not (r < tol or r / r0 < tol) and it < maxit:
+            self.assemble(u, True)
+            self._apply_bc(u, True)
+            self._lin.setup()
+            self._lin.solve(self.b, dx)
+            u -= dx
+            it += 1
+            self.assemble(u, False)
+            self._apply_bc(u, False)
+            r = float(torch.linalg.vector_norm(self.b))
+            if r != r:
+                raise RuntimeError("Newton solver diverged (NaN residual)")
+        if not (r < tol or r / r0 < tol):
+            raise RuntimeError("Newton solver did not converge because maximum number of iterations reached")
+        self.newton_its = it
+        return u
+
+    def errors(self, u):
+        d, x, y = self.data, self.xq, self.yq
+        exq = torch.stack([d["sx"](x, y), d["sy"](x, y), d["drs"](x, y), p_exact(x, y), q_exact(x, y),
+                           d["qx"](x, y)], -1).to(torch.float64).contiguous()
+        work = torch.empty(int(self.lib.cm_mixed_workspace_doubles()), dtype=torch.float64,
+                           device=self.mesh.device)
+        _capi.check(self.lib.cm_mixed_m1_errors(
+            self.nq, self.rule.ctypes.data, self.C, self.E, self.V, _capi.ptr(self.mesh.cells),
+            _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
+            _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))
+        return tuple(math.sqrt(float(v)) for v in work[:3].cpu())

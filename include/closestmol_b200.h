@@ -361,6 +361,20 @@ int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, cons
                        const double* coords, const int32_t* cell_edges, const double* sign,
                        int32_t nedges, const double* u, const double* exact_q, double* work, void* stream);
 
+/* k = 1 (RT2 x DG1 x CG2, recorded table test_for_paper_convergence.py:211-217): 17 local dofs per cell
+ * [8 fluxes: (lambda_j N_i, lambda_k N_i) for the facets i = 0,1,2 with end points j < k, then lambda_1 N_1,
+ * lambda_2 N_2 | 3 DG1 values | 6 CG2 values: vertices, then the facets' mid points]; global dofs
+ * [2 per edge | 2 per cell | 3 per cell | vertices | edges].  Je[289][ncells], Fe[17][ncells] entry-major;
+ * assembled by cm_csr_gather like the k = 0 tensors. */
+int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps,
+                      int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells,
+                      const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
+                      const double* f2q, const double* f3q, double* Je, double* Fe, void* stream);
+int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t ncells, int32_t nedges, int32_t nverts,
+                       const int32_t* cells, const double* coords, const int32_t* cell_edges,
+                       const double* sign, const double* u, const double* exact_q, double* work,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

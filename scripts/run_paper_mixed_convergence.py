@@ -1,16 +1,17 @@
-"""Port of convergence/test_for_paper_convergence.py (deg = 0: RT1 x DG0 x CG1) onto the GPU path
-(closestmolecule_b200.mixed.PaperMixedSystem): same mesh ladder (:74,88), markers (:90-94), data (:52-56,
-63-71), Newton tolerances (:161-164) and the same table layout (:195); the recorded k=0 table is at :200-207."""
+"""Port of convergence/test_for_paper_convergence.py (deg = 0: RT1 x DG0 x CG1, deg = 1: RT2 x DG1 x CG2) onto the
+GPU path (closestmolecule_b200.mixed.PaperMixedSystem / PaperMixedSystemK1): same mesh ladder (:74,88), markers
+(:90-94), data (:52-56,63-71), Newton tolerances (:161-164) and the same table layout (:195); the recorded tables
+are at :200-207 (k=0) and :211-217 (k=1, stab = 0.1, stab2 = 2)."""
 import math
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from closestmolecule_b200 import *  # noqa: E402,F401,F403
-from closestmolecule_b200.mixed import PaperMixedSystem  # noqa: E402
+from closestmolecule_b200.mixed import PaperMixedSystem, PaperMixedSystemK1  # noqa: E402
 
 
-def main(nkmax=7):
+def main(nkmax=7, deg=0):
     hh, nn, es, ep, eq, rs, rp, rq, its = [], [], [], [], [], [0.0], [0.0], [0.0], []
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
@@ -22,7 +23,10 @@ def main(nkmax=7):
         CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, right)
         CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
         hh.append(mesh.hmax())
-        system = PaperMixedSystem(mesh, bdry, D1=1.0, D2=1.5, stab=0.05, stab2=1.0)
+        if deg == 0:
+            system = PaperMixedSystem(mesh, bdry, D1=1.0, D2=1.5, stab=0.05, stab2=1.0)      # :70-71
+        else:
+            system = PaperMixedSystemK1(mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=1.0 * (deg + 1))
         nn.append(system.N)
         u = system.solve(tol=1e-7)
         its.append(system.newton_its)
@@ -46,4 +50,4 @@ def main(nkmax=7):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 7)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 7, int(sys.argv[2]) if len(sys.argv) > 2 else 0)

@@ -72,3 +72,60 @@ def test_recorded_k0_table_through_the_gpu_path():
         assert got[k][0] == ref[k][0] and got[k][1] == ref[k][1]
         for a, b in zip(got[k][2::2], ref[k][2::2]):
             assert abs(a - b) <= 0.011 * 10 ** np.floor(np.log10(b)), (a, b)
+
+
+# ---- k = 1: RT2 x DG1 x CG2 ---------------------------------------------------------------------------------
+def _system_k1(n):
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    mesh = cm.UnitSquareMesh(n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    return PaperMixedSystemK1(mesh, bd)
+
+
+@pytest.mark.parametrize("n", [3, 8])
+def test_k1_assembly_matches_oracle(n):
+    from oracle import paper_m1
+    S, O = _system_k1(n), paper_m1.PaperM1(n)
+    rng = np.random.default_rng(2)
+    un = np.concatenate([rng.standard_normal(2 * O.E + 2 * O.C), 0.5 + rng.random(3 * O.C),
+                         1.0 + rng.random(O.V + O.E)])
+    u = torch.tensor(un, device=S.mesh.device)
+    vals, b = S.assemble(u, True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    scale = abs(J).max()
+    assert abs(got - J).max() < 1e-12 * scale, abs(got - J).max() / scale
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+
+
+def test_k1_newton_solution_and_errors_match_oracle():
+    from oracle import paper_m1
+    n = 4
+    S, O = _system_k1(n), paper_m1.PaperM1(n)
+    u = S.solve()
+    uo = O.solve()
+    assert S.newton_its == O.newton_its
+    assert np.linalg.norm(u.cpu().numpy() - uo) / np.linalg.norm(uo) < 1e-8
+    assert np.allclose(S.errors(u), O.errors(uo), rtol=1e-8)
+
+
+def test_recorded_k1_table_through_the_gpu_path():
+    """The first recorded k=1 table (test_for_paper_convergence.py:211-217) through the GPU path: levels 3-5 digit
+    for digit, the two coarsest as the oracle (tests/test_oracle_golden.py::test_paper_k1_table_rt2_dg1_cg2)."""
+    from test_oracle_golden import PAPER_K1
+    spec = importlib.util.spec_from_file_location("paper_conv", os.path.join(ROOT, "scripts",
+                                                                             "run_paper_mixed_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    levels = 5
+    rows, its = mod.main(levels, deg=1)
+    got = [[float(t) for t in r.replace("&", " ").split()] for r in rows]
+    ref = [[float(t) for t in r.replace("&", " ").split()] for r in PAPER_K1[:levels]]
+    for k in range(2, levels):
+        assert rows[k].split() == PAPER_K1[k].split(), (rows[k], PAPER_K1[k])
+    for k in range(2):
+        assert got[k][:6] == ref[k][:6], (rows[k], PAPER_K1[k])
+        assert abs(got[k][6] - ref[k][6]) <= 0.011 * 10 ** np.floor(np.log10(ref[k][6])), (got[k], ref[k])

@@ -60,3 +60,39 @@ def test_tables_match_oracle_and_gather_lists_assemble():
     rows_of_slot = np.repeat(np.arange(S.N), np.diff(rp))
     assert np.array_equal(rows_of_slot[S.kq_map.numpy()], S.E + S.C + qrows)
     assert np.array_equal(col[S.kq_map.numpy()], S.E + S.C + t.ncol.numpy())
+
+
+def test_k1_tables_and_constant_facet_operator_match_oracle():
+    """RT2 x DG1 x CG2 host tables of PaperMixedSystemK1 against oracle/paper_m1.py: dof numbering, the
+    constant facet matrix / vector (tabulated with torch at setup) and the gather lists."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    n = 4
+    mesh = cm.UnitSquareMesh(n, n, device="cpu")
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    S, O = PaperMixedSystemK1(mesh, bd, tables_only=True), paper_m1.PaperM1(n)
+    assert S.N == O.N == 3 * O.E + 5 * O.C + O.V
+    assert np.array_equal(S.cell_dofs.numpy(), O.cell_dofs)
+    assert np.array_equal(S.sign.numpy(), O.sign)
+    # facet-only contribution of the oracle = full assembly minus the cell part: evaluate through linearity
+    u = np.linspace(0.5, 1.5, O.N)
+    rows, cols, vals = [], [], []
+    b = np.zeros(O.N)
+    O._exterior(u, b, rows, cols, vals, True)
+    O._interior(u, b, rows, cols, vals, True)
+    import scipy.sparse as sp
+    Jf = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(O.N, O.N)).tocsr()
+    Kf = sp.csr_matrix((S.Kf.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N))
+    assert abs(Kf - Jf).max() < 1e-12 * abs(Jf).max()
+    assert np.max(np.abs(Kf @ u + S.cvec.numpy() - b)) < 1e-12 * np.max(np.abs(b))
+    # gather lists
+    rng = np.random.default_rng(0)
+    Je = rng.standard_normal((S.C, 289))
+    got = _emulate_gather(S.mat_ptr, S.mat_idx, torch.tensor(Je.T.copy().ravel()))
+    cd = S.cell_dofs.numpy()
+    ref = sp.coo_matrix((Je.ravel(), (np.repeat(cd, 17, axis=1).ravel(), np.tile(cd, (1, 17)).ravel())),
+                        shape=(S.N, S.N)).tocsr()
+    assert abs(sp.csr_matrix((got.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N)) - ref).max() < 1e-13
