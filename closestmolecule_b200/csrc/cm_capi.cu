@@ -490,4 +490,23 @@ int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t ncells, int3
                          work, (cudaStream_t)stream);
 }
 
+int cm_cg2_exterior_facets(int32_t nq, const double* rule_host, double stab2, int32_t nfe,
+                           const int32_t* fverts, const int32_t* fcell, const int32_t* kind,
+                           const int32_t* cells, const double* coords, const double* qex, const double* pex,
+                           double* Jx, double* cx, double* nat, void* stream) {
+  CM_CHECK_ARG(nfe >= 0, "bad size");
+  CM_CHECK_ARG(nfe == 0 || (rule_host && fverts && fcell && kind && cells && coords && qex && pex && Jx && cx && nat),
+               "null pointer");
+  return cg2_exterior_facets(nq, rule_host, stab2, nfe, fverts, fcell, kind, cells, coords, qex, pex, Jx, cx, nat,
+                             (cudaStream_t)stream);
+}
+
+int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, int32_t nfi,
+                           const int32_t* fverts, const int32_t* fcell, const int32_t* cells,
+                           const double* coords, double* Ji, void* stream) {
+  CM_CHECK_ARG(nfi >= 0, "bad size");
+  CM_CHECK_ARG(nfi == 0 || (rule_host && fverts && fcell && cells && coords && Ji), "null pointer");
+  return cg2_interior_facets(nq, rule_host, gamma, nfi, fverts, fcell, cells, coords, Ji, (cudaStream_t)stream);
+}
+
 }  // extern "C"

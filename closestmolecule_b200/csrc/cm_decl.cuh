@@ -162,4 +162,11 @@ int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double
 int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV, const int* cells,
                     const double* coords, const int* cell_edges, const double* sign, const double* u,
                     const double* exq, double* work, cudaStream_t st);
+int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, const int* fverts,
+                        const int* fcell, const int* kind, const int* cells, const double* coords,
+                        const double* qex, const double* pex, double* Jx, double* cx, double* nat,
+                        cudaStream_t st);
+int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, const int* fverts,
+                        const int* fcell, const int* cells, const double* coords, double* Ji,
+                        cudaStream_t st);
 }  // namespace cm

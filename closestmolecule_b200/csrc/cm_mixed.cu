@@ -429,6 +429,214 @@ mixed_m1_errors_kernel(const MxRule R, const int ncells, const int nE, const int
     for (int m = 0; m < 3; ++m) partial[3 * blockIdx.x + m] = sh[m][0];
 }
 
+// ---- CG2 facet operators of the q-equation for k = 1 (state independent: once per mesh) ---------------------
+struct FacetRule {
+  int nq;
+  double s[8], w[8];  // Gauss-Legendre on [0,1]
+};
+
+__device__ __forceinline__ void cg2_values(const double* lam, double* phi) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) phi[i] = lam[i] * (2.0 * lam[i] - 1.0);
+  phi[3] = 4.0 * lam[1] * lam[2];
+  phi[4] = 4.0 * lam[0] * lam[2];
+  phi[5] = 4.0 * lam[0] * lam[1];
+}
+
+// d phi_k / dn for the 6 CG2 functions of a cell with barycentric gradients (gx, gy)
+__device__ __forceinline__ void cg2_normal_derivs(const double* lam, const double* gx, const double* gy,
+                                                  const double nx, const double ny, double* d) {
+  double gn[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gn[i] = gx[i] * nx + gy[i] * ny;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[i] = (4.0 * lam[i] - 1.0) * gn[i];
+  d[3] = 4.0 * (lam[1] * gn[2] + lam[2] * gn[1]);
+  d[4] = 4.0 * (lam[0] * gn[2] + lam[2] * gn[0]);
+  d[5] = 4.0 * (lam[0] * gn[1] + lam[1] * gn[0]);
+}
+
+// exterior facets: Jx[36][nfe] = sum ds cq phi_k phi_l, cx[6][nfe] = sum ds cd q_ex phi_k,
+// nat[2][nfe] = natural p data on the two flux dofs of the facet (kind bit 4), with
+//   cq = [kind&1] (r2vec.n) W + stab2 (hK neg(r2vec.n)^2 + 8/hK),  cd = [kind&2] (r2vec.n) W - stab2 (...)
+// (test_for_paper_convergence.py:142-145,148-149,152-153; hK = FacetArea, r2vec = (1,0))
+__global__ void __launch_bounds__(kMxThreads)
+cg2_exterior_facets_kernel(const FacetRule R, const double stab2, const int nfe,
+                           const int* __restrict__ fverts, const int* __restrict__ fcell,
+                           const int* __restrict__ kind, const int* __restrict__ cells,
+                           const double2* __restrict__ coords, const double* __restrict__ qex,
+                           const double* __restrict__ pex, double* __restrict__ Jx,
+                           double* __restrict__ cx, double* __restrict__ nat) {
+  const int f = blockIdx.x * kMxThreads + threadIdx.x;
+  if (f >= nfe) return;
+  const int va = fverts[2 * f], vb = fverts[2 * f + 1], c = fcell[f], kd = kind[f];
+  int la = 0, lb = 0;
+  double2 X[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int v = cells[3 * (size_t)c + i];
+    X[i] = coords[v];
+    if (v == va) la = i;
+    if (v == vb) lb = i;
+  }
+  const int lo = 3 - la - lb;  // local vertex opposite the facet
+  const double tx = X[lb].x - X[la].x, ty = X[lb].y - X[la].y;
+  const double L = sqrt(tx * tx + ty * ty);
+  const double gnx = ty / L, gny = -tx / L;  // global normal: tangent (low -> high vertex) rotated clockwise
+  double nx = gnx, ny = gny;
+  if (nx * (X[lo].x - X[la].x) + ny * (X[lo].y - X[la].y) > 0.0) { nx = -nx; ny = -ny; }
+  const double sgn = (nx * gnx + ny * gny) > 0.0 ? 1.0 : -1.0;
+  const double bn = nx;
+  const double neg = 0.5 * (fabs(bn) - bn);
+  const double pen = stab2 * (L * neg * neg + 8.0 / L);
+  double J[36], cv[6], n0 = 0.0, n1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 36; ++i) J[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cv[i] = 0.0;
+  for (int k = 0; k < R.nq; ++k) {
+    const double s = R.s[k];
+    double lam[3] = {0.0, 0.0, 0.0};
+    lam[la] = 1.0 - s;
+    lam[lb] = s;
+    const double x = X[la].x + s * tx, y = X[la].y + s * ty;
+    const double t = kFourPi * x * y, W = t * t;
+    const double ds = R.w[k] * L;
+    const double cq = ((kd & 1) ? bn * W : 0.0) + pen;
+    const double cd = ((kd & 2) ? bn * W : 0.0) - pen;
+    double phi[6];
+    cg2_values(lam, phi);
+    const double dq = ds * cd * qex[(size_t)f * R.nq + k];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      cv[a] += dq * phi[a];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) J[6 * a + b] += ds * cq * phi[a] * phi[b];
+    }
+    if (kd & 4) {
+      const double pw = ds * W * pex[(size_t)f * R.nq + k];
+      n0 += pw * (1.0 - s);
+      n1 += pw * s;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 36; ++i) Jx[(size_t)i * nfe + f] = J[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cx[(size_t)i * nfe + f] = cv[i];
+  nat[f] = n0 * sgn / L;
+  nat[(size_t)nfe + f] = n1 * sgn / L;
+}
+
+// interior facets: Ji[144][nfi], row-major over the 12 macro dofs (6 of cell0 = '+', then 6 of cell1):
+// gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS with hK = FacetArea (:144).  One thread per (row, facet).
+__global__ void __launch_bounds__(kMxThreads)
+cg2_interior_facets_kernel(const FacetRule R, const double gamma, const int nfi,
+                           const int* __restrict__ fverts, const int* __restrict__ fcell,
+                           const int* __restrict__ cells, const double2* __restrict__ coords,
+                           double* __restrict__ Ji) {
+  const long long t = (long long)blockIdx.x * kMxThreads + threadIdx.x;
+  if (t >= 12ll * nfi) return;
+  const int row = (int)(t / nfi), f = (int)(t % nfi);
+  const int va = fverts[2 * f], vb = fverts[2 * f + 1];
+  int la[2], lb[2];
+  double gx[2][3], gy[2][3];
+  double2 A = make_double2(0.0, 0.0), B = A, O = A;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int c = fcell[2 * f + side];
+    double2 X[3];
+    la[side] = lb[side] = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int v = cells[3 * (size_t)c + i];
+      X[i] = coords[v];
+      if (v == va) la[side] = i;
+      if (v == vb) lb[side] = i;
+    }
+    const double j00 = X[1].x - X[0].x, j01 = X[2].x - X[0].x, j10 = X[1].y - X[0].y, j11 = X[2].y - X[0].y;
+    const double id = 1.0 / (j00 * j11 - j01 * j10);
+    gx[side][1] = j11 * id;  gy[side][1] = -j01 * id;
+    gx[side][2] = -j10 * id; gy[side][2] = j00 * id;
+    gx[side][0] = -(gx[side][1] + gx[side][2]);
+    gy[side][0] = -(gy[side][1] + gy[side][2]);
+    if (side == 0) {
+      A = X[la[0]];
+      B = X[lb[0]];
+      O = X[3 - la[0] - lb[0]];
+    }
+  }
+  const double tx = B.x - A.x, ty = B.y - A.y;
+  const double L = sqrt(tx * tx + ty * ty);
+  double nx = ty / L, ny = -tx / L;
+  if (nx * (O.x - A.x) + ny * (O.y - A.y) > 0.0) { nx = -nx; ny = -ny; }  // n+ = outward normal of cell0
+  double J[12];
+#pragma unroll
+  for (int b = 0; b < 12; ++b) J[b] = 0.0;
+  for (int k = 0; k < R.nq; ++k) {
+    const double s = R.s[k];
+    const double x = A.x + s * tx, y = A.y + s * ty;
+    const double tt = kFourPi * x * y;
+    const double coef = gamma * L * L * R.w[k] * L * (tt * tt);
+    double d[12];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      double lam[3] = {0.0, 0.0, 0.0};
+      lam[la[side]] = 1.0 - s;
+      lam[lb[side]] = s;
+      cg2_normal_derivs(lam, gx[side], gy[side], nx, ny, d + 6 * side);
+    }
+#pragma unroll
+    for (int b = 6; b < 12; ++b) d[b] = -d[b];
+    const double dr = coef * d[row];
+#pragma unroll
+    for (int b = 0; b < 12; ++b) J[b] += dr * d[b];
+  }
+#pragma unroll
+  for (int b = 0; b < 12; ++b) Ji[((size_t)row * 12 + b) * nfi + f] = J[b];
+}
+
+static int facet_rule_arg(int nq, const double* rule_host, FacetRule& R) {
+  if (nq < 1 || nq > 8 || rule_host == nullptr) return CM_E_INVALID;
+  R.nq = nq;
+  for (int k = 0; k < nq; ++k) {
+    R.s[k] = rule_host[2 * k];
+    R.w[k] = rule_host[2 * k + 1];
+  }
+  return CM_OK;
+}
+
+int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, const int* fverts,
+                        const int* fcell, const int* kind, const int* cells, const double* coords,
+                        const double* qex, const double* pex, double* Jx, double* cx, double* nat,
+                        cudaStream_t st) {
+  FacetRule R;
+  if (facet_rule_arg(nq, rule_host, R)) {
+    set_error("cm_cg2_exterior_facets: bad facet rule (1..8 points)");
+    return CM_E_INVALID;
+  }
+  if (nfe <= 0) return CM_OK;
+  cg2_exterior_facets_kernel<<<(nfe + kMxThreads - 1) / kMxThreads, kMxThreads, 0, st>>>(
+      R, stab2, nfe, fverts, fcell, kind, cells, (const double2*)coords, qex, pex, Jx, cx, nat);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, const int* fverts,
+                        const int* fcell, const int* cells, const double* coords, double* Ji,
+                        cudaStream_t st) {
+  FacetRule R;
+  if (facet_rule_arg(nq, rule_host, R)) {
+    set_error("cm_cg2_interior_facets: bad facet rule (1..8 points)");
+    return CM_E_INVALID;
+  }
+  if (nfi <= 0) return CM_OK;
+  const long long nt = 12ll * nfi;
+  cg2_interior_facets_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
+      R, gamma, nfi, fverts, fcell, cells, (const double2*)coords, Ji);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
 static int mx_rule(int nq, const double* rule_host, MxRule& R) {
   if (nq < 1 || nq > kMxRule || rule_host == nullptr) return CM_E_INVALID;
   R.nq = nq;

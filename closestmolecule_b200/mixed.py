@@ -328,8 +328,9 @@ class PaperMixedSystemK1:
     """RT2 x DG1 x CG2 'paper' system on the GPU: per Newton step cm_mixed_m1_cells (17 x 17 element tensors),
     cm_csr_gather, cm_spmv, cm_apply_dirichlet and the pivoting LU (cm_blu_*).  The q-q facet operator (C0IP
     jump penalty on CG2, weak outflow data, boundary penalty; :142-145,152-153) and the natural p data on the
-    flux rows (:148-149) are state independent: they are tabulated once per mesh with torch on the device
-    (setup, like the forcing at the quadrature points) and enter every step as a constant matrix / vector."""
+    flux rows (:148-149) are state independent: cm_cg2_exterior_facets / cm_cg2_interior_facets tabulate them
+    once per mesh and they enter every step as a constant matrix / vector (_facet_tables is the torch
+    restatement of the same operator for the CPU table test)."""
 
     def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=2.0, degree=6, tables_only=False):
         if not tables_only:
@@ -382,8 +383,13 @@ class PaperMixedSystemK1:
         qd = torch.cat([q0 + cells, q0 + V + ce], 1)
         self.sd, self.pd, self.qd = sd, pd, qd
         self.cell_dofs = cd = torch.cat([sd, pd, qd], 1)                               # [C,17]
-        # constant facet operator (COO) and vectors
-        fr, fcn, fv, self.cvec = self._facet_tables(degree)
+        # constant facet operator (COO) and vectors: CUDA kernels (cm_cg2_*_facets); the torch tabulation
+        # _facet_tables is the host restatement used by the CPU table test and the GPU cross-check
+        if tables_only:
+            fr, fcn, fv, self.cvec = self._facet_tables(degree)
+            cv_rows = cv_vals = None
+        else:
+            fr, fcn, fv, cv_rows, cv_vals = self._facet_tables_cuda(degree)
         rows_c = cd.repeat_interleave(17, dim=1).flatten()
         cols_c = cd.repeat(1, 17).flatten()
         self._key, self.rowptr, self.col = _csr_from_pairs(torch.cat([rows_c, fr]), torch.cat([cols_c, fcn]), N)
@@ -395,8 +401,23 @@ class PaperMixedSystemK1:
         entv = (torch.arange(17, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
         self.vec_ptr, order = _gather_lists(cd.flatten(), N)
         self.vec_idx = entv[order].to(torch.int32).contiguous()
-        self.Kf = torch.zeros(self.nnz, dtype=torch.float64, device=dev)
-        self.Kf.index_add_(0, torch.searchsorted(self._key, fr * N + fcn), fv)
+        fslot = torch.searchsorted(self._key, fr * N + fcn)
+        if tables_only:
+            self.Kf = torch.zeros(self.nnz, dtype=torch.float64, device=dev)
+            self.Kf.index_add_(0, fslot, fv)
+        else:   # deterministic: per-slot gather lists in facet order (exterior, then interior)
+            st = _capi.stream_ptr()
+            ptr, order = _gather_lists(fslot, self.nnz)
+            self.Kf = torch.empty(self.nnz, dtype=torch.float64, device=dev)
+            fv = fv.contiguous()
+            _capi.check(self.lib.cm_csr_gather(self.nnz, _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
+                                               _capi.ptr(fv), _capi.ptr(self.Kf), 0, st))
+            ptr, order = _gather_lists(cv_rows, N)
+            self.cvec = torch.empty(N, dtype=torch.float64, device=dev)
+            cv_vals = cv_vals.contiguous()
+            _capi.check(self.lib.cm_csr_gather(N, _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
+                                               _capi.ptr(cv_vals), _capi.ptr(self.cvec), 0, st))
+            torch.cuda.current_stream().synchronize()
         self.diag_slot_all = (torch.searchsorted(self._key, torch.arange(N, device=dev) * (N + 1))
                               - self.rowptr[:-1].long()).to(torch.int32)
         if tables_only:
@@ -487,6 +508,58 @@ class PaperMixedSystemK1:
         cols.append(md.repeat(1, 12).flatten())
         vals.append(Ji.flatten())
         return torch.cat(rows), torch.cat(cols), torch.cat(vals), cvec
+
+    def _facet_tables_cuda(self, degree):
+        """The same operator from the CUDA kernels: returns COO (rows, cols, vals) of the q-q facet matrix and
+        (rows, vals) of the constant vector, both in kernel storage order (entry-major over facets)."""
+        mesh, fc, dev, lib = self.mesh, self.mesh.facets(), self.mesh.device, self.lib
+        m = (degree + 2) // 2
+        p, w = np.polynomial.legendre.leggauss(m)
+        rule = np.ascontiguousarray(np.stack([0.5 * (p + 1.0), 0.5 * w], 1), dtype=np.float64)
+        s = torch.tensor(rule[:, 0], device=dev)
+        st = _capi.stream_ptr()
+        f64 = dict(dtype=torch.float64, device=dev)
+        # exterior
+        ext = torch.nonzero(fc.cell1 < 0).flatten()
+        nfe = ext.numel()
+        fv_e = fc.verts[ext].to(torch.int32).contiguous()
+        fc_e = fc.cell0[ext].to(torch.int32).contiguous()
+        mk = self.bdry.values[ext]
+        kind = (((mk == 30) | (mk == 32)).to(torch.int32) + 2 * (mk == 31).to(torch.int32)
+                + 4 * ((mk == 31) | (mk == 32)).to(torch.int32)).contiguous()
+        A = mesh.coords[fv_e[:, 0].long()]
+        B = mesh.coords[fv_e[:, 1].long()]
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        qex = q_exact(Pq[..., 0], Pq[..., 1]).to(torch.float64).contiguous()
+        pex = p_exact(Pq[..., 0], Pq[..., 1]).to(torch.float64).contiguous()
+        Jx, cx, nat = torch.empty(36 * nfe, **f64), torch.empty(6 * nfe, **f64), torch.empty(2 * nfe, **f64)
+        _capi.check(lib.cm_cg2_exterior_facets(m, rule.ctypes.data, self.stab2, nfe, _capi.ptr(fv_e), _capi.ptr(fc_e),
+                                               _capi.ptr(kind), _capi.ptr(mesh.cells), _capi.ptr(mesh.coords),
+                                               _capi.ptr(qex), _capi.ptr(pex), _capi.ptr(Jx), _capi.ptr(cx),
+                                               _capi.ptr(nat), st))
+        qd_e = self.qd[fc_e.long()].T.contiguous()                                    # [6,nfe]
+        ia = torch.arange(6, device=dev).repeat_interleave(6)
+        ib = torch.arange(6, device=dev).repeat(6)
+        rows = [qd_e[ia].flatten()]
+        cols = [qd_e[ib].flatten()]
+        vals = [Jx]
+        cv_rows = [qd_e.flatten(), 2 * ext, 2 * ext + 1]
+        cv_vals = [cx, nat]
+        # interior
+        fi = torch.nonzero(fc.cell1 >= 0).flatten()
+        nfi = fi.numel()
+        fv_i = fc.verts[fi].to(torch.int32).contiguous()
+        fc_i = torch.stack([fc.cell0[fi], fc.cell1[fi]], 1).to(torch.int32).contiguous()
+        Ji = torch.empty(144 * nfi, **f64)
+        _capi.check(lib.cm_cg2_interior_facets(m, rule.ctypes.data, self.gamma, nfi, _capi.ptr(fv_i), _capi.ptr(fc_i),
+                                               _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(Ji), st))
+        md = torch.cat([self.qd[fc_i[:, 0].long()], self.qd[fc_i[:, 1].long()]], 1).T.contiguous()   # [12,nfi]
+        ja = torch.arange(12, device=dev).repeat_interleave(12)
+        jb = torch.arange(12, device=dev).repeat(12)
+        rows.append(md[ja].flatten())
+        cols.append(md[jb].flatten())
+        vals.append(Ji)
+        return torch.cat(rows), torch.cat(cols), torch.cat(vals), torch.cat(cv_rows), torch.cat(cv_vals)
 
     def _rt_values(self):
         """RT2 basis values at the cell quadrature points [C,nq,8,2] (setup: the projection of sig_ex)."""

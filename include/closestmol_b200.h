@@ -375,6 +375,22 @@ int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t ncells, int3
                        const double* sign, const double* u, const double* exact_q, double* work,
                        void* stream);
 
+/* CG2 facet operators of the k = 1 q-equation (state independent, once per mesh; :142-145,148-149,152-153).
+ * rule_host[2*nq] = (s, w) Gauss-Legendre on [0,1].  fverts[nf*2] ascending vertex ids.
+ *   exterior: fcell[nfe] attached cell, kind bits 1: (r2vec.n) q w W ds, 2: (r2vec.n) q_ex w W ds,
+ *     4: natural p data on the facet's two flux dofs; the boundary penalty stab2 (hK neg(r2vec.n)^2 + 8/hK)
+ *     (q - q_ex) w ds applies to every listed facet.  qex / pex[nfe*nq]: q_ex, p_ex at the facet points.
+ *     Outputs entry-major: Jx[36][nfe] (6 x 6 on the attached cell's CG2 dofs), cx[6][nfe], nat[2][nfe].
+ *   interior: fcell[nfi*2] = (cell0 = '+', cell1); Ji[144][nfi], 12 x 12 on (cell0's 6, cell1's 6) CG2 dofs:
+ *     gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS with hK = FacetArea. */
+int cm_cg2_exterior_facets(int32_t nq, const double* rule_host, double stab2, int32_t nfe,
+                           const int32_t* fverts, const int32_t* fcell, const int32_t* kind,
+                           const int32_t* cells, const double* coords, const double* qex, const double* pex,
+                           double* Jx, double* cx, double* nat, void* stream);
+int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, int32_t nfi,
+                           const int32_t* fverts, const int32_t* fcell, const int32_t* cells,
+                           const double* coords, double* Ji, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,17 @@ def test_recorded_k1_table_through_the_gpu_path():
     for k in range(2):
         assert got[k][:6] == ref[k][:6], (rows[k], PAPER_K1[k])
         assert abs(got[k][6] - ref[k][6]) <= 0.011 * 10 ** np.floor(np.log10(ref[k][6])), (got[k], ref[k])
+
+
+def test_k1_cuda_facet_operator_matches_host_tabulation():
+    """cm_cg2_exterior_facets / cm_cg2_interior_facets against the torch restatement (_facet_tables), which the CPU
+    test tests/test_mixed_tables.py compares with the oracle."""
+    S = _system_k1(6)
+    fr, fcn, fv, cvec = S._facet_tables(6)
+    Kf = torch.zeros(S.nnz, dtype=torch.float64, device=S.mesh.device)
+    Kf.index_add_(0, torch.searchsorted(S._key, fr * S.N + fcn), fv)
+    assert float((S.Kf - Kf).abs().max()) < 1e-12 * float(Kf.abs().max())
+    assert float((S.cvec - cvec).abs().max()) < 1e-12 * float(cvec.abs().max())
+    # deterministic: two builds give the same bits
+    S2 = _system_k1(6)
+    assert torch.equal(S.Kf, S2.Kf) and torch.equal(S.cvec, S2.cvec)
