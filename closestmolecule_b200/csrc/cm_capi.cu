@@ -509,4 +509,15 @@ int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, in
   return cg2_interior_facets(nq, rule_host, gamma, nfi, fverts, fcell, cells, coords, Ji, (cudaStream_t)stream);
 }
 
+int cm_mixed_p2_cells(int32_t nq, const double* rule_host, double D1, double D2, double concentration,
+                      double inv_dt, int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells,
+                      const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
+                      const double* p_old, double* Je, double* Fe, void* stream) {
+  CM_CHECK_ARG(ncells >= 1 && nedges >= 3 && nverts >= 3 && concentration > 0.0, "bad size or concentration");
+  CM_CHECK_ARG(rule_host && cells && coords && cell_edges && sign && u && Fe, "null pointer");
+  CM_CHECK_ARG(inv_dt == 0.0 || p_old != nullptr, "transient form needs p_old");
+  return mixed_p2_cells(nq, rule_host, D1, D2, concentration, inv_dt, ncells, nedges, nverts, cells, coords,
+                        cell_edges, sign, u, p_old, Je, Fe, (cudaStream_t)stream);
+}
+
 }  // extern "C"

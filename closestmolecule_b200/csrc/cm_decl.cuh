@@ -169,4 +169,8 @@ int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, 
 int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, const int* fverts,
                         const int* fcell, const int* cells, const double* coords, double* Ji,
                         cudaStream_t st);
+int mixed_p2_cells(int nq, const double* rule_host, double D1, double D2, double conc, double inv_dt, int ncells,
+                   int nE, int nV, const int* cells, const double* coords, const int* cell_edges,
+                   const double* sign, const double* u, const double* p_old, double* Je, double* Fe,
+                   cudaStream_t st);
 }  // namespace cm

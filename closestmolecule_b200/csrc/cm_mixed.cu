@@ -10,7 +10,7 @@
 namespace cm {
 
 constexpr int kMxThreads = 128;
-constexpr int kMxRule = 16;
+constexpr int kMxRule = 40;
 constexpr int kMxBlocks = 592;
 
 struct MxRule {
@@ -637,6 +637,189 @@ int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, 
   return CM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Production mixed formulation DG2 x RT3 x CG3 (advection_diffusion_mixed.py:147-150,196-216).
+// 31 local dofs [p: 6 DG2 | s: 15 RT3 | q: 10 CG3]; bases:
+//   DG2: lambda_i (2 lambda_i - 1), 4 lambda_j lambda_k;
+//   RT3: per facet i (end points j < k): lambda_j^2 N_i, lambda_j lambda_k N_i, lambda_k^2 N_i with
+//        N_i = sigma_i (x - X_i)/(2|K|); interior: lambda_i lambda_m N_i (unsigned), i = 1,2, m = 0,1,2;
+//   CG3: Lagrange P3 (vertices; per facet the node nearer the lower vertex, then the other; bubble).
+// Global dofs [6 per cell | 3 per edge, 6 per cell | vertices, 2 per edge, 1 per cell].
+// One thread per (test function, cell), as for k = 1.
+// ------------------------------------------------------------------------------------------------
+struct P2Cell {
+  double X[3], Y[3], gx[3], gy[3], adet, rs[3];
+  double pe[6], se[15], qe[10], po[6];
+};
+
+struct P2Point {
+  double a, x, y;
+  double Rx[15], Ry[15], dr[15], drD[15], chi[6], phi[10], phix[10];
+};
+
+__device__ __forceinline__ void p2m_load_cell(const int c, const int C, const int E, const int V,
+                                              const int* __restrict__ cells,
+                                              const double2* __restrict__ coords,
+                                              const int* __restrict__ cell_edges,
+                                              const double* __restrict__ sign, const double* __restrict__ u,
+                                              const double* __restrict__ p_old, P2Cell& K) {
+  int v[3], e[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    v[i] = cells[3 * (size_t)c + i];
+    e[i] = cell_edges[3 * (size_t)c + i];
+    const double2 P = coords[v[i]];
+    K.X[i] = P.x;
+    K.Y[i] = P.y;
+  }
+  const double j00 = K.X[1] - K.X[0], j01 = K.X[2] - K.X[0], j10 = K.Y[1] - K.Y[0], j11 = K.Y[2] - K.Y[0];
+  const double det = j00 * j11 - j01 * j10, id = 1.0 / det;
+  K.adet = fabs(det);
+  K.gx[1] = j11 * id;  K.gy[1] = -j01 * id;
+  K.gx[2] = -j10 * id; K.gy[2] = j00 * id;
+  K.gx[0] = -(K.gx[1] + K.gx[2]);
+  K.gy[0] = -(K.gy[1] + K.gy[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) K.rs[i] = sign[3 * (size_t)c + i] / K.adet;
+  const size_t s0 = 6 * (size_t)C, q0 = s0 + 3 * (size_t)E + 6 * (size_t)C;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    K.pe[b] = u[6 * (size_t)c + b];
+    K.po[b] = p_old ? p_old[6 * (size_t)c + b] : 0.0;
+    K.se[9 + b] = u[s0 + 3 * (size_t)E + 6 * (size_t)c + b];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) K.se[3 * i + m] = u[s0 + 3 * (size_t)e[i] + m];
+    K.qe[i] = u[q0 + v[i]];
+    K.qe[3 + 2 * i] = u[q0 + V + 2 * (size_t)e[i]];
+    K.qe[4 + 2 * i] = u[q0 + V + 2 * (size_t)e[i] + 1];
+  }
+  K.qe[9] = u[q0 + V + 2 * (size_t)E + c];
+}
+
+__device__ __forceinline__ void p2m_eval_point(const P2Cell& K, const double l1, const double l2, const double w,
+                                               const double D1, const double D2, P2Point& Q) {
+  const double lam[3] = {1.0 - l1 - l2, l1, l2};
+  Q.x = lam[0] * K.X[0] + lam[1] * K.X[1] + lam[2] * K.X[2];
+  Q.y = lam[0] * K.Y[0] + lam[1] * K.Y[1] + lam[2] * K.Y[2];
+  const double t = kFourPi * Q.x * Q.y;
+  Q.a = w * K.adet * (t * t);
+  // RT3: (facet i, quadratic lambda_a lambda_b); facets: (j,j), (j,k), (k,k); interior: i in {1,2}, (i, m)
+  const int fi[15] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 1, 1, 1, 2, 2, 2};
+  const int fa[15] = {1, 1, 2, 0, 0, 2, 0, 0, 1, 1, 1, 1, 2, 2, 2};
+  const int fb[15] = {1, 2, 2, 0, 2, 2, 0, 1, 1, 0, 1, 2, 0, 1, 2};
+#pragma unroll
+  for (int m = 0; m < 15; ++m) {
+    const int i = fi[m], a = fa[m], b = fb[m];
+    const double c = (m < 9) ? K.rs[i] : 1.0 / K.adet;
+    const double dx = Q.x - K.X[i], dy = Q.y - K.Y[i];
+    const double qv = lam[a] * lam[b];
+    const double qgx = lam[a] * K.gx[b] + lam[b] * K.gx[a];
+    const double qgy = lam[a] * K.gy[b] + lam[b] * K.gy[a];
+    Q.Rx[m] = qv * dx * c;
+    Q.Ry[m] = qv * dy * c;
+    const double dxx = c * (qgx * dx + qv);
+    const double dyy = c * (qgy * dy + qv);
+    Q.dr[m] = dxx + dyy + 2.0 * Q.Rx[m] / Q.x + 2.0 * Q.Ry[m] / Q.y;
+    Q.drD[m] = D2 * (dxx + 2.0 * Q.Rx[m] / Q.x) + D1 * (dyy + 2.0 * Q.Ry[m] / Q.y);
+  }
+  const int ej[3] = {1, 0, 0}, ek[3] = {2, 2, 1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double l = lam[i];
+    Q.chi[i] = l * (2.0 * l - 1.0);
+    Q.chi[3 + i] = 4.0 * lam[ej[i]] * lam[ek[i]];
+    Q.phi[i] = 0.5 * l * (3.0 * l - 1.0) * (3.0 * l - 2.0);
+    Q.phix[i] = 0.5 * (27.0 * l * l - 18.0 * l + 2.0) * K.gx[i];
+    const double lj = lam[ej[i]], lk = lam[ek[i]], gj = K.gx[ej[i]], gk = K.gx[ek[i]];
+    Q.phi[3 + 2 * i] = 4.5 * lj * lk * (3.0 * lj - 1.0);
+    Q.phix[3 + 2 * i] = 4.5 * ((gj * lk + lj * gk) * (3.0 * lj - 1.0) + lj * lk * 3.0 * gj);
+    Q.phi[4 + 2 * i] = 4.5 * lk * lj * (3.0 * lk - 1.0);
+    Q.phix[4 + 2 * i] = 4.5 * ((gk * lj + lk * gj) * (3.0 * lk - 1.0) + lk * lj * 3.0 * gk);
+  }
+  Q.phi[9] = 27.0 * lam[0] * lam[1] * lam[2];
+  Q.phix[9] = 27.0 * (K.gx[0] * lam[1] * lam[2] + lam[0] * K.gx[1] * lam[2] + lam[0] * lam[1] * K.gx[2]);
+}
+
+// Je: [961][ncells] (31 x 31 row-major, entry-major over cells), Fe: [31][ncells]
+__global__ void __launch_bounds__(kMxThreads)
+mixed_p2_cells_kernel(const MxRule R, const double D1, const double D2, const double conc, const double inv_dt,
+                      const int ncells, const int nE, const int nV, const int* __restrict__ cells,
+                      const double2* __restrict__ coords, const int* __restrict__ cell_edges,
+                      const double* __restrict__ sign, const double* __restrict__ u,
+                      const double* __restrict__ p_old, double* __restrict__ Je, double* __restrict__ Fe) {
+  const long long t = (long long)blockIdx.x * kMxThreads + threadIdx.x;
+  if (t >= 31ll * ncells) return;
+  const int row = (int)(t / ncells), c = (int)(t % ncells);
+  P2Cell K;
+  p2m_load_cell(c, ncells, nE, nV, cells, coords, cell_edges, sign, u, p_old, K);
+  double J[31], F = 0.0;
+#pragma unroll
+  for (int b = 0; b < 31; ++b) J[b] = 0.0;
+  const double gs_scale = 1.0 / (4.0 * conc * 3.14159265358979323846), gs_lin = kFourPi * conc;
+  for (int k = 0; k < R.nq; ++k) {
+    P2Point Q;
+    p2m_eval_point(K, R.l1[k], R.l2[k], R.w[k], D1, D2, Q);
+    double p = 0.0, po = 0.0, sx = 0.0, sy = 0.0, drDs = 0.0, q = 0.0, qx = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      p += K.pe[b] * Q.chi[b];
+      po += K.po[b] * Q.chi[b];
+    }
+#pragma unroll
+    for (int m = 0; m < 15; ++m) {
+      sx += K.se[m] * Q.Rx[m];
+      sy += K.se[m] * Q.Ry[m];
+      drDs += K.se[m] * Q.drD[m];
+    }
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+      q += K.qe[m] * Q.phi[m];
+      qx += K.qe[m] * Q.phix[m];
+    }
+    const double x2 = Q.x * Q.x;
+    // Gstar (advection_diffusion_mixed.py:17-23): conditional(|p/(4 c pi) - q| > 1e-3, (p/q) p r2^2, 4 pi c p r2^2)
+    const bool cond = fabs(gs_scale * p - q) > 1e-3;
+    const double qs = cond ? q : 1.0;
+    const double G = cond ? p / qs * p * x2 : gs_lin * p * x2;
+    const double Gp = cond ? 2.0 * p / qs * x2 : gs_lin * x2;
+    const double Gq = cond ? -p * p / (qs * qs) * x2 : 0.0;
+    const double a = Q.a;
+    if (row < 6) {  // v = chi_row: div_rad(D s) v W (+ (p - p_old)/dt v W)
+      const double ch = Q.chi[row];
+      F += a * (drDs + inv_dt * (p - po)) * ch;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) J[b] += a * inv_dt * ch * Q.chi[b];
+#pragma unroll
+      for (int m = 0; m < 15; ++m) J[6 + m] += a * ch * Q.drD[m];
+    } else if (row < 21) {  // tau = Psi: (s + G e_x).tau W - p div_rad(tau) W
+      const int r = row - 6;
+      const double rx = Q.Rx[r], ry = Q.Ry[r], dra = Q.dr[r];
+      F += a * (sx * rx + sy * ry + G * rx - p * dra);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) J[b] += a * (Gp * rx - dra) * Q.chi[b];
+#pragma unroll
+      for (int m = 0; m < 15; ++m) J[6 + m] += a * (rx * Q.Rx[m] + ry * Q.Ry[m]);
+#pragma unroll
+      for (int m = 0; m < 10; ++m) J[21 + m] += a * Gq * rx * Q.phi[m];
+    } else {  // w = phi: (dq/dx + x^2 p) w W
+      const double ph = Q.phi[row - 21];
+      F += a * (qx + x2 * p) * ph;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) J[b] += a * x2 * Q.chi[b] * ph;
+#pragma unroll
+      for (int m = 0; m < 10; ++m) J[21 + m] += a * ph * Q.phix[m];
+    }
+  }
+  Fe[(size_t)row * ncells + c] = F;
+  if (Je != nullptr) {
+#pragma unroll
+    for (int b = 0; b < 31; ++b) Je[((size_t)row * 31 + b) * ncells + c] = J[b];
+  }
+}
+
 static int mx_rule(int nq, const double* rule_host, MxRule& R) {
   if (nq < 1 || nq > kMxRule || rule_host == nullptr) return CM_E_INVALID;
   R.nq = nq;
@@ -727,6 +910,23 @@ int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV,
   CM_LAUNCH_CHECK();
   mixed_final_sum_kernel<<<1, 32, 0, st>>>(kMxBlocks, work + 4, work);
   CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int mixed_p2_cells(int nq, const double* rule_host, double D1, double D2, double conc, double inv_dt, int ncells,
+                   int nE, int nV, const int* cells, const double* coords, const int* cell_edges,
+                   const double* sign, const double* u, const double* p_old, double* Je, double* Fe,
+                   cudaStream_t st) {
+  MxRule R;
+  if (mx_rule(nq, rule_host, R)) {
+    set_error("cm_mixed_p2_cells: bad quadrature rule (1..%d points)", kMxRule);
+    return CM_E_INVALID;
+  }
+  const long long nt = 31ll * ncells;
+  mixed_p2_cells_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
+      R, D1, D2, conc, inv_dt, ncells, nE, nV, cells, (const double2*)coords, cell_edges, sign, u, p_old, Je, Fe);
+  CM_LAUNCH_CHECK();
+  CM_BYTES((double)ncells * (12.0 + 12.0 + 24.0 + 248.0 + 248.0 + (Je ? 7688.0 : 0.0)));
   return CM_OK;
 }
 

@@ -21,7 +21,7 @@ from .assembler import PQAssembler
 from .forms import EF_ADV, EF_DATA, EF_PENALTY, PQPrimalForm
 from .manufactured import _torchify, p_exact, q_exact
 from .mesh import DOLFIN_EPS
-from .quadrature import facet_rule, triangle_rule
+from .quadrature import collapsed_triangle_rule, facet_rule, triangle_rule
 from .solver import BandedLULinearSolver
 from .space import FiniteElement, FunctionSpace, MixedElement
 
@@ -672,3 +672,295 @@ class PaperMixedSystemK1:
             _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
             _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))
         return tuple(math.sqrt(float(v)) for v in work[:3].cpu())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# production mixed formulation DG2 x RT3 x CG3 (advection_diffusion_mixed.py:94-269)
+# ---------------------------------------------------------------------------------------------------------
+class ProductionMixedSystem:
+    """solve_problem_instance of advection_diffusion_mixed.py (deg = 2: DG2 x RT3 x CG3, :147-150) on the GPU:
+    cm_mixed_p2_cells (31 x 31 element tensors, production Gstar), cm_csr_gather, cm_apply_dirichlet, cm_blu_*
+    ('mumps', :223).  Markers right = 21, top = 22, left = 23, bottom = 24.  The natural p data on the right / top
+    facets (:203-204) and the Dirichlet values are boundary data tabulated once with torch; the RT3 projection of
+    the flux (:243) assembles its mass matrix with the same gather machinery and solves it with the LU."""
+
+    RIGHT, TOP, LEFT, BOTTOM = 21, 22, 23, 24
+    CELL_DEGREE, FACET_POINTS = 10, 6
+
+    def __init__(self, mesh, bdry, concentration, sigma, gamma, V1, D1, D2, dt=None):
+        _capi.require_cuda(mesh.coords)
+        self.lib = _capi.lib()
+        self.mesh, self.bdry = mesh, bdry
+        self.c, self.sigma, self.gamma, self.V1 = float(concentration), float(sigma), float(gamma), float(V1)
+        self.D1, self.D2 = float(D1), float(D2)
+        self.inv_dt = 0.0 if dt is None else 1.0 / float(dt)
+        dev = mesh.device
+        fc = mesh.facets()
+        V, C, E = mesh.num_vertices(), mesh.num_cells(), fc.num
+        self.V, self.C, self.E = V, C, E
+        self.np_, self.ns = 6 * C, 3 * E + 6 * C
+        self.q0 = self.np_ + self.ns
+        self.N = N = self.q0 + V + 2 * E + C
+        cells = mesh.cells.long()
+        X = mesh.coords
+        fa = torch.stack([cells[:, 1], cells[:, 0], cells[:, 0]], 1)
+        fb = torch.stack([cells[:, 2], cells[:, 2], cells[:, 1]], 1)
+        key = torch.minimum(fa, fb) * V + torch.maximum(fa, fb)
+        allkey = fc.verts[:, 0].long() * V + fc.verts[:, 1].long()
+        ce = torch.searchsorted(allkey, key)
+        A, B = X[fc.verts[:, 0].long()], X[fc.verts[:, 1].long()]
+        t = B - A
+        self.elen = t.pow(2).sum(1).sqrt()
+        self.enorm = torch.stack([t[:, 1], -t[:, 0]], 1) / self.elen[:, None]
+        Xc = X[cells]
+        self.Xc = Xc
+        self.sign = torch.sign(((0.5 * (A + B)[ce] - Xc) * self.enorm[ce]).sum(-1)).to(torch.float64).contiguous()
+        self.cell_edges = ce.to(torch.int32).contiguous()
+        det = ((Xc[:, 1, 0] - Xc[:, 0, 0]) * (Xc[:, 2, 1] - Xc[:, 0, 1])
+               - (Xc[:, 2, 0] - Xc[:, 0, 0]) * (Xc[:, 1, 1] - Xc[:, 0, 1]))
+        g1 = torch.stack([Xc[:, 2, 1] - Xc[:, 0, 1], -(Xc[:, 2, 0] - Xc[:, 0, 0])], 1) / det[:, None]
+        g2 = torch.stack([-(Xc[:, 1, 1] - Xc[:, 0, 1]), Xc[:, 1, 0] - Xc[:, 0, 0]], 1) / det[:, None]
+        self.grads = torch.stack([-(g1 + g2), g1, g2], 1)
+        self.area = 0.5 * det.abs()
+        pts, wts = collapsed_triangle_rule(self.CELL_DEGREE)
+        self.rule = np.ascontiguousarray(np.concatenate([pts, wts[:, None]], 1), dtype=np.float64)
+        self.nq = self.rule.shape[0]
+        self.lamq = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
+        self.Pq = torch.einsum("qi,cid->cqd", self.lamq, Xc)
+        cid = torch.arange(C, device=dev)[:, None]
+        ar = lambda k: torch.arange(k, device=dev)[None, :]
+        self.pd = 6 * cid + ar(6)
+        s0 = self.np_
+        self.sd = torch.cat([s0 + 3 * ce[:, i, None] + ar(3) for i in range(3)] + [s0 + 3 * E + 6 * cid + ar(6)], 1)
+        q0 = self.q0
+        self.qd = torch.cat([q0 + cells] + [q0 + V + 2 * ce[:, i, None] + ar(2) for i in range(3)]
+                            + [q0 + V + 2 * E + cid], 1)
+        self.cell_dofs = cd = torch.cat([self.pd, self.sd, self.qd], 1)                  # [C,31]
+        rows_c = cd.repeat_interleave(31, dim=1).flatten()
+        cols_c = cd.repeat(1, 31).flatten()
+        self._key, self.rowptr, self.col = _csr_from_pairs(rows_c, cols_c, N)
+        self.nnz = int(self.col.numel())
+        slot_c = torch.searchsorted(self._key, rows_c * N + cols_c)
+        ent = (torch.arange(961, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.mat_ptr, order = _gather_lists(slot_c, self.nnz)
+        self.mat_idx = ent[order].to(torch.int32).contiguous()
+        entv = (torch.arange(31, device=dev)[None, :] * C + torch.arange(C, device=dev)[:, None]).flatten()
+        self.vec_ptr, order = _gather_lists(cd.flatten(), N)
+        self.vec_idx = entv[order].to(torch.int32).contiguous()
+        self.diag_slot_all = (torch.searchsorted(self._key, torch.arange(N, device=dev) * (N + 1))
+                              - self.rowptr[:-1].long()).to(torch.int32)
+        self.nat = self._natural()
+        self._bc_tables()
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.Je = torch.empty(961 * C, **f64)
+        self.Fe = torch.empty(31 * C, **f64)
+        self.vals = torch.zeros(self.nnz, **f64)
+        self.b = torch.zeros(N, **f64)
+        self.u = torch.zeros(N, **f64)
+        self.p_old = torch.zeros(6 * C, **f64)
+        self._lin = None
+        self.newton_its, self.converged = 0, False
+
+    # -- boundary data ---------------------------------------------------------------------------------------
+    def p_initial(self, x, y):          # PInitial.eval (:40-44)
+        sb = self.sigma * torch.exp(-4 / 3 * math.pi * self.gamma * x ** 3)
+        base = self.c / self.V1 * torch.exp(-4 / 3 * math.pi * self.c * x ** 3)
+        return torch.where(y > 0, base * (1 - sb / torch.where(y > 0, y, torch.ones_like(y))), base)
+
+    def q_initial(self, x):             # QInitial.eval (:87-88)
+        return 1 / (4 * math.pi * self.V1) * torch.exp(-4 / 3 * math.pi * self.c * x ** 3)
+
+    def _facet_geometry(self, fidx):
+        mesh, fc = self.mesh, self.mesh.facets()
+        A = mesh.coords[fc.verts[fidx, 0].long()]
+        B = mesh.coords[fc.verts[fidx, 1].long()]
+        t = B - A
+        L = t.pow(2).sum(1).sqrt()
+        nrm = torch.stack([t[:, 1], -t[:, 0]], 1) / L[:, None]
+        opp = mesh.coords[mesh.cells.long()[fc.cell0[fidx].long(), fc.loc0[fidx].long()]]
+        flip = ((opp - A) * nrm).sum(1) > 0
+        return L, torch.where(flip[:, None], -nrm, nrm), A, B
+
+    def _gauss(self):
+        p, w = np.polynomial.legendre.leggauss(self.FACET_POINTS)
+        dev = self.mesh.device
+        return torch.tensor(0.5 * (p + 1.0), device=dev), torch.tensor(0.5 * w, device=dev)
+
+    def _natural(self):
+        """+ p_right (tau.n) W ds(right) + p_top (tau.n) W ds(top) (:203-204): the facet's own three functions."""
+        fc, dev = self.mesh.facets(), self.mesh.device
+        sel = torch.nonzero((fc.cell1 < 0) & ((self.bdry.values == self.RIGHT) | (self.bdry.values == self.TOP))).flatten()
+        L, nrm, A, B = self._facet_geometry(sel)
+        s, w = self._gauss()
+        P = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        x, y = P[..., 0], P[..., 1]
+        W = (4.0 * math.pi * x * y) ** 2
+        sgn = torch.sign((nrm * self.enorm[sel]).sum(1))
+        pw = w[None, :] * W * self.p_initial(x, y)
+        out = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        for m, tr in enumerate(((1 - s) ** 2, (1 - s) * s, s ** 2)):
+            out[self.np_ + 3 * sel + m] = (pw * tr[None, :]).sum(1) * sgn
+        return out
+
+    def _bc_tables(self):
+        """s = 0 on the left facets (:181-182), q = q_initial at the CG3 nodes of the right facets (:187)."""
+        fc, mesh, dev = self.mesh.facets(), self.mesh, self.mesh.device
+        left = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == self.LEFT)).flatten()
+        sdofs = (self.np_ + 3 * left[:, None] + torch.arange(3, device=dev)[None, :]).flatten()
+        right = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == self.RIGHT)).flatten()
+        va, vb = fc.verts[right, 0].long(), fc.verts[right, 1].long()
+        xa, xb = mesh.coords[va, 0], mesh.coords[vb, 0]
+        val = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        has = torch.zeros(self.N, dtype=torch.bool, device=dev)
+        for d, xv in ((self.q0 + va, xa), (self.q0 + vb, xb), (self.q0 + self.V + 2 * right, (2 * xa + xb) / 3),
+                      (self.q0 + self.V + 2 * right + 1, (xa + 2 * xb) / 3)):
+            val[d] = self.q_initial(xv)
+            has[d] = True
+        has[sdofs] = True
+        dofs = torch.nonzero(has).flatten()
+        self.bc_dofs = dofs.to(torch.int32).contiguous()
+        self.bc_vals = val[dofs].contiguous()
+        self.bc_diag = self.diag_slot_all[dofs].contiguous()
+
+    # -- per Newton step ----------------------------------------------------------------------------------------
+    def assemble(self, u, want_jac=True):
+        lib, st, mesh = self.lib, _capi.stream_ptr(), self.mesh
+        _capi.check(lib.cm_mixed_p2_cells(
+            self.nq, self.rule.ctypes.data, self.D1, self.D2, self.c, self.inv_dt, self.C, self.E, self.V,
+            _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign),
+            _capi.ptr(u), _capi.ptr(self.p_old) if self.inv_dt else None,
+            _capi.ptr(self.Je) if want_jac else None, _capi.ptr(self.Fe), st))
+        _capi.check(lib.cm_csr_gather(self.N, _capi.ptr(self.vec_ptr), _capi.ptr(self.vec_idx),
+                                      _capi.ptr(self.Fe), _capi.ptr(self.b), 0, st))
+        self.b += self.nat
+        if want_jac:
+            _capi.check(lib.cm_csr_gather(self.nnz, _capi.ptr(self.mat_ptr), _capi.ptr(self.mat_idx),
+                                          _capi.ptr(self.Je), _capi.ptr(self.vals), 0, st))
+        return (self.vals if want_jac else None), self.b
+
+    def _apply_bc(self, u, with_matrix):
+        _capi.check(self.lib.cm_apply_dirichlet(
+            1, self.bc_dofs.numel(), _capi.ptr(self.bc_dofs), _capi.ptr(self.bc_diag), _capi.ptr(self.bc_vals),
+            _capi.ptr(u), _capi.ptr(self.rowptr), _capi.ptr(self.vals) if with_matrix else None,
+            _capi.ptr(self.b), _capi.stream_ptr()))
+
+    def solve(self, tol=1e-8, maxit=10):
+        """Newton from the current self.u with 'mumps' (:219-226): abs / rel tolerance 1e-8, at most 10 iterations."""
+        u, dev = self.u, self.mesh.device
+        self.assemble(u, False)
+        self._apply_bc(u, False)
+        r0 = r = float(torch.linalg.vector_norm(self.b))
+        if self._lin is None:
+            self._lin = BandedLULinearSolver(_Holder(dev, self.rowptr, self.col, self.N, self.vals, self.b))
+        dx = torch.empty_like(u)
+        it = 0
+        while not (r < tol or (r0 > 0 and r / r0 < tol)) and it < maxit:
+            self.assemble(u, True)
+            self._apply_bc(u, True)
+            self._lin.setup()
+            self._lin.solve(self.b, dx)
+            u -= dx
+            it += 1
+            self.assemble(u, False)
+            self._apply_bc(u, False)
+            r = float(torch.linalg.vector_norm(self.b))
+            if r != r:
+                raise RuntimeError("Newton solver diverged (NaN residual)")
+        self.newton_its, self.converged = it, bool(r < tol or (r0 > 0 and r / r0 < tol))
+        if not self.converged:
+            raise RuntimeError("Newton solver did not converge because maximum number of iterations reached")
+        return u
+
+    # -- post-processing (:243, 261-263) -------------------------------------------------------------------------
+    def _rt_values(self, lam, P, cells=None):
+        idx = slice(None) if cells is None else cells
+        Xc, area, sign = self.Xc[idx], self.area[idx], self.sign[idx]
+        funcs = []
+        for i in range(3):
+            j, k = _OTHER[i]
+            funcs += [(i, j, j, sign[:, i]), (i, j, k, sign[:, i]), (i, k, k, sign[:, i])]
+        for i in (1, 2):
+            funcs += [(i, i, m, None) for m in range(3)]
+        R = []
+        for i, a, b, sg in funcs:
+            c = (1.0 if sg is None else sg) / (2 * area)
+            R.append((lam[..., a] * lam[..., b])[..., None] * (P - Xc[:, None, i, :]) * c[:, None, None])
+        return torch.stack(R, 2)
+
+    def flux(self, u=None):
+        """project(D 4 pi r2^2 s_h, RT3): RT3 coefficient vector [3E + 6C]."""
+        u = self.u if u is None else u
+        dev = self.mesh.device
+        lam = self.lamq[None].expand(self.C, -1, -1)
+        R = self._rt_values(lam, self.Pq)
+        a = torch.tensor(self.rule[:, 2], device=dev)[None, :] * (2 * self.area)[:, None]
+        x = self.Pq[..., 0]
+        s = torch.einsum("cqad,ca->cqd", R, u[self.sd])
+        f = 4 * math.pi * (x * x)[..., None] * s * torch.tensor([self.D2, self.D1], device=dev)[None, None, :]
+        Me = torch.einsum("cq,cqad,cqbd->cab", a, R, R)
+        be = torch.einsum("cq,cqad,cqd->ca", a, R, f)
+        sl = self.sd - self.np_
+        ns = self.ns
+        rows = sl.repeat_interleave(15, dim=1).flatten()
+        cols = sl.repeat(1, 15).flatten()
+        key, rp, col = _csr_from_pairs(rows, cols, ns)
+        ptr, order = _gather_lists(torch.searchsorted(key, rows * ns + cols), key.numel())
+        vals = torch.empty(key.numel(), dtype=torch.float64, device=dev)
+        st = _capi.stream_ptr()
+        src = Me.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(key.numel(), _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
+                                           _capi.ptr(src), _capi.ptr(vals), 0, st))
+        ptr2, order2 = _gather_lists(sl.flatten(), ns)
+        rhs = torch.empty(ns, dtype=torch.float64, device=dev)
+        src2 = be.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(ns, _capi.ptr(ptr2), _capi.ptr(order2.to(torch.int32).contiguous()),
+                                           _capi.ptr(src2), _capi.ptr(rhs), 0, st))
+        lin = BandedLULinearSolver(_Holder(dev, rp, col, ns, vals, rhs))
+        lin.setup()
+        out = torch.empty_like(rhs)
+        lin.solve(rhs, out)
+        return out
+
+    def bottom_flux(self, fl):
+        """(r2 part, r1 part, total) of V1 * assemble(dot(flux, n) 4 pi r1^2 ds(bottom)) (:261-263)."""
+        fc, mesh = self.mesh.facets(), self.mesh
+        sel = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == self.BOTTOM)).flatten()
+        L, nrm, A, B = self._facet_geometry(sel)
+        s, w = self._gauss()
+        cell = fc.cell0[sel].long()
+        cv = mesh.cells.long()[cell]
+        va = (fc.verts[sel, 0].long()[:, None] == cv).to(torch.float64)
+        vb = (fc.verts[sel, 1].long()[:, None] == cv).to(torch.float64)
+        lam = va[:, None, :] * (1.0 - s)[None, :, None] + vb[:, None, :] * s[None, :, None]
+        P = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        R = self._rt_values(lam, P, cell)
+        f = torch.einsum("nqad,na->nqd", R, fl[(self.sd - self.np_)[cell]])
+        wgt = w[None, :] * L[:, None] * 4 * math.pi * P[..., 1] ** 2
+        r2 = self.V1 * float((wgt * f[..., 0] * nrm[:, None, 0]).sum())
+        r1 = self.V1 * float((wgt * f[..., 1] * nrm[:, None, 1]).sum())
+        return r2, r1, r2 + r1
+
+
+def solve_problem_instance_mixed(concentration, t_final, dt, mesh, bdry, sigma, gamma, results, V1, D1, D2,
+                                 output_filename=None, steady_state=False):
+    """advection_diffusion_mixed.py:94-269 with its own discretisation (DG2 x RT3 x CG3) on the GPU: same
+    signature, `results` row (:268) and return value (flux, total_flux); no XDMF output (file name ignored)."""
+    system = ProductionMixedSystem(mesh, bdry, concentration, sigma, gamma, V1, D1, D2, None if steady_state else dt)
+    if steady_state:
+        t_final = 0
+    t = 0
+    if not steady_state:   # p_old = interpolate(p_initial, DG2): nodal values at the vertices and edge mid points
+        Xc = system.Xc
+        nodes = torch.cat([Xc, 0.5 * (Xc[:, [1, 0, 0]] + Xc[:, [2, 2, 1]])], 1)            # [C,6,2]
+        system.p_old.copy_(system.p_initial(nodes[..., 0], nodes[..., 1]).flatten())
+    while t <= t_final:
+        print("t=%.3f" % t)
+        system.solve()
+        system.p_old.copy_(system.u[:system.np_])      # assign(p_old, p_h)
+        t += dt
+    flux = system.flux()
+    r2f, r1f, total = system.bottom_flux(flux)
+    approx = 4 * math.pi * D1 * sigma * (concentration / (gamma + concentration))           # :264
+    results.append([sigma, gamma, concentration, r1f, r2f, total, approx])
+    solve_problem_instance_mixed.last_system = system
+    return flux, total

@@ -391,6 +391,19 @@ int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, in
                            const int32_t* fverts, const int32_t* fcell, const int32_t* cells,
                            const double* coords, double* Ji, void* stream);
 
+/* Production mixed formulation DG2 x RT3 x CG3 (advection_diffusion_mixed.py:147-150,196-216; deg = 2): element
+ * residual Fe[31][ncells] and Jacobian Je[961][ncells] (entry-major; Je may be NULL) of the cell integrals
+ *   [(p - p_old)/dt] v W + div_rad(D s) v W + (s + Gstar(p,q) e_x).tau W - p div_rad(tau) W + (dq/dx + x^2 p) w W
+ * with the production Gstar conditional (:17-23).  Local dofs [6 DG2 | 15 RT3: per facet i (end points j < k)
+ * lambda_j^2 N_i, lambda_j lambda_k N_i, lambda_k^2 N_i, then lambda_i lambda_m N_i for i = 1,2, m = 0,1,2 |
+ * 10 CG3: vertices, two nodes per facet, bubble]; global dofs [6 per cell | 3 per edge, 6 per cell | vertices,
+ * 2 per edge, 1 per cell].  p_old[6*ncells] (DG2 coefficients) is read when inv_dt != 0.  rule_host: up to 40
+ * points.  Assembled by cm_csr_gather, solved by cm_blu_*. */
+int cm_mixed_p2_cells(int32_t nq, const double* rule_host, double D1, double D2, double concentration,
+                      double inv_dt, int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells,
+                      const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
+                      const double* p_old, double* Je, double* Fe, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
