@@ -89,15 +89,19 @@ def UnitSquareMesh(nx, ny, device=None):
     return RectangleMesh(Point(0.0, 0.0), Point(1.0, 1.0), nx, ny, device=device)
 
 
-def MappedRectangleMesh(nx, ny, r2_max, r1_max, sigma, gamma, device=None):
+def MappedRectangleMesh(nx, ny, r2_max, r1_max, sigma, gamma, device=None, grading=1.0):
     """Boundary-fitted structured stand-in for the FreeFem++ production mesh
     (meshes/automated_exp_meshing.edp:17-26; same labels as create_flat_boundary.py:70-77):
-    r2 in [0,r2_max], r1 in [f(r2), r1_max], f = sigma*exp(-4/3*pi*gamma*r2^3)."""
-    m = RectangleMesh(Point(0.0, 0.0), Point(r2_max, 1.0), nx, ny, device=device)
-    x = m.coords[:, 0]
-    eta = m.coords[:, 1]
+    r2 in [0,r2_max], r1 in [f(r2), r1_max], f = sigma*exp(-4/3*pi*gamma*r2^3).  grading > 1 clusters the grid
+    lines towards r2 = 0 and the reaction boundary (r2 = r2_max*xi^g, r1 = f + eta^g*(r1_max - f)), where the
+    solution has its exp(-4/3 pi c r2^3) layer."""
+    m = RectangleMesh(Point(0.0, 0.0), Point(1.0, 1.0), nx, ny, device=device)
+    xi = m.coords[:, 0].clone()
+    eta = m.coords[:, 1].clone()
+    x = r2_max * xi ** grading
     f = sigma * torch.exp(-4.0 / 3.0 * math.pi * gamma * x ** 3)
-    m.coords[:, 1] = f + eta * (r1_max - f)
+    m.coords[:, 0] = x
+    m.coords[:, 1] = f + eta ** grading * (r1_max - f)
     return m
 
 

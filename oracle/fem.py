@@ -73,15 +73,18 @@ def unit_square_mesh(nx, ny):
     return rectangle_mesh(0.0, 0.0, 1.0, 1.0, nx, ny)
 
 
-def mapped_rectangle_mesh(nx, ny, r2_max, r1_max, sigma, gamma):
+def mapped_rectangle_mesh(nx, ny, r2_max, r1_max, sigma, gamma, grading=1.0):
     """Boundary-fitted structured stand-in for the FreeFem++ production mesh
     (meshes/automated_exp_meshing.edp:17-26): r2 in [0,r2_max], r1 in [f(r2), r1_max] with
-    f = sigma*exp(-4/3*pi*gamma*r2^3); same topology/numbering as rectangle_mesh."""
-    m = rectangle_mesh(0.0, 0.0, r2_max, 1.0, nx, ny)
-    x = m.coords[:, 0]
-    eta = m.coords[:, 1]
+    f = sigma*exp(-4/3*pi*gamma*r2^3); same topology/numbering as rectangle_mesh.  grading > 1 clusters the grid
+    lines towards r2 = 0 and the reaction boundary."""
+    m = rectangle_mesh(0.0, 0.0, 1.0, 1.0, nx, ny)
+    xi = m.coords[:, 0].copy()
+    eta = m.coords[:, 1].copy()
+    x = r2_max * xi ** grading
     f = sigma * np.exp(-4.0 / 3.0 * np.pi * gamma * x ** 3)
-    m.coords[:, 1] = f + eta * (r1_max - f)
+    m.coords[:, 0] = x
+    m.coords[:, 1] = f + eta ** grading * (r1_max - f)
     return m
 
 

@@ -5,9 +5,10 @@ boundary (sigma, gamma) so that the finite-element total fluxes of the productio
 
 Same functions and call structure (required_rate :11, jacobian :15-25, finite_element_fluxes :59-86, the
 least_squares call :115-118); the FreeFem++ / gmsh / dolfin-convert meshing of create_mesh (:28-56) is replaced by
-the boundary-fitted structured mesh MappedRectangleMesh(n, n, r2_max, r1_max, sigma, gamma), and
+the boundary-fitted structured mesh MappedRectangleMesh(n, n, r2_max, r1_max, sigma, gamma, grading=2) (grid lines
+clustered at r2 = 0 and at the reaction boundary, where the exp(-4/3 pi c r2^3) layer sits), and
 solve_problem_instance is closestmolecule_b200.mixed.solve_problem_instance_mixed (same signature and return).
-usage: python scripts/run_boundary_correction.py [n=24] [max_nfev=6]"""
+usage: python scripts/run_boundary_correction.py [n=32] [max_nfev=6]"""
 import os
 import sys
 import time
@@ -18,6 +19,9 @@ from scipy.optimize import least_squares
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from closestmolecule_b200 import MappedRectangleMesh, structured_boundary_markers  # noqa: E402
 from closestmolecule_b200.mixed import solve_problem_instance_mixed as solve_problem_instance  # noqa: E402
+
+
+GRADING = 2.0
 
 
 def required_rate(conc, sigma, gamma):
@@ -35,7 +39,7 @@ def finite_element_fluxes(parameters, sigma_orig, gamma_orig, c_vals, r1_max, r2
     sigma, gamma = float(parameters[0]), float(parameters[1])
     print(f'New sigma: {sigma} new gamma: {gamma}')
     V1 = 4 * np.pi * np.power(r1_max - sigma, 3) / 3
-    mesh = MappedRectangleMesh(n, n, r2_max, r1_max, sigma, gamma)
+    mesh = MappedRectangleMesh(n, n, r2_max, r1_max, sigma, gamma, grading=GRADING)
     bdry = structured_boundary_markers(mesh)
     finite_ele_fluxes = []
     for c in c_vals:
@@ -49,7 +53,7 @@ def finite_element_fluxes(parameters, sigma_orig, gamma_orig, c_vals, r1_max, r2
     return finite_ele_fluxes - required_rate(c_vals, sigma_orig, gamma_orig)
 
 
-def main(n=24, max_nfev=6, c_vals=(1, 2, 4, 8)):
+def main(n=32, max_nfev=6, c_vals=(1, 2, 4, 8)):
     sigma_orig, gamma_orig = 0.1, 1
     r1_max = r2_max = 5
     D_A = D_B = 1
@@ -72,4 +76,4 @@ def main(n=24, max_nfev=6, c_vals=(1, 2, 4, 8)):
 
 
 if __name__ == '__main__':
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 24, int(sys.argv[2]) if len(sys.argv) > 2 else 6)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 32, int(sys.argv[2]) if len(sys.argv) > 2 else 6)
