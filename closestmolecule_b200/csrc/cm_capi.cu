@@ -520,4 +520,24 @@ int cm_mixed_p2_cells(int32_t nq, const double* rule_host, double D1, double D2,
                         cell_edges, sign, u, p_old, Je, Fe, (cudaStream_t)stream);
 }
 
+int64_t cm_p1_sparsity_workspace_bytes(int32_t nv, int32_t ncells, int32_t nextra) {
+  if (nv < 1 || ncells < 1 || nextra < 0) {
+    set_error("cm_p1_sparsity_workspace_bytes: bad argument");
+    return CM_E_INVALID;
+  }
+  return (int64_t)p1_sparsity_workspace_bytes(nv, ncells, nextra);
+}
+
+int cm_build_p1_sparsity(int32_t nv, int32_t ncells, const int32_t* cells, int32_t nextra,
+                         const int32_t* extra_pairs, int32_t* rowptr, int32_t* col, int64_t col_capacity,
+                         int64_t* nnz_host, void* workspace, int64_t workspace_bytes, void* stream) {
+  CM_CHECK_ARG(nv >= 1 && ncells >= 1 && nextra >= 0, "bad size");
+  CM_CHECK_ARG(cells && rowptr && col && workspace && (nextra == 0 || extra_pairs), "null pointer");
+  long long nnz = 0;
+  const int rc = build_p1_sparsity(nv, ncells, cells, nextra, extra_pairs, rowptr, col, col_capacity, &nnz,
+                                   workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
+  if (nnz_host) *nnz_host = nnz;
+  return rc;
+}
+
 }  // extern "C"

@@ -173,4 +173,8 @@ int mixed_p2_cells(int nq, const double* rule_host, double D1, double D2, double
                    int nE, int nV, const int* cells, const double* coords, const int* cell_edges,
                    const double* sign, const double* u, const double* p_old, double* Je, double* Fe,
                    cudaStream_t st);
+// cm_sparsity.cu
+size_t p1_sparsity_workspace_bytes(int nv, int ncells, int nextra);
+int build_p1_sparsity(int nv, int ncells, const int* cells, int nextra, const int* extra, int* rowptr, int* col,
+                      long long col_capacity, long long* nnz_host, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace cm

@@ -15,6 +15,8 @@ import numpy as np
 import torch
 
 DOLFIN_EPS = 3.0e-16
+# CUDA meshes build the P1 pattern with cm_build_p1_sparsity (env CM_LIBRARY_SPARSITY=0: torch sort/unique instead)
+LIBRARY_SPARSITY = __import__("os").environ.get("CM_LIBRARY_SPARSITY", "0") != "0"
 
 
 class Point:
@@ -164,6 +166,29 @@ def _build_facets(mesh):
     return Facets(verts, cell0, cell1, loc0, loc1)
 
 
+def _library_sparsity(V, cells, extra):
+    """(rowptr int32 [V+1], col int32 [nnz]) from cm_build_p1_sparsity."""
+    import ctypes as C
+
+    from . import _capi
+    lib = _capi.lib()
+    dev = cells.device
+    ncells = cells.shape[0]
+    nextra = 0 if extra is None else extra.shape[0]
+    nbytes = int(lib.cm_p1_sparsity_workspace_bytes(V, ncells, nextra))
+    if nbytes <= 0:
+        raise _capi.CMError(lib.cm_last_error().decode())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    cap = 9 * ncells + 2 * nextra
+    rowptr = torch.empty(V + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(cap, dtype=torch.int32, device=dev)
+    nnz = C.c_int64(0)
+    _capi.check(lib.cm_build_p1_sparsity(V, ncells, _capi.ptr(cells), nextra, _capi.ptr(extra), _capi.ptr(rowptr),
+                                         _capi.ptr(col), cap, C.byref(nnz), _capi.ptr(ws), nbytes,
+                                         _capi.stream_ptr(dev)))
+    return rowptr, col[:nnz.value].clone()
+
+
 class P1Topology:
     """Node-level CSR pattern of the P1 space (DOLFIN SparsityPatternBuilder [ext]) and
     the row-owner gather tables of include/closestmol_b200.h."""
@@ -172,24 +197,32 @@ class P1Topology:
         V = mesh.num_vertices()
         c = mesh.cells.long()
         dev = c.device
-        rows = c.repeat_interleave(3, dim=1).flatten()
-        cols = c.repeat(1, 3).flatten()
-        keys = [rows * V + cols]
+        o0 = o1 = None
         if with_interior_facets:
+            # the macro element of an interior facet adds only the (opp0, opp1) couple: every other pair shares a cell
             fc = mesh.facets()
             fi = fc.interior()
-            ar = torch.arange(fi.numel(), device=dev)
             o0 = c[fc.cell0[fi].long(), fc.loc0[fi].long()]
             o1 = c[fc.cell1[fi].long(), fc.loc1[fi].long()]
-            # the macro element adds only the (opp0,opp1) couple: every other pair shares a cell
-            keys += [o0 * V + o1, o1 * V + o0]
-            del ar
-        key = torch.unique(torch.cat(keys))          # sorted
-        r = key // V
-        self.ncol = (key % V).to(torch.int32).contiguous()
-        deg = torch.bincount(r, minlength=V)
-        rp = torch.zeros(V + 1, dtype=torch.int64, device=dev)
-        rp[1:] = torch.cumsum(deg, 0)
+        if c.is_cuda and LIBRARY_SPARSITY:
+            # a9 through the library (cm_build_p1_sparsity: radix sort + unique of the row*V+col keys)
+            extra = torch.stack([o0, o1], 1).to(torch.int32).contiguous() if with_interior_facets else None
+            rp32, self.ncol = _library_sparsity(V, mesh.cells, extra)
+            rp = rp32.long()
+            deg = rp[1:] - rp[:-1]
+            key = torch.repeat_interleave(torch.arange(V, device=dev), deg) * V + self.ncol.long()
+        else:   # CPU tensors (host-logic tests): the same pattern with torch
+            rows = c.repeat_interleave(3, dim=1).flatten()
+            cols = c.repeat(1, 3).flatten()
+            keys = [rows * V + cols]
+            if with_interior_facets:
+                keys += [o0 * V + o1, o1 * V + o0]
+            key = torch.unique(torch.cat(keys))          # sorted
+            r = key // V
+            self.ncol = (key % V).to(torch.int32).contiguous()
+            deg = torch.bincount(r, minlength=V)
+            rp = torch.zeros(V + 1, dtype=torch.int64, device=dev)
+            rp[1:] = torch.cumsum(deg, 0)
         assert int(rp[-1]) * 4 < 2 ** 31, "P-Q nnz exceeds int32 (DOLFIN la_index is 32 bit too)"
         self.nrowptr = rp.to(torch.int32).contiguous()
         self.maxdeg = int(deg.max())

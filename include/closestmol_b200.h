@@ -404,6 +404,18 @@ int cm_mixed_p2_cells(int32_t nq, const double* rule_host, double D1, double D2,
                       const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
                       const double* p_old, double* Je, double* Fe, void* stream);
 
+/* ---- a9: sparsity pattern of the P1 space (DOLFIN SparsityPatternBuilder [ext], triggered by
+ * FunctionSpace(mesh, MixedElement([P0,P1])) at advection_diffusion_convergence.py:149-151 and the first assemble).
+ * Node-level CSR with sorted columns: union over cells of vertex x vertex, plus the nextra vertex couples of
+ * extra_pairs[nextra*2] inserted symmetrically (the two vertices opposite every interior facet: the C0IP dS
+ * pattern).  col needs capacity for 9*ncells + 2*nextra entries at most; the number of entries is returned in
+ * nnz_host (the stream is synchronised once).  The blocked P-Q pattern follows from the node pattern (see the
+ * value layout at the top of this header). */
+int64_t cm_p1_sparsity_workspace_bytes(int32_t nv, int32_t ncells, int32_t nextra);
+int cm_build_p1_sparsity(int32_t nv, int32_t ncells, const int32_t* cells, int32_t nextra,
+                         const int32_t* extra_pairs, int32_t* rowptr, int32_t* col, int64_t col_capacity,
+                         int64_t* nnz_host, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

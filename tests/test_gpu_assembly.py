@@ -192,3 +192,29 @@ def test_structured_sweep_matches_gather_and_oracle(name, meshkind, nx, ny):
     v3, b3 = a_sweep.assemble(u, True)
     v4, b4 = a_sweep.assemble(u, True)
     assert torch.equal(v3, v4) and torch.equal(b3, b4)
+
+
+@pytest.mark.parametrize("with_facets", [False, True])
+def test_library_sparsity_matches_host_pattern(with_facets, monkeypatch):
+    """a9: cm_build_p1_sparsity (the path CUDA meshes take) against the torch pattern of the same mesh on the CPU and
+    against the oracle's DOLFIN-pattern restatement, on a structured, a mapped and a renumbered mesh."""
+    from oracle import fem
+    import closestmolecule_b200.mesh as cmmesh
+    monkeypatch.setattr(cmmesh, "LIBRARY_SPARSITY", True)
+    g = torch.Generator().manual_seed(5)
+    for mesh in (_mesh("unit", 37, 11), _mesh("mapped", 20, 33)):
+        for shuffle in (False, True):
+            m = mesh
+            if shuffle:
+                V = mesh.num_vertices()
+                new = torch.randperm(V, generator=g).to(mesh.device)
+                coords = torch.empty_like(mesh.coords)
+                coords[new] = mesh.coords
+                cells, _ = torch.sort(new[mesh.cells.long()], dim=1)
+                m = cm.Mesh(coords, cells.to(torch.int32), device=mesh.device)
+            t = m.topology(with_facets)
+            host = cm.Mesh(m.coords.cpu(), m.cells.cpu(), device="cpu").topology(with_facets)
+            assert torch.equal(t.nrowptr.cpu(), host.nrowptr) and torch.equal(t.ncol.cpu(), host.ncol)
+            om = fem.Mesh(m.coords.cpu().numpy(), m.cells.cpu().numpy())
+            rp, col = fem.p1_node_pattern(om, with_facets)
+            assert np.array_equal(t.nrowptr.cpu().numpy(), rp) and np.array_equal(t.ncol.cpu().numpy(), col)
