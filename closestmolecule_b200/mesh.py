@@ -16,7 +16,7 @@ import torch
 
 DOLFIN_EPS = 3.0e-16
 # CUDA meshes build the P1 pattern with cm_build_p1_sparsity (env CM_LIBRARY_SPARSITY=0: torch sort/unique instead)
-LIBRARY_SPARSITY = __import__("os").environ.get("CM_LIBRARY_SPARSITY", "0") != "0"
+LIBRARY_SPARSITY = __import__("os").environ.get("CM_LIBRARY_SPARSITY", "1") != "0"
 
 
 class Point:
