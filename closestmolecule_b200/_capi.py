@@ -106,6 +106,9 @@ _PROTOS = {
     "cm_mixed_p2_cells": ([_I, _P, _D, _D, _D, _D, _I, _I, _I] + [_P] * 8 + [_P], C.c_int),
     "cm_p1_sparsity_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_build_p1_sparsity": ([_I, _I, _P, _I, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64), _P, C.c_int64, _P], C.c_int),
+    "cm_vec_scratch_doubles": ([], C.c_int64),
+    "cm_dot_batch": ([C.c_int64, _P, C.c_int64, _I, _P, _P, _P, _P], C.c_int),
+    "cm_axpy_batch": ([C.c_int64, _P, C.c_int64, _I, _P, _D, _P, _P, _P, _P], C.c_int),
     "cm_csr_gather": ([_I, _P, _P, _P, _P, _I, _P], C.c_int),
     "cm_csr_add_mapped": ([_I, _P, _P, _P, _P], C.c_int),
     "cm_mixed_workspace_doubles": ([], C.c_int64),

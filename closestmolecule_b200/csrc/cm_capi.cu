@@ -540,4 +540,20 @@ int cm_build_p1_sparsity(int32_t nv, int32_t ncells, const int32_t* cells, int32
   return rc;
 }
 
+int64_t cm_vec_scratch_doubles(void) { return (int64_t)vec_scratch_doubles(); }
+
+int cm_dot_batch(int64_t n, const double* V, int64_t vstride, int32_t nvec, const double* w, double* out,
+                 double* scratch, void* stream) {
+  CM_CHECK_ARG(n >= 1 && nvec >= 1 && vstride >= n, "bad size");
+  CM_CHECK_ARG(V && w && out && scratch, "null pointer");
+  return multi_dot(n, V, vstride, nvec, w, out, scratch, (cudaStream_t)stream);
+}
+
+int cm_axpy_batch(int64_t n, const double* V, int64_t vstride, int32_t nvec, const double* h, double sign,
+                  double* w, double* norm2_out, double* scratch, void* stream) {
+  CM_CHECK_ARG(n >= 1 && nvec >= 1 && vstride >= n, "bad size");
+  CM_CHECK_ARG(V && h && w && scratch, "null pointer");
+  return multi_axpy(n, V, vstride, nvec, h, sign, w, norm2_out, scratch, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -43,6 +43,7 @@ int multi_dot(long long n, const double* Vbase, long long vstride, int nvec, con
               double* out, double* scratch, cudaStream_t st);
 int multi_axpy(long long n, const double* Vbase, long long vstride, int nvec, const double* h,
                double sign, double* w, double* norm2_out, double* scratch, cudaStream_t st);
+size_t vec_scratch_doubles();
 int vec_scale(long long n, const double* x, const double* a_dev, double a_host, int invert,
               double* y, cudaStream_t st);
 

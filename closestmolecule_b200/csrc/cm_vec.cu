@@ -300,4 +300,6 @@ int vec_scale_slice(VecSlice sl, const double* x, double a, int invert, double* 
   return CM_OK;
 }
 
+size_t vec_scratch_doubles() { return (size_t)kVecGrid * kGroup; }
+
 }  // namespace cm

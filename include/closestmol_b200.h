@@ -416,6 +416,18 @@ int cm_build_p1_sparsity(int32_t nv, int32_t ncells, const int32_t* cells, int32
                          const int32_t* extra_pairs, int32_t* rowptr, int32_t* col, int64_t col_capacity,
                          int64_t* nnz_host, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Fused Krylov vector kernels (the building blocks of the GMRES orthogonalisation, exported for reuse and tests):
+ *   cm_dot_batch : out[k] = <V_k, w>, k < nvec, V_k = V + k*vstride -- every group of up to 8 basis vectors in
+ *                  ONE pass over w (classical Gram-Schmidt reads w once per group, not once per vector);
+ *   cm_axpy_batch: w += sign * sum_k h[k] V_k (h on the device) and, when norm2_out != NULL, *norm2_out = |w|^2
+ *                  from the same pass.
+ * scratch: cm_vec_scratch_doubles() device doubles.  Fixed grid and summation order: bit-reproducible. */
+int64_t cm_vec_scratch_doubles(void);
+int cm_dot_batch(int64_t n, const double* V, int64_t vstride, int32_t nvec, const double* w, double* out,
+                 double* scratch, void* stream);
+int cm_axpy_batch(int64_t n, const double* V, int64_t vstride, int32_t nvec, const double* h, double sign,
+                  double* w, double* norm2_out, double* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -377,3 +377,31 @@ def test_newton_supg_on_production_like_geometry(meshkind, nx, ny):
     err = np.linalg.norm(u.vector().cpu().numpy() - x) / np.linalg.norm(x)
     assert err < 1e-8, (err, s.linear_iterations)
     assert max(s.linear_iterations) < 80, s.linear_iterations
+
+
+def test_fused_krylov_vector_kernels_match_torch():
+    """cm_dot_batch / cm_axpy_batch (the GMRES orthogonalisation kernels) against torch, including group
+    boundaries (nvec = 1, 8, 9, 19) and a vector length that is not a multiple of anything."""
+    from closestmolecule_b200 import _capi
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    dev = torch.device("cuda")
+    n, stride = 100003, 100008
+    g = torch.Generator(device="cpu").manual_seed(1)
+    scratch = torch.empty(int(lib.cm_vec_scratch_doubles()), dtype=torch.float64, device=dev)
+    for nvec in (1, 8, 9, 19):
+        V = torch.randn(nvec, stride, generator=g, dtype=torch.float64).to(dev)
+        w = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
+        out = torch.empty(nvec, dtype=torch.float64, device=dev)
+        _capi.check(lib.cm_dot_batch(n, P(V), stride, nvec, P(w), P(out), P(scratch), st))
+        ref = V[:, :n] @ w
+        assert float((out - ref).abs().max()) < 1e-11 * float(ref.abs().max() + 1)
+        h = torch.randn(nvec, generator=g, dtype=torch.float64).to(dev)
+        w2 = w.clone()
+        nrm = torch.empty(1, dtype=torch.float64, device=dev)
+        _capi.check(lib.cm_axpy_batch(n, P(V), stride, nvec, P(h), -1.0, P(w2), P(nrm), P(scratch), st))
+        wref = w - h @ V[:, :n]
+        assert float((w2 - wref).abs().max()) < 1e-12 * float(wref.abs().max())
+        assert abs(float(nrm) - float(wref @ wref)) < 1e-11 * float(wref @ wref)
+        out2 = torch.empty_like(out)
+        _capi.check(lib.cm_dot_batch(n, P(V), stride, nvec, P(w), P(out2), P(scratch), st))
+        assert torch.equal(out, out2)        # bit-reproducible
