@@ -405,3 +405,20 @@ def test_fused_krylov_vector_kernels_match_torch():
         out2 = torch.empty_like(out)
         _capi.check(lib.cm_dot_batch(n, P(V), stride, nvec, P(w), P(out2), P(scratch), st))
         assert torch.equal(out, out2)        # bit-reproducible
+
+
+def test_laplace_convergence_driver_config1():
+    """BASELINE config 1 (SphericalLaplace_convergence.py) through the GPU path: DoF column (n+1)^2, expected orders
+    (README.md:118: h in H1, h^2 in L2), and the same errors as the oracle's restatement of the script."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "run_laplace_convergence.py")
+    spec = importlib.util.spec_from_file_location("lap_conv", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.main(7)
+    assert r["dofs"] == [(2 ** (k + 1) + 1) ** 2 for k in range(7)]
+    assert 0.95 < r["r1"][-1] < 1.05 and 1.9 < r["r0"][-1] < 2.1
+    ref = scalar.solve_fa(64)
+    assert abs(r["e1"][5] / ref["e1"] - 1) < 1e-2 and abs(r["e0"][5] / ref["e0"] - 1) < 5e-2
