@@ -156,11 +156,12 @@ size_t mixed_workspace_doubles();
 int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cells, const double* coords,
                     const int* cell_edges, const double* sign, int nE, const double* u, const double* exq,
                     double* work, cudaStream_t st);
-int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, int ncells, int nE,
+int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, double gcoef, int qmode,
+                   double q_react, int ncells, int nE,
                    int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
                    const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
                    cudaStream_t st);
-int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV, const int* cells,
+int mixed_m1_errors(int nq, const double* rule_host, int full_grad, int ncells, int nE, int nV, const int* cells,
                     const double* coords, const int* cell_edges, const double* sign, const double* u,
                     const double* exq, double* work, cudaStream_t st);
 int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, const int* fverts,

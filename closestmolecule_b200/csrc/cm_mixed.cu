@@ -229,7 +229,7 @@ struct M1Cell {
 
 struct M1Point {
   double a, x, y;            // weight * |det| * W, coordinates
-  double Rx[8], Ry[8], dr[8], drD[8], chi[3], phi[6], phix[6];
+  double Rx[8], Ry[8], dr[8], drD[8], chi[3], phi[6], phix[6], phiy[6];
 };
 
 __device__ __forceinline__ void m1_load_cell(const int c, const int ncells, const int nE, const int nV,
@@ -301,18 +301,21 @@ __device__ __forceinline__ void m1_eval_point(const M1Cell& K, const double l1, 
     Q.chi[i] = lam[i];
     Q.phi[i] = lam[i] * (2.0 * lam[i] - 1.0);
     Q.phix[i] = (4.0 * lam[i] - 1.0) * K.gx[i];
+    Q.phiy[i] = (4.0 * lam[i] - 1.0) * K.gy[i];
   }
   const int ej[3] = {1, 0, 0}, ek[3] = {2, 2, 1};
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     Q.phi[3 + i] = 4.0 * lam[ej[i]] * lam[ek[i]];
     Q.phix[3 + i] = 4.0 * (lam[ej[i]] * K.gx[ek[i]] + lam[ek[i]] * K.gx[ej[i]]);
+    Q.phiy[3 + i] = 4.0 * (lam[ej[i]] * K.gy[ek[i]] + lam[ek[i]] * K.gy[ej[i]]);
   }
 }
 
 // Je: [289][ncells] (row-major local (test, trial), entry-major over cells), Fe: [17][ncells]
 __global__ void __launch_bounds__(kMxThreads)
-mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const double geps, const int ncells,
+mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const double geps, const double gcoef,
+                      const int qmode, const double q_react, const int ncells,
                       const int nE, const int nV, const int* __restrict__ cells,
                       const double2* __restrict__ coords, const int* __restrict__ cell_edges,
                       const double* __restrict__ sign, const double* __restrict__ u,
@@ -329,7 +332,7 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
   for (int k = 0; k < R.nq; ++k) {
     M1Point Q;
     m1_eval_point(K, R.l1[k], R.l2[k], R.w[k], D1, D2, Q);
-    double sx = 0.0, sy = 0.0, drDs = 0.0, p = 0.0, q = 0.0;
+    double sx = 0.0, sy = 0.0, drDs = 0.0, p = 0.0, q = 0.0, qx = 0.0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       sx += K.se[m] * Q.Rx[m];
@@ -339,10 +342,13 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
 #pragma unroll
     for (int b = 0; b < 3; ++b) p += K.pe[b] * Q.chi[b];
 #pragma unroll
-    for (int m = 0; m < 6; ++m) q += K.qe[m] * Q.phi[m];
+    for (int m = 0; m < 6; ++m) {
+      q += K.qe[m] * Q.phi[m];
+      qx += K.qe[m] * Q.phix[m];
+    }
     const double x2 = Q.x * Q.x;
     const double iq = 1.0 / (q + geps);
-    const double tg = x2 * p * iq;
+    const double tg = gcoef * x2 * p * iq;
     const double G = tg * p, Gp = 2.0 * tg, Gq = -G * iq;
     const double a = Q.a;
     if (row < 8) {
@@ -361,11 +367,18 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
       for (int b = 0; b < 8; ++b) J[b] -= a * ch * Q.drD[b];
     } else {
       const double ph = Q.phi[row - 11], phx = Q.phix[row - 11];
-      F += a * ((-(2.0 / Q.x) * q + x2 * p - f3q[(size_t)c * R.nq + k]) * ph - q * phx);
+      const double f3 = f3q[(size_t)c * R.nq + k];
 #pragma unroll
       for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * Q.chi[b] * ph;
+      if (qmode == 0) {  // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W
+        F += a * ((-(2.0 / Q.x) * q + x2 * p - f3) * ph - q * phx);
 #pragma unroll
-      for (int m = 0; m < 6; ++m) J[11 + m] -= a * ((2.0 / Q.x) * Q.phi[m] * ph + phx * Q.phi[m]);
+        for (int m = 0; m < 6; ++m) J[11 + m] -= a * ((2.0 / Q.x) * Q.phi[m] * ph + phx * Q.phi[m]);
+      } else {  // ...MixedPrimal_convergence.py:123: (q + r2vec.grad q + r2^2 p) w W
+        F += a * (q_react * q + qx + x2 * p - f3) * ph;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) J[11 + m] += a * (q_react * Q.phi[m] + Q.phix[m]) * ph;
+      }
     }
   }
   Fe[(size_t)row * ncells + c] = F;
@@ -375,9 +388,10 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
   }
 }
 
-// squares of e_div(s), e_0(p), e_1(q) for k = 1; exq[ncells*nq*6] = (s_x, s_y, div_rad s, p, q, dq/dx)
+// squares of e_div(s), e_0(p), e_1(q) for k = 1; exq[ncells*nq*7] = (s_x, s_y, div_rad s, p, q, dq/dx, dq/dy);
+// full_grad: the q error takes the whole gradient (...MixedPrimal_convergence.py:148), else d/dx only (:175)
 __global__ void __launch_bounds__(kMxThreads)
-mixed_m1_errors_kernel(const MxRule R, const int ncells, const int nE, const int nV,
+mixed_m1_errors_kernel(const MxRule R, const int full_grad, const int ncells, const int nE, const int nV,
                        const int* __restrict__ cells, const double2* __restrict__ coords,
                        const int* __restrict__ cell_edges, const double* __restrict__ sign,
                        const double* __restrict__ u, const double* __restrict__ exq,
@@ -390,7 +404,7 @@ mixed_m1_errors_kernel(const MxRule R, const int ncells, const int nE, const int
     for (int k = 0; k < R.nq; ++k) {
       M1Point Q;
       m1_eval_point(K, R.l1[k], R.l2[k], R.w[k], 1.0, 1.0, Q);
-      double sx = 0.0, sy = 0.0, drs = 0.0, p = 0.0, q = 0.0, qx = 0.0;
+      double sx = 0.0, sy = 0.0, drs = 0.0, p = 0.0, q = 0.0, qx = 0.0, qy = 0.0;
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         sx += K.se[m] * Q.Rx[m];
@@ -403,13 +417,14 @@ mixed_m1_errors_kernel(const MxRule R, const int ncells, const int nE, const int
       for (int m = 0; m < 6; ++m) {
         q += K.qe[m] * Q.phi[m];
         qx += K.qe[m] * Q.phix[m];
+        qy += K.qe[m] * Q.phiy[m];
       }
-      const double* ex = exq + ((size_t)c * R.nq + k) * 6;
+      const double* ex = exq + ((size_t)c * R.nq + k) * 7;
       const double d0 = ex[0] - sx, d1 = ex[1] - sy, d2 = ex[2] - drs, dp = ex[3] - p, dq = ex[4] - q,
-                   dqx = ex[5] - qx;
+                   dqx = ex[5] - qx, dqy = full_grad ? ex[6] - qy : 0.0;
       c0 += Q.a * (d0 * d0 + d1 * d1 + d2 * d2);
       c1 += Q.a * (dp * dp);
-      c2 += Q.a * (dq * dq + dqx * dqx);
+      c2 += Q.a * (dq * dq + dqx * dqx + dqy * dqy);
     }
     e0 += c0;
     e1 += c1;
@@ -880,7 +895,8 @@ int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cell
   return CM_OK;
 }
 
-int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, int ncells, int nE,
+int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, double gcoef, int qmode,
+                   double q_react, int ncells, int nE,
                    int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
                    const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
                    cudaStream_t st) {
@@ -891,13 +907,14 @@ int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double
   }
   const long long nt = 17ll * ncells;
   mixed_m1_cells_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
-      R, D1, D2, geps, ncells, nE, nV, cells, (const double2*)coords, cell_edges, sign, u, f2q, f3q, Je, Fe);
+      R, D1, D2, geps, gcoef, qmode, q_react, ncells, nE, nV, cells, (const double2*)coords, cell_edges, sign, u, f2q,
+      f3q, Je, Fe);
   CM_LAUNCH_CHECK();
   CM_BYTES((double)ncells * (12.0 + 12.0 + 24.0 + 136.0 + 16.0 * nq + 136.0 + (Je ? 2312.0 : 0.0)));
   return CM_OK;
 }
 
-int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV, const int* cells,
+int mixed_m1_errors(int nq, const double* rule_host, int full_grad, int ncells, int nE, int nV, const int* cells,
                     const double* coords, const int* cell_edges, const double* sign, const double* u,
                     const double* exq, double* work, cudaStream_t st) {
   MxRule R;
@@ -905,7 +922,7 @@ int mixed_m1_errors(int nq, const double* rule_host, int ncells, int nE, int nV,
     set_error("cm_mixed_m1_errors: bad quadrature rule (1..%d points)", kMxRule);
     return CM_E_INVALID;
   }
-  mixed_m1_errors_kernel<<<kMxBlocks, kMxThreads, 0, st>>>(R, ncells, nE, nV, cells, (const double2*)coords,
+  mixed_m1_errors_kernel<<<kMxBlocks, kMxThreads, 0, st>>>(R, full_grad, ncells, nE, nV, cells, (const double2*)coords,
                                                           cell_edges, sign, u, exq, work + 4);
   CM_LAUNCH_CHECK();
   mixed_final_sum_kernel<<<1, 32, 0, st>>>(kMxBlocks, work + 4, work);

@@ -26,21 +26,22 @@ from .solver import BandedLULinearSolver
 from .space import FiniteElement, FunctionSpace, MixedElement
 
 
-def paper_data(D1, D2):
-    """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = dq_ex/dx + r2^2 p_ex
-    (:124-128), div_rad(sig_ex) and dq_ex/dx for the error norms, as torch callables."""
+def paper_data(D1, D2, gcoef=1.0, q_react=0.0):
+    """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = q_react q_ex + dq_ex/dx + r2^2 p_ex
+    (test_for_paper_convergence.py:124-128; ...MixedPrimal_convergence.py:109-113 with gcoef = D2 4 pi, q_react = 1),
+    div_rad(sig_ex) and grad q_ex for the error norms, as torch callables."""
     import sympy as sm
     x, y = sm.symbols("x y", positive=True)
     pe = sm.sin(sm.pi * x) * sm.sin(sm.pi * y)
     qe = sm.Rational(3, 2) + sm.cos(sm.pi * x * y)
-    G = x ** 2 * pe ** 2 / (qe + DOLFIN_EPS)
+    G = gcoef * x ** 2 * pe ** 2 / (qe + DOLFIN_EPS)
     sx = -sm.diff(pe, x) - G
     sy = -sm.diff(pe, y)
     f2 = sm.diff(x ** 2 * D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * D1 * sy, y) / y ** 2
-    f3 = sm.diff(qe, x) + x ** 2 * pe
+    f3 = q_react * qe + sm.diff(qe, x) + x ** 2 * pe
     drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
     T = lambda e: _torchify(e, (x, y))
-    return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)))
+    return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)), qy=T(sm.diff(qe, y)))
 
 
 class _Holder:
@@ -332,12 +333,21 @@ class PaperMixedSystemK1:
     once per mesh and they enter every step as a constant matrix / vector (_facet_tables is the torch
     restatement of the same operator for the CPU table test)."""
 
-    def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=2.0, degree=6, tables_only=False):
+    def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=2.0, degree=6, tables_only=False,
+                 variant="paper"):
+        """variant 'paper': test_for_paper_convergence.py (deg = 1; markers left 30 / right 31 / rest 32);
+        variant 'galerkin': ...MixedPrimal_convergence.py (BASELINE config 2's own script: G = D2 4 pi r2^2 p^2/q,
+        Galerkin q-equation with reaction, natural p data on the whole boundary, q = q_ex on the facets marked 31,
+        no facet stabilisation; pass D1 = 1e-3, D2 = 1.5e-3, degree = 4)."""
         if not tables_only:
             _capi.require_cuda(mesh.coords)
             self.lib = _capi.lib()
         self.mesh, self.bdry = mesh, bdry
         self.D1, self.D2 = float(D1), float(D2)
+        self.variant = variant
+        self.galerkin = variant == "galerkin"
+        self.gcoef = self.D2 * 4.0 * math.pi if self.galerkin else 1.0
+        self.qmode, self.q_react = (1, 1.0) if self.galerkin else (0, 0.0)
         self.gamma = stab / 2.0 ** 3.5                       # stab/(deg+1)^3.5 (:144)
         self.stab2 = float(stab2)
         dev = mesh.device
@@ -371,7 +381,7 @@ class PaperMixedSystemK1:
         self.lamq = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
         P = torch.einsum("qi,cid->cqd", self.lamq, Xc)
         self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
-        self.data = paper_data(D1, D2)
+        self.data = paper_data(D1, D2, self.gcoef, self.q_react)
         self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
         self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
         # global dofs of the 17 local ones: [2 per edge | 2 per cell | 3 per cell | vertices | edges]
@@ -385,7 +395,12 @@ class PaperMixedSystemK1:
         self.cell_dofs = cd = torch.cat([sd, pd, qd], 1)                               # [C,17]
         # constant facet operator (COO) and vectors: CUDA kernels (cm_cg2_*_facets); the torch tabulation
         # _facet_tables is the host restatement used by the CPU table test and the GPU cross-check
-        if tables_only:
+        if self.galerkin:      # no facet operator: only the natural p data on every exterior facet (:126)
+            fr = fcn = torch.zeros(0, dtype=torch.int64, device=dev)
+            fv = torch.zeros(0, dtype=torch.float64, device=dev)
+            self.cvec = self._natural_all(degree)
+            cv_rows = cv_vals = None
+        elif tables_only:
             fr, fcn, fv, self.cvec = self._facet_tables(degree)
             cv_rows = cv_vals = None
         else:
@@ -402,7 +417,7 @@ class PaperMixedSystemK1:
         self.vec_ptr, order = _gather_lists(cd.flatten(), N)
         self.vec_idx = entv[order].to(torch.int32).contiguous()
         fslot = torch.searchsorted(self._key, fr * N + fcn)
-        if tables_only:
+        if tables_only or self.galerkin:
             self.Kf = torch.zeros(self.nnz, dtype=torch.float64, device=dev)
             self.Kf.index_add_(0, fslot, fv)
         else:   # deterministic: per-slot gather lists in facet order (exterior, then interior)
@@ -509,6 +524,24 @@ class PaperMixedSystemK1:
         vals.append(Ji.flatten())
         return torch.cat(rows), torch.cat(cols), torch.cat(vals), cvec
 
+    def _natural_all(self, degree):
+        """+ p_ex (tau.n) W ds on every exterior facet (...MixedPrimal_convergence.py:126): boundary data vector."""
+        fc, dev = self.mesh.facets(), self.mesh.device
+        m = (degree + 2) // 2
+        p, w = np.polynomial.legendre.leggauss(m)
+        s = torch.tensor(0.5 * (p + 1.0), device=dev)
+        w = torch.tensor(0.5 * w, device=dev)
+        ext = torch.nonzero(fc.cell1 < 0).flatten()
+        L, nrm, A, B = self._facet_geometry(ext)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        x, y = Pq[..., 0], Pq[..., 1]
+        pw = w[None, :] * (4.0 * math.pi * x * y) ** 2 * p_exact(x, y)
+        sgn = torch.sign((nrm * self.enorm[ext]).sum(1))
+        out = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        for slot, lamend in ((0, 1.0 - s), (1, s)):
+            out[2 * ext + slot] = (pw * lamend[None, :]).sum(1) * sgn
+        return out
+
     def _facet_tables_cuda(self, degree):
         """The same operator from the CUDA kernels: returns COO (rows, cols, vals) of the q-q facet matrix and
         (rows, vals) of the constant vector, both in kernel storage order (entry-major over facets)."""
@@ -606,7 +639,8 @@ class PaperMixedSystemK1:
     def assemble(self, u, want_jac=True):
         lib, st, mesh = self.lib, _capi.stream_ptr(), self.mesh
         _capi.check(lib.cm_mixed_m1_cells(
-            self.nq, self.rule.ctypes.data, self.D1, self.D2, DOLFIN_EPS, self.C, self.E, self.V,
+            self.nq, self.rule.ctypes.data, self.D1, self.D2, DOLFIN_EPS, self.gcoef, self.qmode, self.q_react,
+            self.C, self.E, self.V,
             _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign),
             _capi.ptr(u), _capi.ptr(self.f2q), _capi.ptr(self.f3q), _capi.ptr(self.Je) if want_jac else None,
             _capi.ptr(self.Fe), st))
@@ -631,10 +665,23 @@ class PaperMixedSystemK1:
     def solve(self, tol=1e-7, maxit=50):
         dev = self.mesh.device
         fc = self.mesh.facets()
-        le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 30)).flatten()          # left edges (:133)
-        bc, _ = torch.sort(torch.cat([2 * le, 2 * le + 1]))
+        if self.galerkin:   # q = q_ex at the CG2 nodes of the facets marked 31 (...MixedPrimal_convergence.py:117)
+            sel = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 31)).flatten()
+            va, vb = fc.verts[sel, 0].long(), fc.verts[sel, 1].long()
+            XA, XB = self.mesh.coords[va], self.mesh.coords[vb]
+            XM = 0.5 * (XA + XB)
+            val = torch.zeros(self.N, dtype=torch.float64, device=dev)
+            has = torch.zeros(self.N, dtype=torch.bool, device=dev)
+            for d, Xn in ((self.q0 + va, XA), (self.q0 + vb, XB), (self.q0 + self.V + sel, XM)):
+                val[d] = q_exact(Xn[:, 0], Xn[:, 1])
+                has[d] = True
+            bc = torch.nonzero(has).flatten()
+            self.bc_vals = val[bc].contiguous()
+        else:
+            le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 30)).flatten()          # left edges (:133)
+            bc, _ = torch.sort(torch.cat([2 * le, 2 * le + 1]))
+            self.bc_vals = self.sigD()[bc].contiguous()
         self.bc_dofs = bc.to(torch.int32).contiguous()
-        self.bc_vals = self.sigD()[bc].contiguous()
         self.bc_diag = self.diag_slot_all[bc].contiguous()
         u = torch.zeros(self.N, dtype=torch.float64, device=dev)
         self.assemble(u, False)
@@ -664,11 +711,12 @@ class PaperMixedSystemK1:
     def errors(self, u):
         d, x, y = self.data, self.xq, self.yq
         exq = torch.stack([d["sx"](x, y), d["sy"](x, y), d["drs"](x, y), p_exact(x, y), q_exact(x, y),
-                           d["qx"](x, y)], -1).to(torch.float64).contiguous()
+                           d["qx"](x, y), d["qy"](x, y)], -1).to(torch.float64).contiguous()
         work = torch.empty(int(self.lib.cm_mixed_workspace_doubles()), dtype=torch.float64,
                            device=self.mesh.device)
         _capi.check(self.lib.cm_mixed_m1_errors(
-            self.nq, self.rule.ctypes.data, self.C, self.E, self.V, _capi.ptr(self.mesh.cells),
+            self.nq, self.rule.ctypes.data, 1 if self.galerkin else 0, self.C, self.E, self.V,
+            _capi.ptr(self.mesh.cells),
             _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
             _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))
         return tuple(math.sqrt(float(v)) for v in work[:3].cpu())

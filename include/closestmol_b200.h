@@ -365,15 +365,19 @@ int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, cons
  * [8 fluxes: (lambda_j N_i, lambda_k N_i) for the facets i = 0,1,2 with end points j < k, then lambda_1 N_1,
  * lambda_2 N_2 | 3 DG1 values | 6 CG2 values: vertices, then the facets' mid points]; global dofs
  * [2 per edge | 2 per cell | 3 per cell | vertices | edges].  Je[289][ncells], Fe[17][ncells] entry-major;
- * assembled by cm_csr_gather like the k = 0 tensors. */
-int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps,
-                      int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells,
-                      const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
-                      const double* f2q, const double* f3q, double* Je, double* Fe, void* stream);
-int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t ncells, int32_t nedges, int32_t nverts,
-                       const int32_t* cells, const double* coords, const int32_t* cell_edges,
-                       const double* sign, const double* u, const double* exact_q, double* work,
-                       void* stream);
+ * assembled by cm_csr_gather like the k = 0 tensors.
+ * G = gcoef x^2 p^2/(q + geps).  qmode 0: the q-equation of test_for_paper_convergence.py:140-141 (integrated by
+ * parts; its facet terms come from cm_cg2_*_facets); qmode 1: the Galerkin q-equation
+ * (q_react q + r2vec.grad q + r2^2 p) w W of ...MixedPrimal_convergence.py:123 (BASELINE config 2's own script).
+ * cm_mixed_m1_errors: exact_q[ncells*nq*7] = (s_x, s_y, div_rad s, p, q, dq/dx, dq/dy); full_grad selects the q
+ * error with the whole gradient (...MixedPrimal_convergence.py:148) instead of d/dx only (test_for_paper:175). */
+int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps, double gcoef,
+                      int32_t qmode, double q_react, int32_t ncells, int32_t nedges, int32_t nverts,
+                      const int32_t* cells, const double* coords, const int32_t* cell_edges, const double* sign,
+                      const double* u, const double* f2q, const double* f3q, double* Je, double* Fe, void* stream);
+int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t full_grad, int32_t ncells, int32_t nedges,
+                       int32_t nverts, const int32_t* cells, const double* coords, const int32_t* cell_edges,
+                       const double* sign, const double* u, const double* exact_q, double* work, void* stream);
 
 /* CG2 facet operators of the k = 1 q-equation (state independent, once per mesh; :142-145,148-149,152-153).
  * rule_host[2*nq] = (s, w) Gauss-Legendre on [0,1].  fverts[nf*2] ascending vertex ids.

@@ -47,6 +47,12 @@ class PaperM1:
         self.stab, self.stab2 = stab, stab2
         self.gamma = stab / (DEG + 1) ** 3.5                                          # :144
         self.sym = _sym()
+        self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, 1.0, 0, 0.0, 6
+        self._finish_setup()
+
+    def _finish_setup(self):
+        mesh, fc = self.mesh, self.fc
+        E, C, V = self.E, self.C, self.V
         X = mesh.coords
         left = lambda P: fem.near(P[..., 0], 0.0)
         right = lambda P: fem.near(P[..., 0], 1.0)
@@ -66,7 +72,7 @@ class PaperM1:
         self.area, self.Xc, self.grads = 0.5 * np.abs(det), Xc, grads
         mid = 0.5 * (A + B)[ce]
         self.sign = np.sign(((mid - Xc) * self.enorm[ce]).sum(-1))                    # [C,3]
-        self.pts, self.wts = fem.triangle_rule(6)
+        self.pts, self.wts = fem.triangle_rule(self.degree)
         self.lam = np.stack([1 - self.pts[:, 0] - self.pts[:, 1], self.pts[:, 0], self.pts[:, 1]], 1)   # [nq,3]
         self.P = np.einsum("qi,cid->cqd", self.lam, Xc)
         # global dof numbers of the 17 local dofs
@@ -103,7 +109,7 @@ class PaperM1:
         return np.stack(R, 2), np.stack(dxx, 2), np.stack(dyy, 2)
 
     def assemble(self, u, want_jac=True):
-        mesh, C = self.mesh, self.C
+        mesh, C, D1, D2 = self.mesh, self.C, self.D1, self.D2
         lam, P = self.lam, self.P
         x, y = P[:, :, 0], P[:, :, 1]
         W = (4 * np.pi * x * y) ** 2
@@ -121,14 +127,19 @@ class PaperM1:
         q = np.einsum("cqk,ck->cq", phi, qe)
         x2 = x * x
         iq = 1.0 / (q + DOLFIN_EPS)
-        G, Gp, Gq = x2 * p * p * iq, 2 * x2 * p * iq, -x2 * p * p * iq * iq
+        gc = self.gcoef
+        G, Gp, Gq = gc * x2 * p * p * iq, 2 * gc * x2 * p * iq, -gc * x2 * p * p * iq * iq
         f2, f3 = self.sym["f2"](x, y), self.sym["f3"](x, y)
         Fe = np.zeros((C, 17))
         Fe[:, :8] = np.einsum("cq,cqa->ca", a, np.einsum("cqd,cqad->cqa", s, R) + G[..., None] * Rx
                               - p[..., None] * dr)
         Fe[:, 8:11] = np.einsum("cq,cqb->cb", a * (-np.einsum("cqa,ca->cq", drD, se) + f2), chi)
-        Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * (-(2 / x) * q + x2 * p - f3), phi)
-                      - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
+        if self.qmode == 0:
+            Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * (-(2 / x) * q + x2 * p - f3), phi)
+                          - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
+        else:   # (q_react q + dq/dx + x^2 p - f3) w W  (...MixedPrimal_convergence.py:123,128)
+            qx = np.einsum("cqk,ck->cq", gphi[..., 0], qe)
+            Fe[:, 11:] = np.einsum("cq,cqk->ck", a * (self.q_react * q + qx + x2 * p - f3), phi)
         b = np.zeros(self.N)
         np.add.at(b, self.cell_dofs.ravel(), Fe.ravel())
         rows, cols, vals = [], [], []
@@ -139,8 +150,11 @@ class PaperM1:
             Je[:, :8, 11:] = np.einsum("cq,cqa,cqk->cak", a * Gq, Rx, phi)
             Je[:, 8:11, :8] = -np.einsum("cq,cqb,cqa->cba", a, chi, drD)
             Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2, phi, chi)
-            Je[:, 11:, 11:] = (-np.einsum("cq,cqk,cql->ckl", a * (2 / x), phi, phi)
-                               - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
+            if self.qmode == 0:
+                Je[:, 11:, 11:] = (-np.einsum("cq,cqk,cql->ckl", a * (2 / x), phi, phi)
+                                   - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
+            else:
+                Je[:, 11:, 11:] = np.einsum("cq,cqk,cql->ckl", a, phi, self.q_react * phi + gphi[..., 0])
             rows.append(np.repeat(self.cell_dofs, 17, axis=1).ravel())
             cols.append(np.tile(self.cell_dofs, (1, 17)).ravel())
             vals.append(Je.ravel())
@@ -164,7 +178,7 @@ class PaperM1:
         (q - q_ex) w ds (:142-145,152-153); s-rows: + p_ex (tau.n) W ds(right,rest) (:148-149)."""
         mesh, fc, ext = self.mesh, self.fc, self.ext
         L, nrm, A, B = fem.facet_geometry(mesh, ext)
-        s, w = fem.facet_rule(6)
+        s, w = fem.facet_rule(self.degree)
         cell = fc.cell0[ext]
         lam = self._facet_lam(ext, cell, s)
         Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
@@ -200,7 +214,7 @@ class PaperM1:
         mesh, fc = self.mesh, self.fc
         fi = fc.interior
         L, nrm, A, B = fem.facet_geometry(mesh, fi)
-        s, w = fem.facet_rule(6)
+        s, w = fem.facet_rule(self.degree)
         Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
         W = (4 * np.pi * Pq[..., 0] * Pq[..., 1]) ** 2
         c0, c1 = fc.cell0[fi], fc.cell1[fi]
@@ -277,6 +291,114 @@ class PaperM1:
         qhx = np.einsum("cqk,ck->cq", gphi[..., 0], u[self.qd])
         eq = np.sqrt((a * ((q_ex(x, y) - qh) ** 2 + (self.sym["qx"](x, y) - qhx) ** 2)).sum())
         return float(es), float(ep), float(eq)
+
+
+class MixedPrimalM1(PaperM1):
+    """convergence/SphericalAdvectionDiffusionReaction_MixedPrimal_convergence.py (BASELINE config 2's own script):
+    RT2 x DG1 x CG2 (deg = 1, :93-97), D1 = 1e-3, D2 = 1.5e-3 (:51-52), G = D2 4 pi r2^2 p^2/(q + eps) (:43-44),
+    Galerkin q-equation (q + r2vec.grad q + r2^2 p) w W (:123), natural p data on the whole boundary (:126),
+    q = q_ex on the facets marked 'left' = {x = 1} (:78,117), quadrature degree 4 (:25), Newton 1e-7 with 'umfpack'
+    (:132-138); q error with the whole gradient (:148).  No output of this script is recorded: parity unpinned."""
+
+    def __init__(self, n, D1=1e-3, D2=1.5e-3):
+        self.mesh = mesh = fem.unit_square_mesh(n, n)
+        self.fc = fc = mesh.facets()
+        self.E, self.C, self.V = fc.verts.shape[0], mesh.num_cells, mesh.num_vertices
+        self.N = 3 * self.E + 5 * self.C + self.V
+        self.stab = self.stab2 = self.gamma = 0.0
+        self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, D2 * 4 * np.pi, 1, 1.0, 4
+        self.sym = self._data()
+        self._finish_setup()
+        self.markers = fem.mark_facets(mesh, [(lambda P: fem.near(P[..., 0], 1.0), 31),
+                                              (lambda P: fem.near(P[..., 0], 0.0) | fem.near(P[..., 1], 0.0)
+                                               | fem.near(P[..., 1], 1.0), 32)])
+
+    def _data(self):
+        import sympy as sm
+        x, y = sm.symbols("x y", positive=True)
+        pe = sm.sin(sm.pi * x) * sm.sin(sm.pi * y)
+        qe = sm.Rational(3, 2) + sm.cos(sm.pi * x * y)
+        G = self.gcoef * x ** 2 * pe ** 2 / (qe + DOLFIN_EPS)
+        sx, sy = -sm.diff(pe, x) - G, -sm.diff(pe, y)
+        f2 = sm.diff(x ** 2 * self.D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * self.D1 * sy, y) / y ** 2
+        f3 = qe + sm.diff(qe, x) + x ** 2 * pe
+        drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
+        L = lambda e: sm.lambdify((x, y), e, "numpy")
+        return dict(sx=L(sx), sy=L(sy), f2=L(f2), f3=L(f3), drs=L(drs), qx=L(sm.diff(qe, x)), qy=L(sm.diff(qe, y)))
+
+    def _exterior(self, u, b, rows, cols, vals, want_jac):
+        """+ p_ex (tau.n) W ds on every exterior facet (:126)."""
+        mesh, ext = self.mesh, self.ext
+        L, nrm, A, B = fem.facet_geometry(mesh, ext)
+        s, w = fem.facet_rule(self.degree)
+        Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
+        x, y = Pq[..., 0], Pq[..., 1]
+        pw = w[None, :] * (4 * np.pi * x * y) ** 2 * p_ex(x, y)
+        sgn = np.sign((nrm * self.enorm[ext]).sum(1))
+        for slot, lamend in ((0, 1.0 - s), (1, s)):
+            np.add.at(b, 2 * ext + slot, (pw * lamend[None, :]).sum(1) * sgn)
+
+    def _interior(self, u, b, rows, cols, vals, want_jac):
+        pass
+
+    def bcs(self):
+        fc, mesh = self.fc, self.mesh
+        sel = np.nonzero((fc.cell1 < 0) & (self.markers == 31))[0]
+        va, vb = fc.verts[sel, 0], fc.verts[sel, 1]
+        XA, XB = mesh.coords[va], mesh.coords[vb]
+        XM = 0.5 * (XA + XB)
+        dofs = np.concatenate([self.q0 + va, self.q0 + vb, self.q0 + self.V + sel])
+        vals = np.concatenate([q_ex(XA[:, 0], XA[:, 1]), q_ex(XB[:, 0], XB[:, 1]), q_ex(XM[:, 0], XM[:, 1])])
+        d, i = np.unique(dofs, return_index=True)
+        return d, vals[i]
+
+    def solve(self, tol=1e-7, maxit=50):
+        bc_dofs, g = self.bcs()
+        u = np.zeros(self.N)
+        _, b = self.assemble(u, False)
+        b[bc_dofs] = u[bc_dofs] - g
+        r0 = r = np.linalg.norm(b)
+        it = 0
+        while not (r < tol or r / r0 < tol) and it < maxit:
+            J, _ = self.assemble(u, True)
+            J = J.tolil()
+            J[bc_dofs, :] = 0.0
+            J[bc_dofs, bc_dofs] = 1.0
+            u -= spla.splu(J.tocsc()).solve(b)
+            it += 1
+            _, b = self.assemble(u, False)
+            b[bc_dofs] = u[bc_dofs] - g
+            r = np.linalg.norm(b)
+        self.newton_its = it
+        return u
+
+    def errors(self, u):
+        es, ep, _ = PaperM1.errors(self, u)
+        lam, P = self.lam, self.P
+        x, y = P[:, :, 0], P[:, :, 1]
+        a = self.wts[None, :] * (2 * self.area)[:, None] * (4 * np.pi * x * y) ** 2
+        phi, gphi = p2_basis(np.broadcast_to(lam[None], (self.C,) + lam.shape), self.grads)
+        qe = u[self.qd]
+        qh = np.einsum("cqk,ck->cq", phi, qe)
+        qhx = np.einsum("cqk,ck->cq", gphi[..., 0], qe)
+        qhy = np.einsum("cqk,ck->cq", gphi[..., 1], qe)
+        eq = np.sqrt((a * ((q_ex(x, y) - qh) ** 2 + (self.sym["qx"](x, y) - qhx) ** 2
+                           + (self.sym["qy"](x, y) - qhy) ** 2)).sum())
+        return es, ep, float(eq)
+
+
+def mixed_primal_table(levels=5):
+    rows, prev = [], None
+    for nk in range(levels):
+        m = MixedPrimalM1(2 ** (nk + 1))
+        u = m.solve()
+        h = m.mesh.hmax()
+        e = m.errors(u)
+        r = [0.0, 0.0, 0.0] if prev is None else [np.log(a / b) / np.log(h / prev[0]) for a, b in zip(e, prev[1])]
+        rows.append('{:6d} & {:.4f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} '.format(
+            m.N, h, e[0], r[0], e[1], r[1], e[2], r[2]))
+        prev = (h, e)
+    return rows
 
 
 def table(levels=5, stab=0.1):

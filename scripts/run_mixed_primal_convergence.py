@@ -1,0 +1,48 @@
+"""Port of convergence/SphericalAdvectionDiffusionReaction_MixedPrimal_convergence.py (BASELINE config 2's own script)
+onto the GPU path with ITS OWN discretisation RT2 x DG1 x CG2 (deg = 1, :93-97): same mesh ladder (:71-72), markers
+('left' = {x = 1} -> 31, rest -> 32, :74-80), constants (:51-56), forms (:120-128), boundary condition (:117), Newton
+parameters (:132-138) and table layout (:166).  The reference records no table for it; the Galerkin q-equation gives
+the orders ~1.5 / 2 / 1 for e_div(s) / e_0(p) / e_1(q) (the loss in q is why the SUPG / C0IP variants exist).
+The CG1 x CG1 restatement of the same problem is scripts/run_pq_supg_convergence.py."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from closestmolecule_b200 import *  # noqa: E402,F401,F403
+from closestmolecule_b200.mixed import PaperMixedSystemK1  # noqa: E402
+
+
+def main(nkmax=6):
+    hh, nn, es, ep, eq, rs, rp, rq = [], [], [], [], [], [0.0], [0.0], [0.0]
+    for nk in range(nkmax):
+        nps = pow(2, nk + 1)
+        mesh = RectangleMesh(Point(0, 0), Point(1, 1), nps, nps)
+        bdry = MeshFunction("size_t", mesh, 1)
+        bdry.set_all(0)
+        left, rest = 31, 32
+        CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, left)
+        CompiledSubDomain("(near(x[0],0) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
+        hh.append(mesh.hmax())
+        system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant="galerkin")
+        nn.append(system.N)
+        u = system.solve(tol=1e-7)
+        e = system.errors(u)
+        es.append(e[0]); ep.append(e[1]); eq.append(e[2])
+        if nk > 0:
+            lg = math.log(hh[nk] / hh[nk - 1])
+            rs.append(math.log(es[nk] / es[nk - 1]) / lg)
+            rp.append(math.log(ep[nk] / ep[nk - 1]) / lg)
+            rq.append(math.log(eq[nk] / eq[nk - 1]) / lg)
+    print('====================================================')
+    print('  DoF      h     e_div(s)   r_div(s)   e_0(p)   r_0(p)   e_1(q)  r_1(q)    ')
+    print('====================================================')
+    rows = ['{:6d} & {:.4f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} '.format(
+        nn[k], hh[k], es[k], rs[k], ep[k], rp[k], eq[k], rq[k]) for k in range(nkmax)]
+    print("\n".join(rows))
+    print('====================================================')
+    return rows
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 6)

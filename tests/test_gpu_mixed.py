@@ -143,3 +143,46 @@ def test_k1_cuda_facet_operator_matches_host_tabulation():
     # deterministic: two builds give the same bits
     S2 = _system_k1(6)
     assert torch.equal(S.Kf, S2.Kf) and torch.equal(S.cvec, S2.cvec)
+
+
+# ---- BASELINE config 2's own script: ...MixedPrimal_convergence.py on RT2 x DG1 x CG2 (Galerkin q-equation) ----
+def _system_galerkin(n):
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[0],0) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    return PaperMixedSystemK1(mesh, bd, D1=1e-3, D2=1.5e-3, degree=4, variant="galerkin")
+
+
+def test_mixed_primal_galerkin_assembly_and_newton_match_oracle():
+    from oracle import paper_m1
+    n = 6
+    S, O = _system_galerkin(n), paper_m1.MixedPrimalM1(n)
+    rng = np.random.default_rng(4)
+    un = np.concatenate([rng.standard_normal(2 * O.E + 2 * O.C), 0.5 + rng.random(3 * O.C),
+                         1.0 + rng.random(O.V + O.E)])
+    u = torch.tensor(un, device=S.mesh.device)
+    vals, b = S.assemble(u, True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    assert abs(got - J).max() < 1e-12 * abs(J).max()
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    us, uo = S.solve(), O.solve()
+    assert S.newton_its == O.newton_its
+    assert np.linalg.norm(us.cpu().numpy() - uo) / np.linalg.norm(uo) < 1e-8
+    assert np.allclose(S.errors(us), O.errors(uo), rtol=1e-8)
+
+
+def test_mixed_primal_convergence_driver_matches_oracle_table():
+    """scripts/run_mixed_primal_convergence.py against the oracle's table of the same script (no table is recorded
+    in the reference): identical rows, DoF column 3E + 5C + V, e_0(p) of second order."""
+    from oracle import paper_m1
+    spec = importlib.util.spec_from_file_location("mp_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_mixed_primal_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(5)
+    ref = paper_m1.mixed_primal_table(5)
+    assert [r.split() for r in rows] == [r.split() for r in ref]
+    assert 1.95 < float(rows[-1].replace("&", " ").split()[5]) < 2.05
