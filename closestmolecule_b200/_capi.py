@@ -99,7 +99,7 @@ _PROTOS = {
     "cm_project_flux_dg0": ([_I, _P, _D, _D, _I, _P, _P, _P, _P, _P], C.c_int),
     "cm_functional_boundary_flux": ([_I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_mixed_m0_cells": ([_I, _P, _D, _D, _D, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P], C.c_int),
-    "cm_mixed_m1_cells": ([_I, _P, _D, _D, _D, _D, _I, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cm_mixed_m1_cells": ([_I, _P, _D, _D, _D, _D, _I, _D, _D, _D, _D, _I, _I, _I] + [_P] * 10, C.c_int),
     "cm_mixed_m1_errors": ([_I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_cg2_exterior_facets": ([_I, _P, _D, _I] + [_P] * 10 + [_P], C.c_int),
     "cm_cg2_interior_facets": ([_I, _P, _D, _I] + [_P] * 5 + [_P], C.c_int),

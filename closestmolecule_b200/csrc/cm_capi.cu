@@ -471,15 +471,15 @@ int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, cons
 }
 
 int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps, double gcoef,
-                      int32_t qmode, double q_react, int32_t ncells, int32_t nedges, int32_t nverts,
-                      const int32_t* cells,
+                      int32_t qmode, double q_react, double q_x2p, double q_x2q, double supg_stab,
+                      int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells,
                       const double* coords, const int32_t* cell_edges, const double* sign, const double* u,
                       const double* f2q, const double* f3q, double* Je, double* Fe, void* stream) {
   CM_CHECK_ARG(ncells >= 1 && nedges >= 3 && nverts >= 3, "bad size");
   CM_CHECK_ARG(rule_host && cells && coords && cell_edges && sign && u && f2q && f3q && Fe, "null pointer");
   CM_CHECK_ARG(qmode == 0 || qmode == 1, "qmode must be 0 (paper) or 1 (Galerkin)");
-  return mixed_m1_cells(nq, rule_host, D1, D2, geps, gcoef, qmode, q_react, ncells, nedges, nverts, cells, coords,
-                        cell_edges, sign, u, f2q, f3q, Je, Fe, (cudaStream_t)stream);
+  return mixed_m1_cells(nq, rule_host, D1, D2, geps, gcoef, qmode, q_react, q_x2p, q_x2q, supg_stab, ncells, nedges,
+                        nverts, cells, coords, cell_edges, sign, u, f2q, f3q, Je, Fe, (cudaStream_t)stream);
 }
 
 int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t full_grad, int32_t ncells, int32_t nedges,

@@ -157,7 +157,7 @@ int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cell
                     const int* cell_edges, const double* sign, int nE, const double* u, const double* exq,
                     double* work, cudaStream_t st);
 int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, double gcoef, int qmode,
-                   double q_react, int ncells, int nE,
+                   double q_react, double q_x2p, double q_x2q, double supg_stab, int ncells, int nE,
                    int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
                    const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
                    cudaStream_t st);

@@ -223,7 +223,7 @@ mixed_final_sum_kernel(const int nparts, const double* __restrict__ partial, dou
 // row of the 17 x 17 element Jacobian and its residual entry (entry-major storage, coalesced over cells).
 // ------------------------------------------------------------------------------------------------
 struct M1Cell {
-  double X[3], Y[3], gx[3], gy[3], adet, rs[3];  // rs = sigma_i / (2|K|)
+  double X[3], Y[3], gx[3], gy[3], adet, hK, rs[3];  // rs = sigma_i / (2|K|); hK = CellDiameter (longest edge)
   double se[8], pe[3], qe[6];
 };
 
@@ -250,6 +250,10 @@ __device__ __forceinline__ void m1_load_cell(const int c, const int ncells, cons
   const double j00 = K.X[1] - K.X[0], j01 = K.X[2] - K.X[0], j10 = K.Y[1] - K.Y[0], j11 = K.Y[2] - K.Y[0];
   const double det = j00 * j11 - j01 * j10, id = 1.0 / det;
   K.adet = fabs(det);
+  {
+    const double e2 = (K.X[2] - K.X[1]) * (K.X[2] - K.X[1]) + (K.Y[2] - K.Y[1]) * (K.Y[2] - K.Y[1]);
+    K.hK = sqrt(fmax(fmax(j00 * j00 + j10 * j10, j01 * j01 + j11 * j11), e2));
+  }
   K.gx[1] = j11 * id;  K.gy[1] = -j01 * id;
   K.gx[2] = -j10 * id; K.gy[2] = j00 * id;
   K.gx[0] = -(K.gx[1] + K.gx[2]);
@@ -315,7 +319,8 @@ __device__ __forceinline__ void m1_eval_point(const M1Cell& K, const double l1, 
 // Je: [289][ncells] (row-major local (test, trial), entry-major over cells), Fe: [17][ncells]
 __global__ void __launch_bounds__(kMxThreads)
 mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const double geps, const double gcoef,
-                      const int qmode, const double q_react, const int ncells,
+                      const int qmode, const double q_react, const double q_x2p, const double q_x2q,
+                      const double supg_stab, const int ncells,
                       const int nE, const int nV, const int* __restrict__ cells,
                       const double2* __restrict__ coords, const int* __restrict__ cell_edges,
                       const double* __restrict__ sign, const double* __restrict__ u,
@@ -368,16 +373,21 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
     } else {
       const double ph = Q.phi[row - 11], phx = Q.phix[row - 11];
       const double f3 = f3q[(size_t)c * R.nq + k];
+      if (qmode == 0) {
 #pragma unroll
-      for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * Q.chi[b] * ph;
-      if (qmode == 0) {  // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W
+        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * Q.chi[b] * ph;  // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W
         F += a * ((-(2.0 / Q.x) * q + x2 * p - f3) * ph - q * phx);
 #pragma unroll
         for (int m = 0; m < 6; ++m) J[11 + m] -= a * ((2.0 / Q.x) * Q.phi[m] * ph + phx * Q.phi[m]);
-      } else {  // ...MixedPrimal_convergence.py:123: (q + r2vec.grad q + r2^2 p) w W
-        F += a * (q_react * q + qx + x2 * p - f3) * ph;
+      } else {
+        // (q_react q + r2vec.grad q + r2^2 (q_x2p p + q_x2q q) - f3) (w + tau r2vec.grad w) W, tau = supg_stab hK/2:
+        // ...MixedPrimal_convergence.py:123 (1,1,0,0) and ..._SUPG.py:118-129 (1,0,1,1; "r2**2*q" as written there)
+        const double tw = ph + 0.5 * supg_stab * K.hK * phx;
+        F += a * (q_react * q + qx + x2 * (q_x2p * p + q_x2q * q) - f3) * tw;
 #pragma unroll
-        for (int m = 0; m < 6; ++m) J[11 + m] += a * (q_react * Q.phi[m] + Q.phix[m]) * ph;
+        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * q_x2p * Q.chi[b] * tw;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) J[11 + m] += a * ((q_react + x2 * q_x2q) * Q.phi[m] + Q.phix[m]) * tw;
       }
     }
   }
@@ -896,7 +906,7 @@ int mixed_m0_errors(int nq, const double* rule_host, int ncells, const int* cell
 }
 
 int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double geps, double gcoef, int qmode,
-                   double q_react, int ncells, int nE,
+                   double q_react, double q_x2p, double q_x2q, double supg_stab, int ncells, int nE,
                    int nV, const int* cells, const double* coords, const int* cell_edges, const double* sign,
                    const double* u, const double* f2q, const double* f3q, double* Je, double* Fe,
                    cudaStream_t st) {
@@ -907,8 +917,8 @@ int mixed_m1_cells(int nq, const double* rule_host, double D1, double D2, double
   }
   const long long nt = 17ll * ncells;
   mixed_m1_cells_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
-      R, D1, D2, geps, gcoef, qmode, q_react, ncells, nE, nV, cells, (const double2*)coords, cell_edges, sign, u, f2q,
-      f3q, Je, Fe);
+      R, D1, D2, geps, gcoef, qmode, q_react, q_x2p, q_x2q, supg_stab, ncells, nE, nV, cells, (const double2*)coords,
+      cell_edges, sign, u, f2q, f3q, Je, Fe);
   CM_LAUNCH_CHECK();
   CM_BYTES((double)ncells * (12.0 + 12.0 + 24.0 + 136.0 + 16.0 * nq + 136.0 + (Je ? 2312.0 : 0.0)));
   return CM_OK;

@@ -26,7 +26,7 @@ from .solver import BandedLULinearSolver
 from .space import FiniteElement, FunctionSpace, MixedElement
 
 
-def paper_data(D1, D2, gcoef=1.0, q_react=0.0):
+def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False):
     """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = q_react q_ex + dq_ex/dx + r2^2 p_ex
     (test_for_paper_convergence.py:124-128; ...MixedPrimal_convergence.py:109-113 with gcoef = D2 4 pi, q_react = 1),
     div_rad(sig_ex) and grad q_ex for the error norms, as torch callables."""
@@ -38,7 +38,7 @@ def paper_data(D1, D2, gcoef=1.0, q_react=0.0):
     sx = -sm.diff(pe, x) - G
     sy = -sm.diff(pe, y)
     f2 = sm.diff(x ** 2 * D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * D1 * sy, y) / y ** 2
-    f3 = q_react * qe + sm.diff(qe, x) + x ** 2 * pe
+    f3 = q_react * qe + sm.diff(qe, x) + x ** 2 * (qe if x2_on_q else pe)   # "r2**2*q_ex" in ..._SUPG.py:112
     drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
     T = lambda e: _torchify(e, (x, y))
     return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)), qy=T(sm.diff(qe, y)))
@@ -338,16 +338,21 @@ class PaperMixedSystemK1:
         """variant 'paper': test_for_paper_convergence.py (deg = 1; markers left 30 / right 31 / rest 32);
         variant 'galerkin': ...MixedPrimal_convergence.py (BASELINE config 2's own script: G = D2 4 pi r2^2 p^2/q,
         Galerkin q-equation with reaction, natural p data on the whole boundary, q = q_ex on the facets marked 31,
-        no facet stabilisation; pass D1 = 1e-3, D2 = 1.5e-3, degree = 4)."""
+        no facet stabilisation; pass D1 = 1e-3, D2 = 1.5e-3, degree = 4); variant 'supg': ..._SUPG.py, the same with
+        the SUPG test function and the script's residual q + dq/dx + r2^2 q."""
         if not tables_only:
             _capi.require_cuda(mesh.coords)
             self.lib = _capi.lib()
         self.mesh, self.bdry = mesh, bdry
         self.D1, self.D2 = float(D1), float(D2)
+        if variant not in ("paper", "galerkin", "supg"):
+            raise ValueError(f"unknown variant '{variant}'")
         self.variant = variant
-        self.galerkin = variant == "galerkin"
+        self.galerkin = variant in ("galerkin", "supg")      # cell-only q-equation, natural p data on all of the boundary
         self.gcoef = self.D2 * 4.0 * math.pi if self.galerkin else 1.0
         self.qmode, self.q_react = (1, 1.0) if self.galerkin else (0, 0.0)
+        # 'supg': ...MixedPrimal_convergence_SUPG.py:118-129 (residual q + dq/dx + r2^2 q, test w + hK/2 dw/dx)
+        self.q_x2p, self.q_x2q, self.supg_stab = (0.0, 1.0, 1.0) if variant == "supg" else (1.0, 0.0, 0.0)
         self.gamma = stab / 2.0 ** 3.5                       # stab/(deg+1)^3.5 (:144)
         self.stab2 = float(stab2)
         dev = mesh.device
@@ -381,7 +386,7 @@ class PaperMixedSystemK1:
         self.lamq = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
         P = torch.einsum("qi,cid->cqd", self.lamq, Xc)
         self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
-        self.data = paper_data(D1, D2, self.gcoef, self.q_react)
+        self.data = paper_data(D1, D2, self.gcoef, self.q_react, variant == "supg")
         self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
         self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
         # global dofs of the 17 local ones: [2 per edge | 2 per cell | 3 per cell | vertices | edges]
@@ -640,7 +645,7 @@ class PaperMixedSystemK1:
         lib, st, mesh = self.lib, _capi.stream_ptr(), self.mesh
         _capi.check(lib.cm_mixed_m1_cells(
             self.nq, self.rule.ctypes.data, self.D1, self.D2, DOLFIN_EPS, self.gcoef, self.qmode, self.q_react,
-            self.C, self.E, self.V,
+            self.q_x2p, self.q_x2q, self.supg_stab, self.C, self.E, self.V,
             _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign),
             _capi.ptr(u), _capi.ptr(self.f2q), _capi.ptr(self.f3q), _capi.ptr(self.Je) if want_jac else None,
             _capi.ptr(self.Fe), st))

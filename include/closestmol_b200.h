@@ -367,14 +367,17 @@ int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, cons
  * [2 per edge | 2 per cell | 3 per cell | vertices | edges].  Je[289][ncells], Fe[17][ncells] entry-major;
  * assembled by cm_csr_gather like the k = 0 tensors.
  * G = gcoef x^2 p^2/(q + geps).  qmode 0: the q-equation of test_for_paper_convergence.py:140-141 (integrated by
- * parts; its facet terms come from cm_cg2_*_facets); qmode 1: the Galerkin q-equation
- * (q_react q + r2vec.grad q + r2^2 p) w W of ...MixedPrimal_convergence.py:123 (BASELINE config 2's own script).
+ * parts; its facet terms come from cm_cg2_*_facets); qmode 1: the q-equation
+ * (q_react q + r2vec.grad q + r2^2 (q_x2p p + q_x2q q) - f3)(w + supg_stab hK/2 r2vec.grad w) W:
+ * (1,1,0,0) = ...MixedPrimal_convergence.py:123 (BASELINE config 2's own script, Galerkin),
+ * (1,0,1,1) = ...MixedPrimal_convergence_SUPG.py:118-129 (hK = CellDiameter).
  * cm_mixed_m1_errors: exact_q[ncells*nq*7] = (s_x, s_y, div_rad s, p, q, dq/dx, dq/dy); full_grad selects the q
  * error with the whole gradient (...MixedPrimal_convergence.py:148) instead of d/dx only (test_for_paper:175). */
 int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2, double geps, double gcoef,
-                      int32_t qmode, double q_react, int32_t ncells, int32_t nedges, int32_t nverts,
-                      const int32_t* cells, const double* coords, const int32_t* cell_edges, const double* sign,
-                      const double* u, const double* f2q, const double* f3q, double* Je, double* Fe, void* stream);
+                      int32_t qmode, double q_react, double q_x2p, double q_x2q, double supg_stab,
+                      int32_t ncells, int32_t nedges, int32_t nverts, const int32_t* cells, const double* coords,
+                      const int32_t* cell_edges, const double* sign, const double* u, const double* f2q,
+                      const double* f3q, double* Je, double* Fe, void* stream);
 int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t full_grad, int32_t ncells, int32_t nedges,
                        int32_t nverts, const int32_t* cells, const double* coords, const int32_t* cell_edges,
                        const double* sign, const double* u, const double* exact_q, double* work, void* stream);

@@ -48,6 +48,7 @@ class PaperM1:
         self.gamma = stab / (DEG + 1) ** 3.5                                          # :144
         self.sym = _sym()
         self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, 1.0, 0, 0.0, 6
+        self.q_x2p, self.q_x2q, self.supg_stab = 1.0, 0.0, 0.0
         self._finish_setup()
 
     def _finish_setup(self):
@@ -137,9 +138,11 @@ class PaperM1:
         if self.qmode == 0:
             Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * (-(2 / x) * q + x2 * p - f3), phi)
                           - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
-        else:   # (q_react q + dq/dx + x^2 p - f3) w W  (...MixedPrimal_convergence.py:123,128)
+        else:   # (q_react q + dq/dx + x^2 (x2p p + x2q q) - f3)(w + tau dw/dx) W, tau = supg_stab hK/2
             qx = np.einsum("cqk,ck->cq", gphi[..., 0], qe)
-            Fe[:, 11:] = np.einsum("cq,cqk->ck", a * (self.q_react * q + qx + x2 * p - f3), phi)
+            tw = phi + (0.5 * self.supg_stab * fem.cell_diameter(self.mesh))[:, None, None] * gphi[..., 0]
+            res = self.q_react * q + qx + x2 * (self.q_x2p * p + self.q_x2q * q) - f3
+            Fe[:, 11:] = np.einsum("cq,cqk->ck", a * res, tw)
         b = np.zeros(self.N)
         np.add.at(b, self.cell_dofs.ravel(), Fe.ravel())
         rows, cols, vals = [], [], []
@@ -149,12 +152,14 @@ class PaperM1:
             Je[:, :8, 8:11] = np.einsum("cq,cqa,cqb->cab", a, Gp[..., None] * Rx - dr, chi)
             Je[:, :8, 11:] = np.einsum("cq,cqa,cqk->cak", a * Gq, Rx, phi)
             Je[:, 8:11, :8] = -np.einsum("cq,cqb,cqa->cba", a, chi, drD)
-            Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2, phi, chi)
             if self.qmode == 0:
+                Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2, phi, chi)
                 Je[:, 11:, 11:] = (-np.einsum("cq,cqk,cql->ckl", a * (2 / x), phi, phi)
                                    - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
             else:
-                Je[:, 11:, 11:] = np.einsum("cq,cqk,cql->ckl", a, phi, self.q_react * phi + gphi[..., 0])
+                Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2 * self.q_x2p, tw, chi)
+                Je[:, 11:, 11:] = np.einsum("cq,cqk,cql->ckl", a, tw,
+                                            (self.q_react + x2 * self.q_x2q)[..., None] * phi + gphi[..., 0])
             rows.append(np.repeat(self.cell_dofs, 17, axis=1).ravel())
             cols.append(np.tile(self.cell_dofs, (1, 17)).ravel())
             vals.append(Je.ravel())
@@ -300,17 +305,22 @@ class MixedPrimalM1(PaperM1):
     q = q_ex on the facets marked 'left' = {x = 1} (:78,117), quadrature degree 4 (:25), Newton 1e-7 with 'umfpack'
     (:132-138); q error with the whole gradient (:148).  No output of this script is recorded: parity unpinned."""
 
-    def __init__(self, n, D1=1e-3, D2=1.5e-3):
+    def __init__(self, n, D1=1e-3, D2=1.5e-3, supg=False):
+        """supg=True: ...MixedPrimal_convergence_SUPG.py (:100-129): residual q + dq/dx + r2^2 q ("r2**2*q" as written
+        there) tested with w + stab hK/2 dw/dx (stab = 1, hK = CellDiameter), q = q_ex on {x = 0}, Newton 1e-8."""
+        self.supg = supg
         self.mesh = mesh = fem.unit_square_mesh(n, n)
         self.fc = fc = mesh.facets()
         self.E, self.C, self.V = fc.verts.shape[0], mesh.num_cells, mesh.num_vertices
         self.N = 3 * self.E + 5 * self.C + self.V
         self.stab = self.stab2 = self.gamma = 0.0
         self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, D2 * 4 * np.pi, 1, 1.0, 4
+        self.q_x2p, self.q_x2q, self.supg_stab = (0.0, 1.0, 1.0) if supg else (1.0, 0.0, 0.0)
         self.sym = self._data()
         self._finish_setup()
-        self.markers = fem.mark_facets(mesh, [(lambda P: fem.near(P[..., 0], 1.0), 31),
-                                              (lambda P: fem.near(P[..., 0], 0.0) | fem.near(P[..., 1], 0.0)
+        xin = 0.0 if supg else 1.0            # the facets carrying the q data: {x = 0} (SUPG :77) or {x = 1} (:78)
+        self.markers = fem.mark_facets(mesh, [(lambda P: fem.near(P[..., 0], xin), 31),
+                                              (lambda P: fem.near(P[..., 0], 1.0 - xin) | fem.near(P[..., 1], 0.0)
                                                | fem.near(P[..., 1], 1.0), 32)])
 
     def _data(self):
@@ -321,7 +331,7 @@ class MixedPrimalM1(PaperM1):
         G = self.gcoef * x ** 2 * pe ** 2 / (qe + DOLFIN_EPS)
         sx, sy = -sm.diff(pe, x) - G, -sm.diff(pe, y)
         f2 = sm.diff(x ** 2 * self.D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * self.D1 * sy, y) / y ** 2
-        f3 = qe + sm.diff(qe, x) + x ** 2 * pe
+        f3 = qe + sm.diff(qe, x) + x ** 2 * (qe if self.supg else pe)
         drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
         L = lambda e: sm.lambdify((x, y), e, "numpy")
         return dict(sx=L(sx), sy=L(sy), f2=L(f2), f3=L(f3), drs=L(drs), qx=L(sm.diff(qe, x)), qy=L(sm.diff(qe, y)))
@@ -352,7 +362,8 @@ class MixedPrimalM1(PaperM1):
         d, i = np.unique(dofs, return_index=True)
         return d, vals[i]
 
-    def solve(self, tol=1e-7, maxit=50):
+    def solve(self, tol=None, maxit=50):
+        tol = (1e-8 if self.supg else 1e-7) if tol is None else tol
         bc_dofs, g = self.bcs()
         u = np.zeros(self.N)
         _, b = self.assemble(u, False)
@@ -387,10 +398,10 @@ class MixedPrimalM1(PaperM1):
         return es, ep, float(eq)
 
 
-def mixed_primal_table(levels=5):
+def mixed_primal_table(levels=5, supg=False):
     rows, prev = [], None
     for nk in range(levels):
-        m = MixedPrimalM1(2 ** (nk + 1))
+        m = MixedPrimalM1(2 ** (nk + 1), supg=supg)
         u = m.solve()
         h = m.mesh.hmax()
         e = m.errors(u)

@@ -13,7 +13,9 @@ from closestmolecule_b200 import *  # noqa: E402,F401,F403
 from closestmolecule_b200.mixed import PaperMixedSystemK1  # noqa: E402
 
 
-def main(nkmax=6):
+def main(nkmax=6, variant="galerkin"):
+    """variant 'galerkin': ...MixedPrimal_convergence.py; 'supg': ...MixedPrimal_convergence_SUPG.py (q data on
+    {x = 0} :77, stab = 1 :56, Newton tolerances 1e-8 :138-139, nkmax = 5 :58)."""
     hh, nn, es, ep, eq, rs, rp, rq = [], [], [], [], [], [0.0], [0.0], [0.0]
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
@@ -21,12 +23,13 @@ def main(nkmax=6):
         bdry = MeshFunction("size_t", mesh, 1)
         bdry.set_all(0)
         left, rest = 31, 32
-        CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, left)
-        CompiledSubDomain("(near(x[0],0) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
+        xin, xout = (0, 1) if variant == "supg" else (1, 0)
+        CompiledSubDomain(f"near(x[0],{xin}) && on_boundary").mark(bdry, left)
+        CompiledSubDomain(f"(near(x[0],{xout}) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
         hh.append(mesh.hmax())
-        system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant="galerkin")
+        system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant=variant)
         nn.append(system.N)
-        u = system.solve(tol=1e-7)
+        u = system.solve(tol=1e-8 if variant == "supg" else 1e-7)
         e = system.errors(u)
         es.append(e[0]); ep.append(e[1]); eq.append(e[2])
         if nk > 0:
@@ -45,4 +48,4 @@ def main(nkmax=6):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 6)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 6, sys.argv[2] if len(sys.argv) > 2 else "galerkin")

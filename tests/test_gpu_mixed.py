@@ -186,3 +186,31 @@ def test_mixed_primal_convergence_driver_matches_oracle_table():
     ref = paper_m1.mixed_primal_table(5)
     assert [r.split() for r in rows] == [r.split() for r in ref]
     assert 1.95 < float(rows[-1].replace("&", " ").split()[5]) < 2.05
+
+
+def test_mixed_primal_supg_driver_matches_oracle_table():
+    """...MixedPrimal_convergence_SUPG.py on RT2 x DG1 x CG2 (SUPG test function, hK = CellDiameter, q data on x = 0):
+    assembly parity at a random state, then the driver's table against the oracle's; q converges with order ~2."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    n = 5
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    S = PaperMixedSystemK1(mesh, bd, D1=1e-3, D2=1.5e-3, degree=4, variant="supg")
+    O = paper_m1.MixedPrimalM1(n, supg=True)
+    rng = np.random.default_rng(6)
+    un = np.concatenate([rng.standard_normal(2 * O.E + 2 * O.C), 0.5 + rng.random(3 * O.C),
+                         1.0 + rng.random(O.V + O.E)])
+    vals, b = S.assemble(torch.tensor(un, device=mesh.device), True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    assert abs(got - J).max() < 1e-12 * abs(J).max()
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    spec = importlib.util.spec_from_file_location("mp_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_mixed_primal_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(5, variant="supg")
+    assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_table(5, supg=True)]
+    assert float(rows[-1].replace("&", " ").split()[7]) > 1.9
