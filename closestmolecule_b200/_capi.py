@@ -102,7 +102,7 @@ _PROTOS = {
     "cm_mixed_m1_cells": ([_I, _P, _D, _D, _D, _D, _I, _D, _D, _D, _D, _I, _I, _I] + [_P] * 10, C.c_int),
     "cm_mixed_m1_errors": ([_I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cm_cg2_exterior_facets": ([_I, _P, _D, _I] + [_P] * 10 + [_P], C.c_int),
-    "cm_cg2_interior_facets": ([_I, _P, _D, _I] + [_P] * 5 + [_P], C.c_int),
+    "cm_cg2_interior_facets": ([_I, _P, _D, _I] + [_P] * 6 + [_P], C.c_int),
     "cm_mixed_p2_cells": ([_I, _P, _D, _D, _D, _D, _I, _I, _I] + [_P] * 8 + [_P], C.c_int),
     "cm_p1_sparsity_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_build_p1_sparsity": ([_I, _I, _P, _I, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64), _P, C.c_int64, _P], C.c_int),

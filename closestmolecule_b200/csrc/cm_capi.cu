@@ -506,10 +506,11 @@ int cm_cg2_exterior_facets(int32_t nq, const double* rule_host, double stab2, in
 
 int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, int32_t nfi,
                            const int32_t* fverts, const int32_t* fcell, const int32_t* cells,
-                           const double* coords, double* Ji, void* stream) {
+                           const double* coords, const double* hbar, double* Ji, void* stream) {
   CM_CHECK_ARG(nfi >= 0, "bad size");
   CM_CHECK_ARG(nfi == 0 || (rule_host && fverts && fcell && cells && coords && Ji), "null pointer");
-  return cg2_interior_facets(nq, rule_host, gamma, nfi, fverts, fcell, cells, coords, Ji, (cudaStream_t)stream);
+  return cg2_interior_facets(nq, rule_host, gamma, nfi, fverts, fcell, cells, coords, hbar, Ji,
+                             (cudaStream_t)stream);
 }
 
 int cm_mixed_p2_cells(int32_t nq, const double* rule_host, double D1, double D2, double concentration,

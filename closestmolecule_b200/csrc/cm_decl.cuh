@@ -169,7 +169,7 @@ int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, 
                         const double* qex, const double* pex, double* Jx, double* cx, double* nat,
                         cudaStream_t st);
 int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, const int* fverts,
-                        const int* fcell, const int* cells, const double* coords, double* Ji,
+                        const int* fcell, const int* cells, const double* coords, const double* hbar, double* Ji,
                         cudaStream_t st);
 int mixed_p2_cells(int nq, const double* rule_host, double D1, double D2, double conc, double inv_dt, int ncells,
                    int nE, int nV, const int* cells, const double* coords, const int* cell_edges,

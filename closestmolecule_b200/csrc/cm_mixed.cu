@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kMxThreads)
 cg2_interior_facets_kernel(const FacetRule R, const double gamma, const int nfi,
                            const int* __restrict__ fverts, const int* __restrict__ fcell,
                            const int* __restrict__ cells, const double2* __restrict__ coords,
-                           double* __restrict__ Ji) {
+                           const double* __restrict__ hbar, double* __restrict__ Ji) {
   const long long t = (long long)blockIdx.x * kMxThreads + threadIdx.x;
   if (t >= 12ll * nfi) return;
   const int row = (int)(t / nfi), f = (int)(t % nfi);
@@ -601,7 +601,8 @@ cg2_interior_facets_kernel(const FacetRule R, const double gamma, const int nfi,
     const double s = R.s[k];
     const double x = A.x + s * tx, y = A.y + s * ty;
     const double tt = kFourPi * x * y;
-    const double coef = gamma * L * L * R.w[k] * L * (tt * tt);
+    const double hb = hbar ? hbar[f] : L;  // avg(hK): FacetArea (= L) or the mean CellDiameter of the two cells
+    const double coef = gamma * hb * hb * R.w[k] * L * (tt * tt);
     double d[12];
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
@@ -647,7 +648,7 @@ int cg2_exterior_facets(int nq, const double* rule_host, double stab2, int nfe, 
 }
 
 int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, const int* fverts,
-                        const int* fcell, const int* cells, const double* coords, double* Ji,
+                        const int* fcell, const int* cells, const double* coords, const double* hbar, double* Ji,
                         cudaStream_t st) {
   FacetRule R;
   if (facet_rule_arg(nq, rule_host, R)) {
@@ -657,7 +658,7 @@ int cg2_interior_facets(int nq, const double* rule_host, double gamma, int nfi, 
   if (nfi <= 0) return CM_OK;
   const long long nt = 12ll * nfi;
   cg2_interior_facets_kernel<<<(unsigned)((nt + kMxThreads - 1) / kMxThreads), kMxThreads, 0, st>>>(
-      R, gamma, nfi, fverts, fcell, cells, (const double2*)coords, Ji);
+      R, gamma, nfi, fverts, fcell, cells, (const double2*)coords, hbar, Ji);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

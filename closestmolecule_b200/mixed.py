@@ -345,8 +345,16 @@ class PaperMixedSystemK1:
             self.lib = _capi.lib()
         self.mesh, self.bdry = mesh, bdry
         self.D1, self.D2 = float(D1), float(D2)
-        if variant not in ("paper", "galerkin", "supg"):
+        if variant not in ("paper", "galerkin", "supg", "c0ip"):
             raise ValueError(f"unknown variant '{variant}'")
+        # facet-term layout of the integrated-by-parts q-equation:
+        #   'paper' test_for_paper_convergence.py:142-153 (left 30, right 31, rest 32);
+        #   'c0ip'  ...MixedPrimal_convergence_C0IP.py:144-149 (left 31, right 32, rest 33): inflow term on the left only,
+        #           no weak data / penalty, natural p data on the whole boundary, avg(hK) with hK = CellDiameter, the
+        #           caller passes the signed stab (the script uses -0.00075) and stab2 = 0
+        self.adv_markers, self.dat_markers, self.nat_markers, self.h_cell = (
+            ((31,), (), None, True) if variant == "c0ip" else ((30, 32), (31,), (31, 32), False))
+        self.q_bc_marker, self.s_bc_marker = (32, 31) if variant == "c0ip" else (None, 30)
         self.variant = variant
         self.galerkin = variant in ("galerkin", "supg")      # cell-only q-equation, natural p data on all of the boundary
         self.gcoef = self.D2 * 4.0 * math.pi if self.galerkin else 1.0
@@ -489,8 +497,10 @@ class PaperMixedSystemK1:
         W = (4.0 * math.pi * x * y) ** 2
         phi, _ = _p2_basis(lam, self.grads[cell])
         mk = self.bdry.values[ext]
-        k_adv = ((mk == 30) | (mk == 32)).to(torch.float64)
-        k_dat = (mk == 31).to(torch.float64)
+        isin = lambda ms: (torch.zeros_like(mk, dtype=torch.bool) if not ms
+                           else torch.stack([mk == m_ for m_ in ms]).any(0))
+        k_adv = isin(self.adv_markers).to(torch.float64)
+        k_dat = isin(self.dat_markers).to(torch.float64)
         bn = nrm[:, 0]
         neg = 0.5 * (bn.abs() - bn)
         pen = self.stab2 * (L * neg ** 2 + 8.0 / L)
@@ -503,7 +513,7 @@ class PaperMixedSystemK1:
         rows.append(qd.repeat_interleave(6, dim=1).flatten())
         cols.append(qd.repeat(1, 6).flatten())
         vals.append(Jx.flatten())
-        sel = (mk == 31) | (mk == 32)
+        sel = torch.ones_like(mk, dtype=torch.bool) if self.nat_markers is None else isin(self.nat_markers)
         sgn = torch.sign((nrm * self.enorm[ext]).sum(1))
         pw = ds * W * p_exact(x, y)
         for slot, lamend in ((0, 1.0 - s), (1, s)):
@@ -522,12 +532,20 @@ class PaperMixedSystemK1:
             d.append(sg * torch.einsum("nqkd,nd->nqk", gphi, nrm))
         d = torch.cat(d, 2)
         md = torch.cat([self.qd[c0], self.qd[c1]], 1)
-        coef = self.gamma * (L ** 2)[:, None] * w[None, :] * L[:, None] * W
+        hbar = self._hbar(c0, c1) if self.h_cell else L
+        coef = self.gamma * (hbar ** 2)[:, None] * w[None, :] * L[:, None] * W
         Ji = torch.einsum("nq,nqk,nql->nkl", coef, d, d)
         rows.append(md.repeat_interleave(12, dim=1).flatten())
         cols.append(md.repeat(1, 12).flatten())
         vals.append(Ji.flatten())
         return torch.cat(rows), torch.cat(cols), torch.cat(vals), cvec
+
+    def _hbar(self, c0, c1):
+        """avg(CellDiameter) of the two cells of every interior facet."""
+        Xc = self.mesh.coords[self.mesh.cells.long()]
+        e = torch.stack([Xc[:, 1] - Xc[:, 0], Xc[:, 2] - Xc[:, 0], Xc[:, 2] - Xc[:, 1]], 1)
+        hK = e.pow(2).sum(-1).sqrt().max(1).values
+        return 0.5 * (hK[c0] + hK[c1])
 
     def _natural_all(self, degree):
         """+ p_ex (tau.n) W ds on every exterior facet (...MixedPrimal_convergence.py:126): boundary data vector."""
@@ -563,8 +581,11 @@ class PaperMixedSystemK1:
         fv_e = fc.verts[ext].to(torch.int32).contiguous()
         fc_e = fc.cell0[ext].to(torch.int32).contiguous()
         mk = self.bdry.values[ext]
-        kind = (((mk == 30) | (mk == 32)).to(torch.int32) + 2 * (mk == 31).to(torch.int32)
-                + 4 * ((mk == 31) | (mk == 32)).to(torch.int32)).contiguous()
+        isin = lambda ms: (torch.zeros_like(mk, dtype=torch.bool) if not ms
+                           else torch.stack([mk == m_ for m_ in ms]).any(0))
+        nat = torch.ones_like(mk, dtype=torch.bool) if self.nat_markers is None else isin(self.nat_markers)
+        kind = (isin(self.adv_markers).to(torch.int32) + 2 * isin(self.dat_markers).to(torch.int32)
+                + 4 * nat.to(torch.int32)).contiguous()
         A = mesh.coords[fv_e[:, 0].long()]
         B = mesh.coords[fv_e[:, 1].long()]
         Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
@@ -589,8 +610,10 @@ class PaperMixedSystemK1:
         fv_i = fc.verts[fi].to(torch.int32).contiguous()
         fc_i = torch.stack([fc.cell0[fi], fc.cell1[fi]], 1).to(torch.int32).contiguous()
         Ji = torch.empty(144 * nfi, **f64)
+        hbar = self._hbar(fc_i[:, 0].long(), fc_i[:, 1].long()).contiguous() if self.h_cell else None
         _capi.check(lib.cm_cg2_interior_facets(m, rule.ctypes.data, self.gamma, nfi, _capi.ptr(fv_i), _capi.ptr(fc_i),
-                                               _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(Ji), st))
+                                               _capi.ptr(mesh.cells), _capi.ptr(mesh.coords), _capi.ptr(hbar),
+                                               _capi.ptr(Ji), st))
         md = torch.cat([self.qd[fc_i[:, 0].long()], self.qd[fc_i[:, 1].long()]], 1).T.contiguous()   # [12,nfi]
         ja = torch.arange(12, device=dev).repeat_interleave(12)
         jb = torch.arange(12, device=dev).repeat(12)
@@ -670,22 +693,25 @@ class PaperMixedSystemK1:
     def solve(self, tol=1e-7, maxit=50):
         dev = self.mesh.device
         fc = self.mesh.facets()
-        if self.galerkin:   # q = q_ex at the CG2 nodes of the facets marked 31 (...MixedPrimal_convergence.py:117)
-            sel = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 31)).flatten()
+        val = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        has = torch.zeros(self.N, dtype=torch.bool, device=dev)
+        q_marker = 31 if self.galerkin else self.q_bc_marker
+        if q_marker is not None:   # q = q_ex at the CG2 nodes of the marked facets (...MixedPrimal_convergence.py:117)
+            sel = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == q_marker)).flatten()
             va, vb = fc.verts[sel, 0].long(), fc.verts[sel, 1].long()
             XA, XB = self.mesh.coords[va], self.mesh.coords[vb]
             XM = 0.5 * (XA + XB)
-            val = torch.zeros(self.N, dtype=torch.float64, device=dev)
-            has = torch.zeros(self.N, dtype=torch.bool, device=dev)
             for d, Xn in ((self.q0 + va, XA), (self.q0 + vb, XB), (self.q0 + self.V + sel, XM)):
                 val[d] = q_exact(Xn[:, 0], Xn[:, 1])
                 has[d] = True
-            bc = torch.nonzero(has).flatten()
-            self.bc_vals = val[bc].contiguous()
-        else:
-            le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == 30)).flatten()          # left edges (:133)
-            bc, _ = torch.sort(torch.cat([2 * le, 2 * le + 1]))
-            self.bc_vals = self.sigD()[bc].contiguous()
+        if not self.galerkin:      # flux data on the marked facets: project(sig_ex) for the paper system (:132-133);
+            le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == self.s_bc_marker)).flatten()
+            sdofs = torch.cat([2 * le, 2 * le + 1])
+            # ..._C0IP.py:120,134: s_ex = (0, pi sin(pi x)) has a vanishing normal trace on {x = 0}: zero dofs
+            val[sdofs] = self.sigD()[sdofs] if self.variant == "paper" else 0.0
+            has[sdofs] = True
+        bc = torch.nonzero(has).flatten()
+        self.bc_vals = val[bc].contiguous()
         self.bc_dofs = bc.to(torch.int32).contiguous()
         self.bc_diag = self.diag_slot_all[bc].contiguous()
         u = torch.zeros(self.N, dtype=torch.float64, device=dev)
@@ -720,7 +746,7 @@ class PaperMixedSystemK1:
         work = torch.empty(int(self.lib.cm_mixed_workspace_doubles()), dtype=torch.float64,
                            device=self.mesh.device)
         _capi.check(self.lib.cm_mixed_m1_errors(
-            self.nq, self.rule.ctypes.data, 1 if self.galerkin else 0, self.C, self.E, self.V,
+            self.nq, self.rule.ctypes.data, 0 if self.variant == "paper" else 1, self.C, self.E, self.V,
             _capi.ptr(self.mesh.cells),
             _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
             _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))

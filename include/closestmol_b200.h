@@ -389,14 +389,16 @@ int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t full_grad, i
  *     (q - q_ex) w ds applies to every listed facet.  qex / pex[nfe*nq]: q_ex, p_ex at the facet points.
  *     Outputs entry-major: Jx[36][nfe] (6 x 6 on the attached cell's CG2 dofs), cx[6][nfe], nat[2][nfe].
  *   interior: fcell[nfi*2] = (cell0 = '+', cell1); Ji[144][nfi], 12 x 12 on (cell0's 6, cell1's 6) CG2 dofs:
- *     gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS with hK = FacetArea. */
+ *     gamma avg(hK)^2 (jump(grad q).n+)(jump(grad w).n+) W dS; avg(hK) = hbar[nfi] (e.g. the mean CellDiameter of
+ *     the two cells, ...MixedPrimal_convergence_C0IP.py:98,147) or, with hbar = NULL, the facet length (FacetArea,
+ *     test_for_paper_convergence.py:97). */
 int cm_cg2_exterior_facets(int32_t nq, const double* rule_host, double stab2, int32_t nfe,
                            const int32_t* fverts, const int32_t* fcell, const int32_t* kind,
                            const int32_t* cells, const double* coords, const double* qex, const double* pex,
                            double* Jx, double* cx, double* nat, void* stream);
 int cm_cg2_interior_facets(int32_t nq, const double* rule_host, double gamma, int32_t nfi,
                            const int32_t* fverts, const int32_t* fcell, const int32_t* cells,
-                           const double* coords, double* Ji, void* stream);
+                           const double* coords, const double* hbar, double* Ji, void* stream);
 
 /* Production mixed formulation DG2 x RT3 x CG3 (advection_diffusion_mixed.py:147-150,196-216; deg = 2): element
  * residual Fe[31][ncells] and Jacobian Je[961][ncells] (entry-major; Je may be NULL) of the cell integrals

@@ -51,6 +51,9 @@ class PaperM1:
         self.q_x2p, self.q_x2q, self.supg_stab = 1.0, 0.0, 0.0
         self._finish_setup()
 
+    nat_markers = (31, 32)     # exterior facets carrying the natural p data (None: all of them)
+    h_cell = False             # avg(hK) with hK = CellDiameter instead of FacetArea
+
     def _finish_setup(self):
         mesh, fc = self.mesh, self.fc
         E, C, V = self.E, self.C, self.V
@@ -207,7 +210,8 @@ class PaperM1:
             vals.append(Jx.ravel())
         # natural p data on the s-rows of the right / rest facets: only the two functions of the facet itself
         # have a normal trace there, lambda_end / |F| * sign_out
-        sel = (self.markers[ext] == 31) | (self.markers[ext] == 32)
+        sel = (np.ones(ext.size, dtype=bool) if self.nat_markers is None
+               else np.isin(self.markers[ext], self.nat_markers))
         sgn = np.sign((nrm * self.enorm[ext]).sum(1))
         pw = ds * W * p_ex(x, y)                                                     # [n,nq]
         for slot, lamend in ((0, 1.0 - s), (1, s)):
@@ -230,7 +234,11 @@ class PaperM1:
             d.append(sg * np.einsum("nqkd,nd->nqk", gphi, nrm))
         d = np.concatenate(d, 2)                                                     # [Fi,nq,12]
         md = np.concatenate([self.qd[c0], self.qd[c1]], 1)
-        coef = self.gamma * (L ** 2)[:, None] * w[None, :] * L[:, None] * W
+        hbar = L
+        if self.h_cell:
+            hK = fem.cell_diameter(mesh)
+            hbar = 0.5 * (hK[c0] + hK[c1])
+        coef = self.gamma * (hbar ** 2)[:, None] * w[None, :] * L[:, None] * W
         jq = np.einsum("nqk,nk->nq", d, u[md])
         np.add.at(b, md.ravel(), np.einsum("nq,nqk->nk", coef * jq, d).ravel())
         if want_jac:
@@ -396,6 +404,77 @@ class MixedPrimalM1(PaperM1):
         eq = np.sqrt((a * ((q_ex(x, y) - qh) ** 2 + (self.sym["qx"](x, y) - qhx) ** 2
                            + (self.sym["qy"](x, y) - qhy) ** 2)).sum())
         return es, ep, float(eq)
+
+
+class MixedPrimalC0IPM1(MixedPrimalM1):
+    """convergence/SphericalAdvectionDiffusionReaction_MixedPrimal_convergence_C0IP.py on RT2 x DG1 x CG2:
+    D1 = .01, D2 = .015 (:63-64), G = r2^2 p^2/(q + eps) (:46-47), the q-equation integrated by parts with the
+    inflow term on {x = 0} (:144-146) and the C0IP jump penalty with the MINUS sign, stab = 0.00075,
+    hK = CellDiameter (:68,98,147); natural p data on the whole boundary (:149); essential: q = q_ex on {x = 1},
+    s = s_ex = (0, pi sin(pi x)) on {x = 0}, whose normal trace there is zero (:132-135); Newton 1e-8 (:160-161)."""
+    nat_markers = None
+    h_cell = True
+
+    def __init__(self, n, D1=0.01, D2=0.015, stab=0.00075):
+        self.supg = False
+        self.mesh = mesh = fem.unit_square_mesh(n, n)
+        self.fc = fc = mesh.facets()
+        self.E, self.C, self.V = fc.verts.shape[0], mesh.num_cells, mesh.num_vertices
+        self.N = 3 * self.E + 5 * self.C + self.V
+        self.stab, self.stab2 = stab, 0.0
+        self.gamma = -stab / (DEG + 1) ** 3.5
+        self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, 1.0, 0, 0.0, 4
+        self.q_x2p, self.q_x2q, self.supg_stab = 1.0, 0.0, 0.0
+        self.sym = self._data()
+        self._finish_setup()
+        self.markers = fem.mark_facets(mesh, [(lambda P: fem.near(P[..., 0], 0.0), 31),
+                                              (lambda P: fem.near(P[..., 0], 1.0), 32),
+                                              (lambda P: fem.near(P[..., 1], 0.0) | fem.near(P[..., 1], 1.0), 33)])
+        m = self.markers[self.ext]
+        self.k_adv = (m == 31).astype(float)
+        self.k_dat = np.zeros(m.size)
+
+    def _data(self):
+        d = MixedPrimalM1._data(self)
+        import sympy as sm
+        x, y = sm.symbols("x y", positive=True)
+        pe = sm.sin(sm.pi * x) * sm.sin(sm.pi * y)
+        qe = sm.Rational(3, 2) + sm.cos(sm.pi * x * y)
+        d["f3"] = sm.lambdify((x, y), sm.diff(qe, x) + x ** 2 * pe, "numpy")          # :130
+        return d
+
+    _exterior = PaperM1._exterior
+    _interior = PaperM1._interior
+
+    def bcs(self):
+        fc, mesh = self.fc, self.mesh
+        sel = np.nonzero((fc.cell1 < 0) & (self.markers == 32))[0]
+        va, vb = fc.verts[sel, 0], fc.verts[sel, 1]
+        XA, XB = mesh.coords[va], mesh.coords[vb]
+        XM = 0.5 * (XA + XB)
+        dofs = np.concatenate([self.q0 + va, self.q0 + vb, self.q0 + self.V + sel])
+        vals = np.concatenate([q_ex(XA[:, 0], XA[:, 1]), q_ex(XB[:, 0], XB[:, 1]), q_ex(XM[:, 0], XM[:, 1])])
+        d, i = np.unique(dofs, return_index=True)
+        le = np.nonzero((fc.cell1 < 0) & (self.markers == 31))[0]
+        sd = np.concatenate([2 * le, 2 * le + 1])
+        return np.concatenate([sd, d]), np.concatenate([np.zeros(sd.size), vals[i]])
+
+    def solve(self, tol=1e-8, maxit=50):
+        return MixedPrimalM1.solve(self, tol, maxit)
+
+
+def mixed_primal_c0ip_table(levels=5):
+    rows, prev = [], None
+    for nk in range(levels):
+        m = MixedPrimalC0IPM1(2 ** (nk + 1))
+        u = m.solve()
+        h = m.mesh.hmax()
+        e = m.errors(u)
+        r = [0.0, 0.0, 0.0] if prev is None else [np.log(a / b) / np.log(h / prev[0]) for a, b in zip(e, prev[1])]
+        rows.append('{:6d} & {:.4f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} & {:6.2e} & {:.3f} '.format(
+            m.N, h, e[0], r[0], e[1], r[1], e[2], r[2]))
+        prev = (h, e)
+    return rows
 
 
 def mixed_primal_table(levels=5, supg=False):

@@ -3,6 +3,7 @@ onto the GPU path with ITS OWN discretisation RT2 x DG1 x CG2 (deg = 1, :93-97):
 ('left' = {x = 1} -> 31, rest -> 32, :74-80), constants (:51-56), forms (:120-128), boundary condition (:117), Newton
 parameters (:132-138) and table layout (:166).  The reference records no table for it; the Galerkin q-equation gives
 the orders ~1.5 / 2 / 1 for e_div(s) / e_0(p) / e_1(q) (the loss in q is why the SUPG / C0IP variants exist).
+Variants 'supg' and 'c0ip' are the ..._SUPG.py / ..._C0IP.py siblings on the same elements.
 The CG1 x CG1 restatement of the same problem is scripts/run_pq_supg_convergence.py."""
 import math
 import os
@@ -15,21 +16,30 @@ from closestmolecule_b200.mixed import PaperMixedSystemK1  # noqa: E402
 
 def main(nkmax=6, variant="galerkin"):
     """variant 'galerkin': ...MixedPrimal_convergence.py; 'supg': ...MixedPrimal_convergence_SUPG.py (q data on
-    {x = 0} :77, stab = 1 :56, Newton tolerances 1e-8 :138-139, nkmax = 5 :58)."""
+    {x = 0} :77, stab = 1 :56, Newton tolerances 1e-8 :138-139, nkmax = 5 :58); 'c0ip': ..._convergence_C0IP.py
+    (markers left 31 / right 32 / rest 33 :78-92, D1 = .01, D2 = .015 :63-64, stab = 0.00075 entering with the minus
+    sign :68,147, q = q_ex on the right and s.n = 0 on the left :132-135, Newton 1e-8 :160-161)."""
     hh, nn, es, ep, eq, rs, rp, rq = [], [], [], [], [], [0.0], [0.0], [0.0]
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
         mesh = RectangleMesh(Point(0, 0), Point(1, 1), nps, nps)
         bdry = MeshFunction("size_t", mesh, 1)
         bdry.set_all(0)
-        left, rest = 31, 32
-        xin, xout = (0, 1) if variant == "supg" else (1, 0)
-        CompiledSubDomain(f"near(x[0],{xin}) && on_boundary").mark(bdry, left)
-        CompiledSubDomain(f"(near(x[0],{xout}) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
+        if variant == "c0ip":
+            CompiledSubDomain("near(x[0],0) && on_boundary").mark(bdry, 31)
+            CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, 32)
+            CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, 33)
+            system = PaperMixedSystemK1(mesh, bdry, D1=0.01, D2=0.015, stab=-0.00075, stab2=0.0, degree=4,
+                                        variant=variant)
+        else:
+            left, rest = 31, 32
+            xin, xout = (0, 1) if variant == "supg" else (1, 0)
+            CompiledSubDomain(f"near(x[0],{xin}) && on_boundary").mark(bdry, left)
+            CompiledSubDomain(f"(near(x[0],{xout}) || near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, rest)
+            system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant=variant)
         hh.append(mesh.hmax())
-        system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant=variant)
         nn.append(system.N)
-        u = system.solve(tol=1e-8 if variant == "supg" else 1e-7)
+        u = system.solve(tol=1e-7 if variant == "galerkin" else 1e-8)
         e = system.errors(u)
         es.append(e[0]); ep.append(e[1]); eq.append(e[2])
         if nk > 0:

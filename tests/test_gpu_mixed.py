@@ -214,3 +214,39 @@ def test_mixed_primal_supg_driver_matches_oracle_table():
     rows = mod.main(5, variant="supg")
     assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_table(5, supg=True)]
     assert float(rows[-1].replace("&", " ").split()[7]) > 1.9
+
+
+def test_mixed_primal_c0ip_driver_matches_oracle_table():
+    """...MixedPrimal_convergence_C0IP.py on RT2 x DG1 x CG2 (inflow term on x = 0, jump penalty with avg CellDiameter
+    and the script's minus sign, natural p data everywhere, q data on x = 1, s.n = 0 on x = 0): assembly parity at a
+    random state, the CUDA facet tables against the torch tabulation, then the driver's table against the oracle's."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    n = 5
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 32)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 33)
+    S = PaperMixedSystemK1(mesh, bd, D1=0.01, D2=0.015, stab=-0.00075, stab2=0.0, degree=4, variant="c0ip")
+    O = paper_m1.MixedPrimalC0IPM1(n)
+    fr, fcn, fv, cvec = S._facet_tables(4)
+    Kt = torch.zeros(S.nnz, dtype=torch.float64, device=mesh.device)
+    Kt.index_add_(0, torch.searchsorted(S._key, fr * S.N + fcn), fv)
+    assert float((Kt - S.Kf).abs().max()) < 1e-13 * float(Kt.abs().max())
+    assert float((cvec - S.cvec).abs().max()) < 1e-13 * float(cvec.abs().max())
+    rng = np.random.default_rng(8)
+    un = np.concatenate([rng.standard_normal(2 * O.E + 2 * O.C), 0.5 + rng.random(3 * O.C),
+                         1.0 + rng.random(O.V + O.E)])
+    vals, b = S.assemble(torch.tensor(un, device=mesh.device), True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    assert abs(got - J).max() < 1e-12 * abs(J).max()
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    spec = importlib.util.spec_from_file_location("mp_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_mixed_primal_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(4, variant="c0ip")
+    assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_c0ip_table(4)]
+    assert 1.9 < float(rows[-1].replace("&", " ").split()[5]) < 2.1

@@ -96,3 +96,35 @@ def test_k1_tables_and_constant_facet_operator_match_oracle():
     ref = sp.coo_matrix((Je.ravel(), (np.repeat(cd, 17, axis=1).ravel(), np.tile(cd, (1, 17)).ravel())),
                         shape=(S.N, S.N)).tocsr()
     assert abs(sp.csr_matrix((got.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N)) - ref).max() < 1e-13
+
+
+def test_c0ip_variant_facet_operator_matches_oracle_and_oracle_converges():
+    """...MixedPrimal_convergence_C0IP.py variant: the host tabulation of its facet terms (inflow term on x = 0 only,
+    penalty with avg CellDiameter and the script's minus sign, natural p data on the whole boundary) against
+    oracle/paper_m1.MixedPrimalC0IPM1; the oracle's own table keeps e_0(p) at second order."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    import scipy.sparse as sp
+    n = 4
+    mesh = cm.UnitSquareMesh(n, n, device="cpu")
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 32)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 33)
+    S = PaperMixedSystemK1(mesh, bd, D1=0.01, D2=0.015, stab=-0.00075, stab2=0.0, degree=4, tables_only=True,
+                           variant="c0ip")
+    O = paper_m1.MixedPrimalC0IPM1(n)
+    assert S.gamma == O.gamma < 0
+    u = np.linspace(0.5, 1.5, O.N)
+    rows, cols, vals = [], [], []
+    b = np.zeros(O.N)
+    O._exterior(u, b, rows, cols, vals, True)
+    O._interior(u, b, rows, cols, vals, True)
+    Jf = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(O.N, O.N)).tocsr()
+    Kf = sp.csr_matrix((S.Kf.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N))
+    assert abs(Kf - Jf).max() < 1e-12 * abs(Jf).max()
+    assert np.max(np.abs(Kf @ u + S.cvec.numpy() - b)) < 1e-12 * np.max(np.abs(b))
+    rows = paper_m1.mixed_primal_c0ip_table(3)
+    assert [int(r.split()[0]) for r in rows] == [3 * m.E + 5 * m.C + m.V for m in
+                                                 (paper_m1.MixedPrimalC0IPM1(2 ** (k + 1)) for k in range(3))]
+    assert 1.8 < float(rows[-1].replace("&", " ").split()[5]) < 2.2
