@@ -375,10 +375,13 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
       const double f3 = f3q[(size_t)c * R.nq + k];
       if (qmode == 0) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * Q.chi[b] * ph;  // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W
-        F += a * ((-(2.0 / Q.x) * q + x2 * p - f3) * ph - q * phx);
+        // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W  (q_react = 0,
+        // q_x2p = 1); C0IP_pure_advection_spherical_convergence.py:109-110: (q - div_rad(r2vec) q) w W - ... (1, 0)
+        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * q_x2p * Q.chi[b] * ph;
+        const double cr = q_react - 2.0 / Q.x;
+        F += a * ((cr * q + x2 * q_x2p * p - f3) * ph - q * phx);
 #pragma unroll
-        for (int m = 0; m < 6; ++m) J[11 + m] -= a * ((2.0 / Q.x) * Q.phi[m] * ph + phx * Q.phi[m]);
+        for (int m = 0; m < 6; ++m) J[11 + m] += a * (cr * Q.phi[m] * ph - phx * Q.phi[m]);
       } else {
         // (q_react q + r2vec.grad q + r2^2 (q_x2p p + q_x2q q) - f3) (w + tau r2vec.grad w) W, tau = supg_stab hK/2:
         // ...MixedPrimal_convergence.py:123 (1,1,0,0) and ..._SUPG.py:118-129 (1,0,1,1; "r2**2*q" as written there)

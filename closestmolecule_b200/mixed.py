@@ -26,7 +26,7 @@ from .solver import BandedLULinearSolver
 from .space import FiniteElement, FunctionSpace, MixedElement
 
 
-def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False):
+def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False, x2_coef=1.0):
     """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = q_react q_ex + dq_ex/dx + r2^2 p_ex
     (test_for_paper_convergence.py:124-128; ...MixedPrimal_convergence.py:109-113 with gcoef = D2 4 pi, q_react = 1),
     div_rad(sig_ex) and grad q_ex for the error norms, as torch callables."""
@@ -38,7 +38,7 @@ def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False):
     sx = -sm.diff(pe, x) - G
     sy = -sm.diff(pe, y)
     f2 = sm.diff(x ** 2 * D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * D1 * sy, y) / y ** 2
-    f3 = q_react * qe + sm.diff(qe, x) + x ** 2 * (qe if x2_on_q else pe)   # "r2**2*q_ex" in ..._SUPG.py:112
+    f3 = q_react * qe + sm.diff(qe, x) + x2_coef * x ** 2 * (qe if x2_on_q else pe)   # "r2**2*q_ex" in ..._SUPG.py:112
     drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
     T = lambda e: _torchify(e, (x, y))
     return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)), qy=T(sm.diff(qe, y)))
@@ -334,7 +334,7 @@ class PaperMixedSystemK1:
     restatement of the same operator for the CPU table test)."""
 
     def __init__(self, mesh, bdry, D1=1.0, D2=1.5, stab=0.1, stab2=2.0, degree=6, tables_only=False,
-                 variant="paper"):
+                 variant="paper", supg_stab=1.0):
         """variant 'paper': test_for_paper_convergence.py (deg = 1; markers left 30 / right 31 / rest 32);
         variant 'galerkin': ...MixedPrimal_convergence.py (BASELINE config 2's own script: G = D2 4 pi r2^2 p^2/q,
         Galerkin q-equation with reaction, natural p data on the whole boundary, q = q_ex on the facets marked 31,
@@ -345,22 +345,28 @@ class PaperMixedSystemK1:
             self.lib = _capi.lib()
         self.mesh, self.bdry = mesh, bdry
         self.D1, self.D2 = float(D1), float(D2)
-        if variant not in ("paper", "galerkin", "supg", "c0ip"):
+        if variant not in ("paper", "galerkin", "supg", "c0ip", "pure_supg", "pure_c0ip"):
             raise ValueError(f"unknown variant '{variant}'")
         # facet-term layout of the integrated-by-parts q-equation:
         #   'paper' test_for_paper_convergence.py:142-153 (left 30, right 31, rest 32);
         #   'c0ip'  ...MixedPrimal_convergence_C0IP.py:144-149 (left 31, right 32, rest 33): inflow term on the left only,
         #           no weak data / penalty, natural p data on the whole boundary, avg(hK) with hK = CellDiameter, the
         #           caller passes the signed stab (the script uses -0.00075) and stab2 = 0
+        #   'pure_c0ip' C0IP_pure_advection_spherical_convergence.py:109-113 (inlet 31, outlet 32, char 33): the q-q block
+        #           only (PureAdvectionCG2): inflow term on inlet and char, reaction q, no p coupling, penalty +stab
         self.adv_markers, self.dat_markers, self.nat_markers, self.h_cell = (
-            ((31,), (), None, True) if variant == "c0ip" else ((30, 32), (31,), (31, 32), False))
-        self.q_bc_marker, self.s_bc_marker = (32, 31) if variant == "c0ip" else (None, 30)
+            ((31,), (), None, True) if variant == "c0ip" else ((31, 33), (), None, True) if variant == "pure_c0ip"
+            else ((30, 32), (31,), (31, 32), False))
+        self.q_bc_marker, self.s_bc_marker = (32, 31) if variant in ("c0ip", "pure_c0ip") else (None, 30)
         self.variant = variant
-        self.galerkin = variant in ("galerkin", "supg")      # cell-only q-equation, natural p data on all of the boundary
+        # cell-only q-equation, natural p data on all of the boundary
+        self.galerkin = variant in ("galerkin", "supg", "pure_supg")
         self.gcoef = self.D2 * 4.0 * math.pi if self.galerkin else 1.0
-        self.qmode, self.q_react = (1, 1.0) if self.galerkin else (0, 0.0)
-        # 'supg': ...MixedPrimal_convergence_SUPG.py:118-129 (residual q + dq/dx + r2^2 q, test w + hK/2 dw/dx)
-        self.q_x2p, self.q_x2q, self.supg_stab = (0.0, 1.0, 1.0) if variant == "supg" else (1.0, 0.0, 0.0)
+        self.qmode, self.q_react = (1, 1.0) if self.galerkin else (0, 1.0 if variant == "pure_c0ip" else 0.0)
+        # 'supg': ...MixedPrimal_convergence_SUPG.py:118-129 (residual q + dq/dx + r2^2 q, test w + stab hK/2 dw/dx);
+        # 'pure_supg': SUPG_pure_advection_convergence.py:106-109, the same q-q block with stab = 0.1
+        self.q_x2p, self.q_x2q, self.supg_stab = ((0.0, 1.0, float(supg_stab)) if variant in ("supg", "pure_supg")
+                                                  else (0.0, 0.0, 0.0) if variant == "pure_c0ip" else (1.0, 0.0, 0.0))
         self.gamma = stab / 2.0 ** 3.5                       # stab/(deg+1)^3.5 (:144)
         self.stab2 = float(stab2)
         dev = mesh.device
@@ -394,7 +400,8 @@ class PaperMixedSystemK1:
         self.lamq = torch.tensor(np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], 1), device=dev)
         P = torch.einsum("qi,cid->cqd", self.lamq, Xc)
         self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
-        self.data = paper_data(D1, D2, self.gcoef, self.q_react, variant == "supg")
+        self.data = paper_data(D1, D2, self.gcoef, self.q_react, variant in ("supg", "pure_supg"),
+                               0.0 if variant == "pure_c0ip" else 1.0)
         self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
         self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
         # global dofs of the 17 local ones: [2 per edge | 2 per cell | 3 per cell | vertices | edges]
@@ -751,6 +758,89 @@ class PaperMixedSystemK1:
             _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
             _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))
         return tuple(math.sqrt(float(v)) for v in work[:3].cpu())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scalar CG2 pure-advection problems (SUPG_pure_advection_convergence.py, C0IP_pure_advection_spherical_convergence.py)
+# ---------------------------------------------------------------------------------------------------------
+class PureAdvectionCG2:
+    """solve(lhs == rhs, q_h, bcs=bcQ) of the two scalar CG2 scripts on the GPU.  Their forms are the q-equation of the
+    RT2 x DG1 x CG2 systems above without the p coupling, so the element / facet tensors are the q-q block of
+    cm_mixed_m1_cells (qmode 1 with stab = 0.1: SUPG_pure_advection_convergence.py:106-109; qmode 0 with reaction:
+    C0IP_pure_advection_spherical_convergence.py:109-110) and cm_cg2_exterior_facets / cm_cg2_interior_facets
+    (:111-113, penalty +stab/(deg+1)^3.5 avg(he)^2, he = CellDiameter); that block is cut out of the mixed CSR
+    pattern once per mesh, cm_apply_dirichlet imposes q = q_ex on the inlet (31, SUPG :101) or the outlet (32, C0IP
+    :102) and cm_blu_* solves.  Markers inlet 31 / outlet 32 / char 33 (:72-78).  Dofs: vertices, then edges.
+    NB: with the C0IP script's positive stab = 0.005 the penalty enters against the sign of the (negative) form
+    and the discrete problem is nearly singular (the later ..._MixedPrimal_convergence_C0IP.py:147 flips the sign);
+    `stab` is an argument so that both can be run."""
+
+    STAB = {"supg": 0.1, "c0ip": 0.005}
+
+    def __init__(self, mesh, bdry, kind, stab=None):
+        if kind not in self.STAB:
+            raise ValueError(f"unknown kind '{kind}'")
+        self.kind = kind
+        self.stab = stab = self.STAB[kind] if stab is None else float(stab)
+        self.sys = S = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, stab=stab if kind == "c0ip" else 0.0,
+                                          stab2=0.0, degree=4, variant="pure_" + kind,
+                                          supg_stab=stab if kind == "supg" else 0.0)
+        dev = mesh.device
+        self.N = N = S.V + S.E
+        rows = torch.repeat_interleave(torch.arange(S.N, device=dev), torch.diff(S.rowptr.long()))
+        keep = (rows >= S.q0) & (S.col >= S.q0)
+        self.slots = torch.nonzero(keep).flatten()
+        r = rows[keep] - S.q0
+        self.col = (S.col[keep] - S.q0).to(torch.int32).contiguous()
+        rp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(torch.bincount(r, minlength=N), 0)
+        self.rowptr = rp.to(torch.int32).contiguous()
+        self.diag_slot = torch.searchsorted(r * N + self.col.long(), torch.arange(N, device=dev) * (N + 1)
+                                            ).to(torch.int32).contiguous()
+        fc = mesh.facets()
+        sel = torch.nonzero((fc.cell1 < 0) & (bdry.values == (31 if kind == "supg" else 32))).flatten()
+        va, vb = fc.verts[sel, 0].long(), fc.verts[sel, 1].long()
+        X = mesh.coords
+        val = torch.zeros(N, dtype=torch.float64, device=dev)
+        has = torch.zeros(N, dtype=torch.bool, device=dev)
+        for d, Xn in ((va, X[va]), (vb, X[vb]), (S.V + sel, 0.5 * (X[va] + X[vb]))):
+            val[d] = q_exact(Xn[:, 0], Xn[:, 1])
+            has[d] = True
+        bc = torch.nonzero(has).flatten()
+        self.bc_dofs, self.bc_vals = bc.to(torch.int32).contiguous(), val[bc].contiguous()
+        self.bc_diag = self.diag_slot[bc].contiguous()
+        self._lin = None
+
+    def assemble(self):
+        """(values of the CG2 matrix on (rowptr, col), right-hand side) before the boundary condition."""
+        S = self.sys
+        vals, F0 = S.assemble(torch.zeros(S.N, dtype=torch.float64, device=S.mesh.device), True)
+        self.vals = vals[self.slots].contiguous()
+        self.b = (-F0[S.q0:]).contiguous()        # residual at q = 0 is -rhs
+        return self.vals, self.b
+
+    def solve(self):
+        S, dev = self.sys, self.sys.mesh.device
+        self.assemble()
+        q = torch.zeros(self.N, dtype=torch.float64, device=dev)
+        # cm_apply_dirichlet writes identity rows and b[row] = x[row] - g (the Newton form of DirichletBC.apply); with
+        # x = 0 and the data negated the rows of the linear problem read q = g
+        _capi.check(S.lib.cm_apply_dirichlet(
+            1, self.bc_dofs.numel(), _capi.ptr(self.bc_dofs), _capi.ptr(self.bc_diag),
+            _capi.ptr((-self.bc_vals).contiguous()), _capi.ptr(q), _capi.ptr(self.rowptr), _capi.ptr(self.vals),
+            _capi.ptr(self.b), _capi.stream_ptr()))
+        if self._lin is None:
+            self._lin = BandedLULinearSolver(_Holder(dev, self.rowptr, self.col, self.N, self.vals, self.b))
+        self._lin.setup()
+        self._lin.solve(self.b, q)
+        return q
+
+    def error(self, q):
+        """e_1(q) = (int ((q_ex - q_h)^2 + |grad(q_ex - q_h)|^2) W dx)^(1/2) (:120-122), degree-4 rule."""
+        S = self.sys
+        u = torch.zeros(S.N, dtype=torch.float64, device=S.mesh.device)
+        u[S.q0:] = q
+        return S.errors(u)[2]
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -139,7 +139,7 @@ class PaperM1:
                               - p[..., None] * dr)
         Fe[:, 8:11] = np.einsum("cq,cqb->cb", a * (-np.einsum("cqa,ca->cq", drD, se) + f2), chi)
         if self.qmode == 0:
-            Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * (-(2 / x) * q + x2 * p - f3), phi)
+            Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * ((self.q_react - 2 / x) * q + x2 * self.q_x2p * p - f3), phi)
                           - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
         else:   # (q_react q + dq/dx + x^2 (x2p p + x2q q) - f3)(w + tau dw/dx) W, tau = supg_stab hK/2
             qx = np.einsum("cqk,ck->cq", gphi[..., 0], qe)
@@ -156,8 +156,8 @@ class PaperM1:
             Je[:, :8, 11:] = np.einsum("cq,cqa,cqk->cak", a * Gq, Rx, phi)
             Je[:, 8:11, :8] = -np.einsum("cq,cqb,cqa->cba", a, chi, drD)
             if self.qmode == 0:
-                Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2, phi, chi)
-                Je[:, 11:, 11:] = (-np.einsum("cq,cqk,cql->ckl", a * (2 / x), phi, phi)
+                Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2 * self.q_x2p, phi, chi)
+                Je[:, 11:, 11:] = (np.einsum("cq,cqk,cql->ckl", a * (self.q_react - 2 / x), phi, phi)
                                    - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
             else:
                 Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2 * self.q_x2p, tw, chi)

@@ -250,3 +250,56 @@ def test_mixed_primal_c0ip_driver_matches_oracle_table():
     rows = mod.main(4, variant="c0ip")
     assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_c0ip_table(4)]
     assert 1.9 < float(rows[-1].replace("&", " ").split()[5]) < 2.1
+
+
+# ---- scalar CG2 pure-advection scripts (SUPG_pure_advection_convergence.py, C0IP_pure_advection_spherical_...) ----
+def _pure(n, kind, stab=None):
+    from closestmolecule_b200.mixed import PureAdvectionCG2
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 32)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 33)
+    return PureAdvectionCG2(mesh, bd, kind, stab)
+
+
+@pytest.mark.parametrize("kind", ["supg", "c0ip"])
+def test_pure_advection_matrix_and_solution_match_the_scalar_oracle(kind):
+    from oracle import pure_advection as pa
+    n = 8
+    S, O = _pure(n, kind), pa.PureAdvection(n, kind)
+    assert S.N == O.N
+    vals, b = S.assemble()
+    A, bo = O.assemble()
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    assert abs(got - A).max() < 1e-12 * abs(A).max()
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    d, g = O.bcs()
+    assert np.array_equal(S.bc_dofs.cpu().numpy(), d) and np.allclose(S.bc_vals.cpu().numpy(), g, rtol=0, atol=1e-15)
+    q, qo = S.solve(), O.solve()
+    # the C0IP script's system is poorly conditioned already at n = 8 (cond ~ 5e7)
+    assert np.linalg.norm(q.cpu().numpy() - qo) / np.linalg.norm(qo) < (1e-10 if kind == "supg" else 1e-7)
+    assert abs(S.error(q) - O.error(qo)) < 1e-7 * O.error(qo)
+
+
+def test_pure_advection_drivers_match_oracle_tables():
+    from oracle import pure_advection as pa
+    spec = importlib.util.spec_from_file_location("pa_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_pure_advection_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(5, "supg")
+    assert [r.split() for r in rows] == [r.split() for r in pa.table("supg", 5)]
+    assert 1.9 < float(rows[-1].replace("&", " ").split()[3]) < 2.1
+    # the C0IP script as written: compared on the levels where the system is still well enough conditioned
+    assert [r.split() for r in mod.main(3, "c0ip")] == [r.split() for r in pa.table("c0ip", 3)]
+    # ... and on five levels with the stabilising sign
+    rows, ref, prev = mod.main(5, "c0ip", -0.005), [], None
+    for nk in range(5):
+        m = pa.PureAdvection(2 ** (nk + 1), "c0ip", stab=-0.005)
+        e, h = m.error(m.solve()), m.mesh.hmax()
+        ref.append('{:6d} & {:.4f} & {:6.2e} & {:.3f} '.format(
+            m.N, h, e, 0.0 if prev is None else np.log(e / prev[1]) / np.log(h / prev[0])))
+        prev = (h, e)
+    assert [r.split() for r in rows] == [r.split() for r in ref]
+    assert float(rows[-1].replace("&", " ").split()[3]) > 1.5
