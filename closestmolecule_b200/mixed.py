@@ -795,8 +795,8 @@ class PureAdvectionCG2:
         rp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
         rp[1:] = torch.cumsum(torch.bincount(r, minlength=N), 0)
         self.rowptr = rp.to(torch.int32).contiguous()
-        self.diag_slot = torch.searchsorted(r * N + self.col.long(), torch.arange(N, device=dev) * (N + 1)
-                                            ).to(torch.int32).contiguous()
+        self.diag_slot = (torch.searchsorted(r * N + self.col.long(), torch.arange(N, device=dev) * (N + 1))
+                          - rp[:-1]).to(torch.int32).contiguous()          # position inside the row
         fc = mesh.facets()
         sel = torch.nonzero((fc.cell1 < 0) & (bdry.values == (31 if kind == "supg" else 32))).flatten()
         va, vb = fc.verts[sel, 0].long(), fc.verts[sel, 1].long()
