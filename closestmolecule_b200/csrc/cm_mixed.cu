@@ -373,15 +373,17 @@ mixed_m1_cells_kernel(const MxRule R, const double D1, const double D2, const do
     } else {
       const double ph = Q.phi[row - 11], phx = Q.phix[row - 11];
       const double f3 = f3q[(size_t)c * R.nq + k];
-      if (qmode == 0) {
-#pragma unroll
+      if (qmode != 1) {
         // test_for_paper_convergence.py:140-141: (-div_rad(r2vec) q + r2^2 p) w W - (r2vec.grad w) q W  (q_react = 0,
-        // q_x2p = 1); C0IP_pure_advection_spherical_convergence.py:109-110: (q - div_rad(r2vec) q) w W - ... (1, 0)
-        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * q_x2p * Q.chi[b] * ph;
-        const double cr = q_react - 2.0 / Q.x;
-        F += a * ((cr * q + x2 * q_x2p * p - f3) * ph - q * phx);
+        // q_x2p = 1); C0IP_pure_advection_spherical_convergence.py:109-110: (q - div_rad(r2vec) q) w W - ... (1, 0);
+        // qmode 2: the same with r2vec = (-1,0) (..._C0IP_otherBCs.py:58,131-132)
+        const double dir = qmode == 2 ? -1.0 : 1.0;
 #pragma unroll
-        for (int m = 0; m < 6; ++m) J[11 + m] += a * (cr * Q.phi[m] * ph - phx * Q.phi[m]);
+        for (int b = 0; b < 3; ++b) J[8 + b] += a * x2 * q_x2p * Q.chi[b] * ph;
+        const double cr = q_react - dir * 2.0 / Q.x;
+        F += a * ((cr * q + x2 * q_x2p * p - f3) * ph - dir * q * phx);
+#pragma unroll
+        for (int m = 0; m < 6; ++m) J[11 + m] += a * (cr * Q.phi[m] * ph - dir * phx * Q.phi[m]);
       } else {
         // (q_react q + r2vec.grad q + r2^2 (q_x2p p + q_x2q q) - f3) (w + tau r2vec.grad w) W, tau = supg_stab hK/2:
         // ...MixedPrimal_convergence.py:123 (1,1,0,0) and ..._SUPG.py:118-129 (1,0,1,1; "r2**2*q" as written there)
@@ -514,7 +516,7 @@ cg2_exterior_facets_kernel(const FacetRule R, const double stab2, const int nfe,
   double nx = gnx, ny = gny;
   if (nx * (X[lo].x - X[la].x) + ny * (X[lo].y - X[la].y) > 0.0) { nx = -nx; ny = -ny; }
   const double sgn = (nx * gnx + ny * gny) > 0.0 ? 1.0 : -1.0;
-  const double bn = nx;
+  const double bn = (kd & 8) ? -nx : nx;  // r2vec = (1,0), or (-1,0) with kind bit 8 (..._C0IP_otherBCs.py:58)
   const double neg = 0.5 * (fabs(bn) - bn);
   const double pen = stab2 * (L * neg * neg + 8.0 / L);
   double J[36], cv[6], n0 = 0.0, n1 = 0.0;

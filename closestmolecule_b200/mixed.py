@@ -26,7 +26,7 @@ from .solver import BandedLULinearSolver
 from .space import FiniteElement, FunctionSpace, MixedElement
 
 
-def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False, x2_coef=1.0):
+def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False, x2_coef=1.0, r2dir=1.0):
     """sig_ex = -grad(p_ex) - G(p_ex,q_ex), f2_ex = div_rad(D*sig_ex), f3_ex = q_react q_ex + dq_ex/dx + r2^2 p_ex
     (test_for_paper_convergence.py:124-128; ...MixedPrimal_convergence.py:109-113 with gcoef = D2 4 pi, q_react = 1),
     div_rad(sig_ex) and grad q_ex for the error norms, as torch callables."""
@@ -38,7 +38,8 @@ def paper_data(D1, D2, gcoef=1.0, q_react=0.0, x2_on_q=False, x2_coef=1.0):
     sx = -sm.diff(pe, x) - G
     sy = -sm.diff(pe, y)
     f2 = sm.diff(x ** 2 * D2 * sx, x) / x ** 2 + sm.diff(y ** 2 * D1 * sy, y) / y ** 2
-    f3 = q_react * qe + sm.diff(qe, x) + x2_coef * x ** 2 * (qe if x2_on_q else pe)   # "r2**2*q_ex" in ..._SUPG.py:112
+    # "r2**2*q_ex" in ..._SUPG.py:112; grad(q_ex).r2vec with r2vec = (-1,0) in ..._C0IP_otherBCs.py:117
+    f3 = q_react * qe + r2dir * sm.diff(qe, x) + x2_coef * x ** 2 * (qe if x2_on_q else pe)
     drs = sm.diff(x ** 2 * sx, x) / x ** 2 + sm.diff(y ** 2 * sy, y) / y ** 2
     T = lambda e: _torchify(e, (x, y))
     return dict(sx=T(sx), sy=T(sy), f2=T(f2), f3=T(f3), drs=T(drs), qx=T(sm.diff(qe, x)), qy=T(sm.diff(qe, y)))
@@ -345,7 +346,7 @@ class PaperMixedSystemK1:
             self.lib = _capi.lib()
         self.mesh, self.bdry = mesh, bdry
         self.D1, self.D2 = float(D1), float(D2)
-        if variant not in ("paper", "galerkin", "supg", "c0ip", "pure_supg", "pure_c0ip"):
+        if variant not in ("paper", "galerkin", "supg", "c0ip", "c0ip_other", "pure_supg", "pure_c0ip"):
             raise ValueError(f"unknown variant '{variant}'")
         # facet-term layout of the integrated-by-parts q-equation:
         #   'paper' test_for_paper_convergence.py:142-153 (left 30, right 31, rest 32);
@@ -354,15 +355,21 @@ class PaperMixedSystemK1:
         #           caller passes the signed stab (the script uses -0.00075) and stab2 = 0
         #   'pure_c0ip' C0IP_pure_advection_spherical_convergence.py:109-113 (inlet 31, outlet 32, char 33): the q-q block
         #           only (PureAdvectionCG2): inflow term on inlet and char, reaction q, no p coupling, penalty +stab
+        #   'c0ip_other' ..._C0IP_otherBCs.py:131-137 (left 30, right 31, rest 32): r2vec = (-1,0) in the q-equation,
+        #           inflow term on the left, natural p data on right and rest, s = project(sig_ex) on the left, q = q_ex
+        #           on the right, penalty +stab, hK = CellDiameter
         self.adv_markers, self.dat_markers, self.nat_markers, self.h_cell = (
             ((31,), (), None, True) if variant == "c0ip" else ((31, 33), (), None, True) if variant == "pure_c0ip"
-            else ((30, 32), (31,), (31, 32), False))
-        self.q_bc_marker, self.s_bc_marker = (32, 31) if variant in ("c0ip", "pure_c0ip") else (None, 30)
+            else ((30,), (), (31, 32), True) if variant == "c0ip_other" else ((30, 32), (31,), (31, 32), False))
+        self.q_bc_marker, self.s_bc_marker = ((32, 31) if variant in ("c0ip", "pure_c0ip")
+                                              else (31, 30) if variant == "c0ip_other" else (None, 30))
+        self.r2dir = -1.0 if variant == "c0ip_other" else 1.0
         self.variant = variant
         # cell-only q-equation, natural p data on all of the boundary
         self.galerkin = variant in ("galerkin", "supg", "pure_supg")
         self.gcoef = self.D2 * 4.0 * math.pi if self.galerkin else 1.0
-        self.qmode, self.q_react = (1, 1.0) if self.galerkin else (0, 1.0 if variant == "pure_c0ip" else 0.0)
+        self.qmode, self.q_react = ((1, 1.0) if self.galerkin else (2, 0.0) if variant == "c0ip_other"
+                                    else (0, 1.0 if variant == "pure_c0ip" else 0.0))
         # 'supg': ...MixedPrimal_convergence_SUPG.py:118-129 (residual q + dq/dx + r2^2 q, test w + stab hK/2 dw/dx);
         # 'pure_supg': SUPG_pure_advection_convergence.py:106-109, the same q-q block with stab = 0.1
         self.q_x2p, self.q_x2q, self.supg_stab = ((0.0, 1.0, float(supg_stab)) if variant in ("supg", "pure_supg")
@@ -401,7 +408,7 @@ class PaperMixedSystemK1:
         P = torch.einsum("qi,cid->cqd", self.lamq, Xc)
         self.xq, self.yq = P[:, :, 0].contiguous(), P[:, :, 1].contiguous()
         self.data = paper_data(D1, D2, self.gcoef, self.q_react, variant in ("supg", "pure_supg"),
-                               0.0 if variant == "pure_c0ip" else 1.0)
+                               0.0 if variant == "pure_c0ip" else 1.0, self.r2dir)
         self.f2q = self.data["f2"](self.xq, self.yq).to(torch.float64).contiguous()
         self.f3q = self.data["f3"](self.xq, self.yq).to(torch.float64).contiguous()
         # global dofs of the 17 local ones: [2 per edge | 2 per cell | 3 per cell | vertices | edges]
@@ -508,7 +515,7 @@ class PaperMixedSystemK1:
                            else torch.stack([mk == m_ for m_ in ms]).any(0))
         k_adv = isin(self.adv_markers).to(torch.float64)
         k_dat = isin(self.dat_markers).to(torch.float64)
-        bn = nrm[:, 0]
+        bn = self.r2dir * nrm[:, 0]
         neg = 0.5 * (bn.abs() - bn)
         pen = self.stab2 * (L * neg ** 2 + 8.0 / L)
         ds = w[None, :] * L[:, None]
@@ -592,7 +599,7 @@ class PaperMixedSystemK1:
                            else torch.stack([mk == m_ for m_ in ms]).any(0))
         nat = torch.ones_like(mk, dtype=torch.bool) if self.nat_markers is None else isin(self.nat_markers)
         kind = (isin(self.adv_markers).to(torch.int32) + 2 * isin(self.dat_markers).to(torch.int32)
-                + 4 * nat.to(torch.int32)).contiguous()
+                + 4 * nat.to(torch.int32) + (8 if self.r2dir < 0 else 0)).contiguous()
         A = mesh.coords[fv_e[:, 0].long()]
         B = mesh.coords[fv_e[:, 1].long()]
         Pq = A[:, None, :] + s[None, :, None] * (B - A)[:, None, :]
@@ -715,7 +722,7 @@ class PaperMixedSystemK1:
             le = torch.nonzero((fc.cell1 < 0) & (self.bdry.values == self.s_bc_marker)).flatten()
             sdofs = torch.cat([2 * le, 2 * le + 1])
             # ..._C0IP.py:120,134: s_ex = (0, pi sin(pi x)) has a vanishing normal trace on {x = 0}: zero dofs
-            val[sdofs] = self.sigD()[sdofs] if self.variant == "paper" else 0.0
+            val[sdofs] = self.sigD()[sdofs] if self.variant in ("paper", "c0ip_other") else 0.0
             has[sdofs] = True
         bc = torch.nonzero(has).flatten()
         self.bc_vals = val[bc].contiguous()

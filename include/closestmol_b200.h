@@ -366,8 +366,11 @@ int cm_mixed_m0_errors(int32_t nq, const double* rule_host, int32_t ncells, cons
  * lambda_2 N_2 | 3 DG1 values | 6 CG2 values: vertices, then the facets' mid points]; global dofs
  * [2 per edge | 2 per cell | 3 per cell | vertices | edges].  Je[289][ncells], Fe[17][ncells] entry-major;
  * assembled by cm_csr_gather like the k = 0 tensors.
- * G = gcoef x^2 p^2/(q + geps).  qmode 0: the q-equation of test_for_paper_convergence.py:140-141 (integrated by
- * parts; its facet terms come from cm_cg2_*_facets); qmode 1: the q-equation
+ * G = gcoef x^2 p^2/(q + geps).  qmode 0: the q-equation integrated by parts, its facet terms coming from
+ * cm_cg2_*_facets: ((q_react - div_rad(r2vec)) q + q_x2p r2^2 p - f3) w W - (r2vec.grad w) q W with r2vec = (1,0):
+ * (0,1) = test_for_paper_convergence.py:140-141 and ...MixedPrimal_convergence_C0IP.py:144-145, (1,0) = the q-q block
+ * of C0IP_pure_advection_spherical_convergence.py:109-110; qmode 2: the same with r2vec = (-1,0)
+ * (..._C0IP_otherBCs.py:58,131-132); qmode 1: the q-equation
  * (q_react q + r2vec.grad q + r2^2 (q_x2p p + q_x2q q) - f3)(w + supg_stab hK/2 r2vec.grad w) W:
  * (1,1,0,0) = ...MixedPrimal_convergence.py:123 (BASELINE config 2's own script, Galerkin),
  * (1,0,1,1) = ...MixedPrimal_convergence_SUPG.py:118-129 (hK = CellDiameter).
@@ -385,7 +388,7 @@ int cm_mixed_m1_errors(int32_t nq, const double* rule_host, int32_t full_grad, i
 /* CG2 facet operators of the k = 1 q-equation (state independent, once per mesh; :142-145,148-149,152-153).
  * rule_host[2*nq] = (s, w) Gauss-Legendre on [0,1].  fverts[nf*2] ascending vertex ids.
  *   exterior: fcell[nfe] attached cell, kind bits 1: (r2vec.n) q w W ds, 2: (r2vec.n) q_ex w W ds,
- *     4: natural p data on the facet's two flux dofs; the boundary penalty stab2 (hK neg(r2vec.n)^2 + 8/hK)
+ *     4: natural p data on the facet's two flux dofs, 8: r2vec = (-1,0) instead of (1,0); the boundary penalty stab2 (hK neg(r2vec.n)^2 + 8/hK)
  *     (q - q_ex) w ds applies to every listed facet.  qex / pex[nfe*nq]: q_ex, p_ex at the facet points.
  *     Outputs entry-major: Jx[36][nfe] (6 x 6 on the attached cell's CG2 dofs), cx[6][nfe], nat[2][nfe].
  *   interior: fcell[nfi*2] = (cell0 = '+', cell1); Ji[144][nfi], 12 x 12 on (cell0's 6, cell1's 6) CG2 dofs:

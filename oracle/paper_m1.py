@@ -53,6 +53,7 @@ class PaperM1:
 
     nat_markers = (31, 32)     # exterior facets carrying the natural p data (None: all of them)
     h_cell = False             # avg(hK) with hK = CellDiameter instead of FacetArea
+    r2dir = 1.0                # r2vec = (r2dir, 0) in the q-equation (-1: ..._C0IP_otherBCs.py:58)
 
     def _finish_setup(self):
         mesh, fc = self.mesh, self.fc
@@ -138,9 +139,10 @@ class PaperM1:
         Fe[:, :8] = np.einsum("cq,cqa->ca", a, np.einsum("cqd,cqad->cqa", s, R) + G[..., None] * Rx
                               - p[..., None] * dr)
         Fe[:, 8:11] = np.einsum("cq,cqb->cb", a * (-np.einsum("cqa,ca->cq", drD, se) + f2), chi)
+        rd = self.r2dir                 # r2vec = (rd, 0)
         if self.qmode == 0:
-            Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * ((self.q_react - 2 / x) * q + x2 * self.q_x2p * p - f3), phi)
-                          - np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
+            Fe[:, 11:] = (np.einsum("cq,cqk->ck", a * ((self.q_react - rd * 2 / x) * q + x2 * self.q_x2p * p - f3), phi)
+                          - rd * np.einsum("cq,cqk->ck", a * q, gphi[..., 0]))
         else:   # (q_react q + dq/dx + x^2 (x2p p + x2q q) - f3)(w + tau dw/dx) W, tau = supg_stab hK/2
             qx = np.einsum("cqk,ck->cq", gphi[..., 0], qe)
             tw = phi + (0.5 * self.supg_stab * fem.cell_diameter(self.mesh))[:, None, None] * gphi[..., 0]
@@ -157,8 +159,8 @@ class PaperM1:
             Je[:, 8:11, :8] = -np.einsum("cq,cqb,cqa->cba", a, chi, drD)
             if self.qmode == 0:
                 Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2 * self.q_x2p, phi, chi)
-                Je[:, 11:, 11:] = (np.einsum("cq,cqk,cql->ckl", a * (self.q_react - 2 / x), phi, phi)
-                                   - np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
+                Je[:, 11:, 11:] = (np.einsum("cq,cqk,cql->ckl", a * (self.q_react - rd * 2 / x), phi, phi)
+                                   - rd * np.einsum("cq,cqk,cql->ckl", a, gphi[..., 0], phi))
             else:
                 Je[:, 11:, 8:11] = np.einsum("cq,cqk,cqb->ckb", a * x2 * self.q_x2p, tw, chi)
                 Je[:, 11:, 11:] = np.einsum("cq,cqk,cql->ckl", a, tw,
@@ -195,7 +197,7 @@ class PaperM1:
         phi, _ = p2_basis(lam, self.grads[cell])
         qd = self.qd[cell]
         qh = np.einsum("nqk,nk->nq", phi, u[qd])
-        bn = nrm[:, 0]                                                               # r2vec = (1,0)
+        bn = self.r2dir * nrm[:, 0]                                                  # r2vec = (+-1,0)
         neg = 0.5 * (np.abs(bn) - bn)
         pen = self.stab2 * (L * neg ** 2 + 8.0 / L)
         ds = w[None, :] * L[:, None]
@@ -463,10 +465,42 @@ class MixedPrimalC0IPM1(MixedPrimalM1):
         return MixedPrimalM1.solve(self, tol, maxit)
 
 
-def mixed_primal_c0ip_table(levels=5):
+class MixedPrimalC0IPOtherM1(MixedPrimalC0IPM1):
+    """convergence/SphericalAdvectionDiffusionReaction_MixedPrimal_convergence_C0IP_otherBCs.py on RT2 x DG1 x CG2:
+    r2vec = (-1,0) in the q-equation (:58; G keeps Constant((1,0)), :46-47), D1 = 2, D2 = 1.5 (:55-56), penalty with the
+    PLUS sign, stab = 0.0075 (:60,134), hK = CellDiameter (:85); markers left 30 / right 31 / rest 32 (:78-82); inflow
+    term on the left (:133), natural p data on right and rest (:136-137); essential: s = project(sig_ex) on the left,
+    q = q_ex on the right (:121-124); f3 = grad(q_ex).r2vec + r2^2 p_ex (:117); Newton 1e-8 (:149-150)."""
+    nat_markers = (31, 32)
+    r2dir = -1.0
+
+    def __init__(self, n, D1=2.0, D2=1.5, stab=0.0075):
+        MixedPrimalC0IPM1.__init__(self, n, D1, D2, -stab)         # the parent stores gamma = -stab/(deg+1)^3.5
+        self.markers = fem.mark_facets(self.mesh, [(lambda P: fem.near(P[..., 0], 0.0), 30),
+                                                   (lambda P: fem.near(P[..., 0], 1.0), 31),
+                                                   (lambda P: fem.near(P[..., 1], 0.0) | fem.near(P[..., 1], 1.0), 32)])
+        self.k_adv = (self.markers[self.ext] == 30).astype(float)
+
+    def _data(self):
+        d = MixedPrimalM1._data(self)
+        import sympy as sm
+        x, y = sm.symbols("x y", positive=True)
+        pe = sm.sin(sm.pi * x) * sm.sin(sm.pi * y)
+        qe = sm.Rational(3, 2) + sm.cos(sm.pi * x * y)
+        d["f3"] = sm.lambdify((x, y), -sm.diff(qe, x) + x ** 2 * pe, "numpy")
+        return d
+
+    def bcs(self):
+        dq, gq = MixedPrimalM1.bcs(self)                           # q on the facets marked 31
+        le = np.nonzero((self.fc.cell1 < 0) & (self.markers == 30))[0]
+        sd = np.concatenate([2 * le, 2 * le + 1])
+        return np.concatenate([sd, dq]), np.concatenate([self.sigD()[sd], gq])
+
+
+def mixed_primal_c0ip_table(levels=5, other_bcs=False):
     rows, prev = [], None
     for nk in range(levels):
-        m = MixedPrimalC0IPM1(2 ** (nk + 1))
+        m = (MixedPrimalC0IPOtherM1 if other_bcs else MixedPrimalC0IPM1)(2 ** (nk + 1))
         u = m.solve()
         h = m.mesh.hmax()
         e = m.errors(u)

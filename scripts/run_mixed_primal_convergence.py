@@ -18,14 +18,22 @@ def main(nkmax=6, variant="galerkin"):
     """variant 'galerkin': ...MixedPrimal_convergence.py; 'supg': ...MixedPrimal_convergence_SUPG.py (q data on
     {x = 0} :77, stab = 1 :56, Newton tolerances 1e-8 :138-139, nkmax = 5 :58); 'c0ip': ..._convergence_C0IP.py
     (markers left 31 / right 32 / rest 33 :78-92, D1 = .01, D2 = .015 :63-64, stab = 0.00075 entering with the minus
-    sign :68,147, q = q_ex on the right and s.n = 0 on the left :132-135, Newton 1e-8 :160-161)."""
+    sign :68,147, q = q_ex on the right and s.n = 0 on the left :132-135, Newton 1e-8 :160-161); 'c0ip_other':
+    ..._convergence_C0IP_otherBCs.py (r2vec = (-1,0) in the q-equation :58, D1 = 2, D2 = 1.5, stab = +0.0075,
+    s = project(sig_ex) on the left :121-122, q = q_ex on the right :123)."""
     hh, nn, es, ep, eq, rs, rp, rq = [], [], [], [], [], [0.0], [0.0], [0.0]
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
         mesh = RectangleMesh(Point(0, 0), Point(1, 1), nps, nps)
         bdry = MeshFunction("size_t", mesh, 1)
         bdry.set_all(0)
-        if variant == "c0ip":
+        if variant == "c0ip_other":     # ..._C0IP_otherBCs.py:55-60,78-82: left 30 / right 31 / rest 32, +stab
+            CompiledSubDomain("near(x[0],0) && on_boundary").mark(bdry, 30)
+            CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, 31)
+            CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, 32)
+            system = PaperMixedSystemK1(mesh, bdry, D1=2.0, D2=1.5, stab=0.0075, stab2=0.0, degree=4,
+                                        variant=variant)
+        elif variant == "c0ip":
             CompiledSubDomain("near(x[0],0) && on_boundary").mark(bdry, 31)
             CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, 32)
             CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, 33)

@@ -303,3 +303,33 @@ def test_pure_advection_drivers_match_oracle_tables():
         prev = (h, e)
     assert [r.split() for r in rows] == [r.split() for r in ref]
     assert float(rows[-1].replace("&", " ").split()[3]) > 1.5
+
+
+def test_mixed_primal_c0ip_other_bcs_driver_matches_oracle_table():
+    """..._C0IP_otherBCs.py on RT2 x DG1 x CG2 (r2vec = (-1,0) in the q-equation: qmode 2 of cm_mixed_m1_cells and
+    kind bit 8 of cm_cg2_exterior_facets; s = project(sig_ex) on the left, q = q_ex on the right)."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    n = 5
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    S = PaperMixedSystemK1(mesh, bd, D1=2.0, D2=1.5, stab=0.0075, stab2=0.0, degree=4, variant="c0ip_other")
+    O = paper_m1.MixedPrimalC0IPOtherM1(n)
+    rng = np.random.default_rng(9)
+    un = np.concatenate([rng.standard_normal(2 * O.E + 2 * O.C), 0.5 + rng.random(3 * O.C),
+                         1.0 + rng.random(O.V + O.E)])
+    vals, b = S.assemble(torch.tensor(un, device=mesh.device), True)
+    J, bo = O.assemble(un, True)
+    got = sp.csr_matrix((vals.cpu().numpy(), S.col.cpu().numpy(), S.rowptr.cpu().numpy()), shape=(S.N, S.N))
+    assert abs(got - J).max() < 1e-12 * abs(J).max()
+    assert np.max(np.abs(b.cpu().numpy() - bo)) < 1e-12 * np.max(np.abs(bo))
+    spec = importlib.util.spec_from_file_location("mp_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_mixed_primal_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(4, variant="c0ip_other")
+    assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_c0ip_table(4, other_bcs=True)]
+    assert 1.9 < float(rows[-1].replace("&", " ").split()[5]) < 2.1

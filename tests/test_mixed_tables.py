@@ -128,3 +128,34 @@ def test_c0ip_variant_facet_operator_matches_oracle_and_oracle_converges():
     assert [int(r.split()[0]) for r in rows] == [3 * m.E + 5 * m.C + m.V for m in
                                                  (paper_m1.MixedPrimalC0IPM1(2 ** (k + 1)) for k in range(3))]
     assert 1.8 < float(rows[-1].replace("&", " ").split()[5]) < 2.2
+
+
+def test_c0ip_other_bcs_variant_facet_operator_matches_oracle():
+    """..._C0IP_otherBCs.py variant (r2vec = (-1,0) in the q-equation, penalty +stab with avg CellDiameter, natural p
+    data on right / rest): host tabulation of the facet terms against oracle/paper_m1.MixedPrimalC0IPOtherM1."""
+    from closestmolecule_b200.mixed import PaperMixedSystemK1
+    from oracle import paper_m1
+    import scipy.sparse as sp
+    n = 4
+    mesh = cm.UnitSquareMesh(n, n, device="cpu")
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 30)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 32)
+    S = PaperMixedSystemK1(mesh, bd, D1=2.0, D2=1.5, stab=0.0075, stab2=0.0, degree=4, tables_only=True,
+                           variant="c0ip_other")
+    O = paper_m1.MixedPrimalC0IPOtherM1(n)
+    assert S.gamma == O.gamma > 0
+    u = np.linspace(0.5, 1.5, O.N)
+    rows, cols, vals = [], [], []
+    b = np.zeros(O.N)
+    O._exterior(u, b, rows, cols, vals, True)
+    O._interior(u, b, rows, cols, vals, True)
+    Jf = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(O.N, O.N)).tocsr()
+    Kf = sp.csr_matrix((S.Kf.numpy(), S.col.numpy(), S.rowptr.numpy()), shape=(S.N, S.N))
+    assert abs(Kf - Jf).max() < 1e-12 * abs(Jf).max()
+    assert np.max(np.abs(Kf @ u + S.cvec.numpy() - b)) < 1e-12 * np.max(np.abs(b))
+    f3 = S.data["f3"](torch.tensor([0.3], dtype=torch.float64), torch.tensor([0.7], dtype=torch.float64))
+    assert abs(float(f3) - float(O.sym["f3"](0.3, 0.7))) < 1e-14
+    rows = paper_m1.mixed_primal_c0ip_table(3, other_bcs=True)
+    assert 1.8 < float(rows[-1].replace("&", " ").split()[5]) < 2.0
