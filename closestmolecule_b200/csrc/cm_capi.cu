@@ -477,7 +477,7 @@ int cm_mixed_m1_cells(int32_t nq, const double* rule_host, double D1, double D2,
                       const double* f2q, const double* f3q, double* Je, double* Fe, void* stream) {
   CM_CHECK_ARG(ncells >= 1 && nedges >= 3 && nverts >= 3, "bad size");
   CM_CHECK_ARG(rule_host && cells && coords && cell_edges && sign && u && f2q && f3q && Fe, "null pointer");
-  CM_CHECK_ARG(qmode == 0 || qmode == 1, "qmode must be 0 (paper) or 1 (Galerkin)");
+  CM_CHECK_ARG(qmode >= 0 && qmode <= 2, "qmode must be 0 (integrated by parts), 1 (Galerkin / SUPG) or 2 (0 with r2vec = (-1,0))");
   return mixed_m1_cells(nq, rule_host, D1, D2, geps, gcoef, qmode, q_react, q_x2p, q_x2q, supg_stab, ncells, nedges,
                         nverts, cells, coords, cell_edges, sign, u, f2q, f3q, Je, Fe, (cudaStream_t)stream);
 }
