@@ -753,14 +753,18 @@ class PaperMixedSystemK1:
         self.newton_its = it
         return u
 
-    def errors(self, u):
+    def errors(self, u, full_grad=None):
+        """e_div(s), e_0(p), e_1(q); e_1(q) with d/dx only (test_for_paper_convergence.py:175, the 'paper' default) or
+        with the whole gradient (the MixedPrimal scripts, e.g. ..._C0IP_otherBCs_modified.py:188)."""
+        if full_grad is None:
+            full_grad = self.variant != "paper"
         d, x, y = self.data, self.xq, self.yq
         exq = torch.stack([d["sx"](x, y), d["sy"](x, y), d["drs"](x, y), p_exact(x, y), q_exact(x, y),
                            d["qx"](x, y), d["qy"](x, y)], -1).to(torch.float64).contiguous()
         work = torch.empty(int(self.lib.cm_mixed_workspace_doubles()), dtype=torch.float64,
                            device=self.mesh.device)
         _capi.check(self.lib.cm_mixed_m1_errors(
-            self.nq, self.rule.ctypes.data, 0 if self.variant == "paper" else 1, self.C, self.E, self.V,
+            self.nq, self.rule.ctypes.data, 1 if full_grad else 0, self.C, self.E, self.V,
             _capi.ptr(self.mesh.cells),
             _capi.ptr(self.mesh.coords), _capi.ptr(self.cell_edges), _capi.ptr(self.sign), _capi.ptr(u),
             _capi.ptr(exq), _capi.ptr(work), _capi.stream_ptr()))

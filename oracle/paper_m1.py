@@ -417,7 +417,7 @@ class MixedPrimalC0IPM1(MixedPrimalM1):
     nat_markers = None
     h_cell = True
 
-    def __init__(self, n, D1=0.01, D2=0.015, stab=0.00075):
+    def __init__(self, n, D1=0.01, D2=0.015, stab=0.00075, degree=4):
         self.supg = False
         self.mesh = mesh = fem.unit_square_mesh(n, n)
         self.fc = fc = mesh.facets()
@@ -425,7 +425,7 @@ class MixedPrimalC0IPM1(MixedPrimalM1):
         self.N = 3 * self.E + 5 * self.C + self.V
         self.stab, self.stab2 = stab, 0.0
         self.gamma = -stab / (DEG + 1) ** 3.5
-        self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, 1.0, 0, 0.0, 4
+        self.D1, self.D2, self.gcoef, self.qmode, self.q_react, self.degree = D1, D2, 1.0, 0, 0.0, degree
         self.q_x2p, self.q_x2q, self.supg_stab = 1.0, 0.0, 0.0
         self.sym = self._data()
         self._finish_setup()
@@ -497,10 +497,38 @@ class MixedPrimalC0IPOtherM1(MixedPrimalC0IPM1):
         return np.concatenate([sd, dq]), np.concatenate([self.sigD()[sd], gq])
 
 
-def mixed_primal_c0ip_table(levels=5, other_bcs=False):
+class MixedPrimalC0IPModifiedM1(MixedPrimalC0IPM1):
+    """convergence/SphericalAdvectionDiffusionReaction_MixedPrimal_convergence_C0IP_otherBCs_modified.py on
+    RT2 x DG1 x CG2 (deg = 1 :49): the ancestor of test_for_paper_convergence.py -- r2vec = (1,0), D1 = 2, D2 = 1.5
+    (:43-44), penalty +stab with stab = 1e-3 (:47) and hK = FacetArea (:111), inflow term on the left (:156), the
+    outflow data of q imposed WEAKLY on the right (:164) and no boundary penalty, natural p data on right and rest
+    (:160-161), s = project(sig_ex) on the left as the only essential condition (:146-147), quadrature degree 6 (:38),
+    SNES with tolerances 1e-7 (:171-174; plain Newton steps here), q error with the full gradient (:188)."""
+    nat_markers = (31, 32)
+    h_cell = False
+
+    def __init__(self, n, D1=2.0, D2=1.5, stab=1e-3):
+        MixedPrimalC0IPM1.__init__(self, n, D1, D2, -stab, degree=6)
+        self.markers = fem.mark_facets(self.mesh, [(lambda P: fem.near(P[..., 0], 0.0), 30),
+                                                   (lambda P: fem.near(P[..., 0], 1.0), 31),
+                                                   (lambda P: fem.near(P[..., 1], 0.0) | fem.near(P[..., 1], 1.0), 32)])
+        m = self.markers[self.ext]
+        self.k_adv, self.k_dat = (m == 30).astype(float), (m == 31).astype(float)
+
+    def bcs(self):
+        le = np.nonzero((self.fc.cell1 < 0) & (self.markers == 30))[0]
+        sd = np.concatenate([2 * le, 2 * le + 1])
+        return sd, self.sigD()[sd]
+
+    def solve(self, tol=1e-7, maxit=50):
+        return MixedPrimalM1.solve(self, tol, maxit)
+
+
+def mixed_primal_c0ip_table(levels=5, other_bcs=False, modified=False):
     rows, prev = [], None
     for nk in range(levels):
-        m = (MixedPrimalC0IPOtherM1 if other_bcs else MixedPrimalC0IPM1)(2 ** (nk + 1))
+        m = (MixedPrimalC0IPModifiedM1 if modified else MixedPrimalC0IPOtherM1 if other_bcs
+             else MixedPrimalC0IPM1)(2 ** (nk + 1))
         u = m.solve()
         h = m.mesh.hmax()
         e = m.errors(u)

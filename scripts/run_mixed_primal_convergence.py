@@ -20,14 +20,27 @@ def main(nkmax=6, variant="galerkin"):
     (markers left 31 / right 32 / rest 33 :78-92, D1 = .01, D2 = .015 :63-64, stab = 0.00075 entering with the minus
     sign :68,147, q = q_ex on the right and s.n = 0 on the left :132-135, Newton 1e-8 :160-161); 'c0ip_other':
     ..._convergence_C0IP_otherBCs.py (r2vec = (-1,0) in the q-equation :58, D1 = 2, D2 = 1.5, stab = +0.0075,
-    s = project(sig_ex) on the left :121-122, q = q_ex on the right :123)."""
+    s = project(sig_ex) on the left :121-122, q = q_ex on the right :123); 'c0ip_modified':
+    ..._C0IP_otherBCs_modified.py (r2vec = (1,0), q data imposed weakly on the right :164, hK = FacetArea :111,
+    quadrature degree 6 :38, UnitSquareMesh :98, tolerances 1e-7 :173-174)."""
     hh, nn, es, ep, eq, rs, rp, rq = [], [], [], [], [], [0.0], [0.0], [0.0]
     for nk in range(nkmax):
         nps = pow(2, nk + 1)
         mesh = RectangleMesh(Point(0, 0), Point(1, 1), nps, nps)
         bdry = MeshFunction("size_t", mesh, 1)
         bdry.set_all(0)
-        if variant == "c0ip_other":     # ..._C0IP_otherBCs.py:55-60,78-82: left 30 / right 31 / rest 32, +stab
+        full_grad = None
+        if variant == "c0ip_modified":  # ..._C0IP_otherBCs_modified.py:43-47,98-111: the paper's layout of the facet
+            # terms (weak outflow data, hK = FacetArea, degree 6) without the boundary penalty; left 30/right 31/rest 32
+            mesh = UnitSquareMesh(nps, nps)
+            bdry = MeshFunction("size_t", mesh, 1)
+            bdry.set_all(0)
+            CompiledSubDomain("near(x[0],0) && on_boundary").mark(bdry, 30)
+            CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, 31)
+            CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, 32)
+            system = PaperMixedSystemK1(mesh, bdry, D1=2.0, D2=1.5, stab=1e-3, stab2=0.0, degree=6, variant="paper")
+            full_grad = True
+        elif variant == "c0ip_other":     # ..._C0IP_otherBCs.py:55-60,78-82: left 30 / right 31 / rest 32, +stab
             CompiledSubDomain("near(x[0],0) && on_boundary").mark(bdry, 30)
             CompiledSubDomain("near(x[0],1) && on_boundary").mark(bdry, 31)
             CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bdry, 32)
@@ -47,8 +60,8 @@ def main(nkmax=6, variant="galerkin"):
             system = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, degree=4, variant=variant)
         hh.append(mesh.hmax())
         nn.append(system.N)
-        u = system.solve(tol=1e-7 if variant == "galerkin" else 1e-8)
-        e = system.errors(u)
+        u = system.solve(tol=1e-7 if variant in ("galerkin", "c0ip_modified") else 1e-8)
+        e = system.errors(u, full_grad)
         es.append(e[0]); ep.append(e[1]); eq.append(e[2])
         if nk > 0:
             lg = math.log(hh[nk] / hh[nk - 1])

@@ -333,3 +333,15 @@ def test_mixed_primal_c0ip_other_bcs_driver_matches_oracle_table():
     rows = mod.main(4, variant="c0ip_other")
     assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_c0ip_table(4, other_bcs=True)]
     assert 1.9 < float(rows[-1].replace("&", " ").split()[5]) < 2.1
+
+
+def test_mixed_primal_c0ip_modified_driver_matches_oracle_table():
+    """..._C0IP_otherBCs_modified.py (weak outflow data, FacetArea, degree 6, no boundary penalty, s = project(sig_ex)
+    on the left only): the 'paper' layout with other constants and the full-gradient q error."""
+    from oracle import paper_m1
+    spec = importlib.util.spec_from_file_location("mp_conv", os.path.join(ROOT, "scripts",
+                                                                          "run_mixed_primal_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main(4, variant="c0ip_modified")
+    assert [r.split() for r in rows] == [r.split() for r in paper_m1.mixed_primal_c0ip_table(4, modified=True)]
