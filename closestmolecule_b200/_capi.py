@@ -116,6 +116,9 @@ _PROTOS = {
     "cm_krylov_workspace_bytes": ([_I, _I, _I], C.c_int64),
     "cm_krylov_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _I, _P, C.c_int64,
                          C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
+    "cm_bicgstab_workspace_bytes": ([_I, _I], C.c_int64),
+    "cm_bicgstab_solve": ([_I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _I, _P, C.c_int64,
+                           C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
 }
 
 

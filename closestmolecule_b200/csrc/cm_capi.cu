@@ -216,6 +216,27 @@ int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_
   return rc;
 }
 
+int64_t cm_bicgstab_workspace_bytes(int32_t bs, int32_t nv) {
+  if ((bs != 1 && bs != 2) || nv < 1) return -1;
+  return (int64_t)bicgstab_workspace_bytes(bs, nv);
+}
+
+int cm_bicgstab_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
+                      const int32_t* diag_slot, const double* vals, const double* b, double* x, double rtol,
+                      double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
+                      int32_t* iters_host, double* resid_host, void* stream) {
+  CM_CHECK_ARG(bs == 1 || bs == 2, "bs must be 1 or 2");
+  CM_CHECK_ARG(nv >= 1 && maxit >= 1, "bad size or maxit");
+  CM_CHECK_ARG(nrowptr && ncol && diag_slot && vals && b && x && workspace, "null pointer");
+  int it = 0;
+  double rr = 0.0;
+  const int rc = bicgstab_csr_solve(bs, nv, nrowptr, ncol, diag_slot, vals, b, x, rtol, atol, maxit, workspace,
+                                    (size_t)workspace_bytes, &it, &rr, (cudaStream_t)stream);
+  if (iters_host) *iters_host = it;
+  if (resid_host) *resid_host = rr;
+  return rc;
+}
+
 int cm_stencil_line_factor(int32_t nx, int32_t ny, const double* A, double* lf, double* iu,
                            double* cu, int32_t* err_flag, void* stream) {
   CM_CHECK_ARG(nx >= 1 && ny >= 1 && A && lf && iu && cu && err_flag, "bad argument");

@@ -72,6 +72,11 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
                 int* iters_out, double* resid_out, double* bnorm_out, cudaStream_t st,
                 const VecSlice* sl = nullptr, cm_dist* D = nullptr);
 
+size_t bicgstab_workspace_doubles(long long n);
+int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x, double rtol,
+                   double atol, int maxit, double* work, int* iters_out, double* resid_out,
+                   double* bnorm_out, cudaStream_t st);
+
 // cm_stencil.cu
 int st_extract_blocks(int nx, int ny, const int* nrowptr, const int* ncol, const double* vals,
                       double* PP, double* PQ, double* QP, double* QQ, double* sp, double* sq,
@@ -119,6 +124,10 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
                    int maxit, void* ws, size_t ws_bytes, cm_dist* D, int* iters, double* resid,
                    cudaStream_t st);
 size_t pqs_state_offset_bytes(int nx, int ny, int restart);
+size_t bicgstab_workspace_bytes(int bs, int nv);
+int bicgstab_csr_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
+                       const double* vals, const double* b, double* x, double rtol, double atol, int maxit,
+                       void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
 size_t krylov_workspace_bytes(int bs, int nv, int restart);
 int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
                  const double* vals, const double* b, double* x, double rtol, double atol, int maxit,

@@ -190,4 +190,138 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
   return converged ? CM_OK : 1;  // 1 = not converged within maxit (caller decides)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Right-preconditioned BiCGStab (van der Vorst) on the same fused vector kernels: the 'bicgstab' choice of
+// parameters['newton_solver']['linear_solver'] in DOLFIN.  x0 = 0.  Seven work vectors laid out with one
+// stride so that the fused multi-vector kernels can address pairs of them:
+//   0 rhat | 1 r (holds s between the two half steps) | 2 p | 3 v | 4 t | 5 y = M^-1 p | 6 z = M^-1 s
+// Three host synchronisations per iteration (alpha; omega; rho and ||r||).  One iteration = two operator and two
+// preconditioner applications.
+size_t bicgstab_workspace_doubles(long long n) {
+  const long long ne = (n + 1) & ~1LL;
+  return (size_t)ne * 7 + 16 + (size_t)148 * 4 * 8 + 64;
+}
+
+int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x, double rtol,
+                   double atol, int maxit, double* work, int* iters_out, double* resid_out,
+                   double* bnorm_out, cudaStream_t st) {
+  const long long ne = (n + 1) & ~1LL;
+  double* rh = work;
+  double* r = rh + ne;
+  double* p = r + ne;
+  double* v = p + ne;
+  double* t = v + ne;
+  double* y = t + ne;
+  double* z = y + ne;
+  double* hdev = z + ne;  // 16 scalars
+  double* scratch = hdev + 16;
+  scratch = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+
+  double* hhost = nullptr;
+  CM_CUDA(cudaMallocHost((void**)&hhost, sizeof(double) * 16));
+  struct Guard {
+    double* p;
+    ~Guard() { cudaFreeHost(p); }
+  } guard{hhost};
+  auto put = [&](int slot, int cnt) -> int {  // hhost[slot..slot+cnt) -> hdev (same slots)
+    CM_CUDA(cudaMemcpyAsync(hdev + slot, hhost + slot, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+    return CM_OK;
+  };
+  auto get = [&](int slot, int cnt) -> int {  // hdev -> hhost, then wait
+    CM_CUDA(cudaMemcpyAsync(hhost + slot, hdev + slot, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    return CM_OK;
+  };
+  const size_t vb = sizeof(double) * (size_t)n;
+  int rc;
+  CM_CUDA(cudaMemsetAsync(x, 0, vb, st));
+  CM_CUDA(cudaMemsetAsync(p, 0, vb, st));
+  CM_CUDA(cudaMemsetAsync(v, 0, vb, st));
+  CM_CUDA(cudaMemcpyAsync(r, b, vb, cudaMemcpyDeviceToDevice, st));
+  CM_CUDA(cudaMemcpyAsync(rh, b, vb, cudaMemcpyDeviceToDevice, st));
+  if ((rc = multi_dot(n, rh, ne, 1, r, hdev + 0, scratch, st))) return rc;  // rho = <rhat, r> = ||b||^2
+  if ((rc = get(0, 1))) return rc;
+  const double bnorm = sqrt(hhost[0]);
+  if (bnorm_out) *bnorm_out = bnorm;
+  if (!isfinite(bnorm)) {
+    set_error("bicgstab: right-hand side norm is not finite");
+    return CM_E_BREAKDOWN;
+  }
+  const double target = fmax(rtol * bnorm, atol);
+  double rho_new = hhost[0], rho = 1.0, alpha = 1.0, omega = 1.0, resid = bnorm;
+  int its = 0;
+  bool converged = !(bnorm > target);
+  while (!converged && its < maxit) {
+    if (rho_new == 0.0 || !isfinite(rho_new)) {
+      set_error("bicgstab: breakdown (<rhat, r> = %g) at iteration %d", rho_new, its);
+      return CM_E_BREAKDOWN;
+    }
+    const double beta = (rho_new / rho) * (alpha / omega);
+    rho = rho_new;
+    // p = r + beta (p - omega v)
+    if ((rc = vec_scale(n, p, nullptr, beta, 0, p, st))) return rc;
+    hhost[1] = 1.0;
+    hhost[2] = -beta * omega;
+    if ((rc = put(1, 2))) return rc;
+    if ((rc = multi_axpy(n, r, 2 * ne, 2, hdev + 1, 1.0, p, nullptr, scratch, st))) return rc;  // V = (r, v)
+    if ((rc = Minv(p, y))) return rc;
+    if ((rc = A(y, v))) return rc;
+    if ((rc = multi_dot(n, rh, ne, 1, v, hdev + 3, scratch, st))) return rc;
+    if ((rc = get(3, 1))) return rc;
+    if (hhost[3] == 0.0 || !isfinite(hhost[3])) {
+      set_error("bicgstab: breakdown (<rhat, A M^-1 p> = %g) at iteration %d", hhost[3], its);
+      return CM_E_BREAKDOWN;
+    }
+    alpha = rho / hhost[3];
+    // s = r - alpha v (kept in r), ||s||^2 -> hdev[5]
+    hhost[4] = alpha;
+    if ((rc = put(4, 1))) return rc;
+    if ((rc = multi_axpy(n, v, ne, 1, hdev + 4, -1.0, r, hdev + 5, scratch, st))) return rc;
+    if ((rc = Minv(r, z))) return rc;
+    if ((rc = A(z, t))) return rc;
+    // <s, t>, <t, t>: V = (r, t) with stride 3 ne, against t
+    if ((rc = multi_dot(n, r, 3 * ne, 2, t, hdev + 6, scratch, st))) return rc;
+    if ((rc = get(5, 3))) return rc;
+    ++its;
+    const double snorm = sqrt(fmax(hhost[5], 0.0)), st_ = hhost[6], tt = hhost[7];
+    if (snorm <= target || tt == 0.0) {  // converged at the half step: x += alpha y
+      hhost[8] = alpha;
+      if ((rc = put(8, 1))) return rc;
+      if ((rc = multi_axpy(n, y, ne, 1, hdev + 8, 1.0, x, nullptr, scratch, st))) return rc;
+      CM_CUDA(cudaStreamSynchronize(st));
+      resid = snorm;
+      converged = snorm <= target;
+      if (!converged) {
+        set_error("bicgstab: breakdown (A M^-1 s = 0 with ||s|| = %g) at iteration %d", snorm, its);
+        return CM_E_BREAKDOWN;
+      }
+      break;
+    }
+    omega = st_ / tt;
+    if (omega == 0.0 || !isfinite(omega)) {
+      set_error("bicgstab: breakdown (omega = %g) at iteration %d", omega, its);
+      return CM_E_BREAKDOWN;
+    }
+    // x += alpha y + omega z;  r = s - omega t, ||r||^2 -> hdev[11];  rho_new = <rhat, r> -> hdev[12]
+    hhost[8] = alpha;
+    hhost[9] = omega;
+    hhost[10] = omega;
+    if ((rc = put(8, 3))) return rc;
+    if ((rc = multi_axpy(n, y, ne, 2, hdev + 8, 1.0, x, nullptr, scratch, st))) return rc;  // V = (y, z)
+    if ((rc = multi_axpy(n, t, ne, 1, hdev + 10, -1.0, r, hdev + 11, scratch, st))) return rc;
+    if ((rc = multi_dot(n, rh, ne, 1, r, hdev + 12, scratch, st))) return rc;
+    if ((rc = get(11, 2))) return rc;
+    resid = sqrt(fmax(hhost[11], 0.0));
+    rho_new = hhost[12];
+    if (!isfinite(resid)) {
+      set_error("bicgstab: NaN/Inf residual at iteration %d", its);
+      return CM_E_BREAKDOWN;
+    }
+    if (resid <= target) converged = true;
+  }
+  if (iters_out) *iters_out = its;
+  if (resid_out) *resid_out = resid;
+  return converged ? CM_OK : 1;
+}
+
 }  // namespace cm

@@ -677,4 +677,40 @@ int krylov_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int*
   return rc;
 }
 
+size_t bicgstab_workspace_bytes(int bs, int nv) {
+  const long long n = (long long)bs * nv;
+  return (bicgstab_workspace_doubles(n) + (size_t)bs * bs * nv + 8) * sizeof(double) + 64;
+}
+
+// BiCGStab + (block-)Jacobi on the node CSR layouts: same operator / preconditioner as krylov_solve.
+int bicgstab_csr_solve(int bs, int nv, const int* nrowptr, const int* ncol, const int* diag_slot,
+                       const double* vals, const double* b, double* x, double rtol, double atol, int maxit,
+                       void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st) {
+  if (bicgstab_workspace_bytes(bs, nv) > ws_bytes) {
+    set_error("bicgstab_solve: workspace too small");
+    return CM_E_INVALID;
+  }
+  double* base = align_ws(ws);
+  double* dinv = base;
+  double* wk = base + even((size_t)bs * bs * nv);
+  const int grid = (nv + 255) / 256;
+  jacobi_setup_kernel<<<grid, 256, 0, st>>>(bs, nv, nrowptr, diag_slot, vals, dinv);
+  CM_LAUNCH_CHECK();
+  LinOp A = [&](const double* in, double* out) {
+    return spmv(bs, nv, nrowptr, ncol, vals, in, out, 1.0, nullptr, st);
+  };
+  LinOp Minv = [&](const double* r, double* z) {
+    jacobi_apply_kernel<<<grid, 256, 0, st>>>(bs, nv, dinv, r, z);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? CM_OK : CM_E_CUDA;
+  };
+  double bnorm = 0.0;
+  int rc = bicgstab_solve((long long)bs * nv, A, Minv, b, x, rtol, atol, maxit, wk, iters, resid, &bnorm, st);
+  if (resid && bnorm > 0.0) *resid /= bnorm;
+  if (rc == 1)
+    set_error("cm_bicgstab_solve: BiCGStab did not reach rtol=%g in %d iterations (relative residual %g)",
+              rtol, maxit, resid ? *resid : -1.0);
+  return rc;
+}
+
 }  // namespace cm

@@ -159,13 +159,17 @@ class BandedLULinearSolver:
 
 
 class JacobiKrylovLinearSolver:
-    """GMRES + (block-)Jacobi on the node CSR layouts, any mesh (cm_krylov_solve)."""
+    """GMRES(restart) or BiCGStab + (block-)Jacobi on the node CSR layouts, any mesh (cm_krylov_solve /
+    cm_bicgstab_solve)."""
 
-    def __init__(self, asm, restart=60):
-        self.asm, self.restart = asm, int(restart)
+    def __init__(self, asm, restart=60, method="gmres"):
+        if method not in ("gmres", "bicgstab"):
+            raise ValueError(f"unknown Krylov method '{method}'")
+        self.asm, self.restart, self.method = asm, int(restart), method
         self.lib = _capi.lib()
         t = asm.topo
-        nbytes = int(self.lib.cm_krylov_workspace_bytes(asm.bs, t.nv, self.restart))
+        nbytes = int(self.lib.cm_krylov_workspace_bytes(asm.bs, t.nv, self.restart) if method == "gmres"
+                     else self.lib.cm_bicgstab_workspace_bytes(asm.bs, t.nv))
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=asm.mesh.device)
         self.nbytes = nbytes
         self.last_iterations = 0
@@ -177,10 +181,16 @@ class JacobiKrylovLinearSolver:
     def solve(self, b, x, rtol, atol, maxit):
         t = self.asm.topo
         it, rr = C.c_int32(0), C.c_double(0.0)
-        rc = self.lib.cm_krylov_solve(self.asm.bs, t.nv, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
-                                      _capi.ptr(t.diag_slot), _capi.ptr(self.asm.vals), _capi.ptr(b),
-                                      _capi.ptr(x), rtol, atol, maxit, self.restart, _capi.ptr(self.ws),
-                                      self.nbytes, C.byref(it), C.byref(rr), _capi.stream_ptr())
+        if self.method == "gmres":
+            rc = self.lib.cm_krylov_solve(self.asm.bs, t.nv, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
+                                          _capi.ptr(t.diag_slot), _capi.ptr(self.asm.vals), _capi.ptr(b),
+                                          _capi.ptr(x), rtol, atol, maxit, self.restart, _capi.ptr(self.ws),
+                                          self.nbytes, C.byref(it), C.byref(rr), _capi.stream_ptr())
+        else:
+            rc = self.lib.cm_bicgstab_solve(self.asm.bs, t.nv, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
+                                            _capi.ptr(t.diag_slot), _capi.ptr(self.asm.vals), _capi.ptr(b),
+                                            _capi.ptr(x), rtol, atol, maxit, _capi.ptr(self.ws), self.nbytes,
+                                            C.byref(it), C.byref(rr), _capi.stream_ptr())
         self.last_iterations, self.last_residual = it.value, rr.value
         if rc < 0:
             _capi.check(rc)
@@ -236,9 +246,12 @@ class NonlinearVariationalSolver:
                 raise ValueError(f"unknown linear_solver '{name}'")
             restart = prm["krylov_solver"]["restart"]
             if isinstance(self.problem.form, PQPrimalForm):
+                # the field-split / multigrid preconditioner is applied inexactly (fixed sweeps), which GMRES tolerates
+                # and BiCGStab's short recurrences do not reward: 'bicgstab' selects the same GMRES path here
                 self._linear = StructuredPQLinearSolver(self.asm, restart)
             else:
-                self._linear = JacobiKrylovLinearSolver(self.asm, restart)
+                self._linear = JacobiKrylovLinearSolver(self.asm, restart,
+                                                        "bicgstab" if name == "bicgstab" else "gmres")
         return self._linear
 
     def _prepare(self):

@@ -279,6 +279,15 @@ int cm_krylov_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_
                     double rtol, double atol, int32_t maxit, int32_t restart, void* workspace,
                     int64_t workspace_bytes, int32_t* iters_host, double* resid_host, void* stream);
 
+/* The same operator and preconditioner under right-preconditioned BiCGStab (DOLFIN's 'bicgstab' choice of
+ * parameters['newton_solver']['linear_solver']); x0 = 0; one iteration = two SpMVs.  Returns 0 converged,
+ * 1 not converged within maxit, < 0 error (breakdown included). */
+int64_t cm_bicgstab_workspace_bytes(int32_t bs, int32_t nv);
+int cm_bicgstab_solve(int32_t bs, int32_t nv, const int32_t* nrowptr, const int32_t* ncol,
+                      const int32_t* diag_slot, const double* vals, const double* b, double* x,
+                      double rtol, double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
+                      int32_t* iters_host, double* resid_host, void* stream);
+
 /* ---- a11, direct path: banded LU with partial pivoting (block-tridiagonal organisation) ----------
  * Replaces PETScLUSolver('mumps'|'umfpack'|default LU): advection_diffusion_convergence.py:212,
  * advection_diffusion_mixed.py:223, ...MixedPrimal_convergence.py:136, SphericalLaplace_convergence.py:135

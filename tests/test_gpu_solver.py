@@ -422,3 +422,29 @@ def test_laplace_convergence_driver_config1():
     assert 0.95 < r["r1"][-1] < 1.05 and 1.9 < r["r0"][-1] < 2.1
     ref = scalar.solve_fa(64)
     assert abs(r["e1"][5] / ref["e1"] - 1) < 1e-2 and abs(r["e0"][5] / ref["e0"] - 1) < 5e-2
+
+
+def test_bicgstab_choice_solves_the_scalar_newton_problem():
+    """linear_solver = 'bicgstab' (cm_bicgstab_solve: right-preconditioned BiCGStab + Jacobi on the node CSR) on the
+    scalar nonlinear problem of README.md:109-115: same Newton solution as the direct path, real iterations."""
+    from closestmolecule_b200.manufactured import u_exact
+    n = 32
+    sols = {}
+    for name in ("bicgstab", "mumps"):
+        mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
+        V = cm.FunctionSpace(mesh, "CG", 1)
+        u = cm.Function(V)
+        s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(
+            cm.ScalarADRForm.nonlinear_adr(V), u, [cm.DirichletBC(V, u_exact, "on_boundary")]))
+        s.parameters["newton_solver"]["linear_solver"] = name
+        s.parameters["newton_solver"]["absolute_tolerance"] = 1e-9
+        s.parameters["newton_solver"]["relative_tolerance"] = 1e-9
+        it, conv = s.solve()
+        assert conv
+        sols[name] = u.vector().cpu().numpy()
+        if name == "bicgstab":
+            assert type(s._linear).__name__ == "JacobiKrylovLinearSolver" and s._linear.method == "bicgstab"
+            assert all(k > 0 for k in s.linear_iterations) and s._linear.last_residual < 1e-10
+    assert np.linalg.norm(sols["bicgstab"] - sols["mumps"]) / np.linalg.norm(sols["mumps"]) < 1e-8
+    e1, e0 = scalar.errors(oracle_mesh(mesh), sols["bicgstab"], 4)
+    assert f"{e1:6.2e}" == "1.09e-01" and f"{e0:6.2e}" == "4.29e-04"
