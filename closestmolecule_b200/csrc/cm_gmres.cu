@@ -5,6 +5,7 @@
 // Replaces PETScLUSolver::solve inside NewtonSolver [ext] (advection_diffusion_convergence.py:212).
 #include <math.h>
 
+#include <utility>
 #include <vector>
 
 #include "cm_common.cuh"
@@ -194,12 +195,13 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
 // Right-preconditioned BiCGStab (van der Vorst) on the same fused vector kernels: the 'bicgstab' choice of
 // parameters['newton_solver']['linear_solver'] in DOLFIN.  x0 = 0.  Seven work vectors laid out with one
 // stride so that the fused multi-vector kernels can address pairs of them:
-//   0 rhat | 1 r (holds s between the two half steps) | 2 p | 3 v | 4 t | 5 y = M^-1 p | 6 z = M^-1 s
+//   0 rhat | 1 r (holds s between the two half steps) | 2 p | 3 v | 4 t | 5 y = M^-1 p | 6 z = M^-1 s | 7 p'
+// (p alternates between the slots 2 and 7 so that no kernel updates a vector in place through two pointers).
 // Three host synchronisations per iteration (alpha; omega; rho and ||r||).  One iteration = two operator and two
 // preconditioner applications.
 size_t bicgstab_workspace_doubles(long long n) {
   const long long ne = (n + 1) & ~1LL;
-  return (size_t)ne * 7 + 16 + (size_t)148 * 4 * 8 + 64;
+  return (size_t)ne * 8 + 16 + (size_t)148 * 4 * 8 + 64;
 }
 
 int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x, double rtol,
@@ -213,7 +215,8 @@ int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double*
   double* t = v + ne;
   double* y = t + ne;
   double* z = y + ne;
-  double* hdev = z + ne;  // 16 scalars
+  double* p2 = z + ne;
+  double* hdev = p2 + ne;  // 16 scalars
   double* scratch = hdev + 16;
   scratch = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
 
@@ -259,7 +262,8 @@ int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double*
     const double beta = (rho_new / rho) * (alpha / omega);
     rho = rho_new;
     // p = r + beta (p - omega v)
-    if ((rc = vec_scale(n, p, nullptr, beta, 0, p, st))) return rc;
+    if ((rc = vec_scale(n, p, nullptr, beta, 0, p2, st))) return rc;
+    std::swap(p, p2);
     hhost[1] = 1.0;
     hhost[2] = -beta * omega;
     if ((rc = put(1, 2))) return rc;
