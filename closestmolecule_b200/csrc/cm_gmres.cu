@@ -13,6 +13,25 @@
 
 namespace cm {
 
+// Pinned staging for the few scalars that cross the bus every iteration: allocated once per host thread and
+// grown on demand (cudaMallocHost / cudaFreeHost per solve would cost a device synchronisation each).
+static double* pinned_scalars(size_t n) {
+  thread_local double* buf = nullptr;
+  thread_local size_t cap = 0;
+  if (n > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = 0;
+    if (cudaMallocHost((void**)&buf, sizeof(double) * n) != cudaSuccess) {
+      cudaGetLastError();
+      buf = nullptr;
+      return nullptr;
+    }
+    cap = n;
+  }
+  return buf;
+}
+
 size_t gmres_workspace_doubles(long long n, int restart) {
   const long long ne = (n + 1) & ~1LL;  // even stride keeps double2 loads aligned
   return (size_t)ne * (restart + 1)     // Krylov basis
@@ -61,12 +80,11 @@ int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b,
   double* scratch = hdev + (restart + 4);
   scratch = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
 
-  double* hhost = nullptr;  // pinned staging for the Hessenberg column / coefficients
-  CM_CUDA(cudaMallocHost((void**)&hhost, sizeof(double) * (restart + 4)));
-  struct Guard {
-    double* p;
-    ~Guard() { cudaFreeHost(p); }
-  } guard{hhost};
+  double* hhost = pinned_scalars((size_t)restart + 4);  // staging for the Hessenberg column / coefficients
+  if (!hhost) {
+    set_error("gmres: cudaMallocHost failed");
+    return CM_E_CUDA;
+  }
 
   const int m = restart;
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), y(m);
@@ -220,12 +238,11 @@ int bicgstab_solve(long long n, const LinOp& A, const LinOp& Minv, const double*
   double* scratch = hdev + 16;
   scratch = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
 
-  double* hhost = nullptr;
-  CM_CUDA(cudaMallocHost((void**)&hhost, sizeof(double) * 16));
-  struct Guard {
-    double* p;
-    ~Guard() { cudaFreeHost(p); }
-  } guard{hhost};
+  double* hhost = pinned_scalars(16);
+  if (!hhost) {
+    set_error("bicgstab: cudaMallocHost failed");
+    return CM_E_CUDA;
+  }
   auto put = [&](int slot, int cnt) -> int {  // hhost[slot..slot+cnt) -> hdev (same slots)
     CM_CUDA(cudaMemcpyAsync(hdev + slot, hhost + slot, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
     return CM_OK;
