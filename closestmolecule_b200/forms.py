@@ -80,8 +80,9 @@ class PQPrimalForm:
 
     @classmethod
     def manufactured(cls, V, variant="galerkin", D1=1e-3, D2=1.5e-3, stab=None, sign=-1.0,
-                     c0ip_h="cell", degree=4, bdry=None, left=None, ext_terms=(), pen_stab2=0.0):
-        """P1 x P1 restatement of the manufactured MixedPrimal scripts (p_ex, q_ex of :48-49)."""
+                     c0ip_h="cell", degree=4, bdry=None, left=None, ext_terms=(), pen_stab2=0.0, r2dir=1.0):
+        """P1 x P1 restatement of the manufactured MixedPrimal scripts (p_ex, q_ex of :48-49).  r2dir = -1 (C0IP
+        only): r2vec = (-1,0) in the q-equation as in …_C0IP_otherBCs.py:58 (G keeps its direction, :46-47)."""
         from .manufactured import forcing_torch, q_exact
         if variant == "galerkin":     # …MixedPrimal_convergence.py:120-123
             gc = D2 * 4.0 * math.pi
@@ -93,11 +94,11 @@ class PQPrimalForm:
             return cls(V, D1, D2, G=("power", gc), forcing=f, q_react=1.0, q_x2p=0.0, q_x2q=1.0,
                        supg_stab=1.0 if stab is None else stab, degree=degree)
         if variant == "c0ip":         # …MixedPrimal_convergence_C0IP.py:141-147 / test_for_paper:140-153
-            f = forcing_torch(D1, D2, 1.0, q_react=0.0, x2_on_q=False)
+            f = forcing_torch(D1, D2, 1.0, q_react=0.0, x2_on_q=False, r2dir=r2dir)
             gamma = sign * (7.5e-4 if stab is None else stab) / (1.0 ** 3.5)   # k_q = 1 for CG1
-            return cls(V, D1, D2, G=("power", 1.0), forcing=f, q_adv=0.0, q_divr=1.0, q_ibp=1.0,
+            return cls(V, D1, D2, G=("power", 1.0), forcing=f, q_adv=0.0, q_divr=float(r2dir), q_ibp=float(r2dir),
                        c0ip_gamma=gamma, c0ip_h=c0ip_h, pen_stab2=pen_stab2, ext_terms=ext_terms,
-                       q_data=q_exact, degree=degree)
+                       q_data=q_exact, r2vec=(float(r2dir), 0.0), degree=degree)
         raise ValueError(variant)
 
 

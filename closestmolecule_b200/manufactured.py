@@ -29,9 +29,10 @@ def q_exact(x, y):
     return 1.5 + torch.cos(math.pi * x * y)
 
 
-def forcing_torch(D1, D2, gcoef, q_react=1.0, x2_on_q=False):
+def forcing_torch(D1, D2, gcoef, q_react=1.0, x2_on_q=False, r2dir=1.0):
     """(f2_ex, f3_ex) of …MixedPrimal_convergence.py:111-113: f2 = div_rad(D*sig_ex),
-    sig_ex = -grad(p_ex) - G(p_ex,q_ex) r2vec, f3 = q_react*q_ex + dq_ex/dx + x^2*(p_ex|q_ex)."""
+    sig_ex = -grad(p_ex) - G(p_ex,q_ex) (1,0), f3 = q_react*q_ex + grad(q_ex).r2vec + x^2*(p_ex|q_ex) with
+    r2vec = (r2dir, 0) (-1: …_C0IP_otherBCs.py:58,117)."""
     import sympy as sm
     xs, ys = sm.symbols("x y", positive=True)
     pe = sm.sin(sm.pi * xs) * sm.sin(sm.pi * ys)
@@ -40,7 +41,7 @@ def forcing_torch(D1, D2, gcoef, q_react=1.0, x2_on_q=False):
     sx = -sm.diff(pe, xs) - G
     sy = -sm.diff(pe, ys)
     f2 = sm.diff(xs ** 2 * D2 * sx, xs) / xs ** 2 + sm.diff(ys ** 2 * D1 * sy, ys) / ys ** 2
-    f3 = q_react * qe + sm.diff(qe, xs) + xs ** 2 * (qe if x2_on_q else pe)
+    f3 = q_react * qe + r2dir * sm.diff(qe, xs) + xs ** 2 * (qe if x2_on_q else pe)
     f2t, f3t = _torchify(f2, (xs, ys)), _torchify(f3, (xs, ys))
     return lambda x, y: (f2t(x, y), f3t(x, y))
 

@@ -224,11 +224,12 @@ def test_pq_supg_convergence_rates_on_gpu():
     assert max(max(l) for _, l in r["its"][3:]) <= 20
 
 
-@pytest.mark.parametrize("kind,n", [("minus", 32), ("minus", 64), ("paper", 32)])
+@pytest.mark.parametrize("kind,n", [("minus", 32), ("minus", 64), ("paper", 32), ("other", 32)])
 def test_newton_c0ip_matches_oracle(kind, n):
     """C0IP q-equation (13-point interior-facet pattern, constant facet operator) solved on the GPU:
-    …MixedPrimal_convergence_C0IP.py:141-147 (minus sign, strong q data at x=1) and the "paper"
-    variant test_for_paper_convergence.py:140-153 (plus sign, weak data, boundary penalty)."""
+    …MixedPrimal_convergence_C0IP.py:141-147 (minus sign, strong q data at x=1), the "paper"
+    variant test_for_paper_convergence.py:140-153 (plus sign, weak data, boundary penalty) and
+    …_C0IP_otherBCs.py:55-60,131-134 (r2vec = (-1,0), plus sign, D1 = 2, D2 = 1.5; direct solve)."""
     from closestmolecule_b200.manufactured import p_exact, q_exact
     from util import np_qdata, oracle_ext
     mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), n, n)
@@ -241,6 +242,11 @@ def test_newton_c0ip_matches_oracle(kind, n):
         form = cm.PQPrimalForm.manufactured(V, "c0ip", D1=0.01, D2=0.015, stab=0.05, sign=-1.0,
                                             ext_terms=[(mf, 30, cm.EF_ADV)])
         bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, mf, 31)]
+    elif kind == "other":
+        form = cm.PQPrimalForm.manufactured(V, "c0ip", D1=2.0, D2=1.5, stab=7.5e-3, sign=+1.0, r2dir=-1.0,
+                                            ext_terms=[(mf, 30, cm.EF_ADV)])
+        assert (form.params.q_divr, form.params.q_ibp, form.params.r2x) == (-1.0, -1.0, -1.0)
+        bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, mf, 31)]
     else:
         form = cm.PQPrimalForm.manufactured(
             V, "c0ip", D1=1.0, D2=1.5, stab=0.05, sign=+1.0, c0ip_h="facet", degree=6, pen_stab2=1.0,
@@ -252,6 +258,8 @@ def test_newton_c0ip_matches_oracle(kind, n):
     s.parameters["newton_solver"]["absolute_tolerance"] = 1e-8
     s.parameters["newton_solver"]["relative_tolerance"] = 1e-8
     s.parameters["newton_solver"]["krylov_solver"]["restart"] = 120
+    if kind == "other":
+        s.parameters["newton_solver"]["linear_solver"] = "mumps"
     it, conv = s.solve()
     om = oracle_mesh(mesh)
     ef, ek = oracle_ext(form, om)
