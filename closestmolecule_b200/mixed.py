@@ -788,14 +788,15 @@ class PureAdvectionCG2:
 
     STAB = {"supg": 0.1, "c0ip": 0.005}
 
-    def __init__(self, mesh, bdry, kind, stab=None):
+    def __init__(self, mesh, bdry, kind, stab=None, tables_only=False):
+        """tables_only: host tables (pattern of the q-q block, boundary dofs) without touching the GPU -- CPU tests."""
         if kind not in self.STAB:
             raise ValueError(f"unknown kind '{kind}'")
         self.kind = kind
         self.stab = stab = self.STAB[kind] if stab is None else float(stab)
         self.sys = S = PaperMixedSystemK1(mesh, bdry, D1=1e-3, D2=1.5e-3, stab=stab if kind == "c0ip" else 0.0,
                                           stab2=0.0, degree=4, variant="pure_" + kind,
-                                          supg_stab=stab if kind == "supg" else 0.0)
+                                          supg_stab=stab if kind == "supg" else 0.0, tables_only=tables_only)
         dev = mesh.device
         self.N = N = S.V + S.E
         rows = torch.repeat_interleave(torch.arange(S.N, device=dev), torch.diff(S.rowptr.long()))

@@ -57,3 +57,36 @@ def test_scalar_matrix_is_the_qq_block_of_the_mixed_element_tensors(kind):
     assert abs(Jqq - A).max() < 1e-12 * abs(A).max()
     if kind == "supg":          # same forcing q_ex + dq_ex/dx + r2^2 q_ex
         assert np.abs(-F0[O.q0:] - b).max() < 1e-12 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("kind", ["supg", "c0ip"])
+def test_host_tables_of_the_gpu_port_match_the_oracle_pattern(kind):
+    """PureAdvectionCG2 cuts the q-q block out of the RT2 x DG1 x CG2 pattern: its CSR pattern must contain the scalar
+    oracle's matrix pattern, diag_slot must point at the diagonal INSIDE each row (what cm_apply_dirichlet expects),
+    and the boundary dofs / values must be the oracle's."""
+    import torch
+    import closestmolecule_b200 as cm
+    from closestmolecule_b200.mixed import PureAdvectionCG2
+    n = 4
+    mesh = cm.UnitSquareMesh(n, n, device="cpu")
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    cm.CompiledSubDomain("near(x[0],1) && on_boundary").mark(bd, 32)
+    cm.CompiledSubDomain("(near(x[1],0) || near(x[1],1)) && on_boundary").mark(bd, 33)
+    S = PureAdvectionCG2(mesh, bd, kind, tables_only=True)
+    O = pa.PureAdvection(n, kind)
+    assert S.N == O.N
+    rp, col = S.rowptr.numpy().astype(np.int64), S.col.numpy().astype(np.int64)
+    assert rp[0] == 0 and rp[-1] == col.size and np.all(np.diff(rp) > 0)
+    rows = np.repeat(np.arange(S.N), np.diff(rp))
+    assert np.all(np.diff(rows * S.N + col) > 0)                         # sorted, unique
+    ds = S.diag_slot.numpy().astype(np.int64)
+    assert np.array_equal(col[rp[:-1] + ds], np.arange(S.N))
+    A, _ = O.assemble()
+    A = A.tocoo()
+    have = set((rows * S.N + col).tolist())
+    nz = np.abs(A.data) > 0
+    assert set((A.row[nz].astype(np.int64) * S.N + A.col[nz]).tolist()) <= have
+    d, g = O.bcs()
+    assert np.array_equal(S.bc_dofs.numpy(), d) and np.allclose(S.bc_vals.numpy(), g, rtol=0, atol=1e-15)
+    assert np.array_equal(S.bc_diag.numpy(), ds[d])
