@@ -827,8 +827,12 @@ class PureAdvectionCG2:
         """(values of the CG2 matrix on (rowptr, col), right-hand side) before the boundary condition."""
         S = self.sys
         vals, F0 = S.assemble(torch.zeros(S.N, dtype=torch.float64, device=S.mesh.device), True)
-        self.vals = vals[self.slots].contiguous()
-        self.b = (-F0[S.q0:]).contiguous()        # residual at q = 0 is -rhs
+        if getattr(self, "vals", None) is None:   # persistent buffers: the LU holder keeps pointing at them
+            self.vals = vals[self.slots].contiguous()
+            self.b = (-F0[S.q0:]).contiguous()    # residual at q = 0 is -rhs
+        else:
+            self.vals.copy_(vals[self.slots])
+            self.b.copy_(-F0[S.q0:])
         return self.vals, self.b
 
     def solve(self):
