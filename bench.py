@@ -83,12 +83,19 @@ def cpu_newton_step_sample(nx, ny, repeats=1):
     return best
 
 
+REF_NX, REF_NY = 512, 256          # bounded sample of the reference arm / cpu_baseline leg
+
+
 def reference_arm(args):
-    """--impl reference: the reference's CPU path (FEniCS-equivalent restatement, FEniCS itself is
-    not installable here) timed on this box's host cores; rank 0 only."""
+    """--impl reference: the reference's CPU path (FEniCS-equivalent restatement: serial C cell loop + SuperLU;
+    FEniCS itself is not installable here) timed on this box's host cores; rank 0 only.  Each step is a BOUNDED
+    SAMPLE of the workload: the same Newton step on RectangleMesh 512x256 (a direct sparse LU of the 16 Mi-cell
+    Jacobian neither fits nor finishes on the host).  The line says so: `config` names the mesh that ran,
+    `same_config` is false, and the measured growth exponent of the CPU step time brackets what the per-cell
+    ratio means at the full size."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    nx, ny = 512, 256
+    nx, ny = REF_NX, REF_NY
     for _ in range(args.warmup):
         cpu_newton_step_sample(nx, ny)
     t = []
@@ -98,13 +105,18 @@ def reference_arm(args):
         t.append(rec["total"])
     ms = 1e3 * float(np.mean(t))
     val = rec["cells"] / (ms * 1e-3)
+    small = cpu_newton_step_sample(nx // 2, ny // 2)
+    growth = float(np.log(float(np.mean(t)) / small["total"]) / np.log(4.0))
     sample = (f"one Newton step (C serial cell assembly + SuperLU + residual) on RectangleMesh {nx}x{ny} "
-              f"= {rec['cells']} cells; assemble {rec['assemble']:.2f}s lu {rec['lu']:.2f}s")
+              f"= {rec['cells']} cells; assemble {rec['assemble']:.2f}s lu {rec['lu']:.2f}s; step time grows like "
+              f"cells^{growth:.2f} ({nx // 2}x{ny // 2} -> {nx}x{ny}, this run; 1.64 from 512x256 to 1024x512, "
+              f"profiles/README.md), i.e. cells/s FALLS with the mesh size")
+    cfg = reference_config(args, nx, ny, growth)
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 4096, 2048),
+        "config": cfg, "same_config": False,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -112,30 +124,49 @@ def reference_arm(args):
     print(json.dumps(out))
 
 
+def reference_config(args, nx, ny, growth=None):
+    full_nx = args.nx
+    cfg = {"workload": f"BOUNDED SAMPLE of the P-Q CG1xCG1 manufactured SUPG Newton step: RectangleMesh {nx}x{ny} "
+                       f"({2 * nx * ny} cells) instead of {full_nx}x{full_nx // 2} ({full_nx * full_nx} cells); "
+                       "cells/s of the sample, NOT of the full mesh",
+           "nx": nx, "ny": ny, "cells": 2 * nx * ny, "dofs": 2 * (nx + 1) * (ny + 1),
+           "full_workload": {"nx": full_nx, "ny": full_nx // 2, "cells": full_nx * full_nx},
+           "parallelism": "1 host core (DOLFIN assembles serially; SuperLU is sequential)",
+           "linear_solver": "sparse LU (scipy SuperLU, standing in for MUMPS/UMFPACK), one factorisation per step",
+           "linear_rtol": None, "same_config_as_gpu_arm": False}
+    if growth is not None:
+        cfg["cpu_step_time_growth_exponent"] = growth
+    return cfg
+
+
 METRIC = "cells/s through one Newton step (assemble J+F, BCs, linear solve, update, residual)"
 UNIT = "cells/s"
 
 
 def workload_config(args, nx, ny):
-    if getattr(args, "weak", False) and args.gpus > 1:
-        return {"workload": f"P-Q CG1xCG1 manufactured {getattr(args, 'variant', 'supg').upper()} Newton step on ONE "
-                            f"RectangleMesh {nx}x{ny} ({2 * nx * ny} cells) strip-partitioned over {args.gpus} GPUs "
-                            f"({2 * nx * ny // args.gpus} cells per GPU: weak scaling)",
-                "nx": nx, "ny": ny, "cells": 2 * nx * ny, "cells_per_gpu": 2 * nx * ny // args.gpus,
-                "parallelism": "one mesh strip-partitioned by vertex rows (P2P halo / all-gather / all-reduce kernels over NVLink)",
-                "l2_policy": "inputs larger than L2", "linear_rtol": LIN_RTOL}
-    return {"workload": f"P-Q CG1xCG1 manufactured {getattr(args, 'variant', 'supg').upper()} Newton step on RectangleMesh {nx}x{ny} "
-                        f"({2 * nx * ny} cells) per GPU",
-            "nx": nx, "ny": ny, "cells_per_gpu": 2 * nx * ny, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
-            "parallelism": (f"independent problem instance per GPU x{args.gpus}" if getattr(args, "instances", False)
-                            or args.gpus == 1 else f"one mesh strip-partitioned by vertex rows over {args.gpus} GPUs "
-                            "(P2P halo / all-gather / all-reduce kernels over NVLink)"),
+    gpus = max(1, args.gpus)
+    cells = 2 * nx * ny
+    variant = getattr(args, "variant", "supg").upper()
+    solver = ("pivoting banded LU (cm_blu_*) + 1 refinement step" if getattr(args, "linear_solver", "gmres") == "lu"
+              else f"GMRES({RESTART}) + field split + V(1,2) multigrid / zebra line relaxation")
+    if gpus > 1 and not getattr(args, "instances", False):
+        kind = "weak scaling: the mesh grows with the GPUs" if getattr(args, "weak", False) else "strong scaling"
+        return {"workload": f"P-Q CG1xCG1 manufactured {variant} Newton step on ONE RectangleMesh {nx}x{ny} "
+                            f"({cells} cells) strip-partitioned over {gpus} GPUs ({cells // gpus} cells each; {kind})",
+                "nx": nx, "ny": ny, "cells": cells, "cells_per_gpu": cells // gpus,
+                "dofs": 2 * (nx + 1) * (ny + 1), "dofs_per_gpu": 2 * (nx + 1) * (ny + 1) // gpus,
+                "parallelism": f"one mesh strip-partitioned by vertex rows over {gpus} GPUs (boundary rows pushed over "
+                               "NVLink by the producing kernels, P2P all-gather / all-reduce kernels)",
+                "l2_policy": "inputs larger than L2", "linear_solver": solver, "linear_rtol": LIN_RTOL}
+    return {"workload": f"P-Q CG1xCG1 manufactured {variant} Newton step on RectangleMesh {nx}x{ny} "
+                        f"({cells} cells)" + (f", one independent instance per GPU x{gpus}" if gpus > 1 else ""),
+            "nx": nx, "ny": ny, "cells": cells * gpus, "cells_per_gpu": cells, "dofs_per_gpu": 2 * (nx + 1) * (ny + 1),
+            "parallelism": (f"independent problem instance per GPU x{gpus}" if gpus > 1 else "single GPU"),
             "l2_policy": "inputs larger than L2 (Jacobian 1.9 GB, Krylov basis > 1 GB)",
-            "linear_solver": ("pivoting banded LU (cm_blu_*) + 1 refinement step" if getattr(args, "linear_solver", "gmres") == "lu"
-                              else "GMRES(40) + field split + V(1,2) multigrid / zebra line relaxation"),
-            "linear_rtol": LIN_RTOL}
+            "linear_solver": solver, "linear_rtol": LIN_RTOL}
 
 
+RESTART = 40
 LIN_RTOL = 1e-10
 
 
@@ -248,7 +279,7 @@ def gpu_arm(args):
     X = mesh.coords
     if strong:
         from closestmolecule_b200.multigpu import DistributedPQNewton
-        solver = DistributedPQNewton(form, bcs, restart=40, rtol_lin=LIN_RTOL)
+        solver = DistributedPQNewton(form, bcs, restart=RESTART, rtol_lin=LIN_RTOL)
         uvec = solver.u
         own = solver.own
     else:
@@ -311,7 +342,7 @@ def gpu_arm(args):
     import ctypes as _C
     prof = {}
     prof_steps = 1 if args.steps > 1 else args.steps
-    for cls, name in ((0, "zebra_line_kernel (fine grid)"), (1, "pq_stencil_spmv_kernel"), (2, "pq_sweep_kernel (J+F)")):
+    for cls, name in ((0, ROOF_KERNEL), (1, "pq_stencil_spmv_kernel"), (2, "pq_sweep_kernel (J+F)")):
         n_, ms_, by_ = _C.c_int64(0), _C.c_double(0.0), _C.c_double(0.0)
         lib.cm_profile_report(cls, _C.byref(n_), _C.byref(ms_), _C.byref(by_))
         if n_.value:
@@ -354,6 +385,63 @@ def gpu_arm(args):
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
     e2e_parts = [float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i in range(3)]
 
+    # ---- parity (untimed): the answer of the timed path against an independent solve -----------------------
+    def lin_info():
+        try:
+            return solver.info() if strong else solver._linear.info()
+        except Exception as e:      # LU path etc.
+            return {"note": type(e).__name__}
+
+    def one_step_solution(kind, mesh_, form_, bcs_, u_init):
+        uu = cm.Function(form_.space)
+        sv = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form_, uu, bcs_))
+        sv.parameters["newton_solver"]["linear_solver"] = kind
+        sv.parameters["newton_solver"]["krylov_solver"]["relative_tolerance"] = LIN_RTOL
+        uu.vector().copy_(u_init)
+        sv.newton_step(compute_residual=False)
+        return uu.vector().clone(), (sv.linear_iterations[-1] if sv.linear_iterations else None)
+
+    parity = None
+    if args.variant == "supg" and args.linear_solver == "gmres" and not args.no_parity:
+        if strong:
+            # the strip-partitioned Newton step against the single-GPU Newton step from the same state (rank 0)
+            step()
+            u_dist = solver.gather_solution().clone()
+            if rank == 0:
+                u_one, its_one = one_step_solution("gmres", mesh, form, bcs, u0)
+                parity = {"what": f"state after one Newton step, {world} GPUs (strip-partitioned) vs 1 GPU, same mesh",
+                          "rel_l2_vs_n1": float(torch.linalg.vector_norm(u_dist - u_one) / torch.linalg.vector_norm(u_one)),
+                          "gmres_its": int(solver.linear_iterations[-1]), "gmres_its_n1": its_one}
+                del u_one
+            barrier()
+        elif world == 1:
+            # the multigrid-Krylov Newton step against the pivoting direct solve (cm_blu_*) on the largest mesh whose
+            # factors fit comfortably: same form, same state, 512x256
+            pm = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), REF_NX, REF_NY, device=dev)
+            pV = cm.FunctionSpace(pm, cm.MixedElement([P1, P1]))
+            pbd = cm.MeshFunction("size_t", pm, 1, 0)
+            cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(pbd, 31)
+            pform = cm.PQPrimalForm.manufactured(pV, "supg")
+            pbcs = [cm.DirichletBC(pV.sub(0), p_exact, "on_boundary"), cm.DirichletBC(pV.sub(1), q_exact, pbd, 31)]
+            pu0 = torch.empty(2 * pm.num_vertices(), dtype=torch.float64, device=dev)
+            pu0[0::2] = p_exact(pm.coords[:, 0], pm.coords[:, 1])
+            pu0[1::2] = q_exact(pm.coords[:, 0], pm.coords[:, 1])
+            uk, its_k = one_step_solution("gmres", pm, pform, pbcs, pu0)
+            ud, _ = one_step_solution("mumps", pm, pform, pbcs, pu0)
+            du = torch.linalg.vector_norm(ud - pu0)
+            parity = {"what": f"Newton update of the GMRES+multigrid path vs the pivoting direct LU (cm_blu_*), "
+                              f"RectangleMesh {REF_NX}x{REF_NY}, same state",
+                      "rel_l2_state": float(torch.linalg.vector_norm(uk - ud) / torch.linalg.vector_norm(ud)),
+                      "rel_l2_update": float(torch.linalg.vector_norm(uk - ud) / du) if float(du) > 0 else None,
+                      "gmres_its": its_k}
+            del uk, ud
+
+    zk0 = prof.get(ROOF_KERNEL)
+    prof_mix = 0.2
+    if zk0:
+        unit = 0.5 * (nx + 1) * (ny + 1)
+        prof_mix = float(min(1.0, max(0.0, (80.0 - zk0["algorithmic_bytes_per_launch"] / unit) / 40.0)))
+
     tt = torch.tensor([ms_step, e2e_ms, asm_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -368,7 +456,10 @@ def gpu_arm(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         bytes_asm = 12 * cells + 16 * Vn + 8 * (2 * Vn) + 8 * (4 * nnz) + 8 * (2 * Vn)
-        zk = prof.get("zebra_line_kernel (fine grid)")
+        bytes_asm_rank = bytes_asm / (world if strong else 1)      # every rank assembles its own rows
+        zk = prof.get(ROOF_KERNEL)
+        traffic = ncu_traffic(prof_mix) if (zk and world == 1) else None
+        solver_info = lin_info()
         out = {
             "metric": METRIC, "value": (1 if strong else world) * cells / (ms_step * 1e-3), "unit": UNIT,
             "n_gpus": world,
@@ -386,24 +477,30 @@ def gpu_arm(args):
                     "note": "bytes per rank" if world > 1 else "whole state vector"},
             "gpu_launches": launches,
             "clocks": clocks,
-            # dominant kernel of the step by time share (profiles/): the zebra x-line relaxation on the
-            # finest grid; durations from CUDA events on the launching stream inside the timed region
-            "roofline": {"kernel": "zebra_line_kernel (x-line relaxation, finest grid)", "bound": "hbm",
+            "solver": solver_info,
+            # dominant kernel of the step by time share (profiles/): the fused zebra half sweep (couplings +
+            # x-line solves) on the finest grid, p- and q-block launches; durations from CUDA events on the launching
+            # stream inside the timed region (first timed step); reported on one GPU only
+            "roofline": {"kernel": "zebra_ring_kernel (fused zebra half sweep, finest grid)", "bound": "hbm",
                          "achieved": zk["gbs"] if zk else None, "peak": peak, "unit": "GB/s",
                          "frac": (zk["gbs"] / peak) if zk else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": zk["algorithmic_bytes_per_launch"] if zk else None,
+                         "algorithmic_bytes_per_vertex": "80 with couplings (b, 4 off-line diagonals, 3 factors, the "
+                                                         "neighbour lines of x once, x out), 40 from a zero guess",
                          "avg_launch_us": zk["avg_us"] if zk else None,
                          "share_of_step": (zk["ms_per_step"] / ms_step) if zk else None,
-                         "traffic": TRAFFIC_NCU},
+                         "traffic": traffic["bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None},
             # whole Newton step: algorithmic bytes of every kernel launched by the library in the step
             # (each array once per pass; per rank) over the step time and the measured HBM peak
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "gbs": step_bytes / (ms_step * 1e-3) / 1e9,
                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "peak": peak,
-                              "gmres_iterations": lin_its},
-            "kernels": {**prof, "pq_sweep_kernel roofline frac": (bytes_asm / (asm_ms * 1e-3) / 1e9) / peak},
+                              "gmres_iterations": lin_its, "note": "per rank" if world > 1 else "whole job"},
+            "kernels": {**prof, "pq_sweep_kernel roofline frac (per rank)": (bytes_asm_rank / (asm_ms * 1e-3) / 1e9) / peak},
+            "parity": parity,
         }
         if world == 1 and not args.no_cpu:
-            nxs, nys = 512, 256
+            nxs, nys = REF_NX, REF_NY
             rec = cpu_newton_step_sample(nxs, nys)
             out["cpu_baseline"] = {
                 "value": rec["cells"] / rec["total"], "unit": UNIT, "cores": 1, "kind": "port",
@@ -417,10 +514,25 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-# dram bytes per launch of the roofline kernel from the committed `ncu --set full` capture
-# (profiles/); None until one exists for the current kernel
-TRAFFIC_NCU = 239.7e6  # mean dram read+write of the two fine-grid launch types (150.5 MB zero-guess, 328.9 MB
-# with coupling; ncu --set full, profiles/README.md) -- equal to the algorithmic bytes: no wasted re-reads
+ROOF_KERNEL = "zebra_ring_kernel (fine grid)"
+NCU_CSV = os.path.join(ROOT, "profiles", "ncu_metrics_r2.csv")
+
+
+def ncu_traffic(mix):
+    """dram read + write bytes per launch of the roofline kernel from the committed `ncu --set full` export
+    (profiles/ncu_metrics_r2.csv, written by tools/ncu_export.py from the .ncu-rep of the same kernels), weighted
+    by the launch mix of this run (mix = fraction of zero-guess launches).  None when no capture is committed."""
+    import csv
+    if not os.path.exists(NCU_CSV):
+        return None
+    rows = {}
+    for r in csv.DictReader(open(NCU_CSV)):
+        if r.get("class") in ("zebra_fine_coupled", "zebra_fine_zero"):
+            rows[r["class"]] = float(r["dram_read_bytes"]) + float(r["dram_write_bytes"])
+    if len(rows) != 2:
+        return None
+    return {"bytes_per_launch": mix * rows["zebra_fine_zero"] + (1.0 - mix) * rows["zebra_fine_coupled"],
+            "source": f"profiles/ncu_metrics_r2.csv (ncu --set full), {mix:.2f} zero-guess / {1 - mix:.2f} coupled launches"}
 
 
 def main():
@@ -431,6 +543,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096, help="mesh is nx x nx/2 (default: the 16 Mi-cell mesh)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) parity check after the timed region")
     ap.add_argument("--linear-solver", default="gmres", choices=["gmres", "lu"],
                     help="gmres: multigrid-preconditioned Krylov path (default, the 16 Mi-cell hot path); "
                          "lu: pivoting banded LU on the GPU (needed by --variant galerkin)")

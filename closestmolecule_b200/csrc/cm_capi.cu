@@ -3,6 +3,8 @@
 
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
+#include "cm_halo.cuh"
+#include "cm_mg.cuh"
 
 namespace cm {
 static thread_local char g_err[512] = "";
@@ -300,6 +302,61 @@ void* cm_ipc_open(const void* handle64_host) {
 int cm_ipc_close(void* p) {
   CM_CUDA(cudaIpcCloseMemHandle(p));
   return CM_OK;
+}
+
+void* cm_pqs_create(int32_t nx, int32_t ny, int32_t restart, void* workspace, int64_t workspace_bytes,
+                    const cm_dist* D) {
+  if (nx < 2 || ny < 2 || restart < 1 || workspace == nullptr) {
+    set_error("cm_pqs_create: bad grid, restart or workspace");
+    return nullptr;
+  }
+  if (D != nullptr && !(D->world >= 1 && D->world <= 8 && D->rank >= 0 && D->rank < D->world)) {
+    set_error("cm_pqs_create: bad rank/world");
+    return nullptr;
+  }
+  return pqs_create(nx, ny, restart, workspace, (size_t)workspace_bytes, D);
+}
+
+int cm_pqs_destroy(void* ctx) { return ctx ? pqs_destroy(ctx) : CM_OK; }
+
+int cm_pqs_ctx_setup(void* ctx, const int32_t* nrowptr, const int32_t* ncol, const double* vals, void* stream) {
+  CM_CHECK_ARG(ctx && nrowptr && ncol && vals, "null pointer");
+  return pqs_ctx_setup(ctx, nrowptr, ncol, vals, (cudaStream_t)stream);
+}
+
+int cm_pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double atol, int32_t maxit,
+                     int32_t* iters_host, double* resid_host, void* stream) {
+  CM_CHECK_ARG(ctx && b && x && maxit >= 1, "null pointer or bad maxit");
+  int it = 0;
+  double rr = 0.0;
+  const int rc = pqs_ctx_solve(ctx, b, x, rtol, atol, maxit, &it, &rr, (cudaStream_t)stream);
+  if (iters_host) *iters_host = it;
+  if (resid_host) *resid_host = rr;
+  return rc;
+}
+
+int cm_pqs_ctx_info(void* ctx, int32_t* out8) {
+  CM_CHECK_ARG(ctx && out8, "null pointer");
+  return pqs_ctx_info(ctx, out8);
+}
+
+int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
+                const double* cu, const double* b, double* x, int32_t x_is_zero, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && (colour == 0 || colour == 1), "bad grid or colour");
+  CM_CHECK_ARG(A && lf && iu && cu && b && x, "null pointer");
+  return mg_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, Halo{}, 0, -1, (cudaStream_t)stream);
+}
+
+int cm_mg_resid_restrict(int32_t nxf, int32_t nyf, const double* A, const double* b, const double* x,
+                         double* rc, void* stream) {
+  CM_CHECK_ARG(nxf >= 2 && nyf >= 2 && !(nxf & 1) && !(nyf & 1), "fine grid must have even nx, ny");
+  CM_CHECK_ARG(A && b && x && rc, "null pointer");
+  return mg_resid_restrict(nxf, nyf, A, b, x, rc, Halo{}, 0, -1, (cudaStream_t)stream);
+}
+
+int cm_mg_prolong_odd(int32_t nxc, int32_t nyc, const double* ec, double* xf, void* stream) {
+  CM_CHECK_ARG(nxc >= 1 && nyc >= 1 && ec && xf, "bad argument");
+  return mg_prolong_odd(nxc, nyc, ec, xf, Halo{}, 0, 0, -1, (cudaStream_t)stream);
 }
 
 int64_t cm_pqs_state_offset(int32_t nx, int32_t ny, int32_t restart) {

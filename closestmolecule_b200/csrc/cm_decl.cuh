@@ -3,6 +3,10 @@
 #include "cm_common.cuh"
 
 namespace cm {
+struct Halo;
+}
+
+namespace cm {
 
 int assemble_pq_rows(const cm_pq_params& P, int nv, const int* cells, const double* coords,
                      const int* v2c_ptr, const int* v2c_ent, const int* v2c_slot,
@@ -65,6 +69,29 @@ int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, in
                    cudaStream_t st);
 int dist_allreduce(cm_dist* D, double* vals, int n, cudaStream_t st);
 
+// cm_gmres_dev.cu: device-resident GMRES state (all pointers into the caller's workspace)
+constexpr int kGmresStatus = 8;
+enum GmresStatusSlot { kStJ = 0, kStIts = 1, kStConv = 2, kStResid = 3, kStTarget = 4, kStBnorm = 5,
+                       kStFlag = 6, kStK = 7 };
+struct GmresDev {
+  long long n, ne;
+  int m;
+  double *V, *w, *z;
+  double *dots, *coef, *vscale, *nrm, *H, *cs, *sn, *g, *y, *st;
+  double* partial;
+  unsigned* tickets;
+};
+size_t gmres_dev_doubles(long long n, int m);
+void gmres_dev_layout(GmresDev& G, long long n, int m, double* work);
+int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st);
+int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
+int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
+int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st);
+int gmres_dev_solve_y(const GmresDev& G, cudaStream_t st);
+int gmres_dev_combine(const GmresDev& G, const VecSlice* sl, double* out, int khost, cudaStream_t st);
+int gmres_dev_axpby(const GmresDev& G, const VecSlice* sl, double alpha, const double* x, double beta, double* y,
+                    cudaStream_t st);
+
 // cm_gmres.cu
 size_t gmres_workspace_doubles(long long n, int restart);
 int gmres_solve(long long n, const LinOp& A, const LinOp& Minv, const double* b, double* x,
@@ -89,7 +116,9 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb =
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
                cudaStream_t st, int r0 = 0, int r1 = -1, const double* QQx = nullptr,
-               const int* has_extra = nullptr);
+               const int* has_extra = nullptr, const struct Halo* H = nullptr);
+int st_unscale_dev(int nx, int ny, const double* rbase, long long stride, const double* jptr, const double* vscale,
+                   const double* sp, const double* sq, double* out, cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,
                cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_residual(int nx, int ny, const double* A, const double* b, const double* x, double* r,
@@ -119,7 +148,14 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
               int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
-                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st);
+                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st,
+                   int Ld_forced = -1);
+void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const cm_dist* D);
+int pqs_destroy(void* ctx);
+int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st);
+int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double atol, int maxit, int* iters,
+                  double* resid, cudaStream_t st);
+int pqs_ctx_info(void* ctx, int* out8);
 int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
                    int maxit, void* ws, size_t ws_bytes, cm_dist* D, int* iters, double* resid,
                    cudaStream_t st);

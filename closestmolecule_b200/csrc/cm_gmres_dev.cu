@@ -1,0 +1,393 @@
+// Device-resident restarted GMRES (right preconditioning, classical Gram-Schmidt) for the structured P-Q
+// solver: the Hessenberg column, the Givens rotations, the residual estimate and the iteration counter live
+// on the GPU, so that ONE GMRES iteration is a fixed sequence of kernels without changing arguments (it is
+// captured once as a CUDA graph and replayed, cm_pqsolver.cu):
+//   dot kernel      h_i = <v_i, w> (i <= j) in one pass over w; per-CTA partials, the last CTA to finish
+//                   adds them up in a fixed order (deterministic, no second launch)
+//   [all-reduce]    multi-GPU: one push-and-sum launch for the j+1 numbers (cm_dist.cu)
+//   update kernel   w' = w - sum h_i v_i stored as the NEXT basis vector without normalising it, and
+//                   ||w'||^2 accumulated in the same pass (exact norm of the orthogonalised vector: with a
+//                   multigrid preconditioner A M^-1 = I + small, so ||w'|| << ||w|| and the Pythagorean
+//                   shortcut <w,w> - sum h_i^2 loses every digit)
+//   [all-reduce]    multi-GPU: one number
+//   givens kernel   one thread: h_{j+1,j} = ||w'||, the scale 1/h_{j+1,j} of the new basis vector (applied
+//                   lazily by every kernel that reads the basis: no extra pass to normalise it), Givens
+//                   rotations, residual estimate, convergence flag, j <- j+1
+// The host reads a 64-byte status block per iteration (convergence test) -- nothing else crosses the bus.
+// Replaces PETScLUSolver::solve inside NewtonSolver [ext] (advection_diffusion_convergence.py:212).
+#include <math.h>
+
+#include "cm_common.cuh"
+#include "cm_decl.cuh"
+
+namespace cm {
+
+constexpr int kGB = 256;
+constexpr int kGGrid = 148 * 4;
+constexpr int kGK = 8;   // dot products per pass over w
+
+size_t gmres_dev_doubles(long long n, int m) {
+  const long long ne = (n + 1) & ~1LL;
+  const size_t ngroups = (size_t)(m + 2 + kGK - 1) / kGK;
+  return (size_t)ne * (m + 1) + (size_t)ne * 2        // basis, w, z
+         + 3 * (size_t)(m + 2) + 4                    // dots, coef, vscale, nrm
+         + (size_t)(m + 1) * m + 2 * (size_t)m + (size_t)(m + 1) + (size_t)m   // H, cs, sn, g, y
+         + kGmresStatus + 8                           // status, tickets
+         + ngroups * kGGrid * kGK + 64;               // reduction scratch
+}
+
+void gmres_dev_layout(GmresDev& G, long long n, int m, double* work) {
+  const long long ne = (n + 1) & ~1LL;
+  G.n = n;
+  G.ne = ne;
+  G.m = m;
+  double* p = work;
+  G.V = p; p += (size_t)ne * (m + 1);
+  G.w = p; p += ne;
+  G.z = p; p += ne;
+  G.dots = p; p += m + 2;
+  G.coef = p; p += m + 2;
+  G.vscale = p; p += m + 2;
+  G.nrm = p; p += 4;
+  G.H = p; p += (size_t)(m + 1) * m;
+  G.cs = p; p += m;
+  G.sn = p; p += m;
+  G.g = p; p += m + 1;
+  G.y = p; p += m;
+  G.st = p; p += kGmresStatus;
+  G.tickets = reinterpret_cast<unsigned*>(p); p += 8;
+  p = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+  G.partial = p;
+}
+
+__device__ __forceinline__ double gd_block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+// the vector is [0, n) (sl.len == 0) or the union of two index ranges (strip-partitioned rank)
+__device__ __forceinline__ long long gd_index(long long i, const VecSlice s) {
+  return i < s.len ? s.off0 + i : s.off1 + (i - s.len);
+}
+
+// dots[k] = vscale[k] <V_k, w> for k <= j (V_k holds the unnormalised basis vector);  j = st[0]
+template <bool SLICE>
+__global__ void __launch_bounds__(kGB)
+gd_dot_kernel(const GmresDev G, const VecSlice sl) {
+  __shared__ double sh[32];
+  __shared__ bool s_last;
+  const int j = (int)G.st[kStJ];
+  const int nvec = j + 1;   // V_0..V_j
+  const int ngroups = (nvec + kGK - 1) / kGK;
+  const double* __restrict__ w = G.w;
+  for (int grp = 0; grp < ngroups; ++grp) {
+    const int k0 = grp * kGK;
+    const double* vp[kGK];
+#pragma unroll
+    for (int k = 0; k < kGK; ++k) {
+      const int kk = k0 + k;
+      vp[k] = kk <= j ? G.V + (size_t)kk * G.ne : nullptr;
+    }
+    double acc[kGK];
+#pragma unroll
+    for (int k = 0; k < kGK; ++k) acc[k] = 0.0;
+    if (SLICE) {
+      const long long n = 2 * sl.len;
+      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
+        const long long q = gd_index(i, sl);
+        const double ww = w[q];
+#pragma unroll
+        for (int k = 0; k < kGK; ++k)
+          if (vp[k] != nullptr) acc[k] += vp[k][q] * ww;
+      }
+    } else {
+      const long long n2 = G.n >> 1;
+      const double2* w2 = reinterpret_cast<const double2*>(w);
+      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n2; i += (long long)gridDim.x * kGB) {
+        const double2 ww = w2[i];
+#pragma unroll
+        for (int k = 0; k < kGK; ++k)
+          if (vp[k] != nullptr) {
+            const double2 vv = reinterpret_cast<const double2*>(vp[k])[i];
+            acc[k] += vv.x * ww.x + vv.y * ww.y;
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGK; ++k) {
+      const double s = gd_block_sum(acc[k], sh);
+      if (threadIdx.x == 0) G.partial[((size_t)grp * gridDim.x + blockIdx.x) * kGK + k] = s;
+    }
+  }
+  // the last CTA to finish adds the partials up in CTA order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(G.tickets + 0, 1u);
+    s_last = t == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int kk = 0; kk < nvec; ++kk) {
+    const int grp = kk / kGK, k = kk - grp * kGK;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kGB)
+      v += *reinterpret_cast<const volatile double*>(G.partial + ((size_t)grp * gridDim.x + b) * kGK + k);
+    const double s = gd_block_sum(v, sh);
+    if (threadIdx.x == 0) G.dots[kk] = s * G.vscale[kk];
+  }
+  if (threadIdx.x == 0) G.tickets[0] = 0u;
+}
+
+// V_{j+1} = w - sum_{k<=j} h_k vscale_k V_k (unnormalised), nrm[0] = ||V_{j+1}||^2 over this rank's part
+template <bool SLICE>
+__global__ void __launch_bounds__(kGB)
+gd_update_kernel(const GmresDev G, const VecSlice sl) {
+  extern __shared__ double s_h[];   // m + 2
+  __shared__ double sh[32];
+  __shared__ bool s_last;
+  const int j = (int)G.st[kStJ];
+  for (int k = threadIdx.x; k <= j; k += kGB) s_h[k] = G.dots[k] * G.vscale[k];
+  __syncthreads();
+  double nrm = 0.0;
+  if (j + 1 <= G.m) {
+    double* __restrict__ vout = G.V + (size_t)(j + 1) * G.ne;
+    const double* w = G.w;
+    if (SLICE) {
+      const long long n = 2 * sl.len;
+      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
+        const long long q = gd_index(i, sl);
+        double a = w[q];
+        for (int k = 0; k <= j; ++k) a -= s_h[k] * G.V[(size_t)k * G.ne + q];
+        vout[q] = a;
+        nrm += a * a;
+      }
+    } else {
+      const long long n2 = G.n >> 1;
+      const double2* w2 = reinterpret_cast<const double2*>(w);
+      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n2; i += (long long)gridDim.x * kGB) {
+        double2 a = w2[i];
+        for (int k = 0; k <= j; ++k) {
+          const double2 vv = reinterpret_cast<const double2*>(G.V + (size_t)k * G.ne)[i];
+          a.x -= s_h[k] * vv.x;
+          a.y -= s_h[k] * vv.y;
+        }
+        reinterpret_cast<double2*>(vout)[i] = a;
+        nrm += a.x * a.x + a.y * a.y;
+      }
+    }
+  }
+  const double bs = gd_block_sum(nrm, sh);
+  if (threadIdx.x == 0) G.partial[blockIdx.x] = bs;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(G.tickets + 1, 1u);
+    s_last = t == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += kGB) v += *reinterpret_cast<const volatile double*>(G.partial + b);
+  const double tot = gd_block_sum(v, sh);
+  if (threadIdx.x == 0) {
+    G.nrm[0] = tot;
+    G.tickets[1] = 0u;
+  }
+}
+
+// scalar part of an iteration, one thread: nrm[0] = ||V_{j+1}||^2 (summed over the ranks), dots = column j
+__global__ void gd_givens_kernel(const GmresDev G, const double rtol, const double atol) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* st = G.st;
+  const int j = (int)st[kStJ], m = G.m;
+  const double hn2 = G.nrm[0];
+  const double hn = sqrt(fmax(hn2, 0.0));
+  if (!isfinite(hn2)) {
+    st[kStFlag] = 2.0;   // NaN / Inf in the Arnoldi process
+    st[kStConv] = 0.0;
+    st[kStJ] = (double)(j + 1);
+    return;
+  }
+  if (j + 1 <= m) G.vscale[j + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
+  if (j < 0) {   // start of a cycle: w held the residual, v_0 = w / beta
+    if (st[kStBnorm] < 0.0) {
+      st[kStBnorm] = hn;
+      st[kStTarget] = fmax(rtol * hn, atol);
+    }
+    G.g[0] = hn;
+    st[kStResid] = hn;
+    st[kStConv] = (hn <= st[kStTarget]) ? 1.0 : 0.0;
+    st[kStJ] = 0.0;
+    st[kStK] = 0.0;
+    return;
+  }
+  double* Hc = G.H + (size_t)j * (m + 1);
+  for (int i = 0; i <= j; ++i) Hc[i] = G.dots[i];
+  Hc[j + 1] = hn;
+  for (int i = 0; i < j; ++i) {
+    const double t = G.cs[i] * Hc[i] + G.sn[i] * Hc[i + 1];
+    Hc[i + 1] = -G.sn[i] * Hc[i] + G.cs[i] * Hc[i + 1];
+    Hc[i] = t;
+  }
+  const double d = hypot(Hc[j], Hc[j + 1]);
+  const double c = (d == 0.0) ? 1.0 : Hc[j] / d, s = (d == 0.0) ? 0.0 : Hc[j + 1] / d;
+  G.cs[j] = c;
+  G.sn[j] = s;
+  Hc[j] = d;
+  Hc[j + 1] = 0.0;
+  G.g[j + 1] = -s * G.g[j];
+  G.g[j] = c * G.g[j];
+  const double resid = fabs(G.g[j + 1]);
+  st[kStResid] = resid;
+  st[kStIts] += 1.0;
+  st[kStJ] = (double)(j + 1);
+  st[kStK] = (double)(j + 1);
+  if (resid <= st[kStTarget] || hn <= 1e-300) st[kStConv] = 1.0;   // converged, or lucky breakdown
+}
+
+// start of a solve / of a restart cycle: j = -1 (the next dot + update pair normalises the residual in w)
+__global__ void gd_begin_kernel(const GmresDev G, const int first) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* st = G.st;
+  st[kStJ] = -1.0;
+  st[kStFlag] = 0.0;
+  st[kStConv] = 0.0;
+  st[kStK] = 0.0;
+  if (first) {
+    st[kStIts] = 0.0;
+    st[kStBnorm] = -1.0;
+    st[kStTarget] = 0.0;
+    st[kStResid] = 0.0;
+    G.tickets[0] = 0u;
+    G.tickets[1] = 0u;
+  }
+}
+
+// y = R^{-1} g for the k = st[kStK] columns of the cycle -> coef
+__global__ void gd_solve_y_kernel(const GmresDev G) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int k = (int)G.st[kStK], m = G.m;
+  for (int i = k - 1; i >= 0; --i) {
+    double s = G.g[i];
+    for (int l = i + 1; l < k; ++l) s -= G.H[(size_t)l * (m + 1) + i] * G.coef[l];
+    G.coef[i] = s / G.H[(size_t)i * (m + 1) + i];
+  }
+}
+
+// out = sum_{k < K} coef_k vscale_k V_k   (K = st[kStK])
+template <bool SLICE>
+__global__ void __launch_bounds__(kGB)
+gd_combine_kernel(const GmresDev G, const VecSlice sl, double* __restrict__ out) {
+  extern __shared__ double s_h[];
+  const int K = (int)G.st[kStK];
+  for (int k = threadIdx.x; k < K; k += kGB) s_h[k] = G.coef[k] * G.vscale[k];
+  __syncthreads();
+  const long long n = SLICE ? 2 * sl.len : G.n;
+  for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
+    const long long q = SLICE ? gd_index(i, sl) : i;
+    double a = 0.0;
+    for (int k = 0; k < K; ++k) a += s_h[k] * G.V[(size_t)k * G.ne + q];
+    out[q] = a;
+  }
+}
+
+// y = alpha*x + beta*y on the vector (x may be null: y = beta*y; beta == 0 never reads y)
+template <bool SLICE>
+__global__ void __launch_bounds__(kGB)
+gd_axpby_kernel(const long long ntot, const VecSlice sl, const double alpha, const double* __restrict__ x,
+                const double beta, double* __restrict__ y) {
+  const long long n = SLICE ? 2 * sl.len : ntot;
+  for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
+    const long long q = SLICE ? gd_index(i, sl) : i;
+    double v = (beta != 0.0) ? beta * y[q] : 0.0;
+    if (x != nullptr) v += alpha * x[q];
+    y[q] = v;
+  }
+}
+
+static int gd_grid(long long nelem) {
+  long long g = (nelem + kGB - 1) / kGB;
+  if (g < 1) g = 1;
+  return (int)(g < kGGrid ? g : kGGrid);
+}
+static long long gd_len(const GmresDev& G, const VecSlice* sl) { return sl ? 2 * sl->len : G.n; }
+
+int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st) {
+  gd_begin_kernel<<<1, 32, 0, st>>>(G, first);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+// bytes: every basis vector in use + w once; the iteration index is on the device, the caller passes the
+// value it knows (jhost) for the byte accounting only.  jhost < 0 (start of a cycle): nothing to do.
+int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st) {
+  if (jhost < 0) return CM_OK;
+  const long long len = gd_len(G, sl);
+  const int grid = gd_grid(sl ? len : len / 2);
+  if (sl) gd_dot_kernel<true><<<grid, kGB, 0, st>>>(G, *sl);
+  else gd_dot_kernel<false><<<grid, kGB, 0, st>>>(G, VecSlice{0, 0, 0});
+  CM_BYTES((double)len * 8.0 * (jhost + 2));
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st) {
+  const long long len = gd_len(G, sl);
+  const int grid = gd_grid(sl ? len : len / 2);
+  const size_t smem = (size_t)(G.m + 2) * sizeof(double);
+  if (sl) gd_update_kernel<true><<<grid, kGB, smem, st>>>(G, *sl);
+  else gd_update_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0});
+  CM_BYTES((double)len * 8.0 * (jhost + 3));
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st) {
+  gd_givens_kernel<<<1, 32, 0, st>>>(G, rtol, atol);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_solve_y(const GmresDev& G, cudaStream_t st) {
+  gd_solve_y_kernel<<<1, 32, 0, st>>>(G);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_combine(const GmresDev& G, const VecSlice* sl, double* out, int khost, cudaStream_t st) {
+  const long long len = gd_len(G, sl);
+  const int grid = gd_grid(len);
+  const size_t smem = (size_t)(G.m + 2) * sizeof(double);
+  if (sl) gd_combine_kernel<true><<<grid, kGB, smem, st>>>(G, *sl, out);
+  else gd_combine_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0}, out);
+  CM_BYTES((double)len * 8.0 * (khost + 1));
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_axpby(const GmresDev& G, const VecSlice* sl, double alpha, const double* x, double beta, double* y,
+                    cudaStream_t st) {
+  const long long len = gd_len(G, sl);
+  const int grid = gd_grid(len);
+  if (sl) gd_axpby_kernel<true><<<grid, kGB, 0, st>>>(G.n, *sl, alpha, x, beta, y);
+  else gd_axpby_kernel<false><<<grid, kGB, 0, st>>>(G.n, VecSlice{0, 0, 0}, alpha, x, beta, y);
+  CM_BYTES((double)len * 8.0 * ((x ? 1 : 0) + (beta != 0.0 ? 2 : 1)));
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+}  // namespace cm

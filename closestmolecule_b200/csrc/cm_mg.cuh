@@ -1,0 +1,54 @@
+// Kernel argument blocks and launchers of cm_mg.cu.
+#pragma once
+#include "cm_common.cuh"
+#include "cm_halo.cuh"
+
+namespace cm {
+
+// one zebra half sweep: for l = 0..nlines-1 solve the x-line of grid row jstart + l*jstep,
+//   T x_line = b_line - (A - T) x,   T = tridiagonal part, factors lf / iu / cu (cm_stencil.cu)
+// Line 0 is the strip-boundary line of a multi-GPU partition: it may have to wait for the ghost row it
+// reads (wait: 1 the row below, 2 the row above) and is stored into the neighbour's copy of x as well
+// (push: 1 lower neighbour, 2 upper neighbour).
+struct LineJob {
+  int nx, ny;
+  int jstart, jstep, nlines;
+  int wait, push;
+  const double* A;
+  const double* lf;
+  const double* iu;
+  const double* cu;
+  const double* b;
+  double* x;
+};
+
+struct CoarseLevel {
+  int nx, ny;
+  const double* A;
+  const double* lf;
+  const double* iu;
+  const double* cu;
+  double* b;
+  double* x;
+};
+
+constexpr int kCoarseMaxLevels = 8;
+struct CoarseCycle {
+  int nlev, pre, post;
+  const double* Ainv;   // dense inverse on the last level (nullptr: 30 zebra sweeps there)
+  CoarseLevel lev[kCoarseMaxLevels];
+};
+
+int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu, const double* cu,
+             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st);
+int mg_resid_restrict(int nxf, int nyf, const double* A, const double* b, const double* x, double* rc,
+                      const Halo& H, int Y0, int Y1, cudaStream_t st);
+int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H, int wait_coarse, int r0,
+                   int r1, cudaStream_t st);
+int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st);
+int mg_coarse_max_n1();
+int mg_init_attributes();
+
+Halo dist_halo_args(const cm_dist* D, int chan);
+
+}  // namespace cm

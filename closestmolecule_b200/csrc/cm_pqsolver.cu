@@ -14,6 +14,8 @@
 
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
+#include "cm_halo.cuh"
+#include "cm_mg.cuh"
 
 namespace cm {
 
@@ -56,27 +58,53 @@ struct PQSolver {
 
 static inline size_t even(size_t n) { return (n + 1) & ~(size_t)1; }
 
-static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
-  {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("CM_PRECOND_LOWER"); mode = (e && atoi(e) != 0) ? 1 : 0; }
-    S.diag_split = mode == 0;
-    static int upper = -1;
-    if (upper < 0) { const char* e = getenv("CM_PRECOND_UPPER"); upper = (e && atoi(e) != 0) ? 1 : 0; }
-    S.upper_split = upper != 0;
-    // tuning knobs; defaults 2 q-sweeps and V(1,2): measured at 16 Mi cells (profiles/README.md)
-    // V(1,1) 13 its / 33.9 ms, V(1,2) 11 / 32.9, V(2,2) 10 / 33.9, V(1,0) 19 / 42.4; q-sweeps 1: +1 it
-    static int qs = -1, pre = -1, post = -1, ld = -1;
-    if (qs < 0) { const char* e = getenv("CM_Q_SWEEPS"); qs = (e && atoi(e) > 0) ? atoi(e) : 2; }
-    if (pre < 0) { const char* e = getenv("CM_MG_PRE"); pre = (e && atoi(e) > 0) ? atoi(e) : 1; }
-    if (post < 0) { const char* e = getenv("CM_MG_POST"); post = e ? atoi(e) : 2; }
-    // multi-GPU: levels >= ld are replicated (8 GPUs, 16 Mi cells: ld=2 14.5 ms, ld=3 15.2, ld=4 15.8)
-    if (ld < 0) { const char* e = getenv("CM_DIST_LD"); ld = (e && atoi(e) > 0) ? atoi(e) : 2; }
-    S.q_sweeps = qs;
-    S.pre_smooth = pre;
-    S.post_smooth = post;
-    S.dist_ld = ld;
-  }
+// Tuning knobs, read from the environment by the caller that creates a solver (once per context, never
+// cached in function statics: the C ABI stays re-entrant).  Defaults measured at 16 Mi cells
+// (profiles/README.md): V(1,1) 13 its / 33.9 ms, V(1,2) 11 / 32.9, V(2,2) 10 / 33.9; q-sweeps 1: +1 it.
+struct PQKnobs {
+  int precond_lower = 0, precond_upper = 0;
+  int q_sweeps = 2, pre = 1, post = 2;
+  int dist_ld = 2;          // multi-GPU: levels >= ld are replicated
+  int q_mg = 0, q_sweeps_wide = 6;
+  int graph = 1;            // replay fixed kernel sequences as CUDA graphs
+  int v1 = 0;               // CM_SOLVER_V1=1: first-generation kernels (two-kernel zebra sweeps, host-driven GMRES)
+  int coarse_ncta = 8;      // CTAs of the cluster that runs the fused coarse cycle (1 or 8)
+  int coarse_n1 = -1;       // the fused coarse cycle starts at the first level with nx + 1 <= coarse_n1
+  int gmres_host = 0;       // diagnostics: second-generation preconditioner under the host-driven GMRES (1 GPU)
+  int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
+};
+static int env_int(const char* name, int dflt, int minval) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return v >= minval ? v : dflt;
+}
+static PQKnobs read_knobs() {
+  PQKnobs K;
+  K.precond_lower = env_int("CM_PRECOND_LOWER", 0, 0);
+  K.precond_upper = env_int("CM_PRECOND_UPPER", 0, 0);
+  K.q_sweeps = env_int("CM_Q_SWEEPS", 2, 1);
+  K.pre = env_int("CM_MG_PRE", 1, 1);
+  K.post = env_int("CM_MG_POST", 2, 0);
+  K.dist_ld = env_int("CM_DIST_LD", 2, 0);
+  K.q_mg = env_int("CM_Q_MG", 0, 0);
+  K.q_sweeps_wide = env_int("CM_Q_SWEEPS_WIDE", 6, 1);
+  K.graph = env_int("CM_GRAPH", 1, 0);
+  K.v1 = env_int("CM_SOLVER_V1", 0, 0);
+  K.coarse_ncta = env_int("CM_COARSE_NCTA", 8, 1) >= 8 ? 8 : 1;
+  K.coarse_n1 = env_int("CM_COARSE_N1", K.coarse_ncta == 8 ? 257 : 65, 0);
+  K.gmres_host = env_int("CM_GMRES_HOST", 0, 0);
+  K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
+  return K;
+}
+
+static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base, const PQKnobs& K) {
+  S.diag_split = K.precond_lower == 0;
+  S.upper_split = K.precond_upper != 0;
+  S.q_sweeps = K.q_sweeps;
+  S.pre_smooth = K.pre;
+  S.post_smooth = K.post;
+  S.dist_ld = K.dist_ld;
   S.nx = nx;
   S.ny = ny;
   S.nv = (nx + 1) * (ny + 1);
@@ -145,20 +173,18 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base) {
     Q.b = (k == 0) ? nullptr : take(Q.n);
   }
   S.qAinv = take(S.dense_coarse ? nc * nc : 2);
-  {
-    static int qmg = -1;
-    // 4 Mi cells (profiles/README.md): the V-cycle on the q-block helps the minus-sign variant (114 GMRES
-    // iterations) but diverges on the "paper" variant (Galerkin coarse operators of the transport part): off
-    // by default; line sweeps on the 7-point stand-in instead: 3 sweeps 94 / 222 iterations ("paper" /
-    // minus-sign variant), 6 sweeps 89 / 123
-    if (qmg < 0) { const char* e = getenv("CM_Q_MG"); qmg = e ? atoi(e) : 0; }
-    S.q_mg = qmg != 0;
-    static int qsw = -1;
-    if (qsw < 0) { const char* e = getenv("CM_Q_SWEEPS_WIDE"); qsw = (e && atoi(e) > 0) ? atoi(e) : 6; }
-    S.q_sweeps_wide = qsw;
-  }
+  // 4 Mi cells (profiles/README.md): the V-cycle on the q-block helps the minus-sign C0IP variant (114 GMRES
+  // iterations) but diverges on the "paper" variant (Galerkin coarse operators of the transport part): off
+  // by default; line sweeps on the 7-point stand-in instead: 3 sweeps 94 / 222 iterations ("paper" /
+  // minus-sign variant), 6 sweeps 89 / 123
+  S.q_mg = K.q_mg != 0;
+  S.q_sweeps_wide = K.q_sweeps_wide;
   S.err = (int*)take(4);
-  S.gm = take(gmres_workspace_doubles(2 * (long long)V, restart));
+  {
+    const size_t g1 = gmres_workspace_doubles(2 * (long long)V, restart);
+    const size_t g2 = gmres_dev_doubles(2 * (long long)V, restart);
+    S.gm = take(g1 > g2 ? g1 : g2);
+  }
   S.total_doubles = off;
   return CM_OK;
 }
@@ -228,10 +254,7 @@ struct GraphReplayer {
   long long launches = 0;
   double bytes = 0.0;
   bool enabled = true;
-  GraphReplayer() {
-    const char* e = getenv("CM_GRAPH");
-    enabled = !(e && atoi(e) == 0);
-  }
+  GraphReplayer() { enabled = env_int("CM_GRAPH", 1, 0) != 0; }
   ~GraphReplayer() {
     if (exec) cudaGraphExecDestroy(exec);
     if (cap) cudaStreamDestroy(cap);
@@ -279,7 +302,7 @@ struct GraphReplayer {
 
 size_t pqs_workspace_bytes(int nx, int ny, int restart) {
   PQSolver S;
-  if (pqs_layout(S, nx, ny, restart, nullptr)) return 0;
+  if (pqs_layout(S, nx, ny, restart, nullptr, read_knobs())) return 0;
   return S.total_doubles * sizeof(double) + 64;
 }
 
@@ -288,7 +311,7 @@ static double* align_ws(void* ws) { return (double*)(((uintptr_t)ws + 63) & ~(ui
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
               void* ws, size_t ws_bytes, cudaStream_t st) {
   PQSolver S;
-  int rc = pqs_layout(S, nx, ny, restart, align_ws(ws));
+  int rc = pqs_layout(S, nx, ny, restart, align_ws(ws), read_knobs());
   if (rc) return rc;
   if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
     set_error("pqs_setup: workspace too small");
@@ -326,7 +349,7 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
               int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st) {
   PQSolver S;
-  int rc = pqs_layout(S, nx, ny, restart, align_ws(ws));
+  int rc = pqs_layout(S, nx, ny, restart, align_ws(ws), read_knobs());
   if (rc) return rc;
   if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
     set_error("pqs_solve: workspace too small");
@@ -467,10 +490,10 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
 }
 
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
-                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st) {
+                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st, int Ld_forced) {
   PQSolver S;
   double* base = align_ws(ws);
-  int rc = pqs_layout(S, nx, ny, restart, base);
+  int rc = pqs_layout(S, nx, ny, restart, base, read_knobs());
   if (rc) return rc;
   if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
     set_error("pqs_setup_dist: workspace too small");
@@ -481,10 +504,13 @@ int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* n
     return CM_E_INVALID;
   }
   DistInfo I;
+  if (Ld_forced >= 0) S.dist_ld = Ld_forced;
   dist_info(S, D, base, I);
   for (int r = 1; r < D->world; ++r)
-    if (D->row_begin[r] & 7) {
-      set_error("pqs_setup_dist: row_begin[%d] = %d is not a multiple of 8", r, D->row_begin[r]);
+    if (D->row_begin[r] & ((1 << I.Ld) - 1)) {
+      // strips on level l use row_begin >> l for l <= Ld: anything else truncates the coarse-row ownership
+      set_error("pqs_setup_dist: row_begin[%d] = %d is not a multiple of %d (first replicated level %d)", r,
+                D->row_begin[r], 1 << I.Ld, I.Ld);
       return CM_E_INVALID;
     }
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
@@ -531,7 +557,7 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
                    cudaStream_t st) {
   PQSolver S;
   double* base = align_ws(ws);
-  int rc = pqs_layout(S, nx, ny, restart, base);
+  int rc = pqs_layout(S, nx, ny, restart, base, read_knobs());
   if (rc) return rc;
   if (S.total_doubles * sizeof(double) + 64 > ws_bytes) {
     set_error("pqs_solve_dist: workspace too small");
@@ -590,9 +616,427 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Solver context (cm_pqs_create): second-generation path.  One object per workspace holds the layout, the
+// knobs (read once), the strip neighbours and the captured CUDA graphs, so that repeated Newton steps replay
+// the same graphs (the workspace pointers never change; setup only rewrites array contents).
+//   preconditioner  V-cycle with fused half sweeps (cm_mg.cu): per level  c0 c1 | restricted residual |
+//                   coarser levels | correction on odd rows | (c0 c1) x post;  from the first level with
+//                   lines <= coarse_n1 downwards the whole cycle is one cluster kernel
+//   multi-GPU       no exchange launches inside a preconditioner application: the half sweeps and the
+//                   prolongation push the strip-boundary rows themselves, consumers wait on flags
+//   GMRES           device resident (cm_gmres_dev.cu): one iteration = one graph launch + a 64-byte status
+//                   read; one all-reduce per iteration
+// The 13-point (C0IP) q-block and the triangular field splits run on the first-generation path.
+// ------------------------------------------------------------------------------------------------
+struct CachedGraph {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+  double bytes = 0.0;
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+  }
+};
+
+struct PQContext {
+  PQKnobs K;
+  PQSolver S;
+  int nx, ny, restart;
+  void* ws;
+  size_t ws_bytes;
+  double* base;
+  bool dist = false;
+  cm_dist D{};
+  DistInfo I{};
+  Halo H{};        // strip neighbours (inactive on one GPU)
+  Halo Hoff{};     // inactive: replicated levels
+  int Lc = 0;      // first level of the fused coarse cycle (nlev: none)
+  int wide = 0;
+  bool use_v1 = false;
+  GmresDev G{};
+  double* status_host = nullptr;   // pinned
+  cudaStream_t cap = nullptr;
+  CachedGraph g_iter, g_final;
+  bool graphs_ok = true;
+};
+
+static void pqc_destroy(PQContext* C) {
+  if (!C) return;
+  C->g_iter.destroy();
+  C->g_final.destroy();
+  if (C->cap) cudaStreamDestroy(C->cap);
+  if (C->status_host) cudaFreeHost(C->status_host);
+  delete C;
+}
+
+void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const cm_dist* D) {
+  PQContext* C = new PQContext();
+  C->K = read_knobs();
+  C->nx = nx; C->ny = ny; C->restart = restart;
+  C->ws = ws; C->ws_bytes = ws_bytes;
+  C->base = align_ws(ws);
+  if (pqs_layout(C->S, nx, ny, restart, C->base, C->K) != CM_OK) {
+    set_error("cm_pqs_create: unsupported grid");
+    delete C;
+    return nullptr;
+  }
+  if (C->S.total_doubles * sizeof(double) + 64 > ws_bytes) {
+    set_error("cm_pqs_create: workspace too small");
+    delete C;
+    return nullptr;
+  }
+  PQSolver& S = C->S;
+  // fused coarse cycle: from the first level whose lines fit one warp each
+  const int n1max = C->K.coarse_n1 < mg_coarse_max_n1() ? C->K.coarse_n1 : mg_coarse_max_n1();
+  C->Lc = S.nlev;
+  for (int l = 0; l < S.nlev; ++l)
+    if (S.lev[l].nx + 1 <= n1max && S.nlev - l <= kCoarseMaxLevels && (l == S.nlev - 1 || (S.lev[l].ny & 1) == 0)) {
+      C->Lc = l;
+      break;
+    }
+  if (C->Lc == S.nlev - 1 && !S.dense_coarse) C->Lc = S.nlev;   // a lone coarsest level without dense inverse: sweeps
+  if (D != nullptr && D->world > 1) {
+    C->dist = true;
+    C->D = *D;
+    if (C->base != (double*)D->peer_base[D->rank]) {
+      set_error("cm_pqs_create: workspace must be the (64-byte aligned) IPC allocation registered in cm_dist");
+      delete C;
+      return nullptr;
+    }
+    if (restart + 2 > 64) {
+      set_error("cm_pqs_create: multi-GPU GMRES needs restart <= 62 (one all-reduce carries the Hessenberg column)");
+      delete C;
+      return nullptr;
+    }
+    // strips must start on even rows of every distributed level and divide exactly down to the first
+    // replicated level (zebra colouring of the halo protocol, cm_halo.cuh): clamp Ld to the alignment present
+    int Ld = S.dist_ld;
+    if (Ld > C->Lc) Ld = C->Lc;
+    if (Ld > S.nlev - 1) Ld = S.nlev - 1;
+    for (int r = 1; r < D->world; ++r)
+      while (Ld > 0 && (D->row_begin[r] & ((1 << Ld) - 1)) != 0) --Ld;
+    for (int r = 0; r < D->world; ++r) {
+      const int rows = D->row_begin[r + 1] - D->row_begin[r];
+      while (Ld > 0 && (rows >> (Ld - 1)) < 4) --Ld;   // every distributed level keeps >= 4 rows per strip
+      if ((r > 0 && (D->row_begin[r] & 1)) || rows < 4) {
+        set_error("cm_pqs_create: strip %d starts at row %d with %d rows (need an even start and >= 4 rows)", r,
+                  D->row_begin[r], rows);
+        delete C;
+        return nullptr;
+      }
+    }
+    S.dist_ld = Ld;
+    dist_info(S, &C->D, C->base, C->I);
+    C->I.Ld = Ld;
+    C->H = dist_halo_args(&C->D, 0);
+  }
+  if (mg_init_attributes() != CM_OK) {
+    delete C;
+    return nullptr;
+  }
+  gmres_dev_layout(C->G, 2LL * S.nv, restart, S.gm);
+  C->use_v1 = C->K.v1 != 0 || !S.diag_split || S.upper_split || S.pre_smooth < 1 || S.post_smooth < 1;
+  if (cudaMallocHost((void**)&C->status_host, sizeof(double) * kGmresStatus) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cm_pqs_create: cudaMallocHost failed");
+    delete C;
+    return nullptr;
+  }
+  return C;
+}
+
+int pqs_destroy(void* ctx) {
+  pqc_destroy(static_cast<PQContext*>(ctx));
+  return CM_OK;
+}
+
+int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st) {
+  PQContext* C = static_cast<PQContext*>(ctx);
+  PQSolver& S = C->S;
+  int rc;
+  if (!C->dist) {
+    // same operator hierarchy as the first generation (the kernels of the cycle differ, the factors do not)
+    if ((rc = pqs_setup(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, st))) return rc;
+    int wide = 0;
+    CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    C->wide = wide;
+    return CM_OK;
+  }
+  return pqs_setup_dist(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, &C->D, st, C->I.Ld);
+}
+
+// one V-cycle on the p-block, level l: x = approx. A_l^{-1} b
+static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t st) {
+  PQSolver& S = C->S;
+  PQSLevel& L = S.lev[l];
+  int rc;
+  const bool lev_dist = C->dist && l < C->I.Ld;
+  if (C->dist && l == C->I.Ld) {
+    // first replicated level: every rank contributes its rows of the right-hand side
+    unsigned long long off = (unsigned long long)(b - C->base) + (unsigned long long)C->I.rb[l] * (L.nx + 1);
+    int n = (C->I.re[l] - C->I.rb[l]) * (L.nx + 1);
+    if ((rc = dist_allgather(&C->D, &off, &n, 1, st))) return rc;
+  }
+  if (l >= C->Lc) {
+    CoarseCycle cc{};
+    cc.nlev = S.nlev - l;
+    cc.pre = S.pre_smooth;
+    cc.post = S.post_smooth;
+    cc.Ainv = S.dense_coarse ? S.Ainv : nullptr;
+    for (int k = 0; k < cc.nlev; ++k) {
+      const PQSLevel& Lk = S.lev[l + k];
+      cc.lev[k] = CoarseLevel{Lk.nx, Lk.ny, Lk.A, Lk.lf, Lk.iu, Lk.cu, k == 0 ? const_cast<double*>(b) : Lk.b,
+                              k == 0 ? x : Lk.x};
+    }
+    return mg_coarse_cycle(cc, C->K.coarse_ncta, st);
+  }
+  const Halo& H = lev_dist ? C->H : C->Hoff;
+  const int r0 = lev_dist ? C->I.rb[l] : 0, r1 = lev_dist ? C->I.re[l] : -1;
+  if (l == S.nlev - 1) {
+    if (S.dense_coarse) return st_coarse_apply((int)L.n, S.Ainv, b, x, st);
+    for (int s = 0; s < 30; ++s) {
+      if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st))) return rc;
+      if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+    }
+    return CM_OK;
+  }
+  PQSLevel& Cl = S.lev[l + 1];
+  for (int s = 0; s < S.pre_smooth; ++s) {
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+  }
+  if ((rc = mg_resid_restrict(L.nx, L.ny, L.A, b, x, Cl.b, H, lev_dist ? C->I.rb[l + 1] : 0,
+                              lev_dist ? C->I.re[l + 1] : -1, st)))
+    return rc;
+  if ((rc = vcycle2(C, l + 1, Cl.b, Cl.x, st))) return rc;
+  if ((rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, H, (lev_dist && l + 1 < C->I.Ld) ? 1 : 0, r0, r1, st))) return rc;
+  for (int s = 0; s < S.post_smooth; ++s) {
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+  }
+  return CM_OK;
+}
+
+// z = diag(Mp, Mq)^{-1} ru on the unscaled blocks
+static int precond2(PQContext* C, const double* ru, double* z, cudaStream_t st) {
+  PQSolver& S = C->S;
+  const int V = S.nv;
+  if (C->K.precond_v1 && !C->dist) {
+    int e = vcycle(S, 0, const_cast<double*>(ru), z, st);
+    for (int sw = 0; sw < S.q_sweeps && !e; ++sw) {
+      e = st_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0 ? 1 : 0, st, 0, -1, S.lev[0].r);
+      if (!e) e = st_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, st, 0, -1, S.lev[0].r);
+    }
+    return e;
+  }
+  int rc = vcycle2(C, 0, ru, z, st);
+  if (rc) return rc;
+  const Halo& H = C->dist ? C->H : C->Hoff;
+  const int r0 = C->dist ? C->I.rb[0] : 0, r1 = C->dist ? C->I.re[0] : -1;
+  for (int sw = 0; sw < S.q_sweeps; ++sw) {
+    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, st))) return rc;
+  }
+  return CM_OK;
+}
+
+// run `body` on the stream: replayed from a cached CUDA graph when allowed
+template <class F>
+static int run_cached(PQContext* C, CachedGraph& g, cudaStream_t st, F&& body) {
+  if (!C->K.graph || !C->graphs_ok || g_prof_is_on()) return body(st);
+  if (!g.exec) {
+    if (!C->cap && cudaStreamCreateWithFlags(&C->cap, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      C->graphs_ok = false;
+      return body(st);
+    }
+    if (cudaStreamBeginCapture(C->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      C->graphs_ok = false;
+      return body(st);
+    }
+    const long long l0 = g_launches.load();
+    const double b0 = g_alg_bytes;
+    const int rc = body(C->cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(C->cap, &graph);
+    g.launches = g_launches.load() - l0;
+    g.bytes = g_alg_bytes - b0;
+    g_launches -= g.launches;   // nothing has run yet
+    g_alg_bytes -= g.bytes;
+    if (rc != CM_OK || ce != cudaSuccess || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      C->graphs_ok = false;
+      return rc != CM_OK ? rc : body(st);
+    }
+    if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      C->graphs_ok = false;
+      return body(st);
+    }
+    cudaGraphDestroy(graph);
+  }
+  g_launches += g.launches;
+  g_alg_bytes += g.bytes;
+  if (cudaGraphLaunch(g.exec, st) != cudaSuccess) {
+    set_error("cm_pqs_solve: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CM_E_CUDA;
+  }
+  return CM_OK;
+}
+
+int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double atol, int maxit, int* iters,
+                  double* resid, cudaStream_t st) {
+  PQContext* C = static_cast<PQContext*>(ctx);
+  PQSolver& S = C->S;
+  if (C->use_v1 || C->wide) {
+    if (C->dist)
+      return pqs_solve_dist(C->nx, C->ny, C->restart, b, x, rtol, atol, maxit, C->ws, C->ws_bytes, &C->D, iters,
+                            resid, st);
+    return pqs_solve(C->nx, C->ny, C->restart, b, x, rtol, atol, maxit, C->ws, C->ws_bytes, iters, resid, st);
+  }
+  const int nx = C->nx, ny = C->ny, V = S.nv, n1 = nx + 1, m = C->restart;
+  const int rb = C->dist ? C->I.rb[0] : 0, re = C->dist ? C->I.re[0] : ny + 1;
+  const int vb = rb * n1, ve = re * n1;
+  VecSlice slv{(long long)vb, (long long)V + vb, (long long)(ve - vb)};
+  const VecSlice* sl = C->dist ? &slv : nullptr;
+  const GmresDev& G = C->G;
+  const Halo* Hp = C->dist ? &C->H : nullptr;
+  cm_dist* Dp = C->dist ? &C->D : nullptr;
+  g_prof_fine_nx = nx;
+  int rc;
+  double* hs = C->status_host;
+  auto status = [&]() -> int {   // device status block -> pinned host copy, wait
+    CM_CUDA(cudaMemcpyAsync(hs, G.st, sizeof(double) * kGmresStatus, cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    return CM_OK;
+  };
+  // Gram-Schmidt against the j+1 basis vectors, new (unnormalised) basis vector, its norm, scalar update
+  auto orthogonalise = [&](int jhost, cudaStream_t s_) -> int {
+    int e = gmres_dev_dot(G, sl, jhost, s_);
+    if (!e && jhost >= 0) e = dist_allreduce(Dp, G.dots, m + 1, s_);
+    if (!e) e = gmres_dev_update(G, sl, jhost, s_);
+    if (!e) e = dist_allreduce(Dp, G.nrm, 1, s_);
+    if (!e) e = gmres_dev_givens(G, rtol, atol, s_);
+    return e;
+  };
+  auto normalise = [&](int jhost) -> int { return orthogonalise(jhost, st); };
+  auto apply_A = [&](const double* in, double* out, cudaStream_t s_) -> int {
+    return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, s_, rb, C->dist ? re : -1, nullptr,
+                      nullptr, Hp);
+  };
+  if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
+  if (C->K.gmres_host && !C->dist) {
+    LinOp A = [&](const double* in, double* out) { return apply_A(in, out, st); };
+    LinOp Minv = [&](const double* r, double* z) {
+      int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st);
+      return e ? e : precond2(C, S.ru, z, st);
+    };
+    double bn = 0.0;
+    rc = gmres_solve(2LL * V, A, Minv, S.bs, S.xs, rtol, atol, maxit, m, 0, S.gm, iters, resid, &bn, st);
+    if (rc < 0) return rc;
+    if (resid && bn > 0.0) *resid /= bn;
+    int rc2 = st_interleave(V, S.xs, x, st);
+    return rc2 ? rc2 : rc;
+  }
+  if ((rc = gmres_dev_axpby(G, sl, 0.0, nullptr, 0.0, S.xs, st))) return rc;      // x0 = 0
+  if ((rc = gmres_dev_axpby(G, sl, 1.0, S.bs, 0.0, G.w, st))) return rc;          // r0 = b
+  if ((rc = gmres_dev_begin(G, 1, st))) return rc;
+  if ((rc = normalise(-1))) return rc;
+  if ((rc = status())) return rc;
+  if (hs[kStFlag] == 2.0) {
+    set_error("cm_pqs_solve: right-hand side norm is not finite");
+    return CM_E_BREAKDOWN;
+  }
+  const double bnorm = hs[kStBnorm];
+  bool converged = hs[kStConv] != 0.0;
+  int its = 0;
+  double res = hs[kStResid];
+  while (!converged && its < maxit) {
+    // one restart cycle
+    int j = 0;
+    bool stop = false;
+    while (!stop) {
+      rc = run_cached(C, C->g_iter, st, [&](cudaStream_t s_) -> int {
+        int e = st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
+        if (!e) e = precond2(C, S.ru, G.z, s_);
+        if (!e) e = apply_A(G.z, G.w, s_);
+        if (!e) e = orthogonalise(4, s_);     // byte accounting: a typical mid-cycle iteration, corrected below
+        return e;
+      });
+      if (rc) return rc;
+      if ((rc = status())) return rc;
+      if (hs[kStFlag] == 2.0) {
+        set_error("cm_pqs_solve: NaN/Inf in the Arnoldi process at iteration %d", its);
+        return CM_E_BREAKDOWN;
+      }
+      its = (int)hs[kStIts];
+      j = (int)hs[kStJ];
+      // the captured sequence was accounted with j = 4: correct the two j-dependent kernels (dot: j+2, update: j+3
+      // vector passes for the iteration index j-1 that just ran)
+      CM_BYTES((double)(sl ? 2 * sl->len : G.n) * 8.0 * 2.0 * ((double)(j - 1) - 4.0));
+      res = hs[kStResid];
+      converged = hs[kStConv] != 0.0;
+      stop = converged || its >= maxit || j >= m || hs[kStFlag] == 1.0;
+    }
+    // x += M^{-1} (V y)
+    rc = run_cached(C, C->g_final, st, [&](cudaStream_t s_) -> int {
+      int e = gmres_dev_solve_y(G, s_);
+      if (!e) e = gmres_dev_combine(G, sl, G.w, 8, s_);
+      if (!e) e = st_unscale_dev(nx, ny, G.w, 0, nullptr, nullptr, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
+      if (!e) e = precond2(C, S.ru, G.z, s_);
+      if (!e) e = gmres_dev_axpby(G, sl, 1.0, G.z, 1.0, S.xs, s_);
+      return e;
+    });
+    if (rc) return rc;
+    if (converged || its >= maxit) break;
+    // restart: w = b - A x, normalised into v_0
+    if (C->dist) {
+      double* a2[2] = {S.xs, S.xs + V};
+      if ((rc = halo_rows(C->I, a2, 2, n1, rb, re, st))) return rc;
+    }
+    if ((rc = apply_A(S.xs, G.z, st))) return rc;
+    if ((rc = gmres_dev_axpby(G, sl, 1.0, S.bs, 0.0, G.w, st))) return rc;
+    if ((rc = gmres_dev_axpby(G, sl, -1.0, G.z, 1.0, G.w, st))) return rc;
+    if ((rc = gmres_dev_begin(G, 0, st))) return rc;
+    if ((rc = normalise(-1))) return rc;
+    if ((rc = status())) return rc;
+    res = hs[kStResid];
+    converged = hs[kStConv] != 0.0;
+  }
+  if ((rc = st_interleave(V, S.xs, x, st, vb, ve))) return rc;
+  CM_CUDA(cudaStreamSynchronize(st));
+  if (iters) *iters = its;
+  if (resid) *resid = bnorm > 0.0 ? res / bnorm : res;
+  if (!converged) {
+    set_error("cm_pqs_solve: GMRES did not reach rtol=%g in %d iterations (relative residual %g)", rtol, maxit,
+              bnorm > 0.0 ? res / bnorm : res);
+    return 1;
+  }
+  return CM_OK;
+}
+
+int pqs_ctx_info(void* ctx, int* out8) {
+  PQContext* C = static_cast<PQContext*>(ctx);
+  out8[0] = C->S.nlev;
+  out8[1] = C->Lc;
+  out8[2] = C->dist ? C->I.Ld : -1;
+  out8[3] = (C->use_v1 || C->wide) ? 1 : 2;
+  out8[4] = C->g_iter.exec ? (int)C->g_iter.launches : 0;
+  out8[5] = C->K.coarse_ncta;
+  out8[6] = C->graphs_ok ? 1 : 0;
+  out8[7] = C->wide;
+  return CM_OK;
+}
+
 size_t pqs_state_offset_bytes(int nx, int ny, int restart) {
   PQSolver S;
-  if (pqs_layout(S, nx, ny, restart, (double*)64)) return 0;
+  if (pqs_layout(S, nx, ny, restart, (double*)64, read_knobs())) return 0;
   return (size_t)((char*)S.ustate - (char*)64);
 }
 

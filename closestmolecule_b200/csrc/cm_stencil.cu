@@ -10,6 +10,7 @@
 
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
+#include "cm_halo.cuh"
 
 namespace cm {
 
@@ -158,13 +159,23 @@ __global__ void __launch_bounds__(kSB)
 pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP,
                        const double* __restrict__ PQ, const double* __restrict__ QP,
                        const double* __restrict__ QQ, const double* __restrict__ sp,
-                       const double* __restrict__ sq, const double* __restrict__ x,
+                       const double* __restrict__ sq, const double* x,
                        double* __restrict__ y, const int vb, const int ve,
-                       const double* __restrict__ QQx, const int* __restrict__ has_extra) {
+                       const double* __restrict__ QQx, const int* __restrict__ has_extra, const Halo H) {
   const int nv = (nx + 1) * (ny + 1);
+  const int n1 = nx + 1;
+  if (H.active) {
+    // strip-partitioned rank: the first / last owned row read the ghost rows the neighbours' last half sweeps
+    // pushed (cm_halo.cuh); only the CTAs that touch those rows look at the flags
+    const int c0 = vb + blockIdx.x * kSB, c1 = min(c0 + kSB, ve);
+    if (threadIdx.x == 0) {
+      if (c0 < vb + n1) halo_wait_below(H);
+      if (c1 > ve - n1) halo_wait_above(H);
+    }
+    __syncthreads();
+  }
   const int v = vb + blockIdx.x * kSB + threadIdx.x;
   if (v >= ve) return;
-  const int n1 = nx + 1;
   const unsigned valid = stencil_valid(v % n1, v / n1, nx, ny);
   int off[7];
   stencil_offsets(n1, off);
@@ -199,6 +210,22 @@ unscale_kernel(const int nv, const double* __restrict__ r, const double* __restr
   if (v >= ve) return;
   out[v] = r[v] / sp[v];
   out[nv + v] = r[nv + v] / sq[v];
+}
+
+// same with the source vector chosen on the device: r = vscale[j] * (rbase + stride * j), j = (int)(*jptr) (the
+// Krylov basis vector of the current GMRES iteration, cm_gmres_dev.cu); jptr == nullptr: r = rbase
+__global__ void __launch_bounds__(kSB)
+unscale_dev_kernel(const int nv, const double* __restrict__ rbase, const long long stride,
+                   const double* __restrict__ jptr, const double* __restrict__ vscale,
+                   const double* __restrict__ sp, const double* __restrict__ sq, double* __restrict__ out,
+                   const int vb, const int ve) {
+  const int v = vb + blockIdx.x * kSB + threadIdx.x;
+  if (v >= ve) return;
+  const int j = jptr ? (int)(*jptr) : 0;
+  const double* r = rbase + (size_t)stride * (size_t)j;
+  const double a = vscale ? vscale[j] : 1.0;   // the basis vectors are stored unnormalised
+  out[v] = a * r[v] / sp[v];
+  out[nv + v] = a * r[nv + v] / sq[v];
 }
 
 // r = b - A x  (scalar 7-point stencil; b may be null -> r = -A x)
@@ -590,12 +617,9 @@ int st_zebra_debug_times(unsigned long long* host_out, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pipelined variant of the zebra sweep.  (1) offline_rhs_kernel: the couplings to the neighbouring
-// lines are a plain streaming pass, rhs = b - (A - T) x on the lines of one colour.  (2)
-// line_solve_pipelined_kernel: persistent CTAs, each loops over its lines; the right-hand side and
-// the forward factors of the NEXT line are brought into shared memory by cp.async while the
-// current line is being scanned (double buffering), so HBM keeps streaming during the scans --
-// the lock-step load / scan phases of the one-line-per-CTA kernel left it idle half of the time.
+// Two-kernel variant of the zebra half sweep, kept for the 13-point (C0IP) q-block whose six extra
+// diagonals do not fit the fused kernel of cm_mg.cu: (1) offline_rhs_kernel, a streaming pass
+// rhs = b - (A - T) x on the lines of one colour; (2) line_solve_tma_kernel on that right-hand side.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSB)
 offline_rhs_kernel(const int nx, const int ny, const int jfirst, const int nlines,
@@ -623,101 +647,10 @@ offline_rhs_kernel(const int nx, const int ny, const int jfirst, const int nline
   out[v] = r;
 }
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
-__global__ void __launch_bounds__(1024, 1)
-line_solve_pipelined_kernel(const int nx, const int ny, const int jfirst, const int nlines, const int E,
-                            const double* __restrict__ lf, const double* __restrict__ iu,
-                            const double* __restrict__ cu, const double* __restrict__ rhs,
-                            double* __restrict__ x) {
-  extern __shared__ double sm[];  // 2 stages x (s_z, s_c)
-  const int n1 = nx + 1;
-  __shared__ double sh[64];
-  const int T = blockDim.x, tid = threadIdx.x;
-  int l = blockIdx.x;
-  if (l >= nlines) return;
-  int stage = 0;
-  {
-    const size_t base = (size_t)(jfirst + 2 * l) * n1;
-    double* z = sm;
-    double* c = sm + n1;
-    for (int i = tid; i < n1; i += T) { cp_async8(z + i, rhs + base + i); cp_async8(c + i, lf + base + i); }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (; l < nlines; l += gridDim.x) {
-    const size_t base = (size_t)(jfirst + 2 * l) * n1;
-    double* s_z = sm + (size_t)stage * 2 * n1;
-    double* s_c = s_z + n1;
-    const int ln = l + gridDim.x;
-    if (ln < nlines) {  // prefetch the next line into the other stage
-      const size_t bn = (size_t)(jfirst + 2 * ln) * n1;
-      double* z = sm + (size_t)(stage ^ 1) * 2 * n1;
-      double* c = z + n1;
-      for (int i = tid; i < n1; i += T) { cp_async8(z + i, rhs + bn + i); cp_async8(c + i, lf + bn + i); }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    // back-substitution factors of this line: in flight during the forward scan
-    double piu[5], pcu[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int i = tid + k * T;
-      if (i < n1) { piu[k] = iu[base + i]; pcu[k] = cu[base + i]; }
-    }
-    if (ln < nlines) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    {
-      const int i0 = tid * E, i1 = min(i0 + E, n1);
-      Affine m{1.0, 0.0};
-      for (int i = i0; i < i1; ++i) {
-        const double lv = s_c[i];
-        m.b = s_z[i] - lv * m.b;
-        m.a = -lv * m.a;
-      }
-      double z = affine_exclusive_scan(m, sh);
-      for (int i = i0; i < i1; ++i) {
-        z = s_z[i] - s_c[i] * z;
-        s_z[i] = z;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int i = tid + k * T;
-      if (i < n1) { s_z[i] *= piu[k]; s_c[i] = pcu[k]; }
-    }
-    for (int i = tid + 5 * T; i < n1; i += T) { s_z[i] *= iu[base + i]; s_c[i] = cu[base + i]; }
-    __syncthreads();
-    {
-      const int seg = T - 1 - tid;
-      const int i0 = seg * E, i1 = min(i0 + E, n1);
-      Affine m{1.0, 0.0};
-      for (int i = i1 - 1; i >= i0; --i) {
-        const double cv = s_c[i];
-        m.b = s_z[i] - cv * m.b;
-        m.a = -cv * m.a;
-      }
-      double xn = affine_exclusive_scan(m, sh);
-      for (int i = i1 - 1; i >= i0; --i) {
-        xn = s_z[i] - s_c[i] * xn;
-        s_z[i] = xn;
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < n1; i += T) x[base + i] = s_z[i];
-    __syncthreads();  // this stage is refilled by the prefetch of the next iteration
-    stage ^= 1;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Register-resident line solve: thread t owns E consecutive unknowns of the line and keeps the
-// right-hand side and the three factor arrays in registers (blocked loads; the 40-byte per-thread
-// runs are sector-exact through L1), so shared memory only carries the 2 x 32 warp totals of the
-// scans.  Persistent CTAs loop over lines and pull the next line into L2 while scanning.
+// Register-resident line solves: thread t owns E consecutive unknowns of the line and keeps the right-hand
+// side and the three factor arrays in registers, so shared memory only carries the 2 x 32 warp totals of
+// the scans.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double affine_exclusive_scan_dir(Affine m, double* sh, const bool rev) {
   // exclusive scan in thread order (rev: in reverse thread order); returns the incoming value
@@ -752,141 +685,10 @@ __device__ __forceinline__ double affine_exclusive_scan_dir(Affine m, double* sh
   return r;
 }
 
-template <int E>
-__global__ void __launch_bounds__(1024, 1)
-line_solve_reg_kernel(const int nx, const int ny, const int jfirst, const int nlines,
-                      const double* __restrict__ lf, const double* __restrict__ iu,
-                      const double* __restrict__ cu, const double* __restrict__ rhs,
-                      double* __restrict__ x, const int dbg) {
-  __shared__ double sh[64];
-  const int n1 = nx + 1;
-  const int tid = threadIdx.x;
-  const int i0 = tid * E;
-  const int ne = max(0, min(E, n1 - i0));
-  for (int l = blockIdx.x; l < nlines; l += gridDim.x) {
-    const size_t base = (size_t)(jfirst + 2 * l) * n1 + i0;
-    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 0] = gtime();
-    double r[E], lv[E], iv[E], cv[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { r[e] = rhs[base + e]; lv[e] = lf[base + e]; iv[e] = iu[base + e]; cv[e] = cu[base + e]; }
-    // pull this CTA's next line towards L2 while the scans run
-    if (l + gridDim.x < nlines && ne > 0) {
-      const size_t bn = (size_t)(jfirst + 2 * (l + gridDim.x)) * n1 + i0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(rhs + bn));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(lf + bn));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(iu + bn));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(cu + bn));
-    }
-    // forward: z_i = r_i - l_i z_{i-1}
-    Affine m{1.0, 0.0};
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
-    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 1] = gtime();
-    double z = affine_exclusive_scan_dir(m, sh, false);
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
-    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 2] = gtime();
-    // backward: x_i = w_i - cu_i x_{i+1}
-    m = Affine{1.0, 0.0};
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e)
-      if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
-    double xn = affine_exclusive_scan_dir(m, sh, true);
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e)
-      if (e < ne) { xn = r[e] - cv[e] * xn; r[e] = xn; }
-    if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + 3] = gtime();
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) x[base + e] = r[e];
-    if ((dbg & 32) && tid == 0 && l < 2048) { g_zdbg[l * 8 + 4] = gtime(); g_zdbg[l * 8 + 5] = g_zdbg[l * 8 + 4]; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Hybrid line solve (the default on long lines): coalesced cp.async brings the four arrays of a line
-// into shared memory; every thread pulls its E consecutive unknowns into registers ONCE, the buffers
-// are immediately refilled with the CTA's next line (the copies fly during the scans), both scans
-// run on registers, and the solution leaves through a shared-memory transpose as coalesced stores.
-// ------------------------------------------------------------------------------------------------
-template <int E>
-__global__ void __launch_bounds__(1024, 1)
-line_solve_hybrid_kernel(const int nx, const int ny, const int jfirst, const int nlines,
-                         const double* __restrict__ lf, const double* __restrict__ iu,
-                         const double* __restrict__ cu, const double* __restrict__ rhs,
-                         double* __restrict__ x, const int dbg) {
-  extern __shared__ double sm[];  // s_r, s_l, s_i, s_c, s_x : 5 * n1 doubles
-  __shared__ double sh[64];
-  const int n1 = nx + 1;
-  double* s_r = sm;
-  double* s_l = sm + n1;
-  double* s_i = sm + 2 * n1;
-  double* s_c = sm + 3 * n1;
-  double* s_x = sm + 4 * n1;
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int i0 = tid * E;
-  const int ne = max(0, min(E, n1 - i0));
-  int l = blockIdx.x;
-  if (l >= nlines) return;
-  {
-    const size_t b0 = (size_t)(jfirst + 2 * l) * n1;
-    for (int i = tid; i < n1; i += T) {
-      cp_async8(s_r + i, rhs + b0 + i); cp_async8(s_l + i, lf + b0 + i);
-      cp_async8(s_i + i, iu + b0 + i); cp_async8(s_c + i, cu + b0 + i);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (; l < nlines; l += gridDim.x) {
-    const size_t lbase = (size_t)(jfirst + 2 * l) * n1;
 #define HT(k) do { if ((dbg & 32) && tid == 0 && l < 2048) g_zdbg[l * 8 + (k)] = gtime(); } while (0)
-    HT(0);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    HT(1);
-    double r[E], lv[E], iv[E], cv[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { r[e] = s_r[i0 + e]; lv[e] = s_l[i0 + e]; iv[e] = s_i[i0 + e]; cv[e] = s_c[i0 + e]; }
-    __syncthreads();
-    const int ln = l + gridDim.x;
-    if (ln < nlines) {  // refill the buffers with the next line; the copies overlap the scans
-      const size_t bn = (size_t)(jfirst + 2 * ln) * n1;
-      for (int i = tid; i < n1; i += T) {
-        cp_async8(s_r + i, rhs + bn + i); cp_async8(s_l + i, lf + bn + i);
-        cp_async8(s_i + i, iu + bn + i); cp_async8(s_c + i, cu + bn + i);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    HT(2);
-    Affine m{1.0, 0.0};
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
-    double z = affine_exclusive_scan_dir(m, sh, false);
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
-    HT(3);
-    m = Affine{1.0, 0.0};
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e)
-      if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
-    double xn = affine_exclusive_scan_dir(m, sh, true);
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e)
-      if (e < ne) { xn = r[e] - cv[e] * xn; s_x[i0 + e] = xn; }
-    __syncthreads();
-    HT(4);
-    for (int i = tid; i < n1; i += T) x[lbase + i] = s_x[i];
-    HT(5);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
-// TMA variant of the hybrid line solve: the four arrays of the next line arrive by four
+// TMA line solve (right-hand side given): the four arrays of the next line arrive by four
 // cp.async.bulk copies (UBLKCP) issued by one thread and tracked by an mbarrier -- no per-thread
 // copy instructions at all (8-byte cp.async is issue-bound: ~2.6 us per line).  Lines start on
 // 8-byte boundaries only, so the copy starts at the preceding even element and the shared-memory
@@ -1142,13 +944,13 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, 
 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra) {
+               cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra, const Halo* H) {
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
   CM_BYTES((double)(ve - vb) * 288.0);
   pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve,
-                                                            QQx, has_extra);
+                                                            QQx, has_extra, H ? *H : Halo{});
   prof_end(kProfSpmv, st);
   CM_LAUNCH_CHECK();
   return CM_OK;
@@ -1159,6 +961,17 @@ int st_unscale(int nx, int ny, const double* r, const double* sp, const double* 
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   unscale_kernel<<<grid_for(ve - vb), kSB, 0, st>>>((nx + 1) * (ny + 1), r, sp, sq, out, vb, ve);
+  CM_BYTES((double)(ve - vb) * 48.0);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int st_unscale_dev(int nx, int ny, const double* rbase, long long stride, const double* jptr, const double* vscale,
+                   const double* sp, const double* sq, double* out, cudaStream_t st, int r0, int r1) {
+  int vb, ve;
+  row_range(ny, nx + 1, r0, r1, vb, ve);
+  unscale_dev_kernel<<<grid_for(ve - vb), kSB, 0, st>>>((nx + 1) * (ny + 1), rbase, stride, jptr, vscale, sp, sq, out,
+                                                       vb, ve);
   CM_BYTES((double)(ve - vb) * 48.0);
   CM_LAUNCH_CHECK();
   return CM_OK;
@@ -1236,9 +1049,7 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   const int jfirst = r0 + (((r0 & 1) == colour) ? 0 : 1);
   const int nlines = (r1 - jfirst + 1) / 2;
   if (nlines <= 0) return CM_OK;
-  static int pipe_mode = -1;
-  if (pipe_mode < 0) { const char* e = getenv("CM_ZEBRA_PIPELINED"); pipe_mode = e ? atoi(e) : 4; }
-  if (tmp != nullptr && pipe_mode && (n1 >= 1024 || Ax != nullptr) &&
+  if (tmp != nullptr && (n1 >= 1024 || Ax != nullptr) && n1 <= 5 * 896 &&
       (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
     const bool prof = nx == g_prof_fine_nx;
     CM_BYTES((double)nlines * n1 * (x_zero ? 40.0 : 88.0));
@@ -1251,47 +1062,20 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
       ++g_launches;
       rhs = tmp;
     }
-    static bool attr2 = false;
-    if (!attr2) {
-      CM_CUDA(cudaFuncSetAttribute(line_solve_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
-      attr2 = true;
-    }
     static int dbg2 = -1;
     if (dbg2 < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg2 = e ? atoi(e) : 0; }
     const int grid = nlines < 148 ? nlines : 148;
-    if (pipe_mode >= 4 && n1 <= 5 * 896 && (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
-      static bool attr4 = false;
-      if (!attr4) {
-        CM_CUDA(cudaFuncSetAttribute(line_solve_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024));
-        attr4 = true;
-      }
-      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
-      if (T < 64) T = 64;
-      const int npad = (n1 + 3) & ~1;
-      line_solve_tma_kernel<5><<<grid, T, (4 * (size_t)npad + n1 + 1) * sizeof(double), st>>>(
-          nx, ny, jfirst, nlines, lf, iu, cu, rhs, x, dbg2);
-    } else if (pipe_mode == 3 && n1 <= 5 * 1024 && 5 * (size_t)n1 * sizeof(double) <= 200 * 1024) {
-      static bool attr3 = false;
-      if (!attr3) {
-        CM_CUDA(cudaFuncSetAttribute(line_solve_hybrid_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024));
-        attr3 = true;
-      }
-      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
-      line_solve_hybrid_kernel<5><<<grid, T, 5 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, lf,
-                                                                                    iu, cu, rhs, x, dbg2);
-    } else if (pipe_mode == 2 && n1 <= 5 * 1024) {
-      int T = ((n1 + 4) / 5 + 31) / 32 * 32;
-      line_solve_reg_kernel<5><<<grid, T, 0, st>>>(nx, ny, jfirst, nlines, lf, iu, cu, rhs, x, dbg2);
-    } else {
-      const int T = (n1 > 2048) ? 1024 : 512;
-      int E = (n1 + T - 1) / T;
-      if ((E & 1) == 0) ++E;
-      line_solve_pipelined_kernel<<<grid, T, 4 * (size_t)n1 * sizeof(double), st>>>(nx, ny, jfirst, nlines, E,
-                                                                                    lf, iu, cu, rhs, x);
+    static bool attr4 = false;
+    if (!attr4) {
+      CM_CUDA(cudaFuncSetAttribute(line_solve_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+      attr4 = true;
     }
+    int T = ((n1 + 4) / 5 + 31) / 32 * 32;
+    if (T < 64) T = 64;
+    const int npad = (n1 + 3) & ~1;
+    line_solve_tma_kernel<5><<<grid, T, (4 * (size_t)npad + n1 + 1) * sizeof(double), st>>>(
+        nx, ny, jfirst, nlines, lf, iu, cu, rhs, x, dbg2);
     if (prof) prof_end(kProfZebraFine, st);
     CM_LAUNCH_CHECK();
     return CM_OK;

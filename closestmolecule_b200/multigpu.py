@@ -119,6 +119,9 @@ class DistributedPQNewton:
         self.u = ctx.u
         self.own = slice(2 * ctx.rb * n1, 2 * ctx.re * n1)
         self.scal = torch.zeros(1, dtype=torch.float64, device=mesh.device)
+        self.pqs = self.lib.cm_pqs_create(ctx.nx, ctx.ny, ctx.restart, ctx.base, ctx.nbytes, C.byref(ctx.D))
+        if not self.pqs:
+            raise LinearSolveError("cm_pqs_create failed: " + self.lib.cm_last_error().decode())
         self.linear_iterations = []
         self.history = []
         self.phase_events = None
@@ -152,14 +155,12 @@ class DistributedPQNewton:
         self._assemble(True)
         mark()
         t = asm.topo
-        _capi.check(self.lib.cm_pqs_setup_dist(ctx.nx, ctx.ny, ctx.restart, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
-                                               _capi.ptr(asm.vals), ctx.base, ctx.nbytes, C.byref(ctx.D),
-                                               _capi.stream_ptr()))
+        _capi.check(self.lib.cm_pqs_ctx_setup(self.pqs, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(asm.vals),
+                                              _capi.stream_ptr()))
         mark()
         it, rr = C.c_int32(0), C.c_double(0.0)
-        rc = self.lib.cm_pqs_solve_dist(ctx.nx, ctx.ny, ctx.restart, _capi.ptr(asm.b), _capi.ptr(self.dx),
-                                        self.rtol_lin, 0.0, self.maxit_lin, ctx.base, ctx.nbytes, C.byref(ctx.D),
-                                        C.byref(it), C.byref(rr), _capi.stream_ptr())
+        rc = self.lib.cm_pqs_ctx_solve(self.pqs, _capi.ptr(asm.b), _capi.ptr(self.dx), self.rtol_lin, 0.0,
+                                       self.maxit_lin, C.byref(it), C.byref(rr), _capi.stream_ptr())
         self.linear_iterations.append(it.value)
         if rc < 0:
             _capi.check(rc)
@@ -193,5 +194,16 @@ class DistributedPQNewton:
         torch.cuda.current_stream().synchronize()
         return self.u
 
+    def info(self):
+        out = (C.c_int32 * 8)()
+        _capi.check(self.lib.cm_pqs_ctx_info(self.pqs, out))
+        keys = ("levels", "coarse_cycle_from", "first_replicated_level", "generation", "kernels_per_iteration_graph",
+                "coarse_cluster", "graphs", "wide_q_block")
+        return dict(zip(keys, list(out)))
+
     def close(self):
+        torch.cuda.synchronize()
+        if self.pqs:
+            self.lib.cm_pqs_destroy(self.pqs)
+            self.pqs = None
         self.ctx.close()

@@ -25,7 +25,9 @@ class LinearSolveError(RuntimeError):
 
 
 class StructuredPQLinearSolver:
-    """Field-split GMRES + multigrid on structured meshes (cm_pqs_setup / cm_pqs_solve)."""
+    """Field-split GMRES + multigrid on structured meshes through a solver context (cm_pqs_create /
+    cm_pqs_ctx_setup / cm_pqs_ctx_solve): the context caches the CUDA graphs of one GMRES iteration across
+    the Newton steps and reads the tuning knobs (environment) once, here."""
 
     def __init__(self, asm, restart=40):
         mesh = asm.mesh
@@ -39,20 +41,34 @@ class StructuredPQLinearSolver:
             raise LinearSolveError("cm_pqs_workspace_bytes failed")
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=mesh.device)
         self.nbytes = nbytes
+        self.ctx = self.lib.cm_pqs_create(self.nx, self.ny, self.restart, _capi.ptr(self.ws), nbytes, None)
+        if not self.ctx:
+            raise LinearSolveError("cm_pqs_create failed: " + self.lib.cm_last_error().decode())
         self.last_iterations = 0
         self.last_residual = 0.0
 
+    def __del__(self):
+        ctx, self.ctx = getattr(self, "ctx", None), None
+        if ctx:
+            self.lib.cm_pqs_destroy(ctx)
+
+    def info(self):
+        """{levels, fused coarse cycle from level, first replicated level, kernel generation, ...}"""
+        out = (C.c_int32 * 8)()
+        _capi.check(self.lib.cm_pqs_ctx_info(self.ctx, out))
+        keys = ("levels", "coarse_cycle_from", "first_replicated_level", "generation", "kernels_per_iteration_graph",
+                "coarse_cluster", "graphs", "wide_q_block")
+        return dict(zip(keys, list(out)))
+
     def setup(self):
         t = self.asm.topo
-        _capi.check(self.lib.cm_pqs_setup(self.nx, self.ny, self.restart, _capi.ptr(t.nrowptr),
-                                          _capi.ptr(t.ncol), _capi.ptr(self.asm.vals), _capi.ptr(self.ws),
-                                          self.nbytes, _capi.stream_ptr()))
+        _capi.check(self.lib.cm_pqs_ctx_setup(self.ctx, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
+                                              _capi.ptr(self.asm.vals), _capi.stream_ptr()))
 
     def solve(self, b, x, rtol, atol, maxit):
         it, rr = C.c_int32(0), C.c_double(0.0)
-        rc = self.lib.cm_pqs_solve(self.nx, self.ny, self.restart, _capi.ptr(b), _capi.ptr(x), rtol, atol,
-                                   maxit, _capi.ptr(self.ws), self.nbytes, C.byref(it), C.byref(rr),
-                                   _capi.stream_ptr())
+        rc = self.lib.cm_pqs_ctx_solve(self.ctx, _capi.ptr(b), _capi.ptr(x), rtol, atol, maxit, C.byref(it),
+                                       C.byref(rr), _capi.stream_ptr())
         self.last_iterations, self.last_residual = it.value, rr.value
         if rc < 0:
             _capi.check(rc)
@@ -218,6 +234,7 @@ class NonlinearVariationalSolver:
         }
         self.asm = make_assembler(problem.form)
         self._linear = None
+        self._linear_key = None
         self.history = []
         self.linear_iterations = []
         self.phase_events = None   # set to [] to collect CUDA events around the phases of each step
@@ -228,12 +245,17 @@ class NonlinearVariationalSolver:
         return {"linear_solver": "default", "absolute_tolerance": 1e-10, "relative_tolerance": 1e-9,
                 "maximum_iterations": 50, "relaxation_parameter": 1.0, "error_on_nonconvergence": True,
                 "report": False,
-                "lu_solver": {"max_bytes": None, "refinement_steps": 1},
+                "lu_solver": {"max_bytes": None, "refinement_steps": 1, "allow_krylov_fallback": False},
                 "krylov_solver": {"relative_tolerance": 1e-11, "absolute_tolerance": 0.0,
                                   "maximum_iterations": 400, "restart": 40}}
 
     def _linear_solver(self, prm):
+        key = (prm["linear_solver"], prm["krylov_solver"]["restart"], prm["lu_solver"]["max_bytes"],
+               prm["lu_solver"]["refinement_steps"], prm["lu_solver"].get("allow_krylov_fallback", False))
+        if self._linear is not None and key != self._linear_key:
+            self._linear = None                           # the parameters changed since the solver was built
         if self._linear is None:
+            self._linear_key = key
             name = prm["linear_solver"]
             if name in _LU_ALIASES:
                 try:
@@ -241,7 +263,16 @@ class NonlinearVariationalSolver:
                                                         prm["lu_solver"]["refinement_steps"])
                     return self._linear
                 except LinearSolveError as e:
-                    self.lu_fallback_reason = str(e)      # too large for a direct solve: Krylov path
+                    # too large for a direct solve.  The caller asked for an exact solve: switching to the
+                    # Krylov path (rtol-limited) needs an explicit opt-in, and is announced
+                    if not prm["lu_solver"].get("allow_krylov_fallback", False):
+                        raise LinearSolveError(
+                            f"linear_solver='{name}': {e}; set parameters['newton_solver']['lu_solver']"
+                            "['allow_krylov_fallback'] = True to solve with GMRES to "
+                            "krylov_solver['relative_tolerance'] instead") from e
+                    import warnings
+                    warnings.warn(f"linear_solver='{name}' falls back to the Krylov path: {e}")
+                    self.lu_fallback_reason = str(e)
             elif name not in ("gmres", "bicgstab"):
                 raise ValueError(f"unknown linear_solver '{name}'")
             restart = prm["krylov_solver"]["restart"]
@@ -262,13 +293,38 @@ class NonlinearVariationalSolver:
             self._dx = torch.empty_like(self.problem.u.vector())
         return prm, self._linear_solver(prm)
 
+    def refresh_bcs(self):
+        """Re-evaluate the Dirichlet tables (time-dependent boundary data) before the next assembly."""
+        self._bc = None
+
     def residual_norm(self):
         """||F(u)||_2 with the Dirichlet rows set to u - g (NewtonSolver's convergence measure)."""
         prm, _ = self._prepare()
         u = self.problem.u.vector()
         self.asm.assemble(u, want_jac=False)
         self.asm.apply_bcs(self._bc, u, with_matrix=False)
-        return float(torch.linalg.vector_norm(self.asm.b))
+        return self._norm(self.asm.b)
+
+    def _vec_scratch(self):
+        if getattr(self, "_scr", None) is None:
+            lib, dev = _capi.lib(), self.problem.u.vector().device
+            self._scr = torch.empty(int(lib.cm_vec_scratch_doubles()) + 8, dtype=torch.float64, device=dev)
+            self._sc = torch.zeros(4, dtype=torch.float64, device=dev)
+        return self._scr, self._sc
+
+    def _norm(self, v):
+        """||v||_2 by the library's fused two-stage dot kernel (deterministic) + one 8-byte read."""
+        scr, sc = self._vec_scratch()
+        _capi.check(_capi.lib().cm_dot_batch(v.numel(), _capi.ptr(v), v.numel(), 1, _capi.ptr(v), _capi.ptr(sc),
+                                             _capi.ptr(scr), _capi.stream_ptr()))
+        return float(sc[0].sqrt())
+
+    def _update(self, u, dx, relax):
+        """u <- u - relax*dx (the library's fused axpy kernel)."""
+        scr, sc = self._vec_scratch()
+        sc[1] = relax
+        _capi.check(_capi.lib().cm_axpy_batch(u.numel(), _capi.ptr(dx), dx.numel(), 1, _capi.ptr(sc[1:2]), -1.0,
+                                              _capi.ptr(u), None, _capi.ptr(scr), _capi.stream_ptr()))
 
     def newton_step(self, compute_residual=True):
         """One Newton iteration at the current u: fused J+F assembly, Dirichlet rows, linear-solver
@@ -297,7 +353,7 @@ class NonlinearVariationalSolver:
             raise LinearSolveError(
                 f"Krylov solver did not converge in {lin.last_iterations} iterations "
                 f"(relative residual {lin.last_residual:.3e})")
-        u.add_(self._dx, alpha=-prm["relaxation_parameter"])
+        self._update(u, self._dx, prm["relaxation_parameter"])
         r = self.residual_norm() if compute_residual else None
         mark()
         if marks is not None:   # (assemble J+F, BC + solver setup, Krylov solve, update + residual)

@@ -86,6 +86,7 @@ typedef struct cm_scalar_params {
  * of the fine grid (boundaries multiples of 8 so that three multigrid levels stay aligned).
  * halo_seq / coll_seq are sequence counters the library advances; all ranks must make the same
  * sequence of library calls. */
+struct cm_dist;
 typedef struct cm_dist {
   int32_t rank, world;
   void* peer_base[8];      /* workspace base of every rank as mapped in THIS process (own at [rank]) */
@@ -215,6 +216,25 @@ int cm_pqs_solve(int32_t nx, int32_t ny, int32_t restart, const double* b, doubl
                  double atol, int32_t maxit, void* workspace, int64_t workspace_bytes,
                  int32_t* iters_host, double* resid_host, void* stream);
 
+/* Solver context (preferred entry points; cm_pqs_setup / cm_pqs_solve above remain and run the
+ * first-generation kernels).  cm_pqs_create binds a workspace (and, multi-GPU, a cm_dist describing the strip
+ * partition; NULL on one GPU), reads the tuning knobs from the environment ONCE and caches the CUDA graphs
+ * of one GMRES iteration, so repeated Newton steps replay them.  Per Newton step: cm_pqs_ctx_setup (new
+ * Jacobian values), cm_pqs_ctx_solve.  The context owns no device memory; destroy it before the workspace.
+ *   Kernels: fused zebra half sweeps (couplings + tridiagonal solve + multi-GPU boundary push in one launch,
+ *   inputs streamed by cp.async.bulk), restricted residual on even rows, correction on odd rows, one cluster
+ *   kernel for the coarse levels, device-resident GMRES with one reduction per iteration.
+ * cm_pqs_ctx_info: out8 = {levels, first level of the fused coarse cycle, first replicated level (-1: one
+ *   GPU), generation of the path in use (1|2), kernels per GMRES iteration graph, cluster size of the coarse
+ *   cycle, graphs usable, 13-point q-block present}. */
+void* cm_pqs_create(int32_t nx, int32_t ny, int32_t restart, void* workspace, int64_t workspace_bytes,
+                    const struct cm_dist* dist_or_null);
+int cm_pqs_destroy(void* ctx);
+int cm_pqs_ctx_setup(void* ctx, const int32_t* nrowptr, const int32_t* ncol, const double* vals, void* stream);
+int cm_pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double atol, int32_t maxit,
+                     int32_t* iters_host, double* resid_host, void* stream);
+int cm_pqs_ctx_info(void* ctx, int32_t* out8);
+
 /* ---- (e) multi GPU: strip-partitioned Newton step, one process per GPU ---------------------------
  * The mesh is split into strips of whole vertex rows (RCB along r1 keeps the r2-lines of the line
  * solver intact).  Every rank holds globally indexed arrays in an IPC-shared workspace
@@ -251,6 +271,18 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
                       double rtol, double atol, int32_t maxit, void* workspace,
                       int64_t workspace_bytes, cm_dist* D, int32_t* iters_host, double* resid_host,
                       void* stream);
+
+/* Second-generation building blocks (cm_mg.cu), single-GPU forms, exported for tests:
+ *   cm_mg_zebra: one zebra half sweep (colour = line parity) in ONE launch, x_is_zero skips the couplings;
+ *   cm_mg_resid_restrict: rc = R (b - A x) assuming the residual vanishes on odd fine rows (i.e. right after
+ *     a sweep that ended with colour 1); nxf, nyf even;
+ *   cm_mg_prolong_odd: x += P e on the odd fine rows only (the even rows are overwritten by the colour-0
+ *     half sweep that follows). */
+int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
+                const double* cu, const double* b, double* x, int32_t x_is_zero, void* stream);
+int cm_mg_resid_restrict(int32_t nxf, int32_t nyf, const double* A, const double* b, const double* x,
+                         double* rc, void* stream);
+int cm_mg_prolong_odd(int32_t nxc, int32_t nyc, const double* ec, double* xf, void* stream);
 
 /* Building blocks of the structured solver, exported for tests and reuse.  A is a 7-point stencil
  * stored as diagonals A[k*n + node], n = (nx+1)*(ny+1), k: 0:(-1,-1) 1:(0,-1) 2:(-1,0) 3:(0,0)

@@ -204,7 +204,16 @@ def test_singular_matrix_and_memory_budget_fail_loudly():
         lin.setup()
     with pytest.raises(LinearSolveError, match="budget"):
         BandedLULinearSolver(s.asm, max_bytes=1 << 16)
-    # the Newton front end falls back to the Krylov path when the factors do not fit
+    # the caller asked for an exact solve: when the factors do not fit, the Newton front end refuses ...
     s.parameters["newton_solver"]["lu_solver"]["max_bytes"] = 1 << 16
-    prm, lin2 = s._prepare()
+    with pytest.raises(LinearSolveError, match="allow_krylov_fallback"):
+        s._prepare()
+    # ... unless the Krylov path is allowed explicitly, and then it says so
+    s.parameters["newton_solver"]["lu_solver"]["allow_krylov_fallback"] = True
+    with pytest.warns(UserWarning, match="falls back to the Krylov path"):
+        prm, lin2 = s._prepare()
     assert not isinstance(lin2, BandedLULinearSolver) and "budget" in s.lu_fallback_reason
+    # the solver cache follows the parameters: asking for gmres afterwards builds the Krylov solver
+    s.parameters["newton_solver"]["linear_solver"] = "gmres"
+    prm, lin3 = s._prepare()
+    assert lin3 is not lin2

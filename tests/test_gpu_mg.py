@@ -1,0 +1,230 @@
+"""Second-generation multigrid kernels (csrc/cm_mg.cu) against numpy / scipy restatements of the same
+operations: fused zebra half sweep (shared-memory ring fed by cp.async.bulk on long lines, one CTA per line
+on short ones), restricted residual on even rows, correction on odd rows; and the solver-level equivalence
+of the two kernel generations (same GMRES iteration counts, same solution)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+
+import closestmolecule_b200 as cm
+from closestmolecule_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+
+OFFS = [(-1, -1), (0, -1), (-1, 0), (0, 0), (1, 0), (0, 1), (1, 1)]
+
+
+def _random_stencil(nx, ny, seed):
+    rng = np.random.default_rng(seed)
+    n1 = nx + 1
+    A = np.zeros((7, ny + 1, n1))
+    for k, (dx, dy) in enumerate(OFFS):
+        v = (1.0 + rng.random((ny + 1, n1))) if k == 3 else -(0.1 + 0.05 * rng.random((ny + 1, n1)))
+        if dx == -1: v[:, 0] = 0
+        if dx == 1: v[:, -1] = 0
+        if dy == -1: v[0, :] = 0
+        if dy == 1: v[-1, :] = 0
+        A[k] = v
+    return A, rng
+
+
+def _apply(A, x):
+    """y = A x for the 7-point stencil stored as diagonals (numpy)."""
+    ny1, n1 = x.shape
+    y = np.zeros_like(x)
+    xp = np.pad(x, 1)
+    for k, (dx, dy) in enumerate(OFFS):
+        y += A[k] * xp[1 + dy:1 + dy + ny1, 1 + dx:1 + dx + n1]
+    return y
+
+
+def _line_solve(A, j, rhs):
+    n1 = rhs.size
+    ab = np.zeros((3, n1))
+    ab[0, 1:] = A[4, j, :-1]
+    ab[1] = A[3, j]
+    ab[2, :-1] = A[2, j, 1:]
+    return sla.solve_banded((1, 1), ab, rhs)
+
+
+def _zebra_ref(A, b, x, colour, x_zero):
+    """one half sweep in numpy (only a few lines are checked by the caller: this does all of them)"""
+    ny1, n1 = b.shape
+    xin = np.zeros_like(x) if x_zero else x
+    T = np.zeros_like(A)
+    T[2:5] = A[2:5]
+    off = _apply(A - T, xin)
+    out = x.copy()
+    for j in range(colour, ny1, 2):
+        out[j] = _line_solve(A, j, b[j] - off[j])
+    return out
+
+
+@pytest.mark.parametrize("nx,ny,shift", [(200, 37, 0), (1024, 40, 0), (1024, 1300, 1), (1500, 21, 1), (2048, 330, 0),
+                                         (3000, 9, 1), (4096, 310, 1), (4479, 6, 0)])
+def test_fused_zebra_half_sweeps(nx, ny, shift):
+    """colour 0 from a zero guess, then colour 1 with couplings, then colour 0 with couplings: every line
+    equals scipy's tridiagonal solve with the couplings of the current iterate.  `shift` places b and x one
+    double off a 16-byte boundary (the q-part of a split vector with an odd vertex count): the bulk copies
+    then start one element early and fetch array ends by plain loads."""
+    n1, n = nx + 1, (nx + 1) * (ny + 1)
+    dev = torch.device("cuda")
+    A, rng = _random_stencil(nx, ny, nx + ny)
+    At = torch.tensor(A.reshape(7, n), device=dev)
+    lf, iu, cu = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    bh = rng.standard_normal((ny + 1, n1))
+    # one buffer holds [pad | b | x] so that neighbouring memory is valid and the alignment is controlled
+    buf = torch.full((2 * n + 8,), float("nan"), dtype=torch.float64, device=dev)
+    b = buf[shift:shift + n]
+    xo = shift + n + 2
+    xo += (xo - shift) % 2          # x starts with the same parity as b
+    x = buf[xo:xo + n]
+    assert (b.data_ptr() // 8) % 2 == shift % 2 and (x.data_ptr() // 8) % 2 == shift % 2
+    b.copy_(torch.tensor(bh.reshape(-1)))
+    x.zero_()
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    _capi.check(lib.cm_stencil_line_factor(nx, ny, P(At), P(lf), P(iu), P(cu), P(err), st))
+    assert int(err.item()) == 0
+    lines = sorted({0, 1, 2, 3, ny // 2, ny // 2 + 1, ny - 1, ny})
+    xr = np.zeros((ny + 1, n1))
+    for colour, x_zero in ((0, 1), (1, 0), (0, 0), (1, 0)):
+        _capi.check(lib.cm_mg_zebra(nx, ny, colour, P(At), P(lf), P(iu), P(cu), P(b), P(x), x_zero, st))
+        X = x.cpu().numpy().reshape(ny + 1, n1)
+        assert np.isfinite(X[colour::2]).all()
+        # reference on the checked lines only (the full numpy sweep is slow on the big grids)
+        xin = np.zeros_like(xr) if x_zero else xr
+        for j in lines:
+            if j % 2 != colour:
+                continue
+            rhs = bh[j].copy()
+            for k, (dx, dy) in enumerate(OFFS):
+                if dy == 0 or not (0 <= j + dy <= ny):
+                    continue
+                src = np.zeros(n1)
+                lo, hi = max(0, -dx), min(n1, n1 - dx)
+                src[lo:hi] = xin[j + dy, lo + dx:hi + dx]
+                rhs -= A[k, j] * src
+            ref = _line_solve(A, j, rhs)
+            assert np.max(np.abs(X[j] - ref)) < 1e-12 * (1 + np.max(np.abs(ref))), (colour, j)
+        # continue from the GPU iterate (all lines of the colour were updated there)
+        xr = X.copy()
+    # after a sweep that ends with colour 1 the residual vanishes on the odd rows
+    R = bh - _apply(A, xr)
+    assert np.max(np.abs(R[1::2])) < 1e-11 and np.max(np.abs(R[0::2])) > 1e-4
+
+
+@pytest.mark.parametrize("nx,ny", [(8, 6), (200, 38), (1024, 20), (514, 130)])
+def test_restricted_residual_and_odd_row_correction(nx, ny):
+    n1, n = nx + 1, (nx + 1) * (ny + 1)
+    nxc, nyc = nx // 2, ny // 2
+    m1 = nxc + 1
+    dev = torch.device("cuda")
+    A, rng = _random_stencil(nx, ny, 5 * nx + ny)
+    bh = rng.standard_normal((ny + 1, n1))
+    xh = rng.standard_normal((ny + 1, n1))
+    # make the residual vanish on the odd rows (what a colour-1 half sweep leaves behind)
+    xh = _zebra_ref(A, bh, xh, 1, False)
+    R = bh - _apply(A, xh)
+    assert np.max(np.abs(R[1::2])) < 1e-11
+    # full-weighting restriction of the nested right-diagonal meshes: weights 1 and 1/2 on the six neighbours
+    Rp = np.pad(R, 1)
+    full = np.zeros((nyc + 1, m1))
+    for Y in range(nyc + 1):
+        for k, (dx, dy) in enumerate(OFFS):
+            w = 1.0 if k == 3 else 0.5
+            full[Y] += w * Rp[1 + 2 * Y + dy, 1 + dx:1 + dx + 2 * nxc + 1:2]
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    At = torch.tensor(A.reshape(7, n), device=dev)
+    b = torch.tensor(bh.reshape(-1), device=dev)
+    x = torch.tensor(xh.reshape(-1), device=dev)
+    rc = torch.full(((nyc + 1) * m1,), float("nan"), dtype=torch.float64, device=dev)
+    _capi.check(lib.cm_mg_resid_restrict(nx, ny, P(At), P(b), P(x), P(rc), st))
+    got = rc.cpu().numpy().reshape(nyc + 1, m1)
+    assert np.max(np.abs(got - full)) < 1e-11 * (1 + np.max(np.abs(full)))
+    # prolongation: odd fine rows get the interpolated correction, even rows are left alone
+    ec = rng.standard_normal((nyc + 1, m1))
+    P2 = np.zeros((ny + 1, n1))
+    for iy in range(ny + 1):
+        for ix in range(n1):
+            X, Y, ox, oy = ix // 2, iy // 2, ix & 1, iy & 1
+            if not ox and not oy: e = ec[Y, X]
+            elif ox and not oy: e = 0.5 * (ec[Y, X] + ec[Y, X + 1])
+            elif not ox and oy: e = 0.5 * (ec[Y, X] + ec[Y + 1, X])
+            else: e = 0.5 * (ec[Y, X] + ec[Y + 1, X + 1])
+            P2[iy, ix] = e
+    x0 = xh.copy()
+    ect = torch.tensor(ec.reshape(-1), device=dev)
+    _capi.check(lib.cm_mg_prolong_odd(nxc, nyc, P(ect), P(x), st))
+    got = x.cpu().numpy().reshape(ny + 1, n1)
+    assert np.max(np.abs(got[1::2] - (x0 + P2)[1::2])) < 1e-13
+    assert np.array_equal(got[0::2], x0[0::2])
+
+
+def _supg_solver(nx, ny, restart=40):
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+    from closestmolecule_b200.solver import StructuredPQLinearSolver
+    P1 = cm.FiniteElement("CG", "triangle", 1)
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    form = cm.PQPrimalForm.manufactured(V, "supg")
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, cm.Function(V), bcs))
+    asm = s.asm
+    X = mesh.coords
+    u = torch.empty(2 * mesh.num_vertices(), dtype=torch.float64, device=mesh.device)
+    u[0::2] = p_exact(X[:, 0], X[:, 1])
+    u[1::2] = q_exact(X[:, 0], X[:, 1]) * (1 + 1e-3 * torch.sin(7 * X[:, 0] + 3 * X[:, 1]))
+    bc = asm._bc_tables(bcs)
+    asm.assemble(u, True)
+    asm.apply_bcs(bc, u, True)
+    return asm, (lambda: StructuredPQLinearSolver(asm, restart=restart))
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 32), (256, 128), (1024, 512)])
+def test_kernel_generations_agree(nx, ny, monkeypatch):
+    """The same Jacobian solved by the first-generation path (two-kernel sweeps, full residual / restriction /
+    prolongation, host-driven GMRES with two reductions) and by the second-generation path, with the coarse
+    levels as one cluster kernel, as one single-CTA kernel, and unfused: same iteration counts, same solution."""
+    asm, make = _supg_solver(nx, ny)
+    res = {}
+    for name, env in (("v1", {"CM_SOLVER_V1": "1"}), ("v2", {}), ("v2_cta1", {"CM_COARSE_NCTA": "1"}),
+                      ("v2_unfused", {"CM_COARSE_N1": "0"}), ("v2_nograph", {"CM_GRAPH": "0"})):
+        for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        lin = make()
+        info = lin.info()
+        assert info["generation"] == (1 if name == "v1" else 2), info
+        dx = torch.zeros_like(asm.b)
+        for rep in range(2):          # the second solve replays the cached graphs
+            lin.setup()
+            assert lin.solve(asm.b, dx, 1e-11, 0.0, 200)
+        res[name] = (lin.last_iterations, dx.cpu().numpy().copy(), lin.last_residual)
+    ref_it, ref_x, _ = res["v1"]
+    for name, (it, xx, rr) in res.items():
+        assert abs(it - ref_it) <= 1, {k: v[0] for k, v in res.items()}
+        assert np.linalg.norm(xx - ref_x) / np.linalg.norm(ref_x) < 1e-8, name
+    assert res["v2"][0] == res["v2_cta1"][0] == res["v2_unfused"][0] == res["v2_nograph"][0]
+    assert np.linalg.norm(res["v2"][1] - res["v2_nograph"][1]) == 0.0      # graph replay is bit-identical
+
+
+def test_gmres_restart_path(monkeypatch):
+    """restart = 3 forces several cycles: x += M^{-1} V y, true residual, new cycle (all on the device)."""
+    asm, make = _supg_solver(96, 48, restart=3)
+    lin = make()
+    lin.setup()
+    dx = torch.zeros_like(asm.b)
+    assert lin.solve(asm.b, dx, 1e-10, 0.0, 300)
+    assert lin.last_iterations > 3
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    rp, col, vals = asm.csr()
+    n = dx.numel()
+    Amat = sp.csr_matrix((vals.cpu().numpy(), col.cpu().numpy(), rp.cpu().numpy()), shape=(n, n))
+    ref = spla.splu(Amat.tocsc()).solve(asm.b.cpu().numpy())
+    assert np.linalg.norm(dx.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-7
