@@ -116,181 +116,319 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// zebra half sweep on long lines.  Thread t owns the kE consecutive unknowns [kE t, kE t + kE) of the line
-// (registers); warps are grouped into chunks of CW warps = CW*32*kE unknowns; the input streams of one
-// chunk form one ring stage.  Element k of a chunk sits at position k + 4 + s of its array slot, s = parity
-// of the chunk's first element address / 8 (bulk copies need 16-byte aligned ends; the elements a copy
-// cannot reach at the two ends of an array are fetched by plain loads).
+// zebra half sweep on long lines.  Persistent CTAs; thread t of the consumer warps owns the kE consecutive
+// unknowns [kE t, kE t + kE) of the line in registers.  The input streams of a line arrive ONE WHOLE LINE PER
+// BULK COPY (few large cp.async.bulk operations: the copy engine has a per-operation cost of ~0.2 us, which
+// rules out small tiles) through a ring of S line-sized shared-memory slots in a fixed order
+//     x(lower line), A0, A1, x(upper line), A5, A6, b, lf, iu, cu          (b, lf, iu, cu from a zero guess)
+// and are folded into the right-hand side as they arrive.  A dedicated producer warp issues the copies:
+// full[s] (transaction barrier) tells the consumers that slot s holds stream n, empty[s] (one arrival per
+// consumer warp) tells the producer that it has been read.  Together with every copy the producer pulls the
+// same stream of the CTA's NEXT line into L2 (cp.async.bulk.prefetch.L2): HBM streams one line ahead of the
+// ring, the ring itself refills from L2, and the two block-wide scans of the current line overlap both.
+// Element i of a line sits at position i + 4 + s of its slot, s = parity of the line's first element address / 8
+// (bulk copies need 16-byte aligned ends; the elements a copy cannot reach at the two ends of an array are
+// fetched by plain loads).
 // ------------------------------------------------------------------------------------------------
 constexpr int kE = 5;          // odd: conflict-free 64-bit shared-memory accesses at stride kE
-constexpr int kRingMaxT = 896;
+constexpr int kRingMaxT = 896; // consumer threads + the producer warp
 
-// input stream a of a half sweep: 0 b, 1 lf, 2 iu, 3 cu, 4..7 stencil diagonals 0, 1, 5, 6 (the couplings to
-// the lines below / above), 8 / 9 the current iterate (read on the line below / above)
+// optional phase stamps (%globaltimer) of the first 64 CTAs x 16 lines, for tools/time_ring.py
+__device__ unsigned long long g_ring_dbg[64 * 16 * 8];
+#define RT(k)                                                                                   \
+  do {                                                                                          \
+    if (J.dbg && tid == 0 && blockIdx.x < 64 && it < 16)                                        \
+      g_ring_dbg[((int)blockIdx.x * 16 + it) * 8 + (k)] = global_ns();                          \
+  } while (0)
+
+// stream a of a half sweep, in consumption order
+template <bool COUPLED>
 __device__ __forceinline__ const double* ring_base(const LineJob& J, const size_t nv, const int a) {
+  if (COUPLED) {
+    switch (a) {
+      case 0: return J.x;            // lower line
+      case 1: return J.A;            // diagonal 0: (-1,-1)
+      case 2: return J.A + nv;       // diagonal 1: ( 0,-1)
+      case 3: return J.x;            // upper line
+      case 4: return J.A + 5 * nv;   // diagonal 5: ( 0,+1)
+      case 5: return J.A + 6 * nv;   // diagonal 6: (+1,+1)
+      case 6: return J.b;
+      case 7: return J.lf;
+      case 8: return J.iu;
+      default: return J.cu;
+    }
+  }
   switch (a) {
     case 0: return J.b;
     case 1: return J.lf;
     case 2: return J.iu;
-    case 3: return J.cu;
-    case 4: return J.A;
-    case 5: return J.A + nv;
-    case 6: return J.A + 5 * nv;
-    case 7: return J.A + 6 * nv;
-    default: return J.x;
+    default: return J.cu;
   }
 }
+template <bool COUPLED>
 __device__ __forceinline__ int ring_row(const LineJob& J, const int a, const int j) {
-  if (a == 8) return j > 0 ? j - 1 : 0;
-  if (a == 9) return j < J.ny ? j + 1 : J.ny;
+  if (COUPLED && a == 0) return j > 0 ? j - 1 : 0;
+  if (COUPLED && a == 3) return j < J.ny ? j + 1 : J.ny;
   return j;
 }
 __device__ __forceinline__ int addr_parity(const double* p) {
   return (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+
+// block-wide exclusive scan over the consumer warps only (named barrier 1; the producer warp is not part of it)
+__device__ __forceinline__ double aff_consumer_scan(Aff m, double* sh, const bool rev, const int nw) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int pos = rev ? 31 - lane : lane;
+  const int wpos = rev ? nw - 1 - wid : wid;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double pa = rev ? __shfl_down_sync(0xffffffffu, m.a, o) : __shfl_up_sync(0xffffffffu, m.a, o);
+    const double pb = rev ? __shfl_down_sync(0xffffffffu, m.b, o) : __shfl_up_sync(0xffffffffu, m.b, o);
+    if (pos >= o) m = aff_compose(m, Aff{pa, pb});
+  }
+  if (pos == 31) { sh[2 * wpos] = m.a; sh[2 * wpos + 1] = m.b; }
+  group_bar(1, nw * 32);
+  if (wid == 0) {
+    Aff t = (lane < nw) ? Aff{sh[2 * lane], sh[2 * lane + 1]} : Aff{1.0, 0.0};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, t.a, o);
+      const double pb = __shfl_up_sync(0xffffffffu, t.b, o);
+      if (lane >= o) t = aff_compose(t, Aff{pa, pb});
+    }
+    if (lane < nw) { sh[2 * lane] = t.a; sh[2 * lane + 1] = t.b; }
+  }
+  group_bar(1, nw * 32);
+  double ea = rev ? __shfl_down_sync(0xffffffffu, m.a, 1) : __shfl_up_sync(0xffffffffu, m.a, 1);
+  double eb = rev ? __shfl_down_sync(0xffffffffu, m.b, 1) : __shfl_up_sync(0xffffffffu, m.b, 1);
+  if (pos == 0) { ea = 1.0; eb = 0.0; }
+  double r = eb;
+  if (wpos > 0) r = ea * sh[2 * (wpos - 1) + 1] + eb;
+  group_bar(1, nw * 32);
+  return r;
+}
 
 template <bool COUPLED>
 __global__ void __launch_bounds__(kRingMaxT, 1)
-zebra_ring_kernel(const LineJob J, const Halo H, const int CW, const int S) {
+zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
   constexpr int NARR = COUPLED ? 10 : 4;
   extern __shared__ __align__(16) double sm[];
   __shared__ double sh[64];
   const int n1 = J.nx + 1;
   const size_t nv = (size_t)n1 * (J.ny + 1);
-  const int CH = CW * 32 * kE;          // unknowns per chunk
-  const int SW = CH + 8;                // slot width of one array in a stage (doubles)
-  const int NC = (n1 + CH - 1) / CH;    // chunks per line = warp groups
-  double* s_x = sm + (size_t)S * NARR * SW;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_x + ((n1 + 2) & ~1));
-  // issued[s]: number of the chunk most recently issued into stage s.  The groups share the stages out of
-  // order, and a parity wait alone cannot tell "phase not started" from "two phases later": a consumer first
-  // sees its chunk number here, then waits for the phase of that chunk.
-  volatile int* issued = reinterpret_cast<volatile int*>(bars + S);
+  const int SW = (n1 + 9) & ~1;          // slot width (doubles)
+  double* s_x = sm + (size_t)S * SW;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(s_x + ((n1 + 2) & ~1));
+  unsigned long long* empty = full + S;
   const int tid = threadIdx.x;
-  const int grp = (tid >> 5) / CW;
-  const int nwarps = blockDim.x >> 5;
-  const int gthreads = (min((grp + 1) * CW, nwarps) - grp * CW) * 32;
-  const bool leader = tid == grp * CW * 32;
-  const int i0 = tid * kE;
-  const int ne = max(0, min(kE, n1 - i0));
-  const int k0 = i0 - grp * CH;         // first own element inside the chunk
+  const int ncw = (blockDim.x >> 5) - 1;   // consumer warps; the last warp is the producer
+  const int TC = ncw * 32;
   if ((int)blockIdx.x >= J.nlines) return;
   const int niter = (J.nlines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int ntot = niter * NC;          // chunks this CTA consumes
-
-  // chunk n of this CTA -> stage n % S  (one thread)
-  auto issue = [&](int n) {
-    const int it = n / NC, c = n - it * NC;
-    const int j = J.jstart + ((int)blockIdx.x + it * (int)gridDim.x) * J.jstep;
-    const int len = min(CH, n1 - c * CH);
-    double* stage = sm + (size_t)(n % S) * NARR * SW;
-    unsigned long long* bar = bars + (n % S);
-    issued[n % S] = n;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-    for (int a = 0; a < NARR; ++a) {
-      const double* base = ring_base(J, nv, a);
-      const int p0 = addr_parity(base);
-      // indices relative to the array: the chunk needs [g0 - 1, g0 + len + 1) clipped to the array
-      const long long g0 = (long long)ring_row(J, a, j) * n1 + (long long)c * CH;
-      const int sft = (int)((g0 + p0) & 1);
-      long long nl = g0 - 1, nh = g0 + len + 1;
-      if (nl < 0) nl = 0;
-      if (nh > (long long)nv) nh = (long long)nv;
-      long long t0 = nl - ((nl + p0) & 1), t1 = nh + ((nh + p0) & 1);   // 16-byte aligned ends
-      double* slot = stage + (size_t)a * SW + (4 + sft) - g0;           // slot[E] = element E of the array
-      if (t0 < 0) { t0 += 2; slot[nl] = base[nl]; }
-      if (t1 > (long long)nv) { t1 -= 2; slot[nh - 1] = base[nh - 1]; }
-      const unsigned bytes = (unsigned)(t1 - t0) * 8u;
-      mbar_expect_tx(bar, bytes);
-      tma_g2s(slot + t0, base + t0, bytes, bar);
-    }
-  };
+  const int ntot = niter * NARR;          // streams this CTA consumes
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(bars + s, NARR); issued[s] = -1; }
+    for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (unsigned)ncw); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
+
+  if (tid >= TC) {
+    // ---------------- producer warp: one lane issues, in stream order
+    if (tid != TC) return;
     if (COUPLED && blockIdx.x == 0) {   // line 0 of the job reads the ghost row: wait for the neighbour's push
       if (J.wait == 1) halo_wait_below(H);
       if (J.wait == 2) halo_wait_above(H);
       asm volatile("fence.proxy.async;" ::: "memory");
     }
-    const int npro = min(S, ntot);
-    for (int n = 0; n < npro; ++n) issue(n);
+    int it2 = 0, a = 0;
+    for (int n = 0; n < ntot; ++n) {
+      const int sidx = n % S;
+      if (n >= S) mbar_wait(empty + sidx, (unsigned)(((n / S) - 1) & 1));   // the consumers have read stream n - S
+      const int j = J.jstart + ((int)blockIdx.x + it2 * (int)gridDim.x) * J.jstep;
+      const double* base = ring_base<COUPLED>(J, nv, a);
+      const int p0 = addr_parity(base);
+      // indices relative to the array: the line needs [g0 - 1, g0 + n1 + 1) clipped to the array
+      const long long g0 = (long long)ring_row<COUPLED>(J, a, j) * n1;
+      const int sft = (int)((g0 + p0) & 1);
+      long long nl = g0 - 1, nh = g0 + n1 + 1;
+      if (nl < 0) nl = 0;
+      if (nh > (long long)nv) nh = (long long)nv;
+      long long t0 = nl - ((nl + p0) & 1), t1 = nh + ((nh + p0) & 1);   // 16-byte aligned ends
+      double* slot = sm + (size_t)sidx * SW + (4 + sft) - g0;           // slot[E] = element E of the array
+      // (no proxy fence: the consumers only READ the slot through the generic proxy, and their reads are ordered
+      // before this point by the empty barrier -- a fence here drains the copies in flight, ~0.25 us per stream)
+      if (t0 < 0) { t0 += 2; slot[nl] = base[nl]; }
+      if (t1 > (long long)nv) { t1 -= 2; slot[nh - 1] = base[nh - 1]; }
+      const unsigned bytes = (unsigned)(t1 - t0) * 8u;
+      mbar_expect_tx(full + sidx, bytes);
+      tma_g2s(slot + t0, base + t0, bytes, full + sidx);
+      if (++a == NARR) { a = 0; ++it2; }
+    }
+    return;
   }
 
+  // ---------------- consumer warps
+  const int lane = tid & 31;
+  const int i0 = tid * kE;
+  const int ne = max(0, min(kE, n1 - i0));
   for (int it = 0; it < niter; ++it) {
     const int l = (int)blockIdx.x + it * (int)gridDim.x;
     const int j = J.jstart + l * J.jstep;
     const size_t lbase = (size_t)j * n1;
-    const int n = it * NC + grp;
-    double r[kE], lv[kE], iv[kE], cv[kE];
-    {
-      const double* stage = sm + (size_t)(n % S) * NARR * SW;
-      {
-        long long spins = 0;
-        while (issued[n % S] != n)
-          if (++spins > (1ll << 28)) __trap();
-      }
-      mbar_wait(bars + (n % S), (unsigned)((n / S) & 1));
-      auto at = [&](int a) -> const double* {   // own first element of array a
-        const int sft = (addr_parity(ring_base(J, nv, a)) + ((ring_row(J, a, j) & n1) & 1)) & 1;
-        return stage + (size_t)a * SW + k0 + 4 + sft;
-      };
-      const double* pb = at(0); const double* pl = at(1); const double* pi = at(2); const double* pc = at(3);
+    int n = it * NARR;
+    RT(0);
+    if (J.prefetch && it + 1 < niter) {
+      // every stream of this CTA's NEXT line -> L2, one 128-byte line per prefetch instruction, spread over the
+      // consumer threads (bulk prefetches through the copy engine cost as much as the copies themselves): HBM
+      // streams a line ahead of the ring, the bulk copies then hit L2
+      const int jn = J.jstart + (l + (int)gridDim.x) * J.jstep;
 #pragma unroll
-      for (int e = 0; e < kE; ++e)
-        if (e < ne) { r[e] = pb[e]; lv[e] = pl[e]; iv[e] = pi[e]; cv[e] = pc[e]; }
-      if (COUPLED) {
-        const double* a0 = at(4); const double* a1 = at(5); const double* a5 = at(6); const double* a6 = at(7);
-        const double* xl = at(8); const double* xu = at(9);
-        const bool has_lo = j > 0, has_up = j < J.ny;   // the clamped stand-in rows must not leak NaNs through 0 * x
+      for (int a = 0; a < NARR; ++a) {
+        const char* p = reinterpret_cast<const char*>(ring_base<COUPLED>(J, nv, a) + (size_t)ring_row<COUPLED>(J, a, jn) * n1);
+        for (int c = tid * 128; c < n1 * 8; c += TC * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
+      }
+    }
+    // stream `a` of this line: wait, return the pointer to the own first element
+    auto acquire = [&](const int a) -> const double* {
+      const int sidx = n % S;
+      mbar_wait(full + sidx, (unsigned)((n / S) & 1));
+      const int sft = (addr_parity(ring_base<COUPLED>(J, nv, a)) + ((ring_row<COUPLED>(J, a, j) & n1) & 1)) & 1;
+      return sm + (size_t)sidx * SW + i0 + 4 + sft;
+    };
+    auto release = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + (n % S));
+      ++n;
+    };
+    double r[kE], lv[kE], iv[kE], cv[kE];
+    if (COUPLED) {
+      const bool has_lo = j > 0, has_up = j < J.ny;   // the clamped stand-in rows must not leak NaNs through 0 * x
+      double xn[kE + 1];
+      {
+        const double* p = acquire(0);   // x on the line below: elements i-1 .. i+kE-1
+#pragma unroll
+        for (int e = 0; e <= kE; ++e) xn[e] = (has_lo && ne > 0 && e <= ne && i0 + e - 1 >= 0) ? p[e - 1] : 0.0;
+        release();
+      }
+      RT(1);
+      {
+        const double* p = acquire(1);
+#pragma unroll
+        for (int e = 0; e < kE; ++e) r[e] = (e < ne) ? -p[e] * xn[e] : 0.0;
+        release();
+      }
+      {
+        const double* p = acquire(2);
 #pragma unroll
         for (int e = 0; e < kE; ++e)
-          if (e < ne) {
-            const int i = i0 + e;
-            const double xlm = (has_lo && i > 0) ? xl[e - 1] : 0.0;
-            const double xl0 = has_lo ? xl[e] : 0.0;
-            const double xu0 = has_up ? xu[e] : 0.0;
-            const double xup = (has_up && i < J.nx) ? xu[e + 1] : 0.0;
-            r[e] -= a0[e] * xlm + a1[e] * xl0 + a5[e] * xu0 + a6[e] * xup;
-          }
+          if (e < ne) r[e] -= p[e] * xn[e + 1];
+        release();
       }
-      group_bar(1 + grp, gthreads);   // the stage has been read by its whole group
-      if (leader && n + S < ntot) issue(n + S);
+      {
+        const double* p = acquire(3);   // x on the line above: elements i .. i+kE
+#pragma unroll
+        for (int e = 0; e <= kE; ++e) xn[e] = (has_up && ne > 0 && e <= ne && i0 + e <= J.nx) ? p[e] : 0.0;
+        release();
+      }
+      {
+        const double* p = acquire(4);
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) r[e] -= p[e] * xn[e];
+        release();
+      }
+      {
+        const double* p = acquire(5);
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) r[e] -= p[e] * xn[e + 1];
+        release();
+      }
+      {
+        const double* p = acquire(6);
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) r[e] += p[e];
+        release();
+      }
+    } else {
+      const double* p = acquire(0);
+#pragma unroll
+      for (int e = 0; e < kE; ++e)
+        if (e < ne) r[e] = p[e];
+      release();
     }
+    RT(2);
+    {
+      const double* p = acquire(NARR - 3);
+#pragma unroll
+      for (int e = 0; e < kE; ++e)
+        if (e < ne) lv[e] = p[e];
+      release();
+    }
+    {
+      const double* p = acquire(NARR - 2);
+#pragma unroll
+      for (int e = 0; e < kE; ++e)
+        if (e < ne) iv[e] = p[e];
+      release();
+    }
+    {
+      const double* p = acquire(NARR - 1);
+#pragma unroll
+      for (int e = 0; e < kE; ++e)
+        if (e < ne) cv[e] = p[e];
+      release();
+    }
+    RT(3);
     // forward: z_i = r_i - l_i z_{i-1};  w_i = z_i / u_i
     Aff m{1.0, 0.0};
 #pragma unroll
     for (int e = 0; e < kE; ++e)
       if (e < ne) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
-    double z = aff_block_scan(m, sh, false);
+    double z = aff_consumer_scan(m, sh, false, ncw);
 #pragma unroll
     for (int e = 0; e < kE; ++e)
       if (e < ne) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
+    RT(4);
     // backward: x_i = w_i - (c_i/u_i) x_{i+1}
     m = Aff{1.0, 0.0};
 #pragma unroll
     for (int e = kE - 1; e >= 0; --e)
       if (e < ne) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
-    double xn = aff_block_scan(m, sh, true);
+    double xb = aff_consumer_scan(m, sh, true, ncw);
 #pragma unroll
     for (int e = kE - 1; e >= 0; --e)
-      if (e < ne) { xn = r[e] - cv[e] * xn; s_x[i0 + e] = xn; }
-    __syncthreads();
+      if (e < ne) { xb = r[e] - cv[e] * xb; s_x[i0 + e] = xb; }
+    RT(5);
+    group_bar(1, TC);
+    RT(6);
     double* xo = J.x + lbase;
-    for (int i = tid; i < n1; i += blockDim.x) xo[i] = s_x[i];
+    for (int i = tid; i < n1; i += TC) xo[i] = s_x[i];
+    RT(7);
     if (l == 0 && J.push && H.active) {   // strip-boundary line: also into the neighbour's copy of x
       double* pbase = J.push == 1 ? H.dn_base : H.up_base;
       if (pbase != nullptr) {
         double* xp = halo_peer_ptr(H, pbase, J.x) + lbase;
-        for (int i = tid; i < n1; i += blockDim.x) xp[i] = s_x[i];
+        for (int i = tid; i < n1; i += TC) xp[i] = s_x[i];
       }
-      halo_publish(H, J.push == 1);
+      __threadfence_system();
+      group_bar(1, TC);
+      if (tid == 0) {   // publish (cm_halo.cuh: halo_publish, here with the consumers' barrier)
+        unsigned long long* c = halo_ctl(H);
+        const bool down = J.push == 1;
+        const unsigned long long seq = ld_volatile_u64(c + (down ? kChCntDn : kChCntUp)) + 1ull;
+        c[down ? kChCntDn : kChCntUp] = seq;
+        if (pbase != nullptr)
+          st_release_sys(reinterpret_cast<unsigned long long*>(pbase) + (size_t)H.chan * kChStride +
+                             (down ? kChFlagAbove : kChFlagBelow), seq);
+      }
     }
+    group_bar(1, TC);   // s_x is rewritten by the next line
   }
 }
 
@@ -640,16 +778,27 @@ int mg_init_attributes() {
   return CM_OK;
 }
 
-static bool ring_fits(int n1) { return n1 >= 1024 && (n1 + kE - 1) / kE <= kRingMaxT; }
+static bool ring_fits(int n1) { return n1 >= 1024 && ((n1 + kE - 1) / kE + 31) / 32 * 32 + 32 <= kRingMaxT; }
 
-static void ring_config(int n1, int& T, int& CW, int& S, size_t& smem, int& occ) {
+// shared memory of one CTA: S line-sized slots + the output line + 2 S barriers
+static size_t ring_smem(int n1, int S) {
+  const int SW = (n1 + 9) & ~1;
+  return ((size_t)S * SW + ((n1 + 2) & ~1) + 2 * S + 2) * sizeof(double);
+}
+
+// Ring geometry: from a zero guess the four streams of a line fit (the next line loads during the scans);
+// with couplings 5 of the 10 streams are in flight in shared memory and the rest waits in L2.
+static void ring_config(int n1, int narr, int& T, int& S, size_t& smem, int& occ) {
   const int nw = ((n1 + kE - 1) / kE + 31) / 32;
-  T = nw * 32;
-  CW = n1 > 2049 ? 4 : (n1 > 1025 ? 2 : 1);
-  S = 3;
-  const int CH = CW * 32 * kE, SW = CH + 8;
-  smem = ((size_t)S * 10 * SW + ((n1 + 2) & ~1) + 2 * S + 2) * sizeof(double);
-  occ = n1 > 2049 ? 1 : (n1 > 1025 ? 2 : 4);
+  T = (nw + 1) * 32;   // + the producer warp
+  S = narr == 4 ? 4 : 5;
+  if (const char* e = getenv("CM_RING_S")) { const int v = atoi(e); if (v >= 2 && v <= 16) S = v; }
+  while (S > 2 && ring_smem(n1, S) > 220 * 1024) --S;
+  smem = ring_smem(n1, S);
+  occ = (int)((228 * 1024) / (smem + 1024));
+  if (occ < 1) occ = 1;
+  if (occ > 4) occ = 4;
+  if (occ * T > 2048) occ = 2048 / T;
 }
 
 // lines of `colour` among the rows [r0, r1) of a grid with ny+1 rows; r1 < 0: whole grid.  Multi-GPU strips
@@ -685,17 +834,22 @@ int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   CM_BYTES(bytes);
   if (prof) prof_begin(kProfZebraFine, bytes, st);
   if (ring_fits(n1)) {
-    int T, CW, S, occ;
+    int T, S, occ;
     size_t smem;
-    ring_config(n1, T, CW, S, smem, occ);
+    ring_config(n1, x_zero ? 4 : 10, T, S, smem, occ);
+    if (const char* e = getenv("CM_RING_DBG")) J.dbg = atoi(e);
+    J.prefetch = 0;   // measured: pulling the next line into L2 ahead of the ring costs more than it hides (profiles/README.md)
+    if (const char* e = getenv("CM_RING_PREFETCH")) J.prefetch = atoi(e);
+    if (smem > 220 * 1024) {
+      set_error("zebra ring: %zu bytes of shared memory requested (CM_RING_S too large)", smem);
+      return CM_E_INVALID;
+    }
     if ((rc_attr = mg_init_attributes())) return rc_attr;
     const int grid = J.nlines < 148 * occ ? J.nlines : 148 * occ;
     if (x_zero) {
-      const int CH = CW * 32 * kE, SW = CH + 8;
-      const size_t smem0 = ((size_t)S * 4 * SW + ((n1 + 2) & ~1) + 2 * S + 2) * sizeof(double);
-      zebra_ring_kernel<false><<<grid, T, smem0, st>>>(J, H, CW, S);
+      zebra_ring_kernel<false><<<grid, T, smem, st>>>(J, H, S);
     } else {
-      zebra_ring_kernel<true><<<grid, T, smem, st>>>(J, H, CW, S);
+      zebra_ring_kernel<true><<<grid, T, smem, st>>>(J, H, S);
     }
   } else {
     const int T = (n1 > 2048) ? 512 : ((n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32));
@@ -749,6 +903,10 @@ int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H
 }
 
 int mg_coarse_max_n1() { return 32 * kCE; }
+
+int mg_ring_debug_times(unsigned long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_ring_dbg, sizeof(unsigned long long) * n) == cudaSuccess ? CM_OK : CM_E_CUDA;
+}
 
 int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st) {
   for (int k = 0; k < C.nlev; ++k)

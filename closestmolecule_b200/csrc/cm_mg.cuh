@@ -14,6 +14,8 @@ struct LineJob {
   int nx, ny;
   int jstart, jstep, nlines;
   int wait, push;
+  int prefetch;   // pull the next line of every stream into L2 (long-line kernel)
+  int dbg;   // phase stamps for tools/time_ring.py (0: off, 1: thread 0, 2: leader of the last warp group)
   const double* A;
   const double* lf;
   const double* iu;
@@ -48,6 +50,7 @@ int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H
 int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st);
 int mg_coarse_max_n1();
 int mg_init_attributes();
+int mg_ring_debug_times(unsigned long long* host_out, int n);
 
 Halo dist_halo_args(const cm_dist* D, int chan);
 

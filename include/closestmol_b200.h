@@ -280,6 +280,9 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
  *     half sweep that follows). */
 int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
                 const double* cu, const double* b, double* x, int32_t x_is_zero, void* stream);
+/* diagnostics: %globaltimer phase stamps [cta < 64][line < 16][8] of the last cm_mg_zebra launch that ran with
+ * the environment variable CM_RING_DBG set (tools/time_ring.py) */
+int cm_mg_ring_debug_times(uint64_t* host_out, int32_t n);
 int cm_mg_resid_restrict(int32_t nxf, int32_t nyf, const double* A, const double* b, const double* x,
                          double* rc, void* stream);
 int cm_mg_prolong_odd(int32_t nxc, int32_t nyc, const double* ec, double* xf, void* stream);

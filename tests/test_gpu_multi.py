@@ -18,9 +18,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nx, out):
+def _worker(rank, world, port, nx, out, env):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(env)
     import torch.distributed as dist
     import closestmolecule_b200 as cm
     from closestmolecule_b200.manufactured import p_exact, q_exact
@@ -46,18 +47,25 @@ def _worker(rank, world, port, nx, out):
     sol = d.gather_solution()
     err = float(torch.linalg.vector_norm(sol - u.vector()) / torch.linalg.vector_norm(u.vector()))
     if rank == 0:
-        torch.save(dict(it1=it1, it2=it2, lin1=s.linear_iterations, lin2=d.linear_iterations, err=err), out)
+        torch.save(dict(it1=it1, it2=it2, lin1=s.linear_iterations, lin2=d.linear_iterations, err=err,
+                        info=d.info()), out)
     d.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nx", [128, 512])
-def test_two_gpu_strip_partition_matches_single_gpu(nx, tmp_path):
+# nx = 128 with the fused coarse cycle pushed down to 17-point lines: two distributed levels on the short-line
+# kernel; nx = 128 default: everything below the q-sweeps replicated (first replicated level 0); nx = 512: the
+# 513-unknown lines of the short-line kernel; nx = 1024: the long-line (ring) kernel pushes / waits inline;
+# CM_SOLVER_V1: the first-generation path with explicit exchange launches (same counters and flags)
+@pytest.mark.parametrize("nx,env", [(128, {"CM_COARSE_N1": "17"}), (128, {}), (512, {}), (1024, {}),
+                                    (1024, {"CM_DIST_LD": "1"}), (512, {"CM_SOLVER_V1": "1"})])
+def test_two_gpu_strip_partition_matches_single_gpu(nx, env, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(2, _free_port(), nx, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), nx, out, env), nprocs=2, join=True)
     r = torch.load(out)
     assert r["it1"] == r["it2"] and r["lin1"] == r["lin2"], r
     assert r["err"] < 1e-10, r
+    assert r["info"]["generation"] == (1 if "CM_SOLVER_V1" in env else 2), r
