@@ -81,6 +81,34 @@ __device__ __forceinline__ long long gd_index(long long i, const VecSlice s) {
   return i < s.len ? s.off0 + i : s.off1 + (i - s.len);
 }
 
+// one pass over w for K consecutive basis vectors (fully unrolled: K independent loads in flight per thread)
+template <int K, bool SLICE>
+__device__ __forceinline__ void gd_dot_group(const GmresDev& G, const VecSlice& sl, const double* __restrict__ Vb,
+                                             const double* __restrict__ w, double* acc) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  if (SLICE) {
+    const long long n = 2 * sl.len;
+    for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
+      const long long q = gd_index(i, sl);
+      const double ww = w[q];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += Vb[(size_t)k * G.ne + q] * ww;
+    }
+  } else {
+    const long long n2 = G.n >> 1;
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n2; i += (long long)gridDim.x * kGB) {
+      const double2 ww = w2[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double2 vv = reinterpret_cast<const double2*>(Vb + (size_t)k * G.ne)[i];
+        acc[k] += vv.x * ww.x + vv.y * ww.y;
+      }
+    }
+  }
+}
+
 // dots[k] = vscale[k] <V_k, w> for k <= j (V_k holds the unnormalised basis vector);  j = st[0]
 template <bool SLICE>
 __global__ void __launch_bounds__(kGB)
@@ -93,39 +121,24 @@ gd_dot_kernel(const GmresDev G, const VecSlice sl) {
   const double* __restrict__ w = G.w;
   for (int grp = 0; grp < ngroups; ++grp) {
     const int k0 = grp * kGK;
-    const double* vp[kGK];
-#pragma unroll
-    for (int k = 0; k < kGK; ++k) {
-      const int kk = k0 + k;
-      vp[k] = kk <= j ? G.V + (size_t)kk * G.ne : nullptr;
-    }
+    const int nk = min(kGK, nvec - k0);
+    const double* Vb = G.V + (size_t)k0 * G.ne;
     double acc[kGK];
 #pragma unroll
     for (int k = 0; k < kGK; ++k) acc[k] = 0.0;
-    if (SLICE) {
-      const long long n = 2 * sl.len;
-      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
-        const long long q = gd_index(i, sl);
-        const double ww = w[q];
-#pragma unroll
-        for (int k = 0; k < kGK; ++k)
-          if (vp[k] != nullptr) acc[k] += vp[k][q] * ww;
-      }
-    } else {
-      const long long n2 = G.n >> 1;
-      const double2* w2 = reinterpret_cast<const double2*>(w);
-      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n2; i += (long long)gridDim.x * kGB) {
-        const double2 ww = w2[i];
-#pragma unroll
-        for (int k = 0; k < kGK; ++k)
-          if (vp[k] != nullptr) {
-            const double2 vv = reinterpret_cast<const double2*>(vp[k])[i];
-            acc[k] += vv.x * ww.x + vv.y * ww.y;
-          }
-      }
+    switch (nk) {   // uniform over the grid
+      case 1: gd_dot_group<1, SLICE>(G, sl, Vb, w, acc); break;
+      case 2: gd_dot_group<2, SLICE>(G, sl, Vb, w, acc); break;
+      case 3: gd_dot_group<3, SLICE>(G, sl, Vb, w, acc); break;
+      case 4: gd_dot_group<4, SLICE>(G, sl, Vb, w, acc); break;
+      case 5: gd_dot_group<5, SLICE>(G, sl, Vb, w, acc); break;
+      case 6: gd_dot_group<6, SLICE>(G, sl, Vb, w, acc); break;
+      case 7: gd_dot_group<7, SLICE>(G, sl, Vb, w, acc); break;
+      default: gd_dot_group<8, SLICE>(G, sl, Vb, w, acc); break;
     }
 #pragma unroll
     for (int k = 0; k < kGK; ++k) {
+      if (k >= nk) break;
       const double s = gd_block_sum(acc[k], sh);
       if (threadIdx.x == 0) G.partial[((size_t)grp * gridDim.x + blockIdx.x) * kGK + k] = s;
     }
@@ -170,7 +183,14 @@ gd_update_kernel(const GmresDev G, const VecSlice sl) {
       for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
         const long long q = gd_index(i, sl);
         double a = w[q];
-        for (int k = 0; k <= j; ++k) a -= s_h[k] * G.V[(size_t)k * G.ne + q];
+        const double* vq = G.V + q;
+        int k = 0;
+        for (; k + 4 <= j + 1; k += 4) {   // four independent loads in flight
+          const double v0 = vq[(size_t)k * G.ne], v1 = vq[(size_t)(k + 1) * G.ne];
+          const double v2 = vq[(size_t)(k + 2) * G.ne], v3 = vq[(size_t)(k + 3) * G.ne];
+          a -= s_h[k] * v0 + s_h[k + 1] * v1 + s_h[k + 2] * v2 + s_h[k + 3] * v3;
+        }
+        for (; k <= j; ++k) a -= s_h[k] * vq[(size_t)k * G.ne];
         vout[q] = a;
         nrm += a * a;
       }
@@ -179,8 +199,17 @@ gd_update_kernel(const GmresDev G, const VecSlice sl) {
       const double2* w2 = reinterpret_cast<const double2*>(w);
       for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n2; i += (long long)gridDim.x * kGB) {
         double2 a = w2[i];
-        for (int k = 0; k <= j; ++k) {
-          const double2 vv = reinterpret_cast<const double2*>(G.V + (size_t)k * G.ne)[i];
+        const double2* vq = reinterpret_cast<const double2*>(G.V) + i;
+        const size_t ne2 = (size_t)(G.ne >> 1);
+        int k = 0;
+        for (; k + 4 <= j + 1; k += 4) {   // four independent 16-byte loads in flight
+          const double2 v0 = vq[(size_t)k * ne2], v1 = vq[(size_t)(k + 1) * ne2];
+          const double2 v2 = vq[(size_t)(k + 2) * ne2], v3 = vq[(size_t)(k + 3) * ne2];
+          a.x -= s_h[k] * v0.x + s_h[k + 1] * v1.x + s_h[k + 2] * v2.x + s_h[k + 3] * v3.x;
+          a.y -= s_h[k] * v0.y + s_h[k + 1] * v1.y + s_h[k + 2] * v2.y + s_h[k + 3] * v3.y;
+        }
+        for (; k <= j; ++k) {
+          const double2 vv = vq[(size_t)k * ne2];
           a.x -= s_h[k] * vv.x;
           a.y -= s_h[k] * vv.y;
         }

@@ -37,6 +37,7 @@ struct CoarseLevel {
 constexpr int kCoarseMaxLevels = 8;
 struct CoarseCycle {
   int nlev, pre, post;
+  int dbg;   // phase stamps (diagnostics)
   const double* Ainv;   // dense inverse on the last level (nullptr: 30 zebra sweeps there)
   CoarseLevel lev[kCoarseMaxLevels];
 };
@@ -48,6 +49,8 @@ int mg_resid_restrict(int nxf, int nyf, const double* A, const double* b, const 
 int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H, int wait_coarse, int r0,
                    int r1, cudaStream_t st);
 int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st);
+size_t mg_coarse_smem_bytes(const CoarseCycle& C);
+int mg_coarse_smem_cycle(const CoarseCycle& C, cudaStream_t st);
 int mg_coarse_max_n1();
 int mg_init_attributes();
 int mg_ring_debug_times(unsigned long long* host_out, int n);

@@ -69,7 +69,8 @@ struct PQKnobs {
   int graph = 1;            // replay fixed kernel sequences as CUDA graphs
   int v1 = 0;               // CM_SOLVER_V1=1: first-generation kernels (two-kernel zebra sweeps, host-driven GMRES)
   int coarse_ncta = 8;      // CTAs of the cluster that runs the fused coarse cycle (1 or 8)
-  int coarse_n1 = -1;       // the fused coarse cycle starts at the first level with nx + 1 <= coarse_n1
+  int coarse_n1 = -1;       // the global-memory fused coarse cycle starts at the first level with nx + 1 <= coarse_n1 (0: off)
+  int coarse_smem = 1;      // shared-memory resident cycle (one CTA) from the first level whose arrays fit
   int gmres_host = 0;       // diagnostics: second-generation preconditioner under the host-driven GMRES (1 GPU)
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
 };
@@ -92,7 +93,10 @@ static PQKnobs read_knobs() {
   K.graph = env_int("CM_GRAPH", 1, 0);
   K.v1 = env_int("CM_SOLVER_V1", 0, 0);
   K.coarse_ncta = env_int("CM_COARSE_NCTA", 8, 1) >= 8 ? 8 : 1;
-  K.coarse_n1 = env_int("CM_COARSE_N1", K.coarse_ncta == 8 ? 257 : 65, 0);
+  // measured at 16 Mi cells (profiles/README.md): the cluster kernel with global-memory phases (3-4 us each) is no
+  // faster than separate kernels inside a CUDA graph -> off by default; the shared-memory resident cycle is on
+  K.coarse_n1 = env_int("CM_COARSE_N1", 0, 0);
+  K.coarse_smem = env_int("CM_COARSE_SMEM", 1, 0);
   K.gmres_host = env_int("CM_GMRES_HOST", 0, 0);
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
   return K;
@@ -651,7 +655,8 @@ struct PQContext {
   DistInfo I{};
   Halo H{};        // strip neighbours (inactive on one GPU)
   Halo Hoff{};     // inactive: replicated levels
-  int Lc = 0;      // first level of the fused coarse cycle (nlev: none)
+  int Lc = 0;      // first level of the global-memory fused coarse cycle (nlev: none)
+  int Lsm = 0;     // first level of the shared-memory resident coarse cycle (nlev: none)
   int wide = 0;
   bool use_v1 = false;
   GmresDev G{};
@@ -696,6 +701,19 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
       break;
     }
   if (C->Lc == S.nlev - 1 && !S.dense_coarse) C->Lc = S.nlev;   // a lone coarsest level without dense inverse: sweeps
+  C->Lsm = S.nlev;
+  if (C->K.coarse_smem)
+    for (int l = 0; l < S.nlev; ++l) {
+      if (S.nlev - l > kCoarseMaxLevels) continue;
+      CoarseCycle cc{};
+      cc.nlev = S.nlev - l;
+      for (int k = 0; k < cc.nlev; ++k) { cc.lev[k].nx = S.lev[l + k].nx; cc.lev[k].ny = S.lev[l + k].ny; }
+      const size_t need = mg_coarse_smem_bytes(cc);
+      if (need > 0 && need <= 200 * 1024 && (l < S.nlev - 1 || S.dense_coarse)) {
+        C->Lsm = l;
+        break;
+      }
+    }
   if (D != nullptr && D->world > 1) {
     C->dist = true;
     C->D = *D;
@@ -713,6 +731,7 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
     // replicated level (zebra colouring of the halo protocol, cm_halo.cuh): clamp Ld to the alignment present
     int Ld = S.dist_ld;
     if (Ld > C->Lc) Ld = C->Lc;
+    if (Ld > C->Lsm) Ld = C->Lsm;
     if (Ld > S.nlev - 1) Ld = S.nlev - 1;
     for (int r = 1; r < D->world; ++r)
       while (Ld > 0 && (D->row_begin[r] & ((1 << Ld) - 1)) != 0) --Ld;
@@ -779,7 +798,7 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     int n = (C->I.re[l] - C->I.rb[l]) * (L.nx + 1);
     if ((rc = dist_allgather(&C->D, &off, &n, 1, st))) return rc;
   }
-  if (l >= C->Lc) {
+  if (l >= C->Lc || l >= C->Lsm) {
     CoarseCycle cc{};
     cc.nlev = S.nlev - l;
     cc.pre = S.pre_smooth;
@@ -790,6 +809,7 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
       cc.lev[k] = CoarseLevel{Lk.nx, Lk.ny, Lk.A, Lk.lf, Lk.iu, Lk.cu, k == 0 ? const_cast<double*>(b) : Lk.b,
                               k == 0 ? x : Lk.x};
     }
+    if (l >= C->Lsm) return mg_coarse_smem_cycle(cc, st);
     return mg_coarse_cycle(cc, C->K.coarse_ncta, st);
   }
   const Halo& H = lev_dist ? C->H : C->Hoff;
@@ -1024,7 +1044,7 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
 int pqs_ctx_info(void* ctx, int* out8) {
   PQContext* C = static_cast<PQContext*>(ctx);
   out8[0] = C->S.nlev;
-  out8[1] = C->Lc;
+  out8[1] = C->Lsm < C->Lc ? C->Lsm : C->Lc;
   out8[2] = C->dist ? C->I.Ld : -1;
   out8[3] = (C->use_v1 || C->wide) ? 1 : 2;
   out8[4] = C->g_iter.exec ? (int)C->g_iter.launches : 0;

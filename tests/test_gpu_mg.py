@@ -188,12 +188,15 @@ def _supg_solver(nx, ny, restart=40):
 def test_kernel_generations_agree(nx, ny, monkeypatch):
     """The same Jacobian solved by the first-generation path (two-kernel sweeps, full residual / restriction /
     prolongation, host-driven GMRES with two reductions) and by the second-generation path, with the coarse
-    levels as one cluster kernel, as one single-CTA kernel, and unfused: same iteration counts, same solution."""
+    levels as the shared-memory resident cycle (default), as one cluster kernel with global-memory phases, as one
+    single-CTA kernel of that kind, and unfused: same iteration counts, same solution."""
     asm, make = _supg_solver(nx, ny)
     res = {}
-    for name, env in (("v1", {"CM_SOLVER_V1": "1"}), ("v2", {}), ("v2_cta1", {"CM_COARSE_NCTA": "1"}),
-                      ("v2_unfused", {"CM_COARSE_N1": "0"}), ("v2_nograph", {"CM_GRAPH": "0"})):
-        for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH"):
+    for name, env in (("v1", {"CM_SOLVER_V1": "1"}), ("v2", {}),
+                      ("v2_cluster", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "257"}),
+                      ("v2_cta1", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "65", "CM_COARSE_NCTA": "1"}),
+                      ("v2_unfused", {"CM_COARSE_SMEM": "0"}), ("v2_nograph", {"CM_GRAPH": "0"})):
+        for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH", "CM_COARSE_SMEM"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -209,7 +212,7 @@ def test_kernel_generations_agree(nx, ny, monkeypatch):
     for name, (it, xx, rr) in res.items():
         assert abs(it - ref_it) <= 1, {k: v[0] for k, v in res.items()}
         assert np.linalg.norm(xx - ref_x) / np.linalg.norm(ref_x) < 1e-8, name
-    assert res["v2"][0] == res["v2_cta1"][0] == res["v2_unfused"][0] == res["v2_nograph"][0]
+    assert res["v2"][0] == res["v2_cta1"][0] == res["v2_unfused"][0] == res["v2_nograph"][0] == res["v2_cluster"][0]
     assert np.linalg.norm(res["v2"][1] - res["v2_nograph"][1]) == 0.0      # graph replay is bit-identical
 
 
