@@ -76,7 +76,7 @@ enum GmresStatusSlot { kStJ = 0, kStIts = 1, kStConv = 2, kStResid = 3, kStTarge
 struct GmresDev {
   long long n, ne;
   int m;
-  double *V, *w, *z;
+  double *V, *w, *z, *Z;
   double *dots, *coef, *vscale, *nrm, *H, *cs, *sn, *g, *y, *st;
   double* partial;
   unsigned* tickets;
@@ -116,7 +116,8 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb =
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
                cudaStream_t st, int r0 = 0, int r1 = -1, const double* QQx = nullptr,
-               const int* has_extra = nullptr, const struct Halo* H = nullptr);
+               const int* has_extra = nullptr, const struct Halo* H = nullptr, double* zcopy = nullptr,
+               long long zstride = 0, const double* jptr = nullptr, int halo_channels = 1);
 int st_unscale_dev(int nx, int ny, const double* rbase, long long stride, const double* jptr, const double* vscale,
                    const double* sp, const double* sq, double* out, cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,

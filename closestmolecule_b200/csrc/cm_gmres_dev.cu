@@ -30,6 +30,7 @@ size_t gmres_dev_doubles(long long n, int m) {
   const long long ne = (n + 1) & ~1LL;
   const size_t ngroups = (size_t)(m + 2 + kGK - 1) / kGK;
   return (size_t)ne * (m + 1) + (size_t)ne * 2        // basis, w, z
+         + (size_t)ne * m                             // preconditioned basis Z (flexible variant: x = Z y)
          + 3 * (size_t)(m + 2) + 4                    // dots, coef, vscale, nrm
          + (size_t)(m + 1) * m + 2 * (size_t)m + (size_t)(m + 1) + (size_t)m   // H, cs, sn, g, y
          + kGmresStatus + 8                           // status, tickets
@@ -45,6 +46,7 @@ void gmres_dev_layout(GmresDev& G, long long n, int m, double* work) {
   G.V = p; p += (size_t)ne * (m + 1);
   G.w = p; p += ne;
   G.z = p; p += ne;
+  G.Z = p; p += (size_t)ne * m;
   G.dots = p; p += m + 2;
   G.coef = p; p += m + 2;
   G.vscale = p; p += m + 2;
@@ -317,19 +319,25 @@ __global__ void gd_solve_y_kernel(const GmresDev G) {
   }
 }
 
-// out = sum_{k < K} coef_k vscale_k V_k   (K = st[kStK])
+// out (+)= sum_{k < K} coef_k B_k, K = st[kStK];  B = Z (the preconditioned basis: x += Z y) or, with
+// use_vscale, the unnormalised Krylov basis V
 template <bool SLICE>
 __global__ void __launch_bounds__(kGB)
-gd_combine_kernel(const GmresDev G, const VecSlice sl, double* __restrict__ out) {
+gd_combine_kernel(const GmresDev G, const VecSlice sl, const double* __restrict__ B, const int use_vscale,
+                  const int accumulate, double* __restrict__ out) {
   extern __shared__ double s_h[];
   const int K = (int)G.st[kStK];
-  for (int k = threadIdx.x; k < K; k += kGB) s_h[k] = G.coef[k] * G.vscale[k];
+  for (int k = threadIdx.x; k < K; k += kGB) s_h[k] = G.coef[k] * (use_vscale ? G.vscale[k] : 1.0);
   __syncthreads();
   const long long n = SLICE ? 2 * sl.len : G.n;
   for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
     const long long q = SLICE ? gd_index(i, sl) : i;
-    double a = 0.0;
-    for (int k = 0; k < K; ++k) a += s_h[k] * G.V[(size_t)k * G.ne + q];
+    double a = accumulate ? out[q] : 0.0;
+    int k = 0;
+    for (; k + 4 <= K; k += 4)
+      a += s_h[k] * B[(size_t)k * G.ne + q] + s_h[k + 1] * B[(size_t)(k + 1) * G.ne + q] +
+           s_h[k + 2] * B[(size_t)(k + 2) * G.ne + q] + s_h[k + 3] * B[(size_t)(k + 3) * G.ne + q];
+    for (; k < K; ++k) a += s_h[k] * B[(size_t)k * G.ne + q];
     out[q] = a;
   }
 }
@@ -397,13 +405,14 @@ int gmres_dev_solve_y(const GmresDev& G, cudaStream_t st) {
   return CM_OK;
 }
 
+// x += Z y (the solution update of the flexible variant: no further preconditioner application)
 int gmres_dev_combine(const GmresDev& G, const VecSlice* sl, double* out, int khost, cudaStream_t st) {
   const long long len = gd_len(G, sl);
   const int grid = gd_grid(len);
   const size_t smem = (size_t)(G.m + 2) * sizeof(double);
-  if (sl) gd_combine_kernel<true><<<grid, kGB, smem, st>>>(G, *sl, out);
-  else gd_combine_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0}, out);
-  CM_BYTES((double)len * 8.0 * (khost + 1));
+  if (sl) gd_combine_kernel<true><<<grid, kGB, smem, st>>>(G, *sl, G.Z, 0, 1, out);
+  else gd_combine_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0}, G.Z, 0, 1, out);
+  CM_BYTES((double)len * 8.0 * (khost + 2));
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -237,17 +237,21 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
   __syncthreads();
 
   if (tid >= TC) {
-    // ---------------- producer warp: one lane issues, in stream order
-    if (tid != TC) return;
-    if (COUPLED && blockIdx.x == 0) {   // line 0 of the job reads the ghost row: wait for the neighbour's push
+    // ---------------- producer warp: lane s owns ring slot s and issues the streams s, s + S, s + 2S, ... in order
+    // (one lane per slot: every lane waits on its own pair of barriers only, so no phase can be skipped; the
+    // lanes issue in parallel -- a bulk copy stalls the issuing thread for ~0.25 us)
+    const int ps = tid - TC;
+    if (COUPLED && blockIdx.x == 0 && ps == 0) {   // line 0 of the job reads the ghost row: wait for the neighbour's push
       if (J.wait == 1) halo_wait_below(H);
       if (J.wait == 2) halo_wait_above(H);
       asm volatile("fence.proxy.async;" ::: "memory");
     }
-    int it2 = 0, a = 0;
-    for (int n = 0; n < ntot; ++n) {
-      const int sidx = n % S;
+    __syncwarp();
+    if (ps >= S) return;
+    for (int n = ps; n < ntot; n += S) {
+      const int sidx = ps;
       if (n >= S) mbar_wait(empty + sidx, (unsigned)(((n / S) - 1) & 1));   // the consumers have read stream n - S
+      const int it2 = n / NARR, a = n - it2 * NARR;
       const int j = J.jstart + ((int)blockIdx.x + it2 * (int)gridDim.x) * J.jstep;
       const double* base = ring_base<COUPLED>(J, nv, a);
       const int p0 = addr_parity(base);
@@ -260,13 +264,12 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
       long long t0 = nl - ((nl + p0) & 1), t1 = nh + ((nh + p0) & 1);   // 16-byte aligned ends
       double* slot = sm + (size_t)sidx * SW + (4 + sft) - g0;           // slot[E] = element E of the array
       // (no proxy fence: the consumers only READ the slot through the generic proxy, and their reads are ordered
-      // before this point by the empty barrier -- a fence here drains the copies in flight, ~0.25 us per stream)
+      // before this point by the empty barrier)
       if (t0 < 0) { t0 += 2; slot[nl] = base[nl]; }
       if (t1 > (long long)nv) { t1 -= 2; slot[nh - 1] = base[nh - 1]; }
       const unsigned bytes = (unsigned)(t1 - t0) * 8u;
       mbar_expect_tx(full + sidx, bytes);
       tma_g2s(slot + t0, base + t0, bytes, full + sidx);
-      if (++a == NARR) { a = 0; ++it2; }
     }
     return;
   }
@@ -1029,7 +1032,7 @@ static size_t ring_smem(int n1, int S) {
 static void ring_config(int n1, int narr, int& T, int& S, size_t& smem, int& occ) {
   const int nw = ((n1 + kE - 1) / kE + 31) / 32;
   T = (nw + 1) * 32;   // + the producer warp
-  S = narr == 4 ? 4 : 5;
+  S = narr == 4 ? 4 : 5;   // measured (tools/time_ring.py): 5 slots beat a whole line in flight on 2049-point lines
   if (const char* e = getenv("CM_RING_S")) { const int v = atoi(e); if (v >= 2 && v <= 16) S = v; }
   while (S > 2 && ring_smem(n1, S) > 220 * 1024) --S;
   smem = ring_smem(n1, S);
@@ -1071,7 +1074,11 @@ int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   const double bytes = (double)J.nlines * n1 * (x_zero ? 40.0 : 80.0);
   CM_BYTES(bytes);
   if (prof) prof_begin(kProfZebraFine, bytes, st);
-  if (ring_fits(n1)) {
+  bool use_ring = ring_fits(n1);
+  if (const char* e = getenv("CM_ZEBRA_SMALL_BELOW")) {   // tuning: one CTA per line when the launch has few lines
+    if (J.nlines <= atoi(e)) use_ring = false;
+  }
+  if (use_ring) {
     int T, S, occ;
     size_t smem;
     ring_config(n1, x_zero ? 4 : 10, T, S, smem, occ);

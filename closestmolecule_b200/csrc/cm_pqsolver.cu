@@ -71,6 +71,9 @@ struct PQKnobs {
   int coarse_ncta = 8;      // CTAs of the cluster that runs the fused coarse cycle (1 or 8)
   int coarse_n1 = -1;       // the global-memory fused coarse cycle starts at the first level with nx + 1 <= coarse_n1 (0: off)
   int coarse_smem = 1;      // shared-memory resident cycle (one CTA) from the first level whose arrays fit
+  int q_concurrent = 1;     // q-block sweeps on a second stream, concurrently with the p-block V-cycle
+  int post_coarse = -1;     // post-smoothing sweeps on the levels >= coarse_from (-1: same as post)
+  int coarse_from = 2;
   int gmres_host = 0;       // diagnostics: second-generation preconditioner under the host-driven GMRES (1 GPU)
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
 };
@@ -97,6 +100,9 @@ static PQKnobs read_knobs() {
   // faster than separate kernels inside a CUDA graph -> off by default; the shared-memory resident cycle is on
   K.coarse_n1 = env_int("CM_COARSE_N1", 0, 0);
   K.coarse_smem = env_int("CM_COARSE_SMEM", 1, 0);
+  K.q_concurrent = env_int("CM_Q_CONCURRENT", 1, 0);
+  K.post_coarse = env_int("CM_MG_POST_COARSE", -1, 1);
+  K.coarse_from = env_int("CM_MG_COARSE_FROM", 2, 0);
   K.gmres_host = env_int("CM_GMRES_HOST", 0, 0);
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
   return K;
@@ -653,8 +659,11 @@ struct PQContext {
   bool dist = false;
   cm_dist D{};
   DistInfo I{};
-  Halo H{};        // strip neighbours (inactive on one GPU)
+  Halo H{};        // strip neighbours (inactive on one GPU), channel 0: p-block V-cycle
+  Halo Hq{};       // channel 1: q-block sweeps (they run concurrently with the V-cycle on a second stream)
   Halo Hoff{};     // inactive: replicated levels
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int Lc = 0;      // first level of the global-memory fused coarse cycle (nlev: none)
   int Lsm = 0;     // first level of the shared-memory resident coarse cycle (nlev: none)
   int wide = 0;
@@ -671,6 +680,9 @@ static void pqc_destroy(PQContext* C) {
   C->g_iter.destroy();
   C->g_final.destroy();
   if (C->cap) cudaStreamDestroy(C->cap);
+  if (C->s2) cudaStreamDestroy(C->s2);
+  if (C->ev_fork) cudaEventDestroy(C->ev_fork);
+  if (C->ev_join) cudaEventDestroy(C->ev_join);
   if (C->status_host) cudaFreeHost(C->status_host);
   delete C;
 }
@@ -749,6 +761,15 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
     dist_info(S, &C->D, C->base, C->I);
     C->I.Ld = Ld;
     C->H = dist_halo_args(&C->D, 0);
+    C->Hq = dist_halo_args(&C->D, 1);
+  }
+  if (C->K.q_concurrent) {
+    if (cudaStreamCreateWithFlags(&C->s2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&C->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&C->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      C->K.q_concurrent = 0;
+    }
   }
   if (mg_init_attributes() != CM_OK) {
     delete C;
@@ -802,7 +823,7 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     CoarseCycle cc{};
     cc.nlev = S.nlev - l;
     cc.pre = S.pre_smooth;
-    cc.post = S.post_smooth;
+    cc.post = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
     cc.Ainv = S.dense_coarse ? S.Ainv : nullptr;
     for (int k = 0; k < cc.nlev; ++k) {
       const PQSLevel& Lk = S.lev[l + k];
@@ -832,7 +853,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     return rc;
   if ((rc = vcycle2(C, l + 1, Cl.b, Cl.x, st))) return rc;
   if ((rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, H, (lev_dist && l + 1 < C->I.Ld) ? 1 : 0, r0, r1, st))) return rc;
-  for (int s = 0; s < S.post_smooth; ++s) {
+  const int npost = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
+  for (int s = 0; s < npost; ++s) {
     if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
     if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
   }
@@ -851,13 +873,29 @@ static int precond2(PQContext* C, const double* ru, double* z, cudaStream_t st) 
     }
     return e;
   }
-  int rc = vcycle2(C, 0, ru, z, st);
-  if (rc) return rc;
-  const Halo& H = C->dist ? C->H : C->Hoff;
+  // the two blocks of the field split are independent: the q-sweeps (four launches on the finest grid) go to a
+  // second stream and fill the SMs while the V-cycle works through its latency-bound coarse levels; multi-GPU:
+  // they push / wait on their own halo channel
+  const Halo& H = C->dist ? C->Hq : C->Hoff;
   const int r0 = C->dist ? C->I.rb[0] : 0, r1 = C->dist ? C->I.re[0] : -1;
+  const bool fork = C->K.q_concurrent && !g_prof_is_on();
+  cudaStream_t sq = st;
+  int rc;
+  if (fork) {
+    CM_CUDA(cudaEventRecord(C->ev_fork, st));
+    CM_CUDA(cudaStreamWaitEvent(C->s2, C->ev_fork, 0));
+    sq = C->s2;
+  } else if ((rc = vcycle2(C, 0, ru, z, st))) {
+    return rc;
+  }
   for (int sw = 0; sw < S.q_sweeps; ++sw) {
-    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, st))) return rc;
-    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, sq))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, sq))) return rc;
+  }
+  if (fork) {
+    CM_CUDA(cudaEventRecord(C->ev_join, C->s2));
+    if ((rc = vcycle2(C, 0, ru, z, st))) return rc;
+    CM_CUDA(cudaStreamWaitEvent(st, C->ev_join, 0));
   }
   return CM_OK;
 }
@@ -946,13 +984,14 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
     return e;
   };
   auto normalise = [&](int jhost) -> int { return orthogonalise(jhost, st); };
-  auto apply_A = [&](const double* in, double* out, cudaStream_t s_) -> int {
+  // out = A in; keep_z: also store `in` as the preconditioned basis vector Z_j (flexible GMRES)
+  auto apply_A = [&](const double* in, double* out, cudaStream_t s_, bool keep_z = false) -> int {
     return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, s_, rb, C->dist ? re : -1, nullptr,
-                      nullptr, Hp);
+                      nullptr, Hp, keep_z ? G.Z : nullptr, G.ne, G.st + kStJ, 2);
   };
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
   if (C->K.gmres_host && !C->dist) {
-    LinOp A = [&](const double* in, double* out) { return apply_A(in, out, st); };
+    LinOp A = [&](const double* in, double* out) { return apply_A(in, out, st, false); };
     LinOp Minv = [&](const double* r, double* z) {
       int e = st_unscale(nx, ny, r, S.sp, S.sq, S.ru, st);
       return e ? e : precond2(C, S.ru, z, st);
@@ -985,7 +1024,7 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
       rc = run_cached(C, C->g_iter, st, [&](cudaStream_t s_) -> int {
         int e = st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
         if (!e) e = precond2(C, S.ru, G.z, s_);
-        if (!e) e = apply_A(G.z, G.w, s_);
+        if (!e) e = apply_A(G.z, G.w, s_, true);
         if (!e) e = orthogonalise(4, s_);     // byte accounting: a typical mid-cycle iteration, corrected below
         return e;
       });
@@ -1004,13 +1043,10 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
       converged = hs[kStConv] != 0.0;
       stop = converged || its >= maxit || j >= m || hs[kStFlag] == 1.0;
     }
-    // x += M^{-1} (V y)
+    // x += Z y with Z_k = M^{-1} v_k kept from the iterations: no further preconditioner application
     rc = run_cached(C, C->g_final, st, [&](cudaStream_t s_) -> int {
       int e = gmres_dev_solve_y(G, s_);
-      if (!e) e = gmres_dev_combine(G, sl, G.w, 8, s_);
-      if (!e) e = st_unscale_dev(nx, ny, G.w, 0, nullptr, nullptr, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
-      if (!e) e = precond2(C, S.ru, G.z, s_);
-      if (!e) e = gmres_dev_axpby(G, sl, 1.0, G.z, 1.0, S.xs, s_);
+      if (!e) e = gmres_dev_combine(G, sl, S.xs, 8, s_);
       return e;
     });
     if (rc) return rc;

@@ -161,7 +161,9 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
                        const double* __restrict__ QQ, const double* __restrict__ sp,
                        const double* __restrict__ sq, const double* x,
                        double* __restrict__ y, const int vb, const int ve,
-                       const double* __restrict__ QQx, const int* __restrict__ has_extra, const Halo H) {
+                       const double* __restrict__ QQx, const int* __restrict__ has_extra, const Halo H,
+                       double* __restrict__ zcopy, const long long zstride, const double* __restrict__ jptr,
+                       const int halo_channels) {
   const int nv = (nx + 1) * (ny + 1);
   const int n1 = nx + 1;
   if (H.active) {
@@ -169,8 +171,12 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
     // pushed (cm_halo.cuh); only the CTAs that touch those rows look at the flags
     const int c0 = vb + blockIdx.x * kSB, c1 = min(c0 + kSB, ve);
     if (threadIdx.x == 0) {
-      if (c0 < vb + n1) halo_wait_below(H);
-      if (c1 > ve - n1) halo_wait_above(H);
+      for (int ch = 0; ch < halo_channels; ++ch) {   // p- and q-part were produced on their own channels
+        Halo Hc = H;
+        Hc.chan = ch;
+        if (c0 < vb + n1) halo_wait_below(Hc);
+        if (c1 > ve - n1) halo_wait_above(Hc);
+      }
     }
     __syncthreads();
   }
@@ -200,6 +206,11 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
   }
   y[v] = sp[v] * yp;
   y[nv + v] = sq[v] * yq;
+  if (zcopy != nullptr) {   // flexible GMRES: keep the preconditioned basis vector z_j = x (cm_gmres_dev.cu)
+    double* zj = zcopy + (size_t)zstride * (size_t)(int)(*jptr);
+    zj[v] = x[v];
+    zj[nv + v] = x[nv + v];
+  }
 }
 
 // out = r / s (undo the row equilibration before the unscaled preconditioner)
@@ -944,13 +955,15 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, 
 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
-               cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra, const Halo* H) {
+               cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra, const Halo* H,
+               double* zcopy, long long zstride, const double* jptr, int halo_channels) {
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
   CM_BYTES((double)(ve - vb) * 288.0);
   pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve,
-                                                            QQx, has_extra, H ? *H : Halo{});
+                                                            QQx, has_extra, H ? *H : Halo{}, zcopy, zstride, jptr, halo_channels);
+  if (zcopy) CM_BYTES((double)(ve - vb) * 16.0);
   prof_end(kProfSpmv, st);
   CM_LAUNCH_CHECK();
   return CM_OK;
