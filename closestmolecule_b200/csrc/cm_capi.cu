@@ -28,7 +28,6 @@ struct ProfRec {
 };
 static bool g_prof_on = false;
 bool g_prof_is_on() { return g_prof_on; }
-int g_prof_fine_nx = -1;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {

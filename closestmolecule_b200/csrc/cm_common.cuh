@@ -47,7 +47,6 @@ enum ProfClass { kProfZebraFine = 0, kProfSpmv = 1, kProfAssembly = 2, kProfClas
 void prof_begin(int cls, double bytes, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
 bool g_prof_is_on();
-extern int g_prof_fine_nx;  // nx of the finest grid of the solve in progress
 
 // ---- FIAT "default" triangle rules (15-digit constants as stored by FIAT).
 // Barycentric (l0,l1,l2) = (1-xi-eta, xi, eta) and weight (sums to 1/2).

@@ -132,7 +132,7 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
              const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0 = 0,
              int r1 = -1, double* tmp = nullptr, const double* Ax = nullptr,
-             const int* has_extra = nullptr);
+             const int* has_extra = nullptr, bool prof = false);
 int st_coarse_invert(int nx, int ny, const double* A, double* M, double* Ainv, int* err,
                      cudaStream_t st);
 int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaStream_t st);

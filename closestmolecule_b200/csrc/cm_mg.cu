@@ -1046,7 +1046,7 @@ static void ring_config(int n1, int narr, int& T, int& S, size_t& smem, int& occ
 // (H.active): r0 is even; colour 0 starts at r0 (waits below, pushes down), colour 1 at the last odd row
 // (waits above, pushes up).
 int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu, const double* cu,
-             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st) {
+             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st, bool prof) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
   LineJob J{};
@@ -1070,7 +1070,6 @@ int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
     return CM_OK;
   }
   int rc_attr;
-  const bool prof = nx == g_prof_fine_nx;
   const double bytes = (double)J.nlines * n1 * (x_zero ? 40.0 : 80.0);
   CM_BYTES(bytes);
   if (prof) prof_begin(kProfZebraFine, bytes, st);

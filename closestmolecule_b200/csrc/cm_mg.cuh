@@ -43,7 +43,8 @@ struct CoarseCycle {
 };
 
 int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu, const double* cu,
-             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st);
+             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st,
+             bool prof = false);   // prof: count the launch in the roofline class of bench.py (finest grid)
 int mg_resid_restrict(int nxf, int nyf, const double* A, const double* b, const double* x, double* rc,
                       const Halo& H, int Y0, int Y1, cudaStream_t st);
 int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H, int wait_coarse, int r0,

@@ -221,10 +221,10 @@ static int check_err_flag(PQSolver& S, cudaStream_t st, const char* what) {
 
 // L.r is free during smoothing: it serves as the scratch of the pipelined sweep
 static int zebra_sweep(const PQSLevel& L, const double* A, const double* lf, const double* iu,
-                       const double* cu, const double* b, double* x, bool x_zero, cudaStream_t st) {
-  int rc = st_zebra(L.nx, L.ny, 0, A, lf, iu, cu, b, x, x_zero ? 1 : 0, st, 0, -1, L.r);
+                       const double* cu, const double* b, double* x, bool x_zero, cudaStream_t st, bool prof = false) {
+  int rc = st_zebra(L.nx, L.ny, 0, A, lf, iu, cu, b, x, x_zero ? 1 : 0, st, 0, -1, L.r, nullptr, nullptr, prof);
   if (rc) return rc;
-  return st_zebra(L.nx, L.ny, 1, A, lf, iu, cu, b, x, 0, st, 0, -1, L.r);
+  return st_zebra(L.nx, L.ny, 1, A, lf, iu, cu, b, x, 0, st, 0, -1, L.r, nullptr, nullptr, prof);
 }
 
 static int vcycle_on(PQSolver& S, PQSLevel* lev, const double* Ainv, int l, const double* b, double* x,
@@ -239,12 +239,12 @@ static int vcycle_on(PQSolver& S, PQSLevel* lev, const double* Ainv, int l, cons
   }
   PQSLevel& C = lev[l + 1];
   for (int s = 0; s < S.pre_smooth; ++s)
-    if ((rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, s == 0, st))) return rc;
+    if ((rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, s == 0, st, l == 0))) return rc;
   if ((rc = st_residual(L.nx, L.ny, L.A, b, x, L.r, st))) return rc;
   if ((rc = st_restrict(C.nx, C.ny, L.r, C.b, st))) return rc;
   if ((rc = vcycle_on(S, lev, Ainv, l + 1, C.b, C.x, st))) return rc;
   if ((rc = st_prolong_add(C.nx, C.ny, C.x, x, st))) return rc;
-  for (int s = 0; s < S.post_smooth && !rc; ++s) rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st);
+  for (int s = 0; s < S.post_smooth && !rc; ++s) rc = zebra_sweep(L, L.A, L.lf, L.iu, L.cu, b, x, false, st, l == 0);
   return rc;
 }
 
@@ -366,7 +366,6 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
     return CM_E_INVALID;
   }
   const int V = S.nv;
-  g_prof_fine_nx = nx;
   int wide = 0;  // C0IP interior-facet couplings present?
   CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
   CM_CUDA(cudaStreamSynchronize(st));
@@ -389,8 +388,10 @@ int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rt
         int e3 = CM_OK;
         const int nsw = wide ? S.q_sweeps_wide : S.q_sweeps;
         for (int sw = 0; sw < nsw && !e3; ++sw) {
-          e3 = st_zebra(nx, ny, 0, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, sw == 0 ? 1 : 0, s_, 0, -1, S.lev[0].r);
-          if (!e3) e3 = st_zebra(nx, ny, 1, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, 0, s_, 0, -1, S.lev[0].r);
+          e3 = st_zebra(nx, ny, 0, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, sw == 0 ? 1 : 0, s_, 0, -1, S.lev[0].r, nullptr,
+                        nullptr, true);
+          if (!e3)
+            e3 = st_zebra(nx, ny, 1, Aq, S.qlf, S.qiu, S.qcu, bq, z + V, 0, s_, 0, -1, S.lev[0].r, nullptr, nullptr, true);
         }
         return e3;
       };
@@ -577,7 +578,6 @@ int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, doub
   dist_info(S, D, base, I);
   const int V = S.nv, n1 = nx + 1, rb = I.rb[0], re = I.re[0];
   const int vb = rb * n1, ve = re * n1;
-  g_prof_fine_nx = nx;
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
   LinOp A = [&](const double* in, double* out) {
     double* a2[2] = {const_cast<double*>(in), const_cast<double*>(in) + V};
@@ -845,8 +845,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
   }
   PQSLevel& Cl = S.lev[l + 1];
   for (int s = 0; s < S.pre_smooth; ++s) {
-    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st))) return rc;
-    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st, l == 0))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
   }
   if ((rc = mg_resid_restrict(L.nx, L.ny, L.A, b, x, Cl.b, H, lev_dist ? C->I.rb[l + 1] : 0,
                               lev_dist ? C->I.re[l + 1] : -1, st)))
@@ -855,8 +855,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
   if ((rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, H, (lev_dist && l + 1 < C->I.Ld) ? 1 : 0, r0, r1, st))) return rc;
   const int npost = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
   for (int s = 0; s < npost; ++s) {
-    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
-    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
   }
   return CM_OK;
 }
@@ -889,8 +889,8 @@ static int precond2(PQContext* C, const double* ru, double* z, cudaStream_t st) 
     return rc;
   }
   for (int sw = 0; sw < S.q_sweeps; ++sw) {
-    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, sq))) return rc;
-    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, sq))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, sq, true))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, sq, true))) return rc;
   }
   if (fork) {
     CM_CUDA(cudaEventRecord(C->ev_join, C->s2));
@@ -966,7 +966,6 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
   const GmresDev& G = C->G;
   const Halo* Hp = C->dist ? &C->H : nullptr;
   cm_dist* Dp = C->dist ? &C->D : nullptr;
-  g_prof_fine_nx = nx;
   int rc;
   double* hs = C->status_host;
   auto status = [&]() -> int {   // device status block -> pinned host copy, wait

@@ -1056,7 +1056,7 @@ int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, doub
 
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
              const double* cu, const double* b, double* x, int x_zero, cudaStream_t st, int r0,
-             int r1, double* tmp, const double* Ax, const int* has_extra) {
+             int r1, double* tmp, const double* Ax, const int* has_extra, bool prof) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
   const int jfirst = r0 + (((r0 & 1) == colour) ? 0 : 1);
@@ -1064,7 +1064,6 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
   if (nlines <= 0) return CM_OK;
   if (tmp != nullptr && (n1 >= 1024 || Ax != nullptr) && n1 <= 5 * 896 &&
       (5 * (size_t)n1 + 16) * sizeof(double) <= 200 * 1024) {
-    const bool prof = nx == g_prof_fine_nx;
     CM_BYTES((double)nlines * n1 * (x_zero ? 40.0 : 88.0));
     if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
     const double* rhs = b;
@@ -1075,8 +1074,8 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
       ++g_launches;
       rhs = tmp;
     }
-    static int dbg2 = -1;
-    if (dbg2 < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg2 = e ? atoi(e) : 0; }
+    const char* edbg = getenv("CM_ZEBRA_DEBUG");   // diagnostics (tools/time_kernels.py); read per call, nothing cached
+    const int dbg2 = edbg ? atoi(edbg) : 0;
     const int grid = nlines < 148 ? nlines : 148;
     static bool attr4 = false;
     if (!attr4) {
@@ -1111,11 +1110,10 @@ int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
     set_error("zebra line relaxation: line of %d unknowns exceeds shared memory", n1);
     return CM_E_UNSUPPORTED;
   }
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("CM_ZEBRA_DEBUG"); dbg = e ? atoi(e) : 0; }
+  const char* edbg1 = getenv("CM_ZEBRA_DEBUG");
+  const int dbg = edbg1 ? atoi(edbg1) : 0;
   // algorithmic bytes of this launch: b, l, 1/u, c/u, x per node (+ 4 stencil diagonals and the two
   // neighbouring lines when the current iterate is used)
-  const bool prof = nx == g_prof_fine_nx;
   CM_BYTES((double)nlines * n1 * (x_zero ? 40.0 : 88.0));
   if (prof) prof_begin(kProfZebraFine, (double)nlines * n1 * (x_zero ? 40.0 : 88.0), st);
   if (x_zero)

@@ -1072,39 +1072,143 @@ class ProductionMixedSystem:
             R.append((lam[..., a] * lam[..., b])[..., None] * (P - Xc[:, None, i, :]) * c[:, None, None])
         return torch.stack(R, 2)
 
-    def flux(self, u=None):
-        """project(D 4 pi r2^2 s_h, RT3): RT3 coefficient vector [3E + 6C]."""
-        u = self.u if u is None else u
+    # -- L2 projections (project(): advection_diffusion_mixed.py:238-254) -----------------------------------------
+    def _p3_values(self):
+        """CG3 basis at the cell quadrature points [nq, 10] (vertices, two nodes per facet, bubble; oracle p3_basis)."""
+        lam = self.lamq
+        val = [0.5 * lam[:, i] * (3 * lam[:, i] - 1) * (3 * lam[:, i] - 2) for i in range(3)]
+        for j, k in _OTHER:
+            lj, lk = lam[:, j], lam[:, k]
+            val += [4.5 * lj * lk * (3 * lj - 1), 4.5 * lk * lj * (3 * lk - 1)]
+        val.append(27 * lam[:, 0] * lam[:, 1] * lam[:, 2])
+        return torch.stack(val, -1)
+
+    def _p2_values(self):
+        lam = self.lamq
+        return torch.cat([lam * (2 * lam - 1), torch.stack([4 * lam[:, j] * lam[:, k] for j, k in _OTHER], -1)], -1)
+
+    def _qweights(self):
+        return torch.tensor(self.rule[:, 2], device=self.mesh.device)[None, :] * (2 * self.area)[:, None]   # [C,nq]
+
+    def _global_projector(self, kind):
+        """Mass matrix of the space (constant per mesh): assembled with cm_csr_gather and factorised with cm_blu_*
+        ONCE; returns (basis values at the quadrature points, local dof table, gather lists, solver)."""
+        cache = self.__dict__.setdefault("_proj_cache", {})
+        if kind in cache:
+            return cache[kind]
         dev = self.mesh.device
-        lam = self.lamq[None].expand(self.C, -1, -1)
-        R = self._rt_values(lam, self.Pq)
-        a = torch.tensor(self.rule[:, 2], device=dev)[None, :] * (2 * self.area)[:, None]
-        x = self.Pq[..., 0]
-        s = torch.einsum("cqad,ca->cqd", R, u[self.sd])
-        f = 4 * math.pi * (x * x)[..., None] * s * torch.tensor([self.D2, self.D1], device=dev)[None, None, :]
-        Me = torch.einsum("cq,cqad,cqbd->cab", a, R, R)
-        be = torch.einsum("cq,cqad,cqd->ca", a, R, f)
-        sl = self.sd - self.np_
-        ns = self.ns
-        rows = sl.repeat_interleave(15, dim=1).flatten()
-        cols = sl.repeat(1, 15).flatten()
-        key, rp, col = _csr_from_pairs(rows, cols, ns)
-        ptr, order = _gather_lists(torch.searchsorted(key, rows * ns + cols), key.numel())
+        a = self._qweights()
+        if kind == "rt3":
+            lam = self.lamq[None].expand(self.C, -1, -1)
+            R = self._rt_values(lam, self.Pq)                               # [C,nq,15,2]
+            Me = torch.einsum("cq,cqad,cqbd->cab", a, R, R)
+            sl, n = self.sd - self.np_, self.ns
+        else:
+            R = self._p3_values()                                           # [nq,10]
+            Me = torch.einsum("cq,qa,qb->cab", a, R, R)
+            sl, n = self.qd - self.q0, self.V + 2 * self.E + self.C
+        k = sl.shape[1]
+        rows = sl.repeat_interleave(k, dim=1).flatten()
+        cols = sl.repeat(1, k).flatten()
+        key, rp, col = _csr_from_pairs(rows, cols, n)
+        ptr, order = _gather_lists(torch.searchsorted(key, rows * n + cols), key.numel())
         vals = torch.empty(key.numel(), dtype=torch.float64, device=dev)
         st = _capi.stream_ptr()
         src = Me.flatten().contiguous()
         _capi.check(self.lib.cm_csr_gather(key.numel(), _capi.ptr(ptr), _capi.ptr(order.to(torch.int32).contiguous()),
                                            _capi.ptr(src), _capi.ptr(vals), 0, st))
-        ptr2, order2 = _gather_lists(sl.flatten(), ns)
-        rhs = torch.empty(ns, dtype=torch.float64, device=dev)
-        src2 = be.flatten().contiguous()
-        _capi.check(self.lib.cm_csr_gather(ns, _capi.ptr(ptr2), _capi.ptr(order2.to(torch.int32).contiguous()),
-                                           _capi.ptr(src2), _capi.ptr(rhs), 0, st))
-        lin = BandedLULinearSolver(_Holder(dev, rp, col, ns, vals, rhs))
+        ptr2, order2 = _gather_lists(sl.flatten(), n)
+        rhs = torch.empty(n, dtype=torch.float64, device=dev)
+        lin = BandedLULinearSolver(_Holder(dev, rp, col, n, vals, rhs))
         lin.setup()
+        cache[kind] = (R, sl, (ptr2, order2.to(torch.int32).contiguous()), rhs, lin, n)
+        return cache[kind]
+
+    def project(self, kind, fq):
+        """Unweighted L2 projection of a field given at the cell quadrature points (fq [C,nq], or [C,nq,2] for
+        'rt3') onto 'dg2' (cell-local: the reference mass matrix is inverted once on the host), 'cg3' or 'rt3'."""
+        a = self._qweights()
+        if kind == "dg2":
+            Phi = self._p2_values()                                          # [nq,6]
+            w = torch.tensor(self.rule[:, 2], device=self.mesh.device)
+            Minv = torch.linalg.inv(torch.einsum("q,qa,qb->ab", w, Phi, Phi).cpu()).to(Phi.device)   # 6 x 6, host
+            be = torch.einsum("cq,qa,cq->ca", a, Phi, fq)
+            return (be / (2 * self.area)[:, None]) @ Minv.T                  # [C,6] -> DG2 dofs, cell-major
+        R, sl, (ptr2, order2), rhs, lin, n = self._global_projector(kind)
+        be = torch.einsum("cq,cqad,cqd->ca", a, R, fq) if kind == "rt3" else torch.einsum("cq,qa,cq->ca", a, R, fq)
+        src2 = be.flatten().contiguous()
+        _capi.check(self.lib.cm_csr_gather(n, _capi.ptr(ptr2), _capi.ptr(order2), _capi.ptr(src2), _capi.ptr(rhs), 0,
+                                           _capi.stream_ptr()))
         out = torch.empty_like(rhs)
         lin.solve(rhs, out)
         return out
+
+    def evaluate(self, kind, coef):
+        """Field values at the cell quadrature points from a coefficient vector of 'dg2' / 'cg3' / 'rt3'."""
+        if kind == "dg2":
+            return coef.reshape(self.C, 6) @ self._p2_values().T
+        if kind == "cg3":
+            return coef[self.qd - self.q0] @ self._p3_values().T
+        R = self._global_projector("rt3")[0]
+        return torch.einsum("cqad,ca->cqd", R, coef[self.sd - self.np_])
+
+    def flux(self, u=None):
+        """project(D 4 pi r2^2 s_h, RT3) (:243): RT3 coefficient vector [3E + 6C]."""
+        u = self.u if u is None else u
+        x = self.Pq[..., 0]
+        D = torch.tensor([self.D2, self.D1], device=self.mesh.device)[None, None, :]
+        s = self.evaluate("rt3", u[self.np_:self.q0])
+        return self.project("rt3", 4 * math.pi * (x * x)[..., None] * s * D)
+
+    def s_initial(self, x, y):          # SInitial.eval (:59-68): (0, -c/V1 exp(-4/3 pi c x^3) sigma_b(x) / y^2)
+        sb = self.sigma * torch.exp(-4 / 3 * math.pi * self.gamma * x ** 3)
+        ok = y * y > 0
+        v = -self.c / self.V1 * torch.exp(-4 / 3 * math.pi * self.c * x ** 3) * sb / torch.where(ok, y * y, torch.ones_like(y))
+        return torch.stack([torch.zeros_like(x), torch.where(ok, v, torch.zeros_like(v))], -1)
+
+    def postprocess(self, u=None):
+        """The fields advection_diffusion_mixed.py:238-254 writes per time step, as coefficient vectors:
+        p = project(4 pi r2^2 max(p_h, 0), DG2), q = project(max(q_h, 0), CG3), flux = project(D 4 pi r2^2 s_h, RT3),
+        dif = project(p - p_approx, DG2), dif_flux = project(flux - flux_approx, RT3), with p_approx = 4 pi r2^2
+        interpolate(PInitial, DG2) and flux_approx = D 4 pi r2^2 interpolate(SInitial, RT3) (:232-233).  Deviation:
+        the RT3 interpolant of SInitial is replaced by its L2 projection (FIAT's moment-based RT3 interpolation is
+        not restated; both are third-order approximations of the same field)."""
+        u = self.u if u is None else u
+        x, y = self.Pq[..., 0], self.Pq[..., 1]
+        fourpix2 = 4 * math.pi * x * x
+        p_h = self.evaluate("dg2", u[:self.np_])
+        q_h = self.evaluate("cg3", u[self.q0:])
+        p = self.project("dg2", fourpix2 * torch.clamp(p_h, min=0.0))
+        q = self.project("cg3", torch.clamp(q_h, min=0.0))
+        fl = self.flux(u)
+        Xc = self.Xc
+        nodes = torch.cat([Xc, 0.5 * (Xc[:, [1, 0, 0]] + Xc[:, [2, 2, 1]])], 1)             # DG2 nodes [C,6,2]
+        p_steady = self.p_initial(nodes[..., 0], nodes[..., 1]).flatten()
+        p_approx_q = fourpix2 * self.evaluate("dg2", p_steady)
+        dif = self.project("dg2", self.evaluate("dg2", p.flatten()) - p_approx_q)
+        D = torch.tensor([self.D2, self.D1], device=self.mesh.device)[None, None, :]
+        s_int = self.project("rt3", self.s_initial(x, y))
+        flux_approx_q = fourpix2[..., None] * self.evaluate("rt3", s_int) * D
+        dif_flux = self.project("rt3", self.evaluate("rt3", fl) - flux_approx_q)
+        return {"p": p.flatten(), "q": q, "flux": fl, "dif": dif.flatten(), "dif_flux": dif_flux}
+
+    def vertex_values(self, kind, coef):
+        """What XDMFFile.write stores: the field at the mesh vertices ([V], or [V,2] for 'rt3'); discontinuous
+        fields are averaged over the cells around a vertex."""
+        cells = self.mesh.cells.long()
+        V = self.V
+        cnt = torch.zeros(V, dtype=torch.float64, device=coef.device).index_add_(
+            0, cells.flatten(), torch.ones(cells.numel(), dtype=torch.float64, device=coef.device))
+        if kind == "cg3":
+            return coef[:V].clone()
+        if kind == "dg2":
+            vals = coef.reshape(self.C, 6)[:, :3]
+            return torch.zeros(V, dtype=torch.float64, device=coef.device).index_add_(0, cells.flatten(), vals.flatten()) / cnt
+        lam = torch.eye(3, dtype=torch.float64, device=coef.device)[None].expand(self.C, -1, -1)   # the three vertices
+        R = self._rt_values(lam, self.Xc)
+        f = torch.einsum("cqad,ca->cqd", R, coef[self.sd - self.np_])                              # [C,3,2]
+        out = torch.zeros(V, 2, dtype=torch.float64, device=coef.device).index_add_(0, cells.flatten(), f.reshape(-1, 2))
+        return out / cnt[:, None]
 
     def bottom_flux(self, fl):
         """(r2 part, r1 part, total) of V1 * assemble(dot(flux, n) 4 pi r1^2 ds(bottom)) (:261-263)."""
@@ -1126,10 +1230,78 @@ class ProductionMixedSystem:
         return r2, r1, r2 + r1
 
 
+class XDMFFile:
+    """Minimal XDMFFile(filename).write(name, vertex_values, t) (advection_diffusion_mixed.py:153-156, 246-256 with
+    functions_share_mesh = True): the mesh once, one temporal grid per time with one Attribute per written
+    function (vertex values; vectors get a zero third component, like DOLFIN).  Heavy data go to a raw binary
+    side file <name>.bin (XDMF Format="Binary", little endian, 8-byte reals / 4-byte ints): no HDF5 here."""
+
+    def __init__(self, filename, mesh):
+        import os
+        self.filename = filename
+        self.binname = os.path.splitext(filename)[0] + ".bin"
+        self.mesh = mesh
+        self._bin = open(self.binname, "wb")
+        self._off = 0
+        self._steps = []            # [(t, [(name, kind, offset, n)])]
+        self.parameters = {"rewrite_function_mesh": False, "flush_output": True, "functions_share_mesh": True}
+        self._cells = self._put(mesh.cells.to(torch.int32).cpu().numpy())
+        X = mesh.coords.cpu().numpy()
+        self._coords = self._put(np.ascontiguousarray(X, dtype="<f8"))
+        self._flush()
+
+    def _put(self, arr):
+        arr = np.ascontiguousarray(arr)
+        off = self._off
+        self._bin.write(arr.tobytes())
+        self._off += arr.nbytes
+        return off
+
+    def write(self, name, values, t):
+        v = values.detach().cpu().numpy()
+        if v.ndim == 2:
+            v = np.concatenate([v, np.zeros((v.shape[0], 1))], 1)
+        off = self._put(np.ascontiguousarray(v, dtype="<f8"))
+        if not self._steps or self._steps[-1][0] != t:
+            self._steps.append((t, []))
+        self._steps[-1][1].append((name, "Vector" if v.ndim == 2 else "Scalar", off, v.shape))
+        if self.parameters["flush_output"]:
+            self._flush()
+
+    def _flush(self):
+        import os
+        self._bin.flush()
+        V, C = self.mesh.num_vertices(), self.mesh.num_cells()
+        b = os.path.basename(self.binname)
+        topo = (f'<Topology TopologyType="Triangle" NumberOfElements="{C}"><DataItem Format="Binary" DataType="Int" '
+                f'Precision="4" Endian="Little" Seek="{self._cells}" Dimensions="{C} 3">{b}</DataItem></Topology>')
+        geom = (f'<Geometry GeometryType="XY"><DataItem Format="Binary" DataType="Float" Precision="8" Endian="Little" '
+                f'Seek="{self._coords}" Dimensions="{V} 2">{b}</DataItem></Geometry>')
+        out = ['<?xml version="1.0"?>', '<Xdmf Version="3.0"><Domain>',
+               '<Grid Name="TimeSeries" GridType="Collection" CollectionType="Temporal">']
+        for t, fields in self._steps:
+            out.append(f'<Grid Name="mesh" GridType="Uniform">{topo}{geom}<Time Value="{t}"/>')
+            for name, kind, off, shape in fields:
+                dims = " ".join(str(d) for d in shape)
+                out.append(f'<Attribute Name="{name}" AttributeType="{kind}" Center="Node"><DataItem Format="Binary" '
+                           f'DataType="Float" Precision="8" Endian="Little" Seek="{off}" Dimensions="{dims}">{b}'
+                           '</DataItem></Attribute>')
+            out.append('</Grid>')
+        out += ['</Grid>', '</Domain></Xdmf>']
+        with open(self.filename, "w") as f:
+            f.write("\n".join(out))
+
+    def close(self):
+        self._flush()
+        self._bin.close()
+
+
 def solve_problem_instance_mixed(concentration, t_final, dt, mesh, bdry, sigma, gamma, results, V1, D1, D2,
                                  output_filename=None, steady_state=False):
     """advection_diffusion_mixed.py:94-269 with its own discretisation (DG2 x RT3 x CG3) on the GPU: same
-    signature, `results` row (:268) and return value (flux, total_flux); no XDMF output (file name ignored)."""
+    signature, `results` row (:268) and return value (flux, total_flux).  With an output_filename the fields of
+    :238-254 (clipped p, clipped q, flux, and their differences to the steady-state approximation) are written per
+    time step as vertex values into an XDMF time series (XDMFFile above)."""
     system = ProductionMixedSystem(mesh, bdry, concentration, sigma, gamma, V1, D1, D2, None if steady_state else dt)
     if steady_state:
         t_final = 0
@@ -1138,11 +1310,18 @@ def solve_problem_instance_mixed(concentration, t_final, dt, mesh, bdry, sigma, 
         Xc = system.Xc
         nodes = torch.cat([Xc, 0.5 * (Xc[:, [1, 0, 0]] + Xc[:, [2, 2, 1]])], 1)            # [C,6,2]
         system.p_old.copy_(system.p_initial(nodes[..., 0], nodes[..., 1]).flatten())
+    out = XDMFFile(output_filename, mesh) if output_filename else None
     while t <= t_final:
         print("t=%.3f" % t)
         system.solve()
+        if out is not None:                            # :238-254
+            f = system.postprocess()
+            for name, kind in (("p", "dg2"), ("q", "cg3"), ("flux", "rt3"), ("dif", "dg2"), ("dif_flux", "rt3")):
+                out.write(name, system.vertex_values(kind, f[name]), t)
         system.p_old.copy_(system.u[:system.np_])      # assign(p_old, p_h)
         t += dt
+    if out is not None:
+        out.close()
     flux = system.flux()
     r2f, r1f, total = system.bottom_flux(flux)
     approx = 4 * math.pi * D1 * sigma * (concentration / (gamma + concentration))           # :264
