@@ -346,6 +346,16 @@ int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const d
   return mg_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, Halo{}, 0, -1, (cudaStream_t)stream);
 }
 
+int cm_mg_zebra_mid(int32_t mode, int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
+                    const double* iu, const double* cu, const double* b, double* x, const double* ec, double* bc,
+                    void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && (colour == 0 || colour == 1) && mode >= 0 && mode <= 3, "bad grid, colour or mode");
+  CM_CHECK_ARG(A && lf && iu && cu && b && x, "null pointer");
+  CM_CHECK_ARG(mode != 2 || bc, "mode 2 writes the coarse right-hand side: bc is null");
+  CM_CHECK_ARG(mode != 3 || ec, "mode 3 reads the coarse correction: ec is null");
+  return mg_zebra_mid(mode, nx, ny, colour, A, lf, iu, cu, b, x, ec, bc, (cudaStream_t)stream);
+}
+
 int cm_mg_ring_debug_times(uint64_t* host_out, int32_t n) {
   CM_CHECK_ARG(host_out && n > 0 && n <= 64 * 16 * 8, "bad argument");
   return mg_ring_debug_times((unsigned long long*)host_out, n);

@@ -24,6 +24,22 @@ struct LineJob {
   double* x;
 };
 
+// one half sweep of the cache-resident middle levels (cm_mgmid.cu)
+struct MidJob {
+  int nx, ny;
+  int colour, nlines;
+  int tl;       // threads per line (32 * warps)
+  int groups;   // lines per CTA
+  const double* A;
+  const double* lf;
+  const double* iu;
+  const double* cu;
+  const double* b;
+  double* x;
+  const double* ec;   // mode 3: coarse-grid correction
+  double* bc;         // mode 2: coarse right-hand side
+};
+
 struct CoarseLevel {
   int nx, ny;
   const double* A;
@@ -49,6 +65,11 @@ int mg_resid_restrict(int nxf, int nyf, const double* A, const double* b, const 
                       const Halo& H, int Y0, int Y1, cudaStream_t st);
 int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H, int wait_coarse, int r0,
                    int r1, cudaStream_t st);
+bool mg_mid_fits(int nx, int ny);
+bool mg_mid_fused_restrict_fits(int nx, int ny);
+int mg_mid_init_attributes();
+int mg_zebra_mid(int mode, int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
+                 const double* cu, const double* b, double* x, const double* ec, double* bc, cudaStream_t st);
 int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st);
 size_t mg_coarse_smem_bytes(const CoarseCycle& C);
 int mg_coarse_smem_cycle(const CoarseCycle& C, cudaStream_t st);

@@ -76,6 +76,8 @@ struct PQKnobs {
   int coarse_from = 2;
   int gmres_host = 0;       // diagnostics: second-generation preconditioner under the host-driven GMRES (1 GPU)
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
+  int mid_max_n1 = 1280;    // cache-resident middle levels (cm_mgmid.cu): lines of up to this many unknowns (0: off)
+  int mid_fuse = 1;         // ... with the restricted residual / the prolongation folded into the half sweeps
 };
 static int env_int(const char* name, int dflt, int minval) {
   const char* e = getenv(name);
@@ -105,6 +107,8 @@ static PQKnobs read_knobs() {
   K.coarse_from = env_int("CM_MG_COARSE_FROM", 2, 0);
   K.gmres_host = env_int("CM_GMRES_HOST", 0, 0);
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
+  K.mid_max_n1 = env_int("CM_MID_MAX_N1", 1280, 0);
+  K.mid_fuse = env_int("CM_MID_FUSE", 1, 0);
   return K;
 }
 
@@ -771,7 +775,7 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
       C->K.q_concurrent = 0;
     }
   }
-  if (mg_init_attributes() != CM_OK) {
+  if (mg_init_attributes() != CM_OK || mg_mid_init_attributes() != CM_OK) {
     delete C;
     return nullptr;
   }
@@ -844,6 +848,27 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     return CM_OK;
   }
   PQSLevel& Cl = S.lev[l + 1];
+  const int npost = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
+  if (!lev_dist && L.nx + 1 <= C->K.mid_max_n1 && mg_mid_fits(L.nx, L.ny)) {
+    // cache-resident middle level: latency-built half sweeps, transfers folded into them (cm_mgmid.cu)
+    const bool fuse = C->K.mid_fuse != 0;
+    const bool fuse_rr = fuse && mg_mid_fused_restrict_fits(L.nx, L.ny);
+    for (int s = 0; s < S.pre_smooth; ++s) {
+      if ((rc = mg_zebra_mid(s == 0 ? 0 : 1, L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, nullptr, nullptr, st))) return rc;
+      const bool last = s + 1 == S.pre_smooth;
+      if ((rc = mg_zebra_mid(last && fuse_rr ? 2 : 1, L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, nullptr, Cl.b, st)))
+        return rc;
+    }
+    if (!fuse_rr && (rc = mg_resid_restrict(L.nx, L.ny, L.A, b, x, Cl.b, C->Hoff, 0, -1, st))) return rc;
+    if ((rc = vcycle2(C, l + 1, Cl.b, Cl.x, st))) return rc;
+    if (!fuse && (rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, C->Hoff, 0, 0, -1, st))) return rc;
+    for (int s = 0; s < npost; ++s) {
+      if ((rc = mg_zebra_mid(s == 0 && fuse ? 3 : 1, L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, Cl.x, nullptr, st)))
+        return rc;
+      if ((rc = mg_zebra_mid(1, L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, nullptr, nullptr, st))) return rc;
+    }
+    return CM_OK;
+  }
   for (int s = 0; s < S.pre_smooth; ++s) {
     if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st, l == 0))) return rc;
     if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
@@ -853,7 +878,6 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     return rc;
   if ((rc = vcycle2(C, l + 1, Cl.b, Cl.x, st))) return rc;
   if ((rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, H, (lev_dist && l + 1 < C->I.Ld) ? 1 : 0, r0, r1, st))) return rc;
-  const int npost = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
   for (int s = 0; s < npost; ++s) {
     if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
     if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;

@@ -280,6 +280,15 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
  *     half sweep that follows). */
 int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
                 const double* cu, const double* b, double* x, int32_t x_is_zero, void* stream);
+/* Half sweeps of the cache-resident middle levels (cm_mgmid.cu; lines of up to 1280 unknowns, whole grid):
+ *   mode 0: colour half sweep from a zero guess;  mode 1: with couplings;
+ *   mode 2: colour-1 half sweep fused with the restricted residual, bc[(ny/2+1)*(nx/2+1)] = R (b - A x)
+ *           (lines of up to 640 unknowns, nx and ny even);
+ *   mode 3: colour-0 half sweep that reads x + P ec on the odd rows (prolongation folded in; the odd rows of
+ *           x itself are NOT updated: the colour-1 half sweep that must follow overwrites them). */
+int cm_mg_zebra_mid(int32_t mode, int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
+                    const double* iu, const double* cu, const double* b, double* x, const double* ec, double* bc,
+                    void* stream);
 /* diagnostics: %globaltimer phase stamps [cta < 64][line < 16][8] of the last cm_mg_zebra launch that ran with
  * the environment variable CM_RING_DBG set (tools/time_ring.py) */
 int cm_mg_ring_debug_times(uint64_t* host_out, int32_t n);

@@ -162,6 +162,70 @@ def test_restricted_residual_and_odd_row_correction(nx, ny):
     assert np.array_equal(got[0::2], x0[0::2])
 
 
+@pytest.mark.parametrize("nx,ny", [(8, 6), (64, 32), (128, 64), (200, 38), (256, 128), (512, 20), (514, 130),
+                                   (1024, 36), (1278, 10)])
+def test_mid_level_half_sweeps(nx, ny):
+    """cm_mgmid.cu: mode 0 / 1 half sweeps equal scipy's tridiagonal solves; mode 2 (colour 1 + restricted
+    residual in one launch) equals the separate colour-1 sweep followed by cm_mg_resid_restrict BIT FOR BIT in x
+    and to rounding in the coarse right-hand side; mode 3 (colour 0 reading x + P e on the odd rows) equals
+    cm_mg_prolong_odd followed by a colour-0 sweep."""
+    n1, n = nx + 1, (nx + 1) * (ny + 1)
+    nxc, nyc = nx // 2, ny // 2
+    m1 = nxc + 1
+    dev = torch.device("cuda")
+    A, rng = _random_stencil(nx, ny, 3 * nx + ny)
+    At = torch.tensor(A.reshape(7, n), device=dev)
+    lf, iu, cu = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    bh = rng.standard_normal((ny + 1, n1))
+    b = torch.tensor(bh.reshape(-1), device=dev)
+    x = torch.full((n,), float("nan"), dtype=torch.float64, device=dev)
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    _capi.check(lib.cm_stencil_line_factor(nx, ny, P(At), P(lf), P(iu), P(cu), P(err), st))
+    assert int(err.item()) == 0
+
+    def mid(mode, colour, xx, ec=None, bc=None):
+        _capi.check(lib.cm_mg_zebra_mid(mode, nx, ny, colour, P(At), P(lf), P(iu), P(cu), P(b), P(xx),
+                                        P(ec) if ec is not None else None, P(bc) if bc is not None else None, st))
+
+    # colour 0 from a zero guess (x holds NaN: it must not be read), colour 1 with couplings, colour 0 with couplings
+    mid(0, 0, x)
+    x[torch.isnan(x)] = 0.0
+    xr = np.zeros((ny + 1, n1))
+    xr = _zebra_ref(A, bh, xr, 0, True)
+    assert np.max(np.abs(x.cpu().numpy().reshape(ny + 1, n1) - xr)) < 1e-12 * (1 + np.max(np.abs(xr)))
+    for colour in (1, 0):
+        xr = x.cpu().numpy().reshape(ny + 1, n1).copy()
+        mid(1, colour, x)
+        ref = _zebra_ref(A, bh, xr, colour, False)
+        got = x.cpu().numpy().reshape(ny + 1, n1)
+        assert np.max(np.abs(got - ref)) < 1e-12 * (1 + np.max(np.abs(ref))), colour
+    fused_ok = nx % 2 == 0 and ny % 2 == 0
+    if fused_ok and nx + 1 <= 640:
+        # mode 2 against the two separate launches
+        x1 = x.clone()
+        mid(1, 1, x1)
+        rc1 = torch.full(((nyc + 1) * m1,), float("nan"), dtype=torch.float64, device=dev)
+        _capi.check(lib.cm_mg_resid_restrict(nx, ny, P(At), P(b), P(x1), P(rc1), st))
+        x2 = x.clone()
+        rc2 = torch.full(((nyc + 1) * m1,), float("nan"), dtype=torch.float64, device=dev)
+        mid(2, 1, x2, bc=rc2)
+        assert torch.equal(x1, x2)
+        assert torch.isfinite(rc2).all()
+        assert float((rc1 - rc2).abs().max()) < 1e-12 * (1 + float(rc1.abs().max()))
+        x.copy_(x2)
+    if fused_ok:
+        ec = torch.tensor(rng.standard_normal((nyc + 1) * m1), device=dev)
+        x1 = x.clone()
+        _capi.check(lib.cm_mg_prolong_odd(nxc, nyc, P(ec), P(x1), st))
+        mid(1, 0, x1)
+        x2 = x.clone()
+        mid(3, 0, x2, ec=ec)
+        X1, X2 = (v.cpu().numpy().reshape(ny + 1, n1) for v in (x1, x2))
+        assert np.max(np.abs(X1[0::2] - X2[0::2])) < 1e-12 * (1 + np.max(np.abs(X1)))
+        assert np.array_equal(X2[1::2], x.cpu().numpy().reshape(ny + 1, n1)[1::2])   # odd rows untouched
+
+
 def _supg_solver(nx, ny, restart=40):
     from closestmolecule_b200.manufactured import p_exact, q_exact
     from closestmolecule_b200.solver import StructuredPQLinearSolver
@@ -195,8 +259,10 @@ def test_kernel_generations_agree(nx, ny, monkeypatch):
     for name, env in (("v1", {"CM_SOLVER_V1": "1"}), ("v2", {}),
                       ("v2_cluster", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "257"}),
                       ("v2_cta1", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "65", "CM_COARSE_NCTA": "1"}),
-                      ("v2_unfused", {"CM_COARSE_SMEM": "0"}), ("v2_nograph", {"CM_GRAPH": "0"})):
-        for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH", "CM_COARSE_SMEM"):
+                      ("v2_unfused", {"CM_COARSE_SMEM": "0"}), ("v2_nograph", {"CM_GRAPH": "0"}),
+                      ("v2_nomid", {"CM_MID_MAX_N1": "0"}), ("v2_mid_unfused", {"CM_MID_FUSE": "0"})):
+        for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH", "CM_COARSE_SMEM", "CM_MID_MAX_N1",
+                  "CM_MID_FUSE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
