@@ -81,6 +81,7 @@ _PROTOS = {
     "cm_mg_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P], C.c_int),
     "cm_mg_zebra_mid": ([_I, _I, _I, _I] + [_P] * 8 + [_P], C.c_int),
     "cm_mg_ring_debug_times": ([_P, _I], C.c_int),
+    "cm_mg_smem_debug_times": ([_P, _I], C.c_int),
     "cm_mg_resid_restrict": ([_I, _I] + [_P] * 4 + [_P], C.c_int),
     "cm_mg_prolong_odd": ([_I, _I, _P, _P, _P], C.c_int),
     "cm_ipc_alloc": ([C.c_int64], C.c_void_p),

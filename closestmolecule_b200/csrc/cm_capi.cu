@@ -361,6 +361,11 @@ int cm_mg_ring_debug_times(uint64_t* host_out, int32_t n) {
   return mg_ring_debug_times((unsigned long long*)host_out, n);
 }
 
+int cm_mg_smem_debug_times(uint64_t* host_out, int32_t n) {
+  CM_CHECK_ARG(host_out && n > 0 && n <= 64, "bad argument");
+  return mg_smem_debug_times((unsigned long long*)host_out, n);
+}
+
 int cm_mg_resid_restrict(int32_t nxf, int32_t nyf, const double* A, const double* b, const double* x,
                          double* rc, void* stream) {
   CM_CHECK_ARG(nxf >= 2 && nyf >= 2 && !(nxf & 1) && !(nyf & 1), "fine grid must have even nx, ny");

@@ -70,9 +70,9 @@ int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, in
 int dist_allreduce(cm_dist* D, double* vals, int n, cudaStream_t st);
 
 // cm_gmres_dev.cu: device-resident GMRES state (all pointers into the caller's workspace)
-constexpr int kGmresStatus = 8;
+constexpr int kGmresStatus = 16;
 enum GmresStatusSlot { kStJ = 0, kStIts = 1, kStConv = 2, kStResid = 3, kStTarget = 4, kStBnorm = 5,
-                       kStFlag = 6, kStK = 7 };
+                       kStFlag = 6, kStK = 7, kStMaxit = 8 };
 struct GmresDev {
   long long n, ne;
   int m;
@@ -83,10 +83,14 @@ struct GmresDev {
 };
 size_t gmres_dev_doubles(long long n, int m);
 void gmres_dev_layout(GmresDev& G, long long n, int m, double* work);
-int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st);
+int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st, int maxit = 1 << 30);
 int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
 int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
-int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st);
+// cond_handle != 0: a cudaGraphConditionalHandle; the kernel sets it to "another iteration is needed" (the GMRES
+// cycle runs as a WHILE node of a CUDA graph, cm_pqsolver.cu)
+int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st, unsigned long long cond_handle = 0);
+// adds a one-thread kernel node to `graph` that evaluates the same condition from the current status block
+int gmres_dev_add_cond_node(cudaGraph_t graph, cudaGraphNode_t* node, const GmresDev& G, unsigned long long cond_handle);
 int gmres_dev_solve_y(const GmresDev& G, cudaStream_t st);
 int gmres_dev_combine(const GmresDev& G, const VecSlice* sl, double* out, int khost, cudaStream_t st);
 int gmres_dev_axpby(const GmresDev& G, const VecSlice* sl, double alpha, const double* x, double beta, double* y,

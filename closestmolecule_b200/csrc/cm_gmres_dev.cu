@@ -240,9 +240,21 @@ gd_update_kernel(const GmresDev G, const VecSlice sl) {
   }
 }
 
-// scalar part of an iteration, one thread: nrm[0] = ||V_{j+1}||^2 (summed over the ranks), dots = column j
-__global__ void gd_givens_kernel(const GmresDev G, const double rtol, const double atol) {
+// the GMRES cycle as a WHILE node of a CUDA graph: another iteration?
+__device__ __forceinline__ void gd_set_continue(const GmresDev& G, const unsigned long long handle) {
+  if (handle == 0ull) return;
+  const double* st = G.st;
+  const bool cont = st[kStConv] == 0.0 && st[kStFlag] == 0.0 && st[kStIts] < st[kStMaxit] && st[kStJ] < (double)G.m;
+  cudaGraphSetConditional((cudaGraphConditionalHandle)handle, cont ? 1u : 0u);
+}
+
+__global__ void gd_cond_kernel(const GmresDev G, const unsigned long long handle) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gd_set_continue(G, handle);
+}
+
+// scalar part of an iteration, one thread: nrm[0] = ||V_{j+1}||^2 (summed over the ranks), dots = column j
+__device__ __forceinline__ void gd_givens_body(const GmresDev& G, const double rtol, const double atol) {
   double* st = G.st;
   const int j = (int)st[kStJ], m = G.m;
   const double hn2 = G.nrm[0];
@@ -290,8 +302,14 @@ __global__ void gd_givens_kernel(const GmresDev G, const double rtol, const doub
   if (resid <= st[kStTarget] || hn <= 1e-300) st[kStConv] = 1.0;   // converged, or lucky breakdown
 }
 
+__global__ void gd_givens_kernel(const GmresDev G, const double rtol, const double atol, const unsigned long long handle) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gd_givens_body(G, rtol, atol);
+  gd_set_continue(G, handle);
+}
+
 // start of a solve / of a restart cycle: j = -1 (the next dot + update pair normalises the residual in w)
-__global__ void gd_begin_kernel(const GmresDev G, const int first) {
+__global__ void gd_begin_kernel(const GmresDev G, const int first, const int maxit) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* st = G.st;
   st[kStJ] = -1.0;
@@ -299,6 +317,7 @@ __global__ void gd_begin_kernel(const GmresDev G, const int first) {
   st[kStConv] = 0.0;
   st[kStK] = 0.0;
   if (first) {
+    st[kStMaxit] = (double)maxit;
     st[kStIts] = 0.0;
     st[kStBnorm] = -1.0;
     st[kStTarget] = 0.0;
@@ -363,8 +382,8 @@ static int gd_grid(long long nelem) {
 }
 static long long gd_len(const GmresDev& G, const VecSlice* sl) { return sl ? 2 * sl->len : G.n; }
 
-int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st) {
-  gd_begin_kernel<<<1, 32, 0, st>>>(G, first);
+int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st, int maxit) {
+  gd_begin_kernel<<<1, 32, 0, st>>>(G, first, maxit);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }
@@ -393,9 +412,24 @@ int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStrea
   return CM_OK;
 }
 
-int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st) {
-  gd_givens_kernel<<<1, 32, 0, st>>>(G, rtol, atol);
+int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st, unsigned long long cond_handle) {
+  gd_givens_kernel<<<1, 32, 0, st>>>(G, rtol, atol, cond_handle);
   CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
+int gmres_dev_add_cond_node(cudaGraph_t graph, cudaGraphNode_t* node, const GmresDev& G, unsigned long long cond_handle) {
+  GmresDev Gc = G;
+  unsigned long long h = cond_handle;
+  void* args[2] = {&Gc, &h};
+  cudaKernelNodeParams kp{};
+  kp.func = (void*)gd_cond_kernel;
+  kp.gridDim = dim3(1, 1, 1);
+  kp.blockDim = dim3(32, 1, 1);
+  kp.sharedMemBytes = 0;
+  kp.kernelParams = args;
+  kp.extra = nullptr;
+  CM_CUDA(cudaGraphAddKernelNode(node, graph, nullptr, 0, &kp));
   return CM_OK;
 }
 

@@ -782,227 +782,6 @@ coarse_cycle_kernel(const CoarseCycle C) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-memory resident V-cycle for the coarsest levels: ONE CTA, every phase separated by __syncthreads and
-// every array of the current level in shared memory, so a phase costs a few hundred nanoseconds instead of the
-// 3-4 us of a kernel boundary or of a grid / cluster barrier with global-memory round trips (measured,
-// profiles/README.md).  x and b of every level stay resident; the seven operator arrays a sweep reads (the
-// four off-line diagonals and the three line factors) live in one region that is refilled from L2 whenever
-// the cycle changes level.  The tridiagonal diagonals are only needed by the restricted residual and are read
-// from global memory there.
-// ------------------------------------------------------------------------------------------------
-constexpr int kSmemCycleT = 640;   // 20 warps: one line each on a 65 x 33 level; up to 102 registers
-constexpr int kSmemCycleE = 3;   // unknowns per lane: lines of up to 96 unknowns
-
-struct SmOp {   // operator arrays of one level in shared memory
-  const double *a0, *a1, *a5, *a6, *lf, *iu, *cu;
-};
-
-__device__ __forceinline__ void sm_load_op(const CoarseLevel& L, double* op, SmOp& O) {
-  const int n = (L.nx + 1) * (L.ny + 1);
-  const size_t nv = (size_t)n;
-  double* d = op;
-  const double* src[7] = {L.A, L.A + nv, L.A + 5 * nv, L.A + 6 * nv, L.lf, L.iu, L.cu};
-#pragma unroll
-  for (int a = 0; a < 7; ++a)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[(size_t)a * n + i] = __ldg(src[a] + i);
-  O.a0 = d; O.a1 = d + n; O.a5 = d + 2 * (size_t)n; O.a6 = d + 3 * (size_t)n;
-  O.lf = d + 4 * (size_t)n; O.iu = d + 5 * (size_t)n; O.cu = d + 6 * (size_t)n;
-}
-
-// one warp solves line j from shared memory
-__device__ __forceinline__ void sm_line_solve(const int nx, const int ny, const SmOp& O, const double* b, double* x,
-                                              const int j, const bool xzero) {
-  const int n1 = nx + 1, lane = threadIdx.x & 31;
-  const int base = j * n1;
-  const int E = (n1 + 31) >> 5;
-  const int i0 = lane * E;
-  double r[kSmemCycleE], lv[kSmemCycleE], cv[kSmemCycleE], iv[kSmemCycleE];
-  const int lo = (j > 0 ? j - 1 : 0) * n1, up = (j < ny ? j + 1 : ny) * n1;
-#pragma unroll
-  for (int e = 0; e < kSmemCycleE; ++e) {
-    const int i = i0 + e;
-    if (e < E && i < n1) {
-      double s = b[base + i];
-      if (!xzero) {
-        const int im = i > 0 ? i - 1 : 0, ip = i < nx ? i + 1 : nx;
-        if (j > 0) s -= O.a0[base + i] * x[lo + im] + O.a1[base + i] * x[lo + i];
-        if (j < ny) s -= O.a5[base + i] * x[up + i] + O.a6[base + i] * x[up + ip];
-      }
-      r[e] = s;
-      lv[e] = O.lf[base + i];
-      cv[e] = O.cu[base + i];
-      iv[e] = O.iu[base + i];
-    }
-  }
-  Aff m{1.0, 0.0};
-#pragma unroll
-  for (int e = 0; e < kSmemCycleE; ++e)
-    if (e < E && i0 + e < n1) { m.b = r[e] - lv[e] * m.b; m.a = -lv[e] * m.a; }
-  double z = aff_warp_scan(m, false);
-#pragma unroll
-  for (int e = 0; e < kSmemCycleE; ++e)
-    if (e < E && i0 + e < n1) { z = r[e] - lv[e] * z; r[e] = z * iv[e]; }
-  m = Aff{1.0, 0.0};
-#pragma unroll
-  for (int e = kSmemCycleE - 1; e >= 0; --e)
-    if (e < E && i0 + e < n1) { m.b = r[e] - cv[e] * m.b; m.a = -cv[e] * m.a; }
-  double xn = aff_warp_scan(m, true);
-#pragma unroll
-  for (int e = kSmemCycleE - 1; e >= 0; --e)
-    if (e < E && i0 + e < n1) { xn = r[e] - cv[e] * xn; x[base + i0 + e] = xn; }
-}
-
-__device__ __forceinline__ void sm_half_sweep(const int nx, const int ny, const SmOp& O, const double* b, double* x,
-                                              const int colour, const bool xzero) {
-  const int nw = blockDim.x >> 5, w = threadIdx.x >> 5;
-  for (int j = colour + 2 * w; j <= ny; j += 2 * nw) sm_line_solve(nx, ny, O, b, x, j, xzero);
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(kSmemCycleT, 1)
-coarse_smem_kernel(const CoarseCycle C) {
-  extern __shared__ __align__(16) double sm[];
-  const int last = C.nlev - 1;
-  // layout: [x_k, b_k for every level][operator region sized for level 0 of the cycle]
-  __shared__ double* xs[kCoarseMaxLevels];
-  __shared__ double* bs[kCoarseMaxLevels];
-  __shared__ double* s_op;
-  if (threadIdx.x == 0) {
-    double* p = sm;
-    for (int k = 0; k <= last; ++k) {
-      const int n = (C.lev[k].nx + 1) * (C.lev[k].ny + 1);
-      xs[k] = p; p += (n + 1) & ~1;
-      bs[k] = p; p += (n + 1) & ~1;
-    }
-    s_op = p;
-  }
-  __syncthreads();
-  double* op = s_op;
-  SmOp O;
-  {
-    const CoarseLevel& L = C.lev[0];
-    const int n = (L.nx + 1) * (L.ny + 1);
-    const double* bsrc = L.b;   // written by the previous kernel of the stream
-    for (int i = threadIdx.x; i < n; i += blockDim.x) bs[0][i] = bsrc[i];
-    sm_load_op(L, op, O);
-  }
-  __syncthreads();
-  for (int k = 0; k < last; ++k) {
-    const CoarseLevel& L = C.lev[k];
-    const CoarseLevel& N = C.lev[k + 1];
-    for (int s = 0; s < C.pre; ++s) {
-      sm_half_sweep(L.nx, L.ny, O, bs[k], xs[k], 0, s == 0);
-      sm_half_sweep(L.nx, L.ny, O, bs[k], xs[k], 1, false);
-    }
-    {   // restricted residual (odd fine rows have zero residual): coarse b
-      const int n1 = L.nx + 1, m1 = N.nx + 1;
-      const size_t nv = (size_t)n1 * (L.ny + 1);
-      const int ncoarse = m1 * (N.ny + 1);
-      const double* x = xs[k];
-      for (int I = threadIdx.x; I < ncoarse; I += blockDim.x) {
-        const int X = I % m1, Y = I / m1;
-        const int iy = 2 * Y;
-        double acc = 0.0;
-#pragma unroll
-        for (int d = -1; d <= 1; ++d) {
-          const int ix = 2 * X + d;
-          if (ix < 0 || ix > L.nx) continue;
-          const int v = iy * n1 + ix;
-          double s = bs[k][v];
-          // diagonals 2, 3, 4 from global memory (not kept in shared memory), 0, 1, 5, 6 from the operator region
-          if (ix > 0) s -= __ldg(L.A + 2 * nv + v) * x[v - 1];
-          s -= __ldg(L.A + 3 * nv + v) * x[v];
-          if (ix < L.nx) s -= __ldg(L.A + 4 * nv + v) * x[v + 1];
-          if (iy > 0) {
-            if (ix > 0) s -= O.a0[v] * x[v - n1 - 1];
-            s -= O.a1[v] * x[v - n1];
-          }
-          if (iy < L.ny) {
-            s -= O.a5[v] * x[v + n1];
-            if (ix < L.nx) s -= O.a6[v] * x[v + n1 + 1];
-          }
-          acc += (d == 0) ? s : 0.5 * s;
-        }
-        bs[k + 1][I] = acc;
-      }
-    }
-    __syncthreads();
-    sm_load_op(N, op, O);
-    __syncthreads();
-  }
-  {   // coarsest level
-    const CoarseLevel& L = C.lev[last];
-    const int n = (L.nx + 1) * (L.ny + 1);
-    if (C.Ainv != nullptr) {
-      for (int r = threadIdx.x; r < n; r += blockDim.x) {
-        double s = 0.0;
-        for (int c = 0; c < n; ++c) s += __ldg(C.Ainv + (size_t)r * n + c) * bs[last][c];
-        xs[last][r] = s;
-      }
-      __syncthreads();
-    } else {
-      for (int s = 0; s < 30; ++s) {
-        sm_half_sweep(L.nx, L.ny, O, bs[last], xs[last], 0, s == 0);
-        sm_half_sweep(L.nx, L.ny, O, bs[last], xs[last], 1, false);
-      }
-    }
-  }
-  for (int k = last - 1; k >= 0; --k) {
-    const CoarseLevel& L = C.lev[k];
-    const CoarseLevel& N = C.lev[k + 1];
-    const int n1 = L.nx + 1, m1 = N.nx + 1;
-    const int nodd = L.ny / 2;
-    sm_load_op(L, op, O);
-    const double* ec = xs[k + 1];
-    for (int t = threadIdx.x; t < nodd * n1; t += blockDim.x) {
-      const int rr = t / n1, ix = t - rr * n1;
-      const int iy = 2 * rr + 1;
-      const int c0 = (iy >> 1) * m1 + (ix >> 1);
-      xs[k][iy * n1 + ix] += 0.5 * (ec[c0] + ((ix & 1) ? ec[c0 + m1 + 1] : ec[c0 + m1]));
-    }
-    __syncthreads();
-    for (int s = 0; s < C.post; ++s) {
-      sm_half_sweep(L.nx, L.ny, O, bs[k], xs[k], 0, false);
-      sm_half_sweep(L.nx, L.ny, O, bs[k], xs[k], 1, false);
-    }
-  }
-  {
-    const CoarseLevel& L = C.lev[0];
-    const int n = (L.nx + 1) * (L.ny + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) L.x[i] = xs[0][i];
-  }
-}
-
-// shared memory the resident cycle needs for the levels of C (0: it does not apply)
-size_t mg_coarse_smem_bytes(const CoarseCycle& C) {
-  size_t d = 0;
-  for (int k = 0; k < C.nlev; ++k) {
-    if (C.lev[k].nx + 1 > 32 * kSmemCycleE) return 0;
-    const size_t n = (size_t)(C.lev[k].nx + 1) * (C.lev[k].ny + 1);
-    d += 2 * ((n + 1) & ~(size_t)1);
-  }
-  d += 7 * (size_t)(C.lev[0].nx + 1) * (C.lev[0].ny + 1) + 2;
-  return d * sizeof(double);
-}
-
-int mg_coarse_smem_cycle(const CoarseCycle& C, cudaStream_t st) {
-  const size_t smem = mg_coarse_smem_bytes(C);
-  if (smem == 0 || smem > 220 * 1024) {
-    set_error("mg_coarse_smem_cycle: the levels do not fit in shared memory");
-    return CM_E_UNSUPPORTED;
-  }
-  int rc = mg_init_attributes();
-  if (rc) return rc;
-  double bytes = 0.0;
-  for (int k = 0; k < C.nlev; ++k)
-    bytes += (double)(C.lev[k].nx + 1) * (C.lev[k].ny + 1) * 8.0 * (k == 0 ? 19 : 17);   // operator twice, tridiagonal part, b / x
-  CM_BYTES(bytes);
-  coarse_smem_kernel<<<1, kSmemCycleT, smem, st>>>(C);
-  CM_LAUNCH_CHECK();
-  return CM_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 // opt-in shared-memory sizes, once per process (idempotent; called at context creation so that no attribute
@@ -1014,7 +793,6 @@ int mg_init_attributes() {
   CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CM_CUDA(cudaFuncSetAttribute(zebra_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CM_CUDA(cudaFuncSetAttribute(zebra_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CM_CUDA(cudaFuncSetAttribute(coarse_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   done.store(true);
   return CM_OK;
 }

@@ -54,6 +54,7 @@ constexpr int kCoarseMaxLevels = 8;
 struct CoarseCycle {
   int nlev, pre, post;
   int dbg;   // phase stamps (diagnostics)
+  int ainv_smem;   // shared-memory resident cycle: the dense inverse fits in shared memory too
   const double* Ainv;   // dense inverse on the last level (nullptr: 30 zebra sweeps there)
   CoarseLevel lev[kCoarseMaxLevels];
 };
@@ -71,7 +72,9 @@ int mg_mid_init_attributes();
 int mg_zebra_mid(int mode, int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
                  const double* cu, const double* b, double* x, const double* ec, double* bc, cudaStream_t st);
 int mg_coarse_cycle(const CoarseCycle& C, int ncta, cudaStream_t st);
-size_t mg_coarse_smem_bytes(const CoarseCycle& C);
+size_t mg_coarse_smem_bytes(const CoarseCycle& C, bool dense_last);
+int mg_coarse_smem_init_attributes();
+int mg_smem_debug_times(unsigned long long* host_out, int n);   // returns the number of stamps (< 0: error)
 int mg_coarse_smem_cycle(const CoarseCycle& C, cudaStream_t st);
 int mg_coarse_max_n1();
 int mg_init_attributes();

@@ -78,6 +78,9 @@ struct PQKnobs {
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
   int mid_max_n1 = 1280;    // cache-resident middle levels (cm_mgmid.cu): lines of up to this many unknowns (0: off)
   int mid_fuse = 1;         // ... with the restricted residual / the prolongation folded into the half sweeps
+  int graph_while = 1;      // a whole GMRES cycle as ONE graph launch (WHILE node around the iteration, condition set on the device)
+  int q_low_priority = 1;   // the q-block stream gets the lowest priority: its sweeps fill the SMs / the HBM time the p-block
+                            // V-cycle leaves idle on its latency-bound coarse levels instead of competing with its fine sweeps
 };
 static int env_int(const char* name, int dflt, int minval) {
   const char* e = getenv(name);
@@ -109,6 +112,8 @@ static PQKnobs read_knobs() {
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
   K.mid_max_n1 = env_int("CM_MID_MAX_N1", 1280, 0);
   K.mid_fuse = env_int("CM_MID_FUSE", 1, 0);
+  K.graph_while = env_int("CM_GRAPH_WHILE", 1, 0);
+  K.q_low_priority = env_int("CM_Q_LOW_PRIORITY", 1, 0);
   return K;
 }
 
@@ -676,6 +681,10 @@ struct PQContext {
   double* status_host = nullptr;   // pinned
   cudaStream_t cap = nullptr;
   CachedGraph g_iter, g_final;
+  CachedGraph g_cycle;   // [condition] -> WHILE { one GMRES iteration } -> [solve y, x += Z y]
+  long long cycle_iter_launches = 0, cycle_fixed_launches = 0;
+  double cycle_iter_bytes = 0.0, cycle_fixed_bytes = 0.0;
+  bool while_ok = true;
   bool graphs_ok = true;
 };
 
@@ -683,6 +692,7 @@ static void pqc_destroy(PQContext* C) {
   if (!C) return;
   C->g_iter.destroy();
   C->g_final.destroy();
+  C->g_cycle.destroy();
   if (C->cap) cudaStreamDestroy(C->cap);
   if (C->s2) cudaStreamDestroy(C->s2);
   if (C->ev_fork) cudaEventDestroy(C->ev_fork);
@@ -724,8 +734,8 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
       CoarseCycle cc{};
       cc.nlev = S.nlev - l;
       for (int k = 0; k < cc.nlev; ++k) { cc.lev[k].nx = S.lev[l + k].nx; cc.lev[k].ny = S.lev[l + k].ny; }
-      const size_t need = mg_coarse_smem_bytes(cc);
-      if (need > 0 && need <= 200 * 1024 && (l < S.nlev - 1 || S.dense_coarse)) {
+      const size_t need = mg_coarse_smem_bytes(cc, S.dense_coarse);
+      if (need > 0 && (l < S.nlev - 1 || S.dense_coarse)) {
         C->Lsm = l;
         break;
       }
@@ -768,14 +778,16 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
     C->Hq = dist_halo_args(&C->D, 1);
   }
   if (C->K.q_concurrent) {
-    if (cudaStreamCreateWithFlags(&C->s2, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&C->s2, cudaStreamNonBlocking, C->K.q_low_priority ? prio_least : prio_greatest) != cudaSuccess ||
         cudaEventCreateWithFlags(&C->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&C->ev_join, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       C->K.q_concurrent = 0;
     }
   }
-  if (mg_init_attributes() != CM_OK || mg_mid_init_attributes() != CM_OK) {
+  if (mg_init_attributes() != CM_OK || mg_mid_init_attributes() != CM_OK || mg_coarse_smem_init_attributes() != CM_OK) {
     delete C;
     return nullptr;
   }
@@ -924,13 +936,98 @@ static int precond2(PQContext* C, const double* ru, double* z, cudaStream_t st) 
   return CM_OK;
 }
 
+// the capture stream: highest priority, so that the kernel nodes of the p-block V-cycle win the SMs over the
+// q-block sweeps captured from the low-priority second stream (kernel nodes inherit the priority of the stream
+// they were captured on)
+static bool ensure_capture_stream(PQContext* C) {
+  if (C->cap) return true;
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaStreamCreateWithPriority(&C->cap, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
+    cudaGetLastError();
+    C->cap = nullptr;
+    return false;
+  }
+  return true;
+}
+
+// One GMRES cycle as ONE graph:  [condition kernel] -> WHILE { iteration } -> [child graph: final].
+// `iter` and `fin` enqueue their kernels on the stream they are given; the last kernel of `iter` (the Givens
+// kernel) sets the condition from the device-side status block, so no host round trip separates two iterations.
+// Returns false (and leaves g_cycle empty) when the runtime refuses any step: the caller falls back to one
+// graph launch + status read per iteration.
+template <class FI, class FF>
+static bool build_cycle_graph(PQContext* C, unsigned long long* handle_out, FI&& iter, FF&& fin) {
+  if (!ensure_capture_stream(C)) return false;
+  cudaGraph_t g = nullptr, gfin = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = false;
+  do {
+    if (cudaGraphCreate(&g, 0) != cudaSuccess) break;
+    cudaGraphConditionalHandle h;
+    if (cudaGraphConditionalHandleCreate(&h, g, 0, 0) != cudaSuccess) break;
+    *handle_out = (unsigned long long)h;
+    cudaGraphNode_t n_cond = nullptr, n_while = nullptr, n_fin = nullptr;
+    if (gmres_dev_add_cond_node(g, &n_cond, C->G, (unsigned long long)h) != CM_OK) break;
+    cudaGraphNodeParams wp{};
+    wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = h;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    if (cudaGraphAddNode(&n_while, g, &n_cond, 1, &wp) != cudaSuccess) break;
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+    // the iteration, captured straight into the body graph
+    if (cudaStreamBeginCaptureToGraph(C->cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+    long long l0 = g_launches.load();
+    double b0 = g_alg_bytes;
+    int rc = iter(C->cap);
+    cudaGraph_t dummy = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(C->cap, &dummy);
+    C->cycle_iter_launches = g_launches.load() - l0;
+    C->cycle_iter_bytes = g_alg_bytes - b0;
+    g_launches -= C->cycle_iter_launches;   // nothing has run yet
+    g_alg_bytes -= C->cycle_iter_bytes;
+    if (rc != CM_OK || ce != cudaSuccess) break;
+    // the final part (y = R^-1 g, x += Z y) as a child graph behind the loop
+    if (cudaStreamBeginCapture(C->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+    l0 = g_launches.load();
+    b0 = g_alg_bytes;
+    rc = fin(C->cap);
+    ce = cudaStreamEndCapture(C->cap, &gfin);
+    C->cycle_fixed_launches = g_launches.load() - l0 + 1;   // + the condition kernel
+    C->cycle_fixed_bytes = g_alg_bytes - b0;
+    g_launches -= C->cycle_fixed_launches - 1;
+    g_alg_bytes -= C->cycle_fixed_bytes;
+    if (rc != CM_OK || ce != cudaSuccess || gfin == nullptr) break;
+    if (cudaGraphAddChildGraphNode(&n_fin, g, &n_while, 1, gfin) != cudaSuccess) break;
+    if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) break;
+    ok = true;
+  } while (false);
+  cudaGetLastError();
+  if (gfin) cudaGraphDestroy(gfin);
+  if (g) cudaGraphDestroy(g);
+  if (!ok) {
+    if (exec) cudaGraphExecDestroy(exec);
+    // a failed capture may leave the stream capturing: end it
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(C->cap, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+      cudaGraph_t junk = nullptr;
+      cudaStreamEndCapture(C->cap, &junk);
+      if (junk) cudaGraphDestroy(junk);
+    }
+    cudaGetLastError();
+    return false;
+  }
+  C->g_cycle.exec = exec;
+  return true;
+}
+
 // run `body` on the stream: replayed from a cached CUDA graph when allowed
 template <class F>
 static int run_cached(PQContext* C, CachedGraph& g, cudaStream_t st, F&& body) {
   if (!C->K.graph || !C->graphs_ok || g_prof_is_on()) return body(st);
   if (!g.exec) {
-    if (!C->cap && cudaStreamCreateWithFlags(&C->cap, cudaStreamNonBlocking) != cudaSuccess) {
-      cudaGetLastError();
+    if (!ensure_capture_stream(C)) {
       C->graphs_ok = false;
       return body(st);
     }
@@ -997,21 +1094,34 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
     CM_CUDA(cudaStreamSynchronize(st));
     return CM_OK;
   };
-  // Gram-Schmidt against the j+1 basis vectors, new (unnormalised) basis vector, its norm, scalar update
-  auto orthogonalise = [&](int jhost, cudaStream_t s_) -> int {
-    int e = gmres_dev_dot(G, sl, jhost, s_);
-    if (!e && jhost >= 0) e = dist_allreduce(Dp, G.dots, m + 1, s_);
-    if (!e) e = gmres_dev_update(G, sl, jhost, s_);
-    if (!e) e = dist_allreduce(Dp, G.nrm, 1, s_);
-    if (!e) e = gmres_dev_givens(G, rtol, atol, s_);
-    return e;
-  };
-  auto normalise = [&](int jhost) -> int { return orthogonalise(jhost, st); };
   // out = A in; keep_z: also store `in` as the preconditioned basis vector Z_j (flexible GMRES)
   auto apply_A = [&](const double* in, double* out, cudaStream_t s_, bool keep_z = false) -> int {
     return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, s_, rb, C->dist ? re : -1, nullptr,
                       nullptr, Hp, keep_z ? G.Z : nullptr, G.ne, G.st + kStJ, 2);
   };
+  // Gram-Schmidt against the j+1 basis vectors, new (unnormalised) basis vector, its norm, scalar update
+  auto orthogonalise = [&](int jhost, cudaStream_t s_, unsigned long long cond = 0ull) -> int {
+    int e = gmres_dev_dot(G, sl, jhost, s_);
+    if (!e && jhost >= 0) e = dist_allreduce(Dp, G.dots, m + 1, s_);
+    if (!e) e = gmres_dev_update(G, sl, jhost, s_);
+    if (!e) e = dist_allreduce(Dp, G.nrm, 1, s_);
+    if (!e) e = gmres_dev_givens(G, rtol, atol, s_, cond);
+    return e;
+  };
+  // one GMRES iteration / the end of a cycle, as enqueued on a stream (directly, or into a graph)
+  auto iteration = [&](cudaStream_t s_, unsigned long long cond) -> int {
+    int e = st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
+    if (!e) e = precond2(C, S.ru, G.z, s_);
+    if (!e) e = apply_A(G.z, G.w, s_, true);
+    if (!e) e = orthogonalise(4, s_, cond);     // byte accounting: a typical mid-cycle iteration, corrected by the caller
+    return e;
+  };
+  auto cycle_end = [&](cudaStream_t s_) -> int {   // x += Z y with Z_k = M^{-1} v_k kept from the iterations
+    int e = gmres_dev_solve_y(G, s_);
+    if (!e) e = gmres_dev_combine(G, sl, S.xs, 8, s_);
+    return e;
+  };
+  auto normalise = [&](int jhost) -> int { return orthogonalise(jhost, st); };
   if ((rc = st_split_scale(V, b, S.sp, S.sq, S.bs, st, vb, ve))) return rc;
   if (C->K.gmres_host && !C->dist) {
     LinOp A = [&](const double* in, double* out) { return apply_A(in, out, st, false); };
@@ -1028,7 +1138,7 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
   }
   if ((rc = gmres_dev_axpby(G, sl, 0.0, nullptr, 0.0, S.xs, st))) return rc;      // x0 = 0
   if ((rc = gmres_dev_axpby(G, sl, 1.0, S.bs, 0.0, G.w, st))) return rc;          // r0 = b
-  if ((rc = gmres_dev_begin(G, 1, st))) return rc;
+  if ((rc = gmres_dev_begin(G, 1, st, maxit))) return rc;
   if ((rc = normalise(-1))) return rc;
   if ((rc = status())) return rc;
   if (hs[kStFlag] == 2.0) {
@@ -1043,36 +1153,57 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
     // one restart cycle
     int j = 0;
     bool stop = false;
-    while (!stop) {
-      rc = run_cached(C, C->g_iter, st, [&](cudaStream_t s_) -> int {
-        int e = st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
-        if (!e) e = precond2(C, S.ru, G.z, s_);
-        if (!e) e = apply_A(G.z, G.w, s_, true);
-        if (!e) e = orthogonalise(4, s_);     // byte accounting: a typical mid-cycle iteration, corrected below
-        return e;
-      });
-      if (rc) return rc;
+    const bool try_while = C->K.graph && C->K.graph_while && C->graphs_ok && C->while_ok && !g_prof_is_on();
+    if (try_while && !C->g_cycle.exec) {
+      unsigned long long h = 0ull;
+      auto it_body = [&](cudaStream_t s_) -> int { return iteration(s_, h); };
+      if (!build_cycle_graph(C, &h, it_body, cycle_end)) C->while_ok = false;
+    }
+    if (try_while && C->g_cycle.exec) {
+      // the whole cycle is one launch: the WHILE node repeats the iteration until the device-side status says stop
+      const int its0 = its;
+      if (cudaGraphLaunch(C->g_cycle.exec, st) != cudaSuccess) {
+        set_error("cm_pqs_solve: cudaGraphLaunch (GMRES cycle) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return CM_E_CUDA;
+      }
       if ((rc = status())) return rc;
       if (hs[kStFlag] == 2.0) {
-        set_error("cm_pqs_solve: NaN/Inf in the Arnoldi process at iteration %d", its);
+        set_error("cm_pqs_solve: NaN/Inf in the Arnoldi process at iteration %d", (int)hs[kStIts]);
         return CM_E_BREAKDOWN;
       }
       its = (int)hs[kStIts];
       j = (int)hs[kStJ];
-      // the captured sequence was accounted with j = 4: correct the two j-dependent kernels (dot: j+2, update: j+3
-      // vector passes for the iteration index j-1 that just ran)
-      CM_BYTES((double)(sl ? 2 * sl->len : G.n) * 8.0 * 2.0 * ((double)(j - 1) - 4.0));
       res = hs[kStResid];
       converged = hs[kStConv] != 0.0;
-      stop = converged || its >= maxit || j >= m || hs[kStFlag] == 1.0;
+      const int nit = its - its0;
+      g_launches += C->cycle_fixed_launches + (long long)nit * C->cycle_iter_launches;
+      g_alg_bytes += C->cycle_fixed_bytes + (double)nit * C->cycle_iter_bytes;
+      // the captured iteration was accounted with j = 4, the final combine with 8 vectors: correct both
+      const double vb8 = (double)(sl ? 2 * sl->len : G.n) * 8.0;
+      for (int jj = 0; jj < nit; ++jj) CM_BYTES(vb8 * 2.0 * ((double)jj - 4.0));
+      CM_BYTES(vb8 * ((double)j - 8.0));
+    } else {
+      while (!stop) {
+        rc = run_cached(C, C->g_iter, st, [&](cudaStream_t s_) -> int { return iteration(s_, 0ull); });
+        if (rc) return rc;
+        if ((rc = status())) return rc;
+        if (hs[kStFlag] == 2.0) {
+          set_error("cm_pqs_solve: NaN/Inf in the Arnoldi process at iteration %d", its);
+          return CM_E_BREAKDOWN;
+        }
+        its = (int)hs[kStIts];
+        j = (int)hs[kStJ];
+        // the captured sequence was accounted with j = 4: correct the two j-dependent kernels (dot: j+2, update: j+3
+        // vector passes for the iteration index j-1 that just ran)
+        CM_BYTES((double)(sl ? 2 * sl->len : G.n) * 8.0 * 2.0 * ((double)(j - 1) - 4.0));
+        res = hs[kStResid];
+        converged = hs[kStConv] != 0.0;
+        stop = converged || its >= maxit || j >= m || hs[kStFlag] == 1.0;
+      }
+      // x += Z y with Z_k = M^{-1} v_k kept from the iterations: no further preconditioner application
+      rc = run_cached(C, C->g_final, st, cycle_end);
+      if (rc) return rc;
     }
-    // x += Z y with Z_k = M^{-1} v_k kept from the iterations: no further preconditioner application
-    rc = run_cached(C, C->g_final, st, [&](cudaStream_t s_) -> int {
-      int e = gmres_dev_solve_y(G, s_);
-      if (!e) e = gmres_dev_combine(G, sl, S.xs, 8, s_);
-      return e;
-    });
-    if (rc) return rc;
     if (converged || its >= maxit) break;
     // restart: w = b - A x, normalised into v_0
     if (C->dist) {
@@ -1106,7 +1237,7 @@ int pqs_ctx_info(void* ctx, int* out8) {
   out8[1] = C->Lsm < C->Lc ? C->Lsm : C->Lc;
   out8[2] = C->dist ? C->I.Ld : -1;
   out8[3] = (C->use_v1 || C->wide) ? 1 : 2;
-  out8[4] = C->g_iter.exec ? (int)C->g_iter.launches : 0;
+  out8[4] = C->g_iter.exec ? (int)C->g_iter.launches : (C->g_cycle.exec ? (int)C->cycle_iter_launches : 0);
   out8[5] = C->K.coarse_ncta;
   out8[6] = C->graphs_ok ? 1 : 0;
   out8[7] = C->wide;

@@ -292,6 +292,9 @@ int cm_mg_zebra_mid(int32_t mode, int32_t nx, int32_t ny, int32_t colour, const 
 /* diagnostics: %globaltimer phase stamps [cta < 64][line < 16][8] of the last cm_mg_zebra launch that ran with
  * the environment variable CM_RING_DBG set (tools/time_ring.py) */
 int cm_mg_ring_debug_times(uint64_t* host_out, int32_t n);
+/* diagnostics: %globaltimer phase stamps of the last shared-memory resident coarse cycle that ran with CM_COARSE_DBG
+ * set (tools/time_smem_cycle.py); returns the number of stamps written (negative: error code) */
+int cm_mg_smem_debug_times(uint64_t* host_out, int32_t n);
 int cm_mg_resid_restrict(int32_t nxf, int32_t nyf, const double* A, const double* b, const double* x,
                          double* rc, void* stream);
 int cm_mg_prolong_odd(int32_t nxc, int32_t nyc, const double* ec, double* xf, void* stream);

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--iteration", type=int, default=5, help="GMRES iteration whose kernels are listed")
     args = ap.parse_args()
+    # CUPTI records the body of a WHILE graph node once, not per loop trip: trace the one-graph-per-iteration form
+    os.environ.setdefault("CM_GRAPH_WHILE", "0")
     import torch
     import torch.distributed as dist
     import closestmolecule_b200 as cm
