@@ -79,6 +79,9 @@ _PROTOS = {
     "cm_pqs_ctx_solve": ([_P, _P, _P, _D, _D, _I, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P], C.c_int),
     "cm_pqs_ctx_info": ([_P, C.POINTER(C.c_int32)], C.c_int),
     "cm_mg_zebra": ([_I, _I, _I] + [_P] * 6 + [_I, _P], C.c_int),
+    "cm_mg_pack_f32_bytes": ([_I, _I], C.c_int64),
+    "cm_mg_pack_f32": ([_I, _I] + [_P] * 5 + [_P], C.c_int),
+    "cm_mg_zebra_f32": ([_I, _I, _I] + [_P] * 6 + [_I, _P, _P], C.c_int),
     "cm_mg_zebra_mid": ([_I, _I, _I, _I] + [_P] * 8 + [_P], C.c_int),
     "cm_mg_ring_debug_times": ([_P, _I], C.c_int),
     "cm_mg_smem_debug_times": ([_P, _I], C.c_int),

@@ -346,6 +346,27 @@ int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const d
   return mg_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, Halo{}, 0, -1, (cudaStream_t)stream);
 }
 
+int64_t cm_mg_pack_f32_bytes(int32_t nx, int32_t ny) {
+  if (nx < 1 || ny < 1) return 0;
+  return (int64_t)(mg_pack_f32_doubles(nx, ny) * sizeof(double));
+}
+
+int cm_mg_pack_f32(int32_t nx, int32_t ny, const double* A, const double* lf, const double* iu, const double* cu,
+                   void* pack, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && A && lf && iu && cu && pack, "bad argument");
+  CM_CHECK_ARG(((uintptr_t)pack & 15) == 0, "the pack must be 16-byte aligned");
+  return mg_pack_f32(nx, ny, A, lf, iu, cu, (float*)pack, 0, -1, (cudaStream_t)stream);
+}
+
+int cm_mg_zebra_f32(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
+                    const double* cu, const double* b, double* x, int32_t x_is_zero, const void* pack, void* stream) {
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && (colour == 0 || colour == 1), "bad grid or colour");
+  CM_CHECK_ARG(A && lf && iu && cu && b && x && pack, "null pointer");
+  CM_CHECK_ARG(mg_ring_fits(nx), "lines too short (or too long) for the long-line kernel");
+  return mg_zebra(nx, ny, colour, A, lf, iu, cu, b, x, x_is_zero, Halo{}, 0, -1, (cudaStream_t)stream, false,
+                  (const float*)pack);
+}
+
 int cm_mg_zebra_mid(int32_t mode, int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf,
                     const double* iu, const double* cu, const double* b, double* x, const double* ec, double* bc,
                     void* stream) {

@@ -211,10 +211,38 @@ __device__ __forceinline__ double aff_consumer_scan(Aff m, double* sh, const boo
   return r;
 }
 
+// F32: the seven operator streams of a line (4 off-line diagonals, 3 line factors) come from the fp32 pack
+// J.F (rows padded to 16 bytes: no alignment cases) instead of the fp64 arrays, two fp32 lines per ring slot:
+//     x(lower), [A0 A1], x(upper), [A5 A6], b, [lf iu], cu                 (b, [lf iu], cu from a zero guess)
+// 52 instead of 80 bytes per vertex of the colour (28 instead of 40 from a zero guess) and 7 instead of 10
+// streams, so 5 slots hold most of a line.  x, b and every product / sum stay fp64.
+template <bool COUPLED, bool F32>
+__device__ __forceinline__ bool ring_is_f32(const int a) {
+  if (!F32) return false;
+  return COUPLED ? (a == 1 || a == 3 || a >= 5) : (a >= 1);
+}
+// first array of the fp32 pack [A0 A1 A5 A6 lf iu cu] that stream a carries, and how many consecutive ones
 template <bool COUPLED>
+__device__ __forceinline__ void ring_f32_arrays(const int a, int& first, int& count) {
+  if (COUPLED) {
+    first = a == 1 ? 0 : (a == 3 ? 2 : (a == 5 ? 4 : 6));
+    count = a == 6 ? 1 : 2;
+  } else {
+    first = a == 1 ? 4 : 6;
+    count = a == 2 ? 1 : 2;
+  }
+}
+// fp64 stream a of the F32 ordering -> stream number of the fp64 ordering (ring_base / ring_row)
+template <bool COUPLED>
+__device__ __forceinline__ int ring_f32_dstream(const int a) {
+  if (COUPLED) return a == 0 ? 0 : (a == 2 ? 3 : 6);
+  return 0;
+}
+
+template <bool COUPLED, bool F32>
 __global__ void __launch_bounds__(kRingMaxT, 1)
 zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
-  constexpr int NARR = COUPLED ? 10 : 4;
+  constexpr int NARR = F32 ? (COUPLED ? 7 : 3) : (COUPLED ? 10 : 4);
   extern __shared__ __align__(16) double sm[];
   __shared__ double sh[64];
   const int n1 = J.nx + 1;
@@ -253,10 +281,23 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
       if (n >= S) mbar_wait(empty + sidx, (unsigned)(((n / S) - 1) & 1));   // the consumers have read stream n - S
       const int it2 = n / NARR, a = n - it2 * NARR;
       const int j = J.jstart + ((int)blockIdx.x + it2 * (int)gridDim.x) * J.jstep;
-      const double* base = ring_base<COUPLED>(J, nv, a);
+      if (ring_is_f32<COUPLED, F32>(a)) {
+        int first, count;
+        ring_f32_arrays<COUPLED>(a, first, count);
+        const size_t fstride = (size_t)J.n1p * (J.ny + 1);
+        const float* src = J.F + (size_t)first * fstride + (size_t)j * J.n1p;
+        const unsigned lb = (unsigned)J.n1p * 4u;
+        char* dst = reinterpret_cast<char*>(sm + (size_t)sidx * SW);
+        mbar_expect_tx(full + sidx, lb * (unsigned)count);
+        tma_g2s(dst, src, lb, full + sidx);
+        if (count == 2) tma_g2s(dst + lb, src + fstride, lb, full + sidx);
+        continue;
+      }
+      const int ad = F32 ? ring_f32_dstream<COUPLED>(a) : a;
+      const double* base = ring_base<COUPLED>(J, nv, ad);
       const int p0 = addr_parity(base);
       // indices relative to the array: the line needs [g0 - 1, g0 + n1 + 1) clipped to the array
-      const long long g0 = (long long)ring_row<COUPLED>(J, a, j) * n1;
+      const long long g0 = (long long)ring_row<COUPLED>(J, ad, j) * n1;
       const int sft = (int)((g0 + p0) & 1);
       long long nl = g0 - 1, nh = g0 + n1 + 1;
       if (nl < 0) nl = 0;
@@ -284,7 +325,7 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
     const size_t lbase = (size_t)j * n1;
     int n = it * NARR;
     RT(0);
-    if (J.prefetch && it + 1 < niter) {
+    if (!F32 && J.prefetch && it + 1 < niter) {
       // every stream of this CTA's NEXT line -> L2, one 128-byte line per prefetch instruction, spread over the
       // consumer threads (bulk prefetches through the copy engine cost as much as the copies themselves): HBM
       // streams a line ahead of the ring, the bulk copies then hit L2
@@ -296,11 +337,16 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
       }
     }
     // stream `a` of this line: wait, return the pointer to the own first element
-    auto acquire = [&](const int a) -> const double* {
+    auto acquire = [&](const int a) -> const double* {   // a: stream number of the fp64 ordering
       const int sidx = n % S;
       mbar_wait(full + sidx, (unsigned)((n / S) & 1));
       const int sft = (addr_parity(ring_base<COUPLED>(J, nv, a)) + ((ring_row<COUPLED>(J, a, j) & n1) & 1)) & 1;
       return sm + (size_t)sidx * SW + i0 + 4 + sft;
+    };
+    auto acquire_f = [&]() -> const float* {   // fp32 stream: own first element of the (first) line in the slot
+      const int sidx = n % S;
+      mbar_wait(full + sidx, (unsigned)((n / S) & 1));
+      return reinterpret_cast<const float*>(sm + (size_t)sidx * SW) + i0;
     };
     auto release = [&]() {
       __syncwarp();
@@ -318,18 +364,26 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
         release();
       }
       RT(1);
-      {
-        const double* p = acquire(1);
+      if (F32) {
+        const float* p = acquire_f();
+        const float* p2 = p + J.n1p;
 #pragma unroll
-        for (int e = 0; e < kE; ++e) r[e] = (e < ne) ? -p[e] * xn[e] : 0.0;
+        for (int e = 0; e < kE; ++e) r[e] = (e < ne) ? -((double)p[e] * xn[e] + (double)p2[e] * xn[e + 1]) : 0.0;
         release();
-      }
-      {
-        const double* p = acquire(2);
+      } else {
+        {
+          const double* p = acquire(1);
 #pragma unroll
-        for (int e = 0; e < kE; ++e)
-          if (e < ne) r[e] -= p[e] * xn[e + 1];
-        release();
+          for (int e = 0; e < kE; ++e) r[e] = (e < ne) ? -p[e] * xn[e] : 0.0;
+          release();
+        }
+        {
+          const double* p = acquire(2);
+#pragma unroll
+          for (int e = 0; e < kE; ++e)
+            if (e < ne) r[e] -= p[e] * xn[e + 1];
+          release();
+        }
       }
       {
         const double* p = acquire(3);   // x on the line above: elements i .. i+kE
@@ -337,19 +391,28 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
         for (int e = 0; e <= kE; ++e) xn[e] = (has_up && ne > 0 && e <= ne && i0 + e <= J.nx) ? p[e] : 0.0;
         release();
       }
-      {
-        const double* p = acquire(4);
+      if (F32) {
+        const float* p = acquire_f();
+        const float* p2 = p + J.n1p;
 #pragma unroll
         for (int e = 0; e < kE; ++e)
-          if (e < ne) r[e] -= p[e] * xn[e];
+          if (e < ne) r[e] -= (double)p[e] * xn[e] + (double)p2[e] * xn[e + 1];
         release();
-      }
-      {
-        const double* p = acquire(5);
+      } else {
+        {
+          const double* p = acquire(4);
 #pragma unroll
-        for (int e = 0; e < kE; ++e)
-          if (e < ne) r[e] -= p[e] * xn[e + 1];
-        release();
+          for (int e = 0; e < kE; ++e)
+            if (e < ne) r[e] -= p[e] * xn[e];
+          release();
+        }
+        {
+          const double* p = acquire(5);
+#pragma unroll
+          for (int e = 0; e < kE; ++e)
+            if (e < ne) r[e] -= p[e] * xn[e + 1];
+          release();
+        }
       }
       {
         const double* p = acquire(6);
@@ -366,26 +429,44 @@ zebra_ring_kernel(const LineJob J, const Halo H, const int S) {
       release();
     }
     RT(2);
-    {
-      const double* p = acquire(NARR - 3);
+    if (F32) {
+      {
+        const float* p = acquire_f();
+        const float* p2 = p + J.n1p;
 #pragma unroll
-      for (int e = 0; e < kE; ++e)
-        if (e < ne) lv[e] = p[e];
-      release();
-    }
-    {
-      const double* p = acquire(NARR - 2);
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) { lv[e] = (double)p[e]; iv[e] = (double)p2[e]; }
+        release();
+      }
+      {
+        const float* p = acquire_f();
 #pragma unroll
-      for (int e = 0; e < kE; ++e)
-        if (e < ne) iv[e] = p[e];
-      release();
-    }
-    {
-      const double* p = acquire(NARR - 1);
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) cv[e] = (double)p[e];
+        release();
+      }
+    } else {
+      {
+        const double* p = acquire(NARR - 3);
 #pragma unroll
-      for (int e = 0; e < kE; ++e)
-        if (e < ne) cv[e] = p[e];
-      release();
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) lv[e] = p[e];
+        release();
+      }
+      {
+        const double* p = acquire(NARR - 2);
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) iv[e] = p[e];
+        release();
+      }
+      {
+        const double* p = acquire(NARR - 1);
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+          if (e < ne) cv[e] = p[e];
+        release();
+      }
     }
     RT(3);
     // forward: z_i = r_i - l_i z_{i-1};  w_i = z_i / u_i
@@ -789,8 +870,10 @@ coarse_cycle_kernel(const CoarseCycle C) {
 int mg_init_attributes() {
   static std::atomic<bool> done{false};
   if (done.load()) return CM_OK;
-  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(zebra_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CM_CUDA(cudaFuncSetAttribute(zebra_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CM_CUDA(cudaFuncSetAttribute(zebra_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done.store(true);
@@ -798,6 +881,52 @@ int mg_init_attributes() {
 }
 
 static bool ring_fits(int n1) { return n1 >= 1024 && ((n1 + kE - 1) / kE + 31) / 32 * 32 + 32 <= kRingMaxT; }
+bool mg_ring_fits(int nx) { return ring_fits(nx + 1); }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 pack of the operator streams of the long-line kernel: [A0 A1 A5 A6 lf iu cu][row][n1p], n1p = n1 rounded
+// up to 4 floats (every row starts on a 16-byte boundary, the pad is zero).  Written once per Jacobian.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_f32_kernel(const int n1, const int n1p, const size_t nv, const int r0, const int r1, const double* __restrict__ A,
+                const double* __restrict__ lf, const double* __restrict__ iu, const double* __restrict__ cu,
+                float* __restrict__ F) {
+  const size_t fstride = (size_t)n1p * (nv / n1);
+  const long long total = (long long)(r1 - r0) * n1p;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int row = r0 + (int)(t / n1p), i = (int)(t - (long long)(row - r0) * n1p);
+    const size_t o = (size_t)row * n1p + i;
+    const bool on = i < n1;
+    const size_t v = (size_t)row * n1 + (on ? i : 0);
+    F[o] = on ? (float)A[v] : 0.0f;
+    F[fstride + o] = on ? (float)A[nv + v] : 0.0f;
+    F[2 * fstride + o] = on ? (float)A[5 * nv + v] : 0.0f;
+    F[3 * fstride + o] = on ? (float)A[6 * nv + v] : 0.0f;
+    F[4 * fstride + o] = on ? (float)lf[v] : 0.0f;
+    F[5 * fstride + o] = on ? (float)iu[v] : 0.0f;
+    F[6 * fstride + o] = on ? (float)cu[v] : 0.0f;
+  }
+}
+
+size_t mg_pack_f32_doubles(int nx, int ny) {   // doubles of workspace the pack of one level takes
+  const size_t n1p = (size_t)((nx + 1 + 3) & ~3);
+  return (7 * n1p * (size_t)(ny + 1) + 1) / 2 + 2;
+}
+
+// rows [r0, r1) (r1 < 0: all)
+int mg_pack_f32(int nx, int ny, const double* A, const double* lf, const double* iu, const double* cu, float* F,
+                int r0, int r1, cudaStream_t st) {
+  if (r1 < 0) { r0 = 0; r1 = ny + 1; }
+  if (r1 <= r0) return CM_OK;
+  const int n1 = nx + 1, n1p = (n1 + 3) & ~3;
+  const size_t nv = (size_t)n1 * (ny + 1);
+  long long g = ((long long)(r1 - r0) * n1p + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_f32_kernel<<<(int)g, 256, 0, st>>>(n1, n1p, nv, r0, r1, A, lf, iu, cu, F);
+  CM_BYTES((double)(r1 - r0) * n1 * (7 * 8.0 + 7 * 4.0));
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
 
 // shared memory of one CTA: S line-sized slots + the output line + 2 S barriers
 static size_t ring_smem(int n1, int S) {
@@ -810,7 +939,7 @@ static size_t ring_smem(int n1, int S) {
 static void ring_config(int n1, int narr, int& T, int& S, size_t& smem, int& occ) {
   const int nw = ((n1 + kE - 1) / kE + 31) / 32;
   T = (nw + 1) * 32;   // + the producer warp
-  S = narr == 4 ? 4 : 5;   // measured (tools/time_ring.py): 5 slots beat a whole line in flight on 2049-point lines
+  S = narr <= 4 ? narr : 5;   // measured (tools/time_ring.py): 5 slots beat a whole line in flight on 2049-point lines
   if (const char* e = getenv("CM_RING_S")) { const int v = atoi(e); if (v >= 2 && v <= 16) S = v; }
   while (S > 2 && ring_smem(n1, S) > 220 * 1024) --S;
   smem = ring_smem(n1, S);
@@ -824,7 +953,8 @@ static void ring_config(int n1, int narr, int& T, int& S, size_t& smem, int& occ
 // (H.active): r0 is even; colour 0 starts at r0 (waits below, pushes down), colour 1 at the last odd row
 // (waits above, pushes up).
 int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu, const double* cu,
-             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st, bool prof) {
+             const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st, bool prof,
+             const float* F) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
   const int n1 = nx + 1;
   LineJob J{};
@@ -848,17 +978,20 @@ int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
     return CM_OK;
   }
   int rc_attr;
-  const double bytes = (double)J.nlines * n1 * (x_zero ? 40.0 : 80.0);
+  bool use_ring = ring_fits(n1);
+  const bool f32 = use_ring && F != nullptr;
+  const double bytes = (double)J.nlines * n1 * (f32 ? (x_zero ? 28.0 : 52.0) : (x_zero ? 40.0 : 80.0));
   CM_BYTES(bytes);
   if (prof) prof_begin(kProfZebraFine, bytes, st);
-  bool use_ring = ring_fits(n1);
   if (const char* e = getenv("CM_ZEBRA_SMALL_BELOW")) {   // tuning: one CTA per line when the launch has few lines
     if (J.nlines <= atoi(e)) use_ring = false;
   }
   if (use_ring) {
     int T, S, occ;
     size_t smem;
-    ring_config(n1, x_zero ? 4 : 10, T, S, smem, occ);
+    ring_config(n1, f32 ? (x_zero ? 3 : 7) : (x_zero ? 4 : 10), T, S, smem, occ);
+    J.F = f32 ? F : nullptr;
+    J.n1p = (n1 + 3) & ~3;
     if (const char* e = getenv("CM_RING_DBG")) J.dbg = atoi(e);
     J.prefetch = 0;   // measured: pulling the next line into L2 ahead of the ring costs more than it hides (profiles/README.md)
     if (const char* e = getenv("CM_RING_PREFETCH")) J.prefetch = atoi(e);
@@ -868,10 +1001,13 @@ int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, cons
     }
     if ((rc_attr = mg_init_attributes())) return rc_attr;
     const int grid = J.nlines < 148 * occ ? J.nlines : 148 * occ;
-    if (x_zero) {
-      zebra_ring_kernel<false><<<grid, T, smem, st>>>(J, H, S);
+    if (f32) {
+      if (x_zero) zebra_ring_kernel<false, true><<<grid, T, smem, st>>>(J, H, S);
+      else zebra_ring_kernel<true, true><<<grid, T, smem, st>>>(J, H, S);
+    } else if (x_zero) {
+      zebra_ring_kernel<false, false><<<grid, T, smem, st>>>(J, H, S);
     } else {
-      zebra_ring_kernel<true><<<grid, T, smem, st>>>(J, H, S);
+      zebra_ring_kernel<true, false><<<grid, T, smem, st>>>(J, H, S);
     }
   } else {
     const int T = (n1 > 2048) ? 512 : ((n1 > 1024) ? 256 : ((n1 > 128) ? 128 : 32));

@@ -22,6 +22,8 @@ struct LineJob {
   const double* cu;
   const double* b;
   double* x;
+  const float* F;   // fp32 pack of the operator streams (mg_pack_f32), nullptr: fp64 arrays
+  int n1p;          // its row stride
 };
 
 // one half sweep of the cache-resident middle levels (cm_mgmid.cu)
@@ -61,7 +63,12 @@ struct CoarseCycle {
 
 int mg_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu, const double* cu,
              const double* b, double* x, int x_zero, const Halo& H, int r0, int r1, cudaStream_t st,
-             bool prof = false);   // prof: count the launch in the roofline class of bench.py (finest grid)
+             bool prof = false,   // prof: count the launch in the roofline class of bench.py (finest grid)
+             const float* F = nullptr);   // fp32 pack of the operator streams (long-line kernel only)
+bool mg_ring_fits(int nx);
+size_t mg_pack_f32_doubles(int nx, int ny);
+int mg_pack_f32(int nx, int ny, const double* A, const double* lf, const double* iu, const double* cu, float* F,
+                int r0, int r1, cudaStream_t st);
 int mg_resid_restrict(int nxf, int nyf, const double* A, const double* b, const double* x, double* rc,
                       const Halo& H, int Y0, int Y1, cudaStream_t st);
 int mg_prolong_odd(int nxc, int nyc, const double* ec, double* xf, const Halo& H, int wait_coarse, int r0,

@@ -26,6 +26,7 @@ struct PQSLevel {
   int nx, ny;
   size_t n;
   double *A, *lf, *iu, *cu, *x, *b, *r;
+  float* F;   // fp32 pack of the smoother's operator streams (levels of the long-line kernel only)
 };
 
 struct PQSolver {
@@ -49,6 +50,7 @@ struct PQSolver {
   double* QQl;      // 7-point stand-in of the 13-point q-block for the line relaxation (st_lump_extras)
   int* has_extra;   // device flag: any of them non-zero
   double *qlf, *qiu, *qcu;
+  float* qF;        // fp32 pack of the q-block smoother streams (finest grid)
   double *Ainv, *Mwork;
   double *bs, *xs, *tq, *ru, *ustate;
   double* gm;
@@ -78,6 +80,7 @@ struct PQKnobs {
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
   int mid_max_n1 = 1280;    // cache-resident middle levels (cm_mgmid.cu): lines of up to this many unknowns (0: off)
   int mid_fuse = 1;         // ... with the restricted residual / the prolongation folded into the half sweeps
+ int f32_op = 1;           // long-line smoother: operator streams from the fp32 pack (x, b and all arithmetic stay fp64)
   int graph_while = 1;      // a whole GMRES cycle as ONE graph launch (WHILE node around the iteration, condition set on the device)
   int q_low_priority = 1;   // the q-block stream gets the lowest priority: its sweeps fill the SMs / the HBM time the p-block
                             // V-cycle leaves idle on its latency-bound coarse levels instead of competing with its fine sweeps
@@ -112,6 +115,7 @@ static PQKnobs read_knobs() {
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
   K.mid_max_n1 = env_int("CM_MID_MAX_N1", 1280, 0);
   K.mid_fuse = env_int("CM_MID_FUSE", 1, 0);
+  K.f32_op = env_int("CM_F32_OP", 1, 0);
   K.graph_while = env_int("CM_GRAPH_WHILE", 1, 0);
   K.q_low_priority = env_int("CM_Q_LOW_PRIORITY", 1, 0);
   return K;
@@ -192,6 +196,9 @@ static int pqs_layout(PQSolver& S, int nx, int ny, int restart, double* base, co
     Q.b = (k == 0) ? nullptr : take(Q.n);
   }
   S.qAinv = take(S.dense_coarse ? nc * nc : 2);
+  for (int k = 0; k < S.nlev; ++k)
+    S.lev[k].F = mg_ring_fits(S.lev[k].nx) ? (float*)take(mg_pack_f32_doubles(S.lev[k].nx, S.lev[k].ny)) : nullptr;
+  S.qF = mg_ring_fits(nx) ? (float*)take(mg_pack_f32_doubles(nx, ny)) : nullptr;
   // 4 Mi cells (profiles/README.md): the V-cycle on the q-block helps the minus-sign C0IP variant (114 GMRES
   // iterations) but diverges on the "paper" variant (Galerkin coarse operators of the transport part): off
   // by default; line sweeps on the 7-point stand-in instead: 3 sweeps 94 / 222 iterations ("paper" /
@@ -807,6 +814,24 @@ int pqs_destroy(void* ctx) {
   return CM_OK;
 }
 
+// fp32 copies of the operator streams the long-line half sweeps read (own rows of the distributed levels)
+static int pqc_pack_f32(PQContext* C, cudaStream_t st) {
+  PQSolver& S = C->S;
+  if (!C->K.f32_op) return CM_OK;
+  int rc;
+  for (int l = 0; l < S.nlev; ++l) {
+    PQSLevel& L = S.lev[l];
+    if (!L.F) continue;
+    const bool lev_dist = C->dist && l < C->I.Ld;
+    if ((rc = mg_pack_f32(L.nx, L.ny, L.A, L.lf, L.iu, L.cu, L.F, lev_dist ? C->I.rb[l] : 0, lev_dist ? C->I.re[l] : -1, st)))
+      return rc;
+  }
+  if (S.qF && (rc = mg_pack_f32(C->nx, C->ny, S.QQ, S.qlf, S.qiu, S.qcu, S.qF, C->dist ? C->I.rb[0] : 0,
+                                C->dist ? C->I.re[0] : -1, st)))
+    return rc;
+  return CM_OK;
+}
+
 int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st) {
   PQContext* C = static_cast<PQContext*>(ctx);
   PQSolver& S = C->S;
@@ -818,9 +843,11 @@ int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* 
     CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
     CM_CUDA(cudaStreamSynchronize(st));
     C->wide = wide;
-    return CM_OK;
+    return wide ? (int)CM_OK : pqc_pack_f32(C, st);
   }
-  return pqs_setup_dist(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, &C->D, st, C->I.Ld);
+  if ((rc = pqs_setup_dist(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, &C->D, st, C->I.Ld)))
+    return rc;
+  return pqc_pack_f32(C, st);
 }
 
 // one V-cycle on the p-block, level l: x = approx. A_l^{-1} b
@@ -882,8 +909,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     return CM_OK;
   }
   for (int s = 0; s < S.pre_smooth; ++s) {
-    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st, l == 0))) return rc;
-    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, s == 0, H, r0, r1, st, l == 0, C->K.f32_op ? L.F : nullptr))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0, C->K.f32_op ? L.F : nullptr))) return rc;
   }
   if ((rc = mg_resid_restrict(L.nx, L.ny, L.A, b, x, Cl.b, H, lev_dist ? C->I.rb[l + 1] : 0,
                               lev_dist ? C->I.re[l + 1] : -1, st)))
@@ -891,8 +918,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
   if ((rc = vcycle2(C, l + 1, Cl.b, Cl.x, st))) return rc;
   if ((rc = mg_prolong_odd(Cl.nx, Cl.ny, Cl.x, x, H, (lev_dist && l + 1 < C->I.Ld) ? 1 : 0, r0, r1, st))) return rc;
   for (int s = 0; s < npost; ++s) {
-    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
-    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 0, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0, C->K.f32_op ? L.F : nullptr))) return rc;
+    if ((rc = mg_zebra(L.nx, L.ny, 1, L.A, L.lf, L.iu, L.cu, b, x, 0, H, r0, r1, st, l == 0, C->K.f32_op ? L.F : nullptr))) return rc;
   }
   return CM_OK;
 }
@@ -925,8 +952,8 @@ static int precond2(PQContext* C, const double* ru, double* z, cudaStream_t st) 
     return rc;
   }
   for (int sw = 0; sw < S.q_sweeps; ++sw) {
-    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, sq, true))) return rc;
-    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, sq, true))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 0, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, sw == 0, H, r0, r1, sq, true, C->K.f32_op ? S.qF : nullptr))) return rc;
+    if ((rc = mg_zebra(C->nx, C->ny, 1, S.QQ, S.qlf, S.qiu, S.qcu, ru + V, z + V, 0, H, r0, r1, sq, true, C->K.f32_op ? S.qF : nullptr))) return rc;
   }
   if (fork) {
     CM_CUDA(cudaEventRecord(C->ev_join, C->s2));

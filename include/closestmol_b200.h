@@ -280,6 +280,15 @@ int cm_pqs_solve_dist(int32_t nx, int32_t ny, int32_t restart, const double* b, 
  *     half sweep that follows). */
 int cm_mg_zebra(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
                 const double* cu, const double* b, double* x, int32_t x_is_zero, void* stream);
+/* Long-line half sweep with the seven operator streams (off-line diagonals 0, 1, 5, 6 and the line factors) read
+ * from an fp32 pack instead of the fp64 arrays: cm_mg_pack_f32 writes the pack (cm_mg_pack_f32_bytes bytes, 16-byte
+ * aligned, once per Jacobian), cm_mg_zebra_f32 is cm_mg_zebra on it (lines of 1024 .. 4300 unknowns).  x, b and all
+ * arithmetic stay fp64; the result is the line solve of the fp32-rounded operator (a preconditioner detail). */
+int64_t cm_mg_pack_f32_bytes(int32_t nx, int32_t ny);
+int cm_mg_pack_f32(int32_t nx, int32_t ny, const double* A, const double* lf, const double* iu, const double* cu,
+                   void* pack, void* stream);
+int cm_mg_zebra_f32(int32_t nx, int32_t ny, int32_t colour, const double* A, const double* lf, const double* iu,
+                    const double* cu, const double* b, double* x, int32_t x_is_zero, const void* pack, void* stream);
 /* Half sweeps of the cache-resident middle levels (cm_mgmid.cu; lines of up to 1280 unknowns, whole grid):
  *   mode 0: colour half sweep from a zero guess;  mode 1: with couplings;
  *   mode 2: colour-1 half sweep fused with the restricted residual, bc[(ny/2+1)*(nx/2+1)] = R (b - A x)

@@ -115,6 +115,72 @@ def test_fused_zebra_half_sweeps(nx, ny, shift):
     assert np.max(np.abs(R[1::2])) < 1e-11 and np.max(np.abs(R[0::2])) > 1e-4
 
 
+@pytest.mark.parametrize("nx,ny,shift", [(1024, 40, 0), (1500, 21, 1), (2048, 330, 0), (4096, 310, 1), (4099, 7, 0)])
+def test_fused_zebra_half_sweeps_fp32_operator(nx, ny, shift):
+    """cm_mg_zebra_f32: the long-line half sweep with its operator streams read from the fp32 pack equals the
+    sequential line solve (two first-order recurrences, fp64 arithmetic) with the fp32-ROUNDED couplings and line
+    factors, to fp64 rounding; and it differs from the fp64-operator sweep by fp32 rounding only."""
+    n1, n = nx + 1, (nx + 1) * (ny + 1)
+    dev = torch.device("cuda")
+    A, rng = _random_stencil(nx, ny, 7 * nx + ny)
+    At = torch.tensor(A.reshape(7, n), device=dev)
+    lf, iu, cu = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    bh = rng.standard_normal((ny + 1, n1))
+    buf = torch.full((2 * n + 8,), float("nan"), dtype=torch.float64, device=dev)
+    b = buf[shift:shift + n]
+    xo = shift + n + 2
+    xo += (xo - shift) % 2
+    x = buf[xo:xo + n]
+    b.copy_(torch.tensor(bh.reshape(-1)))
+    x.zero_()
+    lib, P, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+    _capi.check(lib.cm_stencil_line_factor(nx, ny, P(At), P(lf), P(iu), P(cu), P(err), st))
+    assert int(err.item()) == 0
+    pack = torch.empty(int(lib.cm_mg_pack_f32_bytes(nx, ny)) // 8, dtype=torch.float64, device=dev)
+    _capi.check(lib.cm_mg_pack_f32(nx, ny, P(At), P(lf), P(iu), P(cu), P(pack), st))
+    r32 = lambda a: a.astype(np.float32).astype(np.float64)
+    A32 = r32(A)
+    L32, I32, C32 = (r32(v.cpu().numpy().reshape(ny + 1, n1)) for v in (lf, iu, cu))
+    lines = sorted({0, 1, 2, 3, ny // 2, ny // 2 + 1, ny - 1, ny})
+    xr = np.zeros((ny + 1, n1))
+    x64 = x.clone()
+    for colour, x_zero in ((0, 1), (1, 0), (0, 0), (1, 0)):
+        x64.copy_(x)
+        _capi.check(lib.cm_mg_zebra(nx, ny, colour, P(At), P(lf), P(iu), P(cu), P(b), P(x64), x_zero, st))
+        _capi.check(lib.cm_mg_zebra_f32(nx, ny, colour, P(At), P(lf), P(iu), P(cu), P(b), P(x), x_zero, P(pack), st))
+        X = x.cpu().numpy().reshape(ny + 1, n1)
+        assert np.isfinite(X[colour::2]).all()
+        xin = np.zeros_like(xr) if x_zero else xr
+        for j in lines:
+            if j % 2 != colour:
+                continue
+            rhs = bh[j].copy()
+            for k, (dx, dy) in enumerate(OFFS):
+                if dy == 0 or not (0 <= j + dy <= ny):
+                    continue
+                src = np.zeros(n1)
+                lo, hi = max(0, -dx), min(n1, n1 - dx)
+                src[lo:hi] = xin[j + dy, lo + dx:hi + dx]
+                rhs -= A32[k, j] * src
+            z = np.empty(n1)
+            acc = 0.0
+            for i in range(n1):
+                acc = rhs[i] - L32[j, i] * acc
+                z[i] = acc
+            w = z * I32[j]
+            ref = np.empty(n1)
+            acc = 0.0
+            for i in range(n1 - 1, -1, -1):
+                acc = w[i] - C32[j, i] * acc
+                ref[i] = acc
+            assert np.max(np.abs(X[j] - ref)) < 1e-11 * (1 + np.max(np.abs(ref))), (colour, j)
+        X64 = x64.cpu().numpy().reshape(ny + 1, n1)
+        d = np.max(np.abs(X[colour::2] - X64[colour::2])) / (1 + np.max(np.abs(X64[colour::2])))
+        assert d < 1e-5, (colour, d)
+        xr = X.copy()
+
+
 @pytest.mark.parametrize("nx,ny", [(8, 6), (200, 38), (1024, 20), (514, 130)])
 def test_restricted_residual_and_odd_row_correction(nx, ny):
     n1, n = nx + 1, (nx + 1) * (ny + 1)
@@ -260,9 +326,10 @@ def test_kernel_generations_agree(nx, ny, monkeypatch):
                       ("v2_cluster", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "257"}),
                       ("v2_cta1", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "65", "CM_COARSE_NCTA": "1"}),
                       ("v2_unfused", {"CM_COARSE_SMEM": "0"}), ("v2_nograph", {"CM_GRAPH": "0"}),
-                      ("v2_nomid", {"CM_MID_MAX_N1": "0"}), ("v2_mid_unfused", {"CM_MID_FUSE": "0"})):
+                      ("v2_nomid", {"CM_MID_MAX_N1": "0"}), ("v2_mid_unfused", {"CM_MID_FUSE": "0"}),
+                      ("v2_f64_operator", {"CM_F32_OP": "0"}), ("v2_host_loop", {"CM_GRAPH_WHILE": "0"})):
         for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH", "CM_COARSE_SMEM", "CM_MID_MAX_N1",
-                  "CM_MID_FUSE"):
+                  "CM_MID_FUSE", "CM_F32_OP", "CM_GRAPH_WHILE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
