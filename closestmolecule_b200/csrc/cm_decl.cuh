@@ -85,7 +85,9 @@ size_t gmres_dev_doubles(long long n, int m);
 void gmres_dev_layout(GmresDev& G, long long n, int m, double* work);
 int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st, int maxit = 1 << 30);
 int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
-int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
+// ru != nullptr: also writes ru = diag(sp | sq)^-1 V_{j+1} (unnormalised), the next preconditioner input
+int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st, const double* sp = nullptr,
+                     const double* sq = nullptr, double* ru = nullptr);
 // cond_handle != 0: a cudaGraphConditionalHandle; the kernel sets it to "another iteration is needed" (the GMRES
 // cycle runs as a WHILE node of a CUDA graph, cm_pqsolver.cu)
 int gmres_dev_givens(const GmresDev& G, double rtol, double atol, cudaStream_t st, unsigned long long cond_handle = 0);
@@ -121,7 +123,8 @@ int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double*
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
                cudaStream_t st, int r0 = 0, int r1 = -1, const double* QQx = nullptr,
                const int* has_extra = nullptr, const struct Halo* H = nullptr, double* zcopy = nullptr,
-               long long zstride = 0, const double* jptr = nullptr, int halo_channels = 1);
+               long long zstride = 0, const double* jptr = nullptr, int halo_channels = 1,
+               const double* xscale = nullptr);   // xscale: y and zcopy are multiplied by xscale[*jptr]
 int st_unscale_dev(int nx, int ny, const double* rbase, long long stride, const double* jptr, const double* vscale,
                    const double* sp, const double* sq, double* out, cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_unscale(int nx, int ny, const double* r, const double* sp, const double* sq, double* out,

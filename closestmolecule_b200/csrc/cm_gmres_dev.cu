@@ -167,9 +167,13 @@ gd_dot_kernel(const GmresDev G, const VecSlice sl) {
 }
 
 // V_{j+1} = w - sum_{k<=j} h_k vscale_k V_k (unnormalised), nrm[0] = ||V_{j+1}||^2 over this rank's part
+// ru != nullptr: also ru = D^-1 V_{j+1} (D = diag(sp | sq), the row equilibration; split layout [p | q] with
+// nhalf entries each): the input of the next preconditioner application, still unnormalised -- the
+// preconditioner is linear, the operator kernel multiplies its result by vscale_{j+1} (cm_stencil.cu)
 template <bool SLICE>
 __global__ void __launch_bounds__(kGB)
-gd_update_kernel(const GmresDev G, const VecSlice sl) {
+gd_update_kernel(const GmresDev G, const VecSlice sl, const double* __restrict__ sp, const double* __restrict__ sq,
+                 double* __restrict__ ru, const long long nhalf) {
   extern __shared__ double s_h[];   // m + 2
   __shared__ double sh[32];
   __shared__ bool s_last;
@@ -194,6 +198,7 @@ gd_update_kernel(const GmresDev G, const VecSlice sl) {
         }
         for (; k <= j; ++k) a -= s_h[k] * vq[(size_t)k * G.ne];
         vout[q] = a;
+        if (ru != nullptr) ru[q] = a / (q < nhalf ? sp[q] : sq[q - nhalf]);
         nrm += a * a;
       }
     } else {
@@ -216,6 +221,13 @@ gd_update_kernel(const GmresDev G, const VecSlice sl) {
           a.y -= s_h[k] * vv.y;
         }
         reinterpret_cast<double2*>(vout)[i] = a;
+        if (ru != nullptr) {
+          const long long e0 = 2 * i, e1 = 2 * i + 1;
+          double2 o;
+          o.x = a.x / (e0 < nhalf ? sp[e0] : sq[e0 - nhalf]);
+          o.y = a.y / (e1 < nhalf ? sp[e1] : sq[e1 - nhalf]);
+          reinterpret_cast<double2*>(ru)[i] = o;
+        }
         nrm += a.x * a.x + a.y * a.y;
       }
     }
@@ -401,13 +413,18 @@ int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t
   return CM_OK;
 }
 
-int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st) {
+int gmres_dev_update(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st, const double* sp,
+                     const double* sq, double* ru) {
   const long long len = gd_len(G, sl);
   const int grid = gd_grid(sl ? len : len / 2);
   const size_t smem = (size_t)(G.m + 2) * sizeof(double);
-  if (sl) gd_update_kernel<true><<<grid, kGB, smem, st>>>(G, *sl);
-  else gd_update_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0});
-  CM_BYTES((double)len * 8.0 * (jhost + 3));
+  if (ru != nullptr && (G.n & 1)) {
+    set_error("gmres_dev_update: the fused unscaling needs an even vector length");
+    return CM_E_INVALID;
+  }
+  if (sl) gd_update_kernel<true><<<grid, kGB, smem, st>>>(G, *sl, sp, sq, ru, G.n / 2);
+  else gd_update_kernel<false><<<grid, kGB, smem, st>>>(G, VecSlice{0, 0, 0}, sp, sq, ru, G.n / 2);
+  CM_BYTES((double)len * 8.0 * (jhost + 3 + (ru ? 2 : 0)));
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

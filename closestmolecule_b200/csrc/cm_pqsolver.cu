@@ -80,7 +80,8 @@ struct PQKnobs {
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
   int mid_max_n1 = 1280;    // cache-resident middle levels (cm_mgmid.cu): lines of up to this many unknowns (0: off)
   int mid_fuse = 1;         // ... with the restricted residual / the prolongation folded into the half sweeps
- int f32_op = 1;           // long-line smoother: operator streams from the fp32 pack (x, b and all arithmetic stay fp64)
+  int fuse_unscale = 1;     // the GMRES update kernel writes the next preconditioner input (no separate unscaling pass)
+  int f32_op = 1;           // long-line smoother: operator streams from the fp32 pack (x, b and all arithmetic stay fp64)
   int graph_while = 1;      // a whole GMRES cycle as ONE graph launch (WHILE node around the iteration, condition set on the device)
   int q_low_priority = 1;   // the q-block stream gets the lowest priority: its sweeps fill the SMs / the HBM time the p-block
                             // V-cycle leaves idle on its latency-bound coarse levels instead of competing with its fine sweeps
@@ -115,6 +116,7 @@ static PQKnobs read_knobs() {
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
   K.mid_max_n1 = env_int("CM_MID_MAX_N1", 1280, 0);
   K.mid_fuse = env_int("CM_MID_FUSE", 1, 0);
+  K.fuse_unscale = env_int("CM_FUSE_UNSCALE", 1, 0);
   K.f32_op = env_int("CM_F32_OP", 1, 0);
   K.graph_while = env_int("CM_GRAPH_WHILE", 1, 0);
   K.q_low_priority = env_int("CM_Q_LOW_PRIORITY", 1, 0);
@@ -1122,22 +1124,26 @@ int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double ato
     return CM_OK;
   };
   // out = A in; keep_z: also store `in` as the preconditioned basis vector Z_j (flexible GMRES)
+  const bool fuse_unscale = C->K.fuse_unscale != 0;
   auto apply_A = [&](const double* in, double* out, cudaStream_t s_, bool keep_z = false) -> int {
     return st_pq_spmv(nx, ny, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, in, out, s_, rb, C->dist ? re : -1, nullptr,
-                      nullptr, Hp, keep_z ? G.Z : nullptr, G.ne, G.st + kStJ, 2);
+                      nullptr, Hp, keep_z ? G.Z : nullptr, G.ne, G.st + kStJ, 2,
+                      (keep_z && fuse_unscale) ? G.vscale : nullptr);
   };
   // Gram-Schmidt against the j+1 basis vectors, new (unnormalised) basis vector, its norm, scalar update
   auto orthogonalise = [&](int jhost, cudaStream_t s_, unsigned long long cond = 0ull) -> int {
     int e = gmres_dev_dot(G, sl, jhost, s_);
     if (!e && jhost >= 0) e = dist_allreduce(Dp, G.dots, m + 1, s_);
-    if (!e) e = gmres_dev_update(G, sl, jhost, s_);
+    if (!e) e = fuse_unscale ? gmres_dev_update(G, sl, jhost, s_, S.sp, S.sq, S.ru) : gmres_dev_update(G, sl, jhost, s_);
     if (!e) e = dist_allreduce(Dp, G.nrm, 1, s_);
     if (!e) e = gmres_dev_givens(G, rtol, atol, s_, cond);
     return e;
   };
   // one GMRES iteration / the end of a cycle, as enqueued on a stream (directly, or into a graph)
   auto iteration = [&](cudaStream_t s_, unsigned long long cond) -> int {
-    int e = st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
+    // the preconditioner input ru = D^-1 V_j comes out of the previous update kernel (unnormalised: apply_A scales)
+    int e = fuse_unscale ? (int)CM_OK
+                         : st_unscale_dev(nx, ny, G.V, G.ne, G.st + kStJ, G.vscale, S.sp, S.sq, S.ru, s_, rb, C->dist ? re : -1);
     if (!e) e = precond2(C, S.ru, G.z, s_);
     if (!e) e = apply_A(G.z, G.w, s_, true);
     if (!e) e = orthogonalise(4, s_, cond);     // byte accounting: a typical mid-cycle iteration, corrected by the caller

@@ -163,7 +163,7 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
                        double* __restrict__ y, const int vb, const int ve,
                        const double* __restrict__ QQx, const int* __restrict__ has_extra, const Halo H,
                        double* __restrict__ zcopy, const long long zstride, const double* __restrict__ jptr,
-                       const int halo_channels) {
+                       const int halo_channels, const double* __restrict__ xscale) {
   const int nv = (nx + 1) * (ny + 1);
   const int n1 = nx + 1;
   if (H.active) {
@@ -204,12 +204,15 @@ pq_stencil_spmv_kernel(const int nx, const int ny, const double* __restrict__ PP
         yq += QQx[(size_t)e * nv + v] * x[nv + jy * n1 + jx];
     }
   }
-  y[v] = sp[v] * yp;
-  y[nv + v] = sq[v] * yq;
+  // xscale: x came out of a preconditioner application to the UNNORMALISED basis vector; the operator and the
+  // preconditioner are linear, so the normalisation 1 / ||V_j|| is applied here, to y and to the kept copy of x
+  const double xs = xscale != nullptr ? xscale[(int)(*jptr)] : 1.0;
+  y[v] = sp[v] * yp * xs;
+  y[nv + v] = sq[v] * yq * xs;
   if (zcopy != nullptr) {   // flexible GMRES: keep the preconditioned basis vector z_j = x (cm_gmres_dev.cu)
     double* zj = zcopy + (size_t)zstride * (size_t)(int)(*jptr);
-    zj[v] = x[v];
-    zj[nv + v] = x[nv + v];
+    zj[v] = x[v] * xs;
+    zj[nv + v] = x[nv + v] * xs;
   }
 }
 
@@ -1037,13 +1040,14 @@ int st_interleave(int nv, const double* xs, double* x, cudaStream_t st, int vb, 
 int st_pq_spmv(int nx, int ny, const double* PP, const double* PQ, const double* QP,
                const double* QQ, const double* sp, const double* sq, const double* x, double* y,
                cudaStream_t st, int r0, int r1, const double* QQx, const int* has_extra, const Halo* H,
-               double* zcopy, long long zstride, const double* jptr, int halo_channels) {
+               double* zcopy, long long zstride, const double* jptr, int halo_channels, const double* xscale) {
   int vb, ve;
   row_range(ny, nx + 1, r0, r1, vb, ve);
   prof_begin(kProfSpmv, (double)(ve - vb) * 288.0, st);
   CM_BYTES((double)(ve - vb) * 288.0);
   pq_stencil_spmv_kernel<<<grid_for(ve - vb), kSB, 0, st>>>(nx, ny, PP, PQ, QP, QQ, sp, sq, x, y, vb, ve,
-                                                            QQx, has_extra, H ? *H : Halo{}, zcopy, zstride, jptr, halo_channels);
+                                                            QQx, has_extra, H ? *H : Halo{}, zcopy, zstride, jptr, halo_channels,
+                                                            xscale);
   if (zcopy) CM_BYTES((double)(ve - vb) * 16.0);
   prof_end(kProfSpmv, st);
   CM_LAUNCH_CHECK();

@@ -327,9 +327,10 @@ def test_kernel_generations_agree(nx, ny, monkeypatch):
                       ("v2_cta1", {"CM_COARSE_SMEM": "0", "CM_COARSE_N1": "65", "CM_COARSE_NCTA": "1"}),
                       ("v2_unfused", {"CM_COARSE_SMEM": "0"}), ("v2_nograph", {"CM_GRAPH": "0"}),
                       ("v2_nomid", {"CM_MID_MAX_N1": "0"}), ("v2_mid_unfused", {"CM_MID_FUSE": "0"}),
-                      ("v2_f64_operator", {"CM_F32_OP": "0"}), ("v2_host_loop", {"CM_GRAPH_WHILE": "0"})):
+                      ("v2_f64_operator", {"CM_F32_OP": "0"}), ("v2_host_loop", {"CM_GRAPH_WHILE": "0"}),
+                      ("v2_unscale_pass", {"CM_FUSE_UNSCALE": "0"})):
         for k in ("CM_SOLVER_V1", "CM_COARSE_NCTA", "CM_COARSE_N1", "CM_GRAPH", "CM_COARSE_SMEM", "CM_MID_MAX_N1",
-                  "CM_MID_FUSE", "CM_F32_OP", "CM_GRAPH_WHILE"):
+                  "CM_MID_FUSE", "CM_F32_OP", "CM_GRAPH_WHILE", "CM_FUSE_UNSCALE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
