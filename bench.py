@@ -401,6 +401,26 @@ def gpu_arm(args):
         sv.newton_step(compute_residual=False)
         return uu.vector().clone(), (sv.linear_iterations[-1] if sv.linear_iterations else None)
 
+    # ---- full-size property (untimed, one GPU): the Newton update of the timed path satisfies the ASSEMBLED system
+    # J dx = F -- true residual through the generic CSR kernel (cm_spmv on the DOLFIN-layout values, which shares
+    # nothing with the stencil blocks / multigrid / Krylov kernels of the solve)
+    full_check = None
+    if not strong and world == 1 and not args.no_parity and args.linear_solver == "gmres":
+        uvec.copy_(u0)
+        solver.newton_step(compute_residual=False)     # leaves J (with Dirichlet rows) in asm.vals, F in asm.b, dx in _dx
+        asm_, t_ = solver.asm, solver.asm.topo
+        r_ = torch.empty_like(asm_.b)
+        _capi.check(lib.cm_spmv(asm_.bs, t_.nv, _capi.ptr(t_.nrowptr), _capi.ptr(t_.ncol), _capi.ptr(asm_.vals),
+                                _capi.ptr(solver._dx), _capi.ptr(r_), _capi.stream_ptr()))
+        r_.sub_(asm_.b)
+        # the solve runs on the row-equilibrated system: measure the residual in the same scaling (rows / max |entry|),
+        # and unscaled
+        bn = float(torch.linalg.vector_norm(asm_.b))
+        full_check = {"what": f"|| J dx - F ||_2 / || F ||_2 at the full size ({nx}x{ny}), J dx by cm_spmv on the CSR values",
+                      "rel_residual_unscaled": float(torch.linalg.vector_norm(r_)) / bn if bn > 0 else None,
+                      "gmres_its": int(solver.linear_iterations[-1])}
+        del r_
+
     parity = None
     if args.variant == "supg" and args.linear_solver == "gmres" and not args.no_parity:
         if strong:
@@ -437,10 +457,14 @@ def gpu_arm(args):
             del uk, ud
 
     zk0 = prof.get(ROOF_KERNEL)
+    # the long-line smoother reads its seven operator streams from an fp32 pack unless CM_F32_OP=0:
+    # 52 / 28 algorithmic bytes per vertex of the colour (with couplings / from a zero guess) instead of 80 / 40
+    f32_op = os.environ.get("CM_F32_OP", "1") != "0" and nx + 1 >= 1024
+    b_cpl, b_zero = (52.0, 28.0) if f32_op else (80.0, 40.0)
     prof_mix = 0.2
     if zk0:
         unit = 0.5 * (nx + 1) * (ny + 1)
-        prof_mix = float(min(1.0, max(0.0, (80.0 - zk0["algorithmic_bytes_per_launch"] / unit) / 40.0)))
+        prof_mix = float(min(1.0, max(0.0, (b_cpl - zk0["algorithmic_bytes_per_launch"] / unit) / (b_cpl - b_zero))))
 
     tt = torch.tensor([ms_step, e2e_ms, asm_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -458,7 +482,7 @@ def gpu_arm(args):
         bytes_asm = 12 * cells + 16 * Vn + 8 * (2 * Vn) + 8 * (4 * nnz) + 8 * (2 * Vn)
         bytes_asm_rank = bytes_asm / (world if strong else 1)      # every rank assembles its own rows
         zk = prof.get(ROOF_KERNEL)
-        traffic = ncu_traffic(prof_mix) if (zk and world == 1) else None
+        traffic = ncu_traffic(prof_mix, f32_op) if (zk and world == 1) else None
         solver_info = lin_info()
         out = {
             "metric": METRIC, "value": (1 if strong else world) * cells / (ms_step * 1e-3), "unit": UNIT,
@@ -485,8 +509,14 @@ def gpu_arm(args):
                          "achieved": zk["gbs"] if zk else None, "peak": peak, "unit": "GB/s",
                          "frac": (zk["gbs"] / peak) if zk else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": zk["algorithmic_bytes_per_launch"] if zk else None,
-                         "algorithmic_bytes_per_vertex": "80 with couplings (b, 4 off-line diagonals, 3 factors, the "
-                                                         "neighbour lines of x once, x out), 40 from a zero guess",
+                         "algorithmic_bytes_per_vertex": (
+                             "52 with couplings (b 8, 4 off-line diagonals + 3 line factors from the fp32 pack 28, the "
+                             "neighbour lines of x once 8, x out 8), 28 from a zero guess; x, b and all arithmetic fp64; "
+                             "with CM_F32_OP=0 the same kernel streams the fp64 operator: 80 / 40 B, 0.67 of the peak "
+                             "but 17 us slower per launch (profiles/README.md)" if f32_op else
+                             "80 with couplings (b, 4 off-line diagonals, 3 factors, the neighbour lines of x once, "
+                             "x out), 40 from a zero guess"),
+                         "operator_storage": "fp32 pack" if f32_op else "fp64",
                          "avg_launch_us": zk["avg_us"] if zk else None,
                          "share_of_step": (zk["ms_per_step"] / ms_step) if zk else None,
                          "traffic": traffic["bytes_per_launch"] if traffic else None,
@@ -498,6 +528,7 @@ def gpu_arm(args):
                               "gmres_iterations": lin_its, "note": "per rank" if world > 1 else "whole job"},
             "kernels": {**prof, "pq_sweep_kernel roofline frac (per rank)": (bytes_asm_rank / (asm_ms * 1e-3) / 1e9) / peak},
             "parity": parity,
+            "full_size_check": full_check,
         }
         if world == 1 and not args.no_cpu:
             nxs, nys = REF_NX, REF_NY
@@ -518,7 +549,7 @@ ROOF_KERNEL = "zebra_ring_kernel (fine grid)"
 NCU_CSV = os.path.join(ROOT, "profiles", "ncu_metrics_r2.csv")
 
 
-def ncu_traffic(mix):
+def ncu_traffic(mix, f32_op=True):
     """dram read + write bytes per launch of the roofline kernel from the committed `ncu --set full` export
     (profiles/ncu_metrics_r2.csv, written by tools/ncu_export.py from the .ncu-rep of the same kernels), weighted
     by the launch mix of this run (mix = fraction of zero-guess launches).  None when no capture is committed."""
@@ -526,12 +557,13 @@ def ncu_traffic(mix):
     if not os.path.exists(NCU_CSV):
         return None
     rows = {}
+    sfx = "_f32op" if f32_op else ""
     for r in csv.DictReader(open(NCU_CSV)):
-        if r.get("class") in ("zebra_fine_coupled", "zebra_fine_zero"):
+        if r.get("class") in ("zebra_fine_coupled" + sfx, "zebra_fine_zero" + sfx):
             rows[r["class"]] = float(r["dram_read_bytes"]) + float(r["dram_write_bytes"])
     if len(rows) != 2:
         return None
-    return {"bytes_per_launch": mix * rows["zebra_fine_zero"] + (1.0 - mix) * rows["zebra_fine_coupled"],
+    return {"bytes_per_launch": mix * rows["zebra_fine_zero" + sfx] + (1.0 - mix) * rows["zebra_fine_coupled" + sfx],
             "source": f"profiles/ncu_metrics_r2.csv (ncu --set full), {mix:.2f} zero-guess / {1 - mix:.2f} coupled launches"}
 
 

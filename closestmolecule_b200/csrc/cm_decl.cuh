@@ -83,6 +83,7 @@ struct GmresDev {
 };
 size_t gmres_dev_doubles(long long n, int m);
 void gmres_dev_layout(GmresDev& G, long long n, int m, double* work);
+void gmres_dev_init();   // occupancy-derived launch geometry, once per process (not inside a stream capture)
 int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st, int maxit = 1 << 30);
 int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st);
 // ru != nullptr: also writes ru = diag(sp | sq)^-1 V_{j+1} (unnormalised), the next preconditioner input

@@ -4,8 +4,15 @@
 // hand-written peer-to-peer kernels over NVLink: the producer writes its boundary rows straight
 // into the neighbour's copy of the same array (same offset), fences, then bumps a sequence flag in
 // the neighbour's memory; the consumer stream runs a one-warp wait kernel on its own flags.
-// Sequence numbers only grow, and the same ghost row is never re-written without a completed
-// two-way exchange in between, so no extra acknowledgement is needed.
+// Sequence numbers only grow.  There is no consumer acknowledgement; write-after-read safety rests on two
+// invariants that the host side ENFORCES (cm_pqs_create rejects / clamps anything else):
+//   * halo rows: strips start on even rows of every distributed level and keep >= 4 rows down to the first
+//     replicated level, so (zebra colouring, cm_halo.cuh) every re-push of a ghost row is preceded in the
+//     pusher's program order by a wait on a push the reader issued after its last read of the old value;
+//   * all-gather targets / all-reduce slots: between two all-gathers of the same array every rank passes at
+//     least one all-reduce (each GMRES iteration has two; the setup all-gather is followed by the solve), and an
+//     all-reduce completes on a rank only after EVERY rank has contributed, i.e. has finished reading what the
+//     previous all-gather delivered; the all-reduce slots themselves alternate by sequence parity.
 #include "cm_common.cuh"
 #include "cm_decl.cuh"
 #include "cm_halo.cuh"
@@ -48,29 +55,41 @@ exchange_kernel(const Halo h, const PushSegs segs_dn, const PushSegs segs_up) {
   }
 }
 
-// all-gather of same-offset segments: CTA k pushes to the k-th other rank; CTA 0 then waits for all.
-// Every CTA takes the launch's sequence number from a snapshot of the counter; the counter itself is
-// advanced by the last CTA to finish (after every CTA has taken its snapshot).
+// all-gather of same-offset segments: kAgSplit CTAs share the push to each other rank (a single CTA moves
+// ~20 GB/s over NVLink: the 2 MB level-2 right-hand side of a 2-GPU run took 116 us that way, in-situ timeline
+// profiles/r2_trace_n2.csv); the last of them to finish publishes the flag in the destination's control block.
+// CTA 0 then waits for the flags of all ranks.  Every CTA takes the launch's sequence number from a snapshot
+// of the counter; the counter itself is advanced by the last CTA of the launch to finish.
 constexpr size_t kAgDone = 19;
+constexpr size_t kAgPart = 40;    // [40, 48): CTAs finished per destination (cumulative)
+constexpr int kAgSplit = 16;
 __global__ void __launch_bounds__(1024)
 allgather_kernel(double* __restrict__ my_base, const Peers peers, const int my_rank, const int world,
                  const PushSegs segs) {
   __shared__ unsigned long long s_seq;
   unsigned long long* ctl = reinterpret_cast<unsigned long long*>(my_base);
-  const int dst = blockIdx.x + (blockIdx.x >= my_rank ? 1 : 0);
+  const int di = blockIdx.x / kAgSplit, part = blockIdx.x - di * kAgSplit;
+  const int dst = di + (di >= my_rank ? 1 : 0);
   if (threadIdx.x == 0) s_seq = ld_volatile_u64(ctl + kCntAg) + 1ull;
   __syncthreads();
   const unsigned long long seq = s_seq;
   double* __restrict__ pb = peers.base[dst];
   for (int s = 0; s < segs.nseg; ++s) {
+    const int chunk = (segs.n[s] + kAgSplit - 1) / kAgSplit;
+    const int i0 = part * chunk, i1 = min(i0 + chunk, segs.n[s]);
     const double* src = my_base + segs.off[s];
     double* d = pb + segs.off[s];
-    for (int i = threadIdx.x; i < segs.n[s]; i += blockDim.x) d[i] = src[i];
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) d[i] = src[i];
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0)
-    st_release_sys(reinterpret_cast<unsigned long long*>(pb) + kCtlAgFlags + my_rank, seq);
+  if (threadIdx.x == 0) {
+    const unsigned long long fin = atomicAdd(ctl + kAgPart + di, 1ull) + 1ull;
+    if (fin == seq * (unsigned long long)kAgSplit) {   // every part of this destination is stored and fenced
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<unsigned long long*>(pb) + kCtlAgFlags + my_rank, seq);
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x < world && threadIdx.x != my_rank) {
     const unsigned long long* f = ctl + kCtlAgFlags + threadIdx.x;
     spin_until(f, seq);
@@ -173,7 +192,7 @@ int dist_allgather(cm_dist* D, const unsigned long long* offs, const int* ns, in
   s.nseg = nseg;
   for (int i = 0; i < nseg; ++i) { s.off[i] = offs[i]; s.n[i] = ns[i]; }
   double* mb = (double*)D->peer_base[D->rank];
-  allgather_kernel<<<D->world - 1, 1024, 0, st>>>(mb, make_peers(D), D->rank, D->world, s);
+  allgather_kernel<<<(D->world - 1) * kAgSplit, 1024, 0, st>>>(mb, make_peers(D), D->rank, D->world, s);
   CM_LAUNCH_CHECK();
   return CM_OK;
 }

@@ -90,12 +90,32 @@ __device__ __forceinline__ void gd_dot_group(const GmresDev& G, const VecSlice& 
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.0;
   if (SLICE) {
-    const long long n = 2 * sl.len;
-    for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
-      const long long q = gd_index(i, sl);
-      const double ww = w[q];
+    // the two index ranges of a strip, each as an optional leading element, 16-byte aligned pairs, optional tail
+    // (the q-part starts at an odd offset when the vertex count is odd)
+    for (int part = 0; part < 2; ++part) {
+      const long long s0 = part ? sl.off1 : sl.off0;
+      const long long lead = s0 & 1;
+      const long long npair = (sl.len - lead) >> 1;
+      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < npair; i += (long long)gridDim.x * kGB) {
+        const long long q = s0 + lead + 2 * i;
+        const double2 ww = *reinterpret_cast<const double2*>(w + q);
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += Vb[(size_t)k * G.ne + q] * ww;
+        for (int k = 0; k < K; ++k) {
+          const double2 vv = *reinterpret_cast<const double2*>(Vb + (size_t)k * G.ne + q);
+          acc[k] += vv.x * ww.x + vv.y * ww.y;
+        }
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (lead) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] += Vb[(size_t)k * G.ne + s0] * w[s0];
+        }
+        if ((sl.len - lead) & 1) {
+          const long long q = s0 + sl.len - 1;
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[k] += Vb[(size_t)k * G.ne + q] * w[q];
+        }
+      }
     }
   } else {
     const long long n2 = G.n >> 1;
@@ -185,21 +205,49 @@ gd_update_kernel(const GmresDev G, const VecSlice sl, const double* __restrict__
     double* __restrict__ vout = G.V + (size_t)(j + 1) * G.ne;
     const double* w = G.w;
     if (SLICE) {
-      const long long n = 2 * sl.len;
-      for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < n; i += (long long)gridDim.x * kGB) {
-        const long long q = gd_index(i, sl);
+      auto one = [&](const long long q) {   // a single element (unaligned ends of a range)
         double a = w[q];
-        const double* vq = G.V + q;
-        int k = 0;
-        for (; k + 4 <= j + 1; k += 4) {   // four independent loads in flight
-          const double v0 = vq[(size_t)k * G.ne], v1 = vq[(size_t)(k + 1) * G.ne];
-          const double v2 = vq[(size_t)(k + 2) * G.ne], v3 = vq[(size_t)(k + 3) * G.ne];
-          a -= s_h[k] * v0 + s_h[k + 1] * v1 + s_h[k + 2] * v2 + s_h[k + 3] * v3;
-        }
-        for (; k <= j; ++k) a -= s_h[k] * vq[(size_t)k * G.ne];
+        for (int k = 0; k <= j; ++k) a -= s_h[k] * G.V[(size_t)k * G.ne + q];
         vout[q] = a;
         if (ru != nullptr) ru[q] = a / (q < nhalf ? sp[q] : sq[q - nhalf]);
         nrm += a * a;
+      };
+      for (int part = 0; part < 2; ++part) {
+        const long long s0 = part ? sl.off1 : sl.off0;
+        const long long lead = s0 & 1;
+        const long long npair = (sl.len - lead) >> 1;
+        const double* sc = part ? sq - nhalf : sp;   // scaling of this range, indexed like the vector
+        for (long long i = blockIdx.x * (long long)kGB + threadIdx.x; i < npair; i += (long long)gridDim.x * kGB) {
+          const long long q = s0 + lead + 2 * i;
+          double2 a = *reinterpret_cast<const double2*>(w + q);
+          const double* vq = G.V + q;
+          int k = 0;
+          for (; k + 4 <= j + 1; k += 4) {   // four independent 16-byte loads in flight
+            const double2 v0 = *reinterpret_cast<const double2*>(vq + (size_t)k * G.ne);
+            const double2 v1 = *reinterpret_cast<const double2*>(vq + (size_t)(k + 1) * G.ne);
+            const double2 v2 = *reinterpret_cast<const double2*>(vq + (size_t)(k + 2) * G.ne);
+            const double2 v3 = *reinterpret_cast<const double2*>(vq + (size_t)(k + 3) * G.ne);
+            a.x -= s_h[k] * v0.x + s_h[k + 1] * v1.x + s_h[k + 2] * v2.x + s_h[k + 3] * v3.x;
+            a.y -= s_h[k] * v0.y + s_h[k + 1] * v1.y + s_h[k + 2] * v2.y + s_h[k + 3] * v3.y;
+          }
+          for (; k <= j; ++k) {
+            const double2 vv = *reinterpret_cast<const double2*>(vq + (size_t)k * G.ne);
+            a.x -= s_h[k] * vv.x;
+            a.y -= s_h[k] * vv.y;
+          }
+          *reinterpret_cast<double2*>(vout + q) = a;
+          if (ru != nullptr) {
+            double2 o;
+            o.x = a.x / sc[q];
+            o.y = a.y / sc[q + 1];
+            *reinterpret_cast<double2*>(ru + q) = o;
+          }
+          nrm += a.x * a.x + a.y * a.y;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+          if (lead) one(s0);
+          if ((sl.len - lead) & 1) one(s0 + sl.len - 1);
+        }
       }
     } else {
       const long long n2 = G.n >> 1;
@@ -402,10 +450,38 @@ int gmres_dev_begin(const GmresDev& G, int first, cudaStream_t st, int maxit) {
 
 // bytes: every basis vector in use + w once; the iteration index is on the device, the caller passes the
 // value it knows (jhost) for the byte accounting only.  jhost < 0 (start of a cycle): nothing to do.
+// CTAs of the dot kernel that are resident at once (78 registers: 3 per SM, not the 4 of kGGrid): a grid-stride
+// loop over more CTAs than fit runs a second, mostly empty wave (ncu: 31 % warps active, 60 % DRAM throughput)
+template <bool SLICE>
+static int gd_dot_resident_grid() {
+  static std::atomic<int> cached{0};
+  int g = cached.load();
+  if (g > 0) return g;
+  int per_sm = 0, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gd_dot_kernel<SLICE>, kGB, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 2;
+  }
+  g = per_sm * sms;
+  if (g > kGGrid) g = kGGrid;
+  cached.store(g);
+  return g;
+}
+
+// once per process, outside any stream capture (cm_pqs_create)
+void gmres_dev_init() {
+  gd_dot_resident_grid<true>();
+  gd_dot_resident_grid<false>();
+}
+
 int gmres_dev_dot(const GmresDev& G, const VecSlice* sl, int jhost, cudaStream_t st) {
   if (jhost < 0) return CM_OK;
   const long long len = gd_len(G, sl);
-  const int grid = gd_grid(sl ? len : len / 2);
+  int grid = gd_grid(sl ? len : len / 2);
+  const int resident = sl ? gd_dot_resident_grid<true>() : gd_dot_resident_grid<false>();
+  if (grid > resident) grid = resident;
   if (sl) gd_dot_kernel<true><<<grid, kGB, 0, st>>>(G, *sl);
   else gd_dot_kernel<false><<<grid, kGB, 0, st>>>(G, VecSlice{0, 0, 0});
   CM_BYTES((double)len * 8.0 * (jhost + 2));

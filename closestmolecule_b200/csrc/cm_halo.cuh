@@ -31,6 +31,7 @@ constexpr int kHaloChannels = 2;
 //   channel c at [8c, 8c+8): [0] flag from below  [1] flag from above  [2] cnt_dn  [3] cnt_up
 //   [16] all-gather counter  [17] all-reduce counter  [18] all-reduce local reader count
 //   [24,32) all-gather flags per source rank   [32,40) all-reduce flags per source rank
+//   [40,48) all-gather: CTAs finished per destination (cumulative, cm_dist.cu)
 //   [48, 48 + 2*8*64) all-reduce slots [parity][src][kCollMax]
 constexpr size_t kChFlagBelow = 0, kChFlagAbove = 1, kChCntDn = 2, kChCntUp = 3, kChStride = 8;
 constexpr size_t kCntAg = 16, kCntAr = 17, kArReaders = 18;

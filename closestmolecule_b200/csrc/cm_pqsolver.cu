@@ -800,6 +800,7 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
     delete C;
     return nullptr;
   }
+  gmres_dev_init();
   gmres_dev_layout(C->G, 2LL * S.nv, restart, S.gm);
   C->use_v1 = C->K.v1 != 0 || !S.diag_split || S.upper_split || S.pre_smooth < 1 || S.post_smooth < 1;
   if (cudaMallocHost((void**)&C->status_host, sizeof(double) * kGmresStatus) != cudaSuccess) {

@@ -27,6 +27,19 @@ class _RawCuda:
         self._owner = owner
 
 
+def strip_partition(ny, world):
+    """Strip partition of the ny+1 vertex rows of a structured mesh over `world` ranks (RCB along r1 keeps the
+    r2-lines of the line solver intact): row_begin[r] .. row_begin[r+1] are the rows rank r owns.  Strip
+    boundaries are multiples of 8 rows, so that they stay EVEN rows on the three finest multigrid levels (the
+    zebra colouring of the inline halo protocol, csrc/cm_halo.cuh, needs even strip starts on every distributed
+    level) and every strip keeps >= 4 rows down to the first replicated level; the last rank takes the rest."""
+    nrows = ny + 1
+    per = (nrows // world) // 8 * 8
+    if per < 8:
+        raise ValueError("too few vertex rows per rank (need >= 8)")
+    return [r * per for r in range(world)] + [nrows]
+
+
 class DistContext:
     def __init__(self, mesh, restart=40):
         if not dist.is_initialized():
@@ -37,11 +50,7 @@ class DistContext:
         self.mesh, self.restart = mesh, int(restart)
         self.nx, self.ny = mesh.nx, mesh.ny
         self.lib = _capi.lib()
-        nrows = self.ny + 1
-        per = (nrows // self.world) // 8 * 8
-        if per < 8:
-            raise ValueError("too few vertex rows per rank (need >= 8)")
-        self.row_begin = [r * per for r in range(self.world)] + [nrows]
+        self.row_begin = strip_partition(self.ny, self.world)
         self.rb, self.re = self.row_begin[self.rank], self.row_begin[self.rank + 1]
         self.nbytes = int(self.lib.cm_pqs_workspace_bytes(self.nx, self.ny, self.restart))
         self.base = self.lib.cm_ipc_alloc(self.nbytes)

@@ -12,11 +12,21 @@ def classify(name, grid, block):
     g = int(re.sub(r"[^0-9,]", "", grid).split(",")[0] or 0)
     b = int(re.sub(r"[^0-9,]", "", block).split(",")[0] or 0)
     if "zebra_ring_kernel" in name:
-        coupled = "<1>" in name or "<true>" in name or "(bool)1" in name
+        m = re.search(r"zebra_ring_kernel<\s*(?:\(bool\))?\s*(\w+)", name)   # first template argument: COUPLED
+        coupled = bool(m) and m.group(1) in ("1", "true")
+        m2 = re.search(r"zebra_ring_kernel<[^,>]*,\s*(?:\(bool\))?\s*(\w+)", name)   # second: F32 operator pack
+        sfx = "_f32op" if (m2 and m2.group(1) in ("1", "true")) else ""
         if b >= 800:
-            return "zebra_fine_coupled" if coupled else "zebra_fine_zero"
-        return ("zebra_level1_coupled" if coupled else "zebra_level1_zero") if b >= 400 else (
-            "zebra_level2_coupled" if coupled else "zebra_level2_zero")
+            return ("zebra_fine_coupled" if coupled else "zebra_fine_zero") + sfx
+        return (("zebra_level1_coupled" if coupled else "zebra_level1_zero") if b >= 400 else (
+            "zebra_level2_coupled" if coupled else "zebra_level2_zero")) + sfx
+    if "zebra_mid_kernel" in name:
+        m = re.search(r"zebra_mid_kernel<\s*(?:\(int\))?\s*(\d)", name)
+        return "zebra_mid_mode" + (m.group(1) if m else "?")
+    if "coarse_smem_kernel" in name:
+        return "coarse_smem_cycle"
+    if "pack_f32" in name:
+        return "pack_f32"
     if "pq_stencil_spmv" in name:
         return "pq_stencil_spmv"
     if "gd_dot_kernel" in name:

@@ -20,6 +20,7 @@ def main(path, title):
     s, e = starts[0], starts[1]
 
     def short(n):
+        n = n.replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
         n = re.sub(r"\(.*", "", n)
         m = re.match(r"(void )?(cm::)?([A-Za-z_0-9:]+)(<[^>]*>)?", n)
         return (m.group(3) + (m.group(4) or "")) if m else n

@@ -103,17 +103,29 @@ def main():
     lines.append("kernel,launches,total_us,avg_us")
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f'"{n}",{c},{t:.1f},{t / c:.2f}')
-    # one GMRES iteration = from one unscale_dev launch to the next
-    starts = [i for i, k in enumerate(ks) if k[2].startswith("unscale_dev")]
-    if len(starts) > args.iteration + 1:
-        a, b = starts[args.iteration], starts[args.iteration + 1]
+    # one GMRES iteration = the kernels after one Givens kernel up to and including the next
+    ends = [i for i, k in enumerate(ks) if k[2].startswith("gd_givens")]
+    if len(ends) > args.iteration + 1:
+        a, b = ends[args.iteration] + 1, ends[args.iteration + 1] + 1
         lines.append(f"# GMRES iteration {args.iteration}: {b - a} kernels, "
-                     f"{(ks[b][0] - ks[a][0]):.1f} us from unscale to unscale")
+                     f"{(ks[b - 1][0] + ks[b - 1][1] - ks[a][0]):.1f} us from the first kernel to the end of the Givens kernel, "
+                     f"{(ks[min(b, len(ks) - 1)][0] - ks[a][0]):.1f} us to the start of the next iteration")
         lines.append("offset_us,dur_us,gap_us,kernel")
         prev_end = ks[a][0]
         for s, d, n in ks[a:b]:
             lines.append(f"{s - ks[a][0]:.1f},{d:.1f},{s - prev_end:.1f},{n}")
             prev_end = max(prev_end, s + d)
+    if ends:
+        # everything outside the GMRES cycle: assembly, Dirichlet rows, solver setup, start of the solve / end of the step
+        def dump(title, seq):
+            lines.append(f"# {title}: {len(seq)} kernels")
+            lines.append("offset_us,dur_us,gap_us,kernel")
+            prev_end = seq[0][0] if seq else 0.0
+            for s_, d_, n_ in seq:
+                lines.append(f"{s_ - t_first:.1f},{d_:.1f},{s_ - prev_end:.1f},{n_}")
+                prev_end = max(prev_end, s_ + d_)
+        dump("step start up to the first Givens kernel", ks[:ends[0] + 1])
+        dump("after the last Givens kernel", ks[ends[-1] + 1:])
     txt = "\n".join(lines)
     out = args.out or os.path.join(ROOT, "gpurun_out", f"trace_n{world}_r{rank}.csv")
     if rank in (0, world // 2):
