@@ -368,15 +368,26 @@ def gpu_arm(args):
     barrier()
     marks = []
     e0, e1 = ev(), ev()
+    side = torch.cuda.Stream()
+    upd = torch.cuda.Event()
+
+    def push_result():
+        # the new iterate is final once the update is enqueued: its device-to-host copy runs on a side stream
+        # while the step evaluates the residual norm of the new iterate (the step's scalar result)
+        upd.record()
+        side.wait_event(upd)
+        with torch.cuda.stream(side):
+            h_out.copy_(dst, non_blocking=True)
+
     e0.record()
     for _ in range(e2e_steps):
         a, b_, c_, d_ = ev(), ev(), ev(), ev()
         a.record()
         dst.copy_(h_in, non_blocking=True)
         b_.record()
-        r = solver.newton_step(compute_residual=True)
+        r = solver.newton_step(compute_residual=True, on_updated=push_result)
         c_.record()
-        h_out.copy_(dst, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)     # the result is on the host
         d_.record()
         torch.cuda.current_stream().synchronize()
         marks.append((a, b_, c_, d_))
@@ -498,7 +509,9 @@ def gpu_arm(args):
             "e2e": {"value": (1 if strong else world) * cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8 + 8),
                     "h2d_ms": e2e_parts[0], "step_ms": e2e_parts[1], "d2h_ms": e2e_parts[2],
-                    "note": "bytes per rank" if world > 1 else "whole state vector"},
+                    "note": ("bytes per rank" if world > 1 else "whole state vector") +
+                            "; d2h_ms is the part of the result copy that is still exposed after the step: it starts on a "
+                            "side stream as soon as the update is enqueued and overlaps the residual evaluation"},
             "gpu_launches": launches,
             "clocks": clocks,
             "solver": solver_info,

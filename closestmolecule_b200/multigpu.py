@@ -151,7 +151,8 @@ class DistributedPQNewton:
         self.ctx.allreduce(self.scal)
         return float(self.scal.sqrt())
 
-    def newton_step(self, compute_residual=True):
+    def newton_step(self, compute_residual=True, on_updated=None):
+        """on_updated: called right after the update of the owned rows has been enqueued (see solver.py)."""
         ctx, asm = self.ctx, self.asm
         marks = [] if self.phase_events is not None else None
 
@@ -177,6 +178,8 @@ class DistributedPQNewton:
             raise LinearSolveError(f"GMRES did not converge in {it.value} iterations (rel. residual {rr.value:.3e})")
         mark()
         self.u[self.own] -= self.dx[self.own]
+        if on_updated is not None:
+            on_updated()
         r = self.residual_norm() if compute_residual else None
         mark()
         if marks is not None:

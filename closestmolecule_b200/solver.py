@@ -326,9 +326,11 @@ class NonlinearVariationalSolver:
         _capi.check(_capi.lib().cm_axpy_batch(u.numel(), _capi.ptr(dx), dx.numel(), 1, _capi.ptr(sc[1:2]), -1.0,
                                               _capi.ptr(u), None, _capi.ptr(scr), _capi.stream_ptr()))
 
-    def newton_step(self, compute_residual=True):
+    def newton_step(self, compute_residual=True, on_updated=None):
         """One Newton iteration at the current u: fused J+F assembly, Dirichlet rows, linear-solver
-        setup, Krylov solve, u <- u - relaxation*dx, then (optionally) the new residual norm."""
+        setup, Krylov solve, u <- u - relaxation*dx, then (optionally) the new residual norm.
+        on_updated: called right after the update has been enqueued (the new iterate is final from there on in
+        stream order) -- e.g. to start its device-to-host copy on a side stream while the residual is evaluated."""
         prm, lin = self._prepare()
         kp = prm["krylov_solver"]
         asm, u = self.asm, self.problem.u.vector()
@@ -354,6 +356,8 @@ class NonlinearVariationalSolver:
                 f"Krylov solver did not converge in {lin.last_iterations} iterations "
                 f"(relative residual {lin.last_residual:.3e})")
         self._update(u, self._dx, prm["relaxation_parameter"])
+        if on_updated is not None:
+            on_updated()
         r = self.residual_norm() if compute_residual else None
         mark()
         if marks is not None:   # (assemble J+F, BC + solver setup, Krylov solve, update + residual)
