@@ -94,6 +94,10 @@ _PROTOS = {
     "cm_ipc_close": ([_P], C.c_int),
     "cm_pqs_state_offset": ([_I, _I, _I], C.c_int64),
     "cm_assemble_pq_cells_structured_rows": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_I, _I, _P], C.c_int),
+    "cm_assemble_pq_cells_structured_blocks": ([C.POINTER(PQParamsC), _I, _I] + [_P] * 7 + [_P, _I, _I, _P], C.c_int),
+    "cm_apply_dirichlet_blocks": ([_I, _P, _I, _P, _P], C.c_int),
+    "cm_pqs_ctx_blocks": ([_P, _P], C.c_int),
+    "cm_pqs_ctx_setup_from_blocks": ([_P, _P], C.c_int),
     "cm_dist_exchange_rows": ([C.POINTER(DistC), C.c_int64, _I, _I, _I, _P], C.c_int),
     "cm_dist_allgather_rows": ([C.POINTER(DistC), C.c_int64, _I, _I, _I, _P], C.c_int),
     "cm_dist_allreduce_sum": ([C.POINTER(DistC), _P, _I, _P], C.c_int),
@@ -173,6 +177,11 @@ def register(name, args, res=C.c_int):
 def check(rc):
     if rc != 0:
         raise CMError(f"closestmol_b200 error {rc}: {lib().cm_last_error().decode()}")
+
+
+class PQBlocksC(C.Structure):
+    """struct cm_pq_blocks (include/closestmol_b200.h): stencil form of the P-Q Jacobian inside a solver workspace"""
+    _fields_ = [(n, C.c_void_p) for n in ("PP", "PQ", "QP", "QQ", "sp", "sq")]
 
 
 def ptr(t):

@@ -40,12 +40,17 @@ class _Base:
         diag = self.topo.diag_slot[node].contiguous()
         return dofs, vals, diag
 
-    def apply_bcs(self, bc_tables, x, with_matrix=True):
+    def apply_bcs(self, bc_tables, x, with_matrix=True, blocks=None):
+        """blocks: the stencil form of the Jacobian the assembly wrote next to the CSR values (PQAssembler.assemble
+        with blocks=...): its Dirichlet rows get the same treatment."""
         dofs, g, diag = bc_tables
         _capi.check(self.lib.cm_apply_dirichlet(
             self.bs, dofs.numel(), _capi.ptr(dofs), _capi.ptr(diag), _capi.ptr(g), _capi.ptr(x),
             _capi.ptr(self.topo.nrowptr), _capi.ptr(self.vals) if with_matrix else None,
             _capi.ptr(self.b), _capi.stream_ptr()))
+        if blocks is not None and with_matrix:
+            _capi.check(self.lib.cm_apply_dirichlet_blocks(dofs.numel(), _capi.ptr(dofs), self.topo.nv,
+                                                           C.byref(blocks), _capi.stream_ptr()))
 
     def _load_vector(self, ncomp, weighted, supg_stab, degree):
         mesh, t = self.mesh, self.topo
@@ -142,10 +147,23 @@ class PQAssembler(_Base):
                 _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(self.Kq), _capi.ptr(self.cq), st))
         torch.cuda.current_stream().synchronize()
 
-    def assemble(self, u, want_jac=True):
-        """Fused J (self.vals, DOLFIN CSR order) + F (self.b) at state u [2V]."""
+    def writes_blocks(self):
+        """True when assemble(..., blocks=...) can hand the linear solver its stencil blocks directly: structured
+        sweep, Jacobian = cell integrals only (7-point pattern)."""
+        mesh, t = self.mesh, self.topo
+        return bool(self.use_sweep and mesh.structured and self.Kq is None and not t.with_interior_facets)
+
+    def assemble(self, u, want_jac=True, blocks=None):
+        """Fused J (self.vals, DOLFIN CSR order) + F (self.b) at state u [2V].  blocks (a _capi.PQBlocksC of a
+        structured solver context): also write the stencil form of J and the row scalings there."""
         mesh, t, form = self.mesh, self.topo, self.form
         p_old = form.p_old.vector() if form.p_old is not None else None
+        if self.writes_blocks() and blocks is not None and want_jac:
+            _capi.check(self.lib.cm_assemble_pq_cells_structured_blocks(
+                C.byref(form.params), mesh.nx, mesh.ny, _capi.ptr(mesh.coords), _capi.ptr(t.nrowptr),
+                _capi.ptr(u), _capi.ptr(p_old), _capi.ptr(self.load), _capi.ptr(self.vals), _capi.ptr(self.b),
+                C.byref(blocks), 0, -1, _capi.stream_ptr()))
+            return self.vals, self.b
         if self.use_sweep and mesh.structured and self.Kq is None and not t.with_interior_facets:
             # structured fast path: no connectivity / gather tables are read
             _capi.check(self.lib.cm_assemble_pq_cells_structured(

@@ -572,6 +572,30 @@ __global__ void dirichlet_kernel(const int bs, const int nrows, const int* __res
   if (lane == 0) b[dof] = x[dof] - g[r];
 }
 
+// the same on the stencil form of the P-Q Jacobian (cm_pq_blocks): identity row, unit row scaling
+__global__ void dirichlet_blocks_kernel(const int nrows, const int* __restrict__ rows, const size_t nv,
+                                        const cm_pq_blocks blk) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int dof = rows[r];
+  const size_t v = (size_t)(dof >> 1);
+  double* __restrict__ B0 = (dof & 1) ? blk.QP : blk.PP;   // coupling to p
+  double* __restrict__ B1 = (dof & 1) ? blk.QQ : blk.PQ;   // coupling to q
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+    B0[(size_t)s * nv + v] = (!(dof & 1) && s == 3) ? 1.0 : 0.0;
+    B1[(size_t)s * nv + v] = ((dof & 1) && s == 3) ? 1.0 : 0.0;
+  }
+  ((dof & 1) ? blk.sq : blk.sp)[v] = 1.0;
+}
+
+int apply_dirichlet_blocks(int nrows, const int* rows, int nv, const cm_pq_blocks& blk, cudaStream_t st) {
+  if (nrows == 0) return CM_OK;
+  dirichlet_blocks_kernel<<<(nrows + 127) / 128, 128, 0, st>>>(nrows, rows, (size_t)nv, blk);
+  CM_LAUNCH_CHECK();
+  return CM_OK;
+}
+
 int apply_dirichlet(int bs, int nrows, const int* rows, const int* diag_slot, const double* g,
                     const double* x, const int* nrowptr, double* vals, double* b, cudaStream_t st) {
   if (nrows == 0) return CM_OK;

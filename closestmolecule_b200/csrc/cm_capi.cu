@@ -414,6 +414,34 @@ int cm_assemble_pq_cells_structured_rows(const cm_pq_params* prm, int32_t nx, in
                            (cudaStream_t)stream, row_begin, row_end);
 }
 
+int cm_assemble_pq_cells_structured_blocks(const cm_pq_params* prm, int32_t nx, int32_t ny, const double* coords,
+                                           const int32_t* nrowptr, const double* u, const double* p_old,
+                                           const double* load, double* vals, double* b, const cm_pq_blocks* blocks,
+                                           int32_t row_begin, int32_t row_end, void* stream) {
+  CM_CHECK_ARG(prm && coords && nrowptr && u && b && vals && blocks, "null pointer");
+  CM_CHECK_ARG(blocks->PP && blocks->PQ && blocks->QP && blocks->QQ && blocks->sp && blocks->sq, "null block pointer");
+  if (row_end < 0) { row_begin = 0; row_end = ny + 1; }
+  CM_CHECK_ARG(nx >= 1 && ny >= 1 && row_begin >= 0 && row_end <= ny + 1, "bad row range");
+  return assemble_pq_sweep(*prm, nx, ny, coords, nrowptr, u, p_old, load, vals, b, (cudaStream_t)stream, row_begin,
+                           row_end, blocks);
+}
+
+int cm_apply_dirichlet_blocks(int32_t nrows, const int32_t* rows, int32_t nv, const cm_pq_blocks* blocks, void* stream) {
+  CM_CHECK_ARG(nrows >= 0 && nv > 0 && blocks && (nrows == 0 || rows), "bad argument");
+  CM_CHECK_ARG(blocks->PP && blocks->PQ && blocks->QP && blocks->QQ && blocks->sp && blocks->sq, "null block pointer");
+  return apply_dirichlet_blocks(nrows, rows, nv, *blocks, (cudaStream_t)stream);
+}
+
+int cm_pqs_ctx_blocks(void* ctx, cm_pq_blocks* out) {
+  CM_CHECK_ARG(ctx && out, "null pointer");
+  return pqs_ctx_blocks(ctx, out);
+}
+
+int cm_pqs_ctx_setup_from_blocks(void* ctx, void* stream) {
+  CM_CHECK_ARG(ctx, "null pointer");
+  return pqs_ctx_setup(ctx, nullptr, nullptr, nullptr, (cudaStream_t)stream, true);
+}
+
 int cm_dist_exchange_rows(cm_dist* D, int64_t array_offset_bytes, int32_t row_doubles,
                           int32_t row_begin, int32_t row_end, void* stream) {
   CM_CHECK_ARG(D && (array_offset_bytes % 8) == 0 && row_doubles > 0 && row_end > row_begin, "bad argument");

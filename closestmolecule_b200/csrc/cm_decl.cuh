@@ -148,20 +148,24 @@ int st_coarse_apply(int n, const double* Ainv, const double* b, double* x, cudaS
 // cm_sweep.cu
 int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                       const int* nrowptr, const double* u, const double* p_old, const double* load,
-                      double* vals, double* b, cudaStream_t st, int row_begin = 0, int row_end = -1);
+                      double* vals, double* b, cudaStream_t st, int row_begin = 0, int row_end = -1,
+                      const cm_pq_blocks* blocks = nullptr);   // blocks: also write the solver's stencil form
 
 // cm_pqsolver.cu
 size_t pqs_workspace_bytes(int nx, int ny, int restart);
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
-              void* ws, size_t ws_bytes, cudaStream_t st);
+              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready = false);
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
               int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
                    const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st,
-                   int Ld_forced = -1);
+                   int Ld_forced = -1, bool blocks_ready = false);
 void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const cm_dist* D);
 int pqs_destroy(void* ctx);
-int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st);
+int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st,
+                  bool blocks_ready = false);   // blocks_ready: the stencil blocks were written by the assembly sweep
+int pqs_ctx_blocks(void* ctx, cm_pq_blocks* out);
+int apply_dirichlet_blocks(int nrows, const int* rows, int nv, const cm_pq_blocks& blk, cudaStream_t st);
 int pqs_ctx_solve(void* ctx, const double* b, double* x, double rtol, double atol, int maxit, int* iters,
                   double* resid, cudaStream_t st);
 int pqs_ctx_info(void* ctx, int* out8);

@@ -315,7 +315,8 @@ int mg_zebra_mid(int mode, int nx, int ny, int colour, const double* A, const do
     J.nlines = ny / 2;
     const int grid = ny / 2 + 1;   // one CTA per even row
     zebra_mid_kernel<2><<<grid, 2 * J.tl, mid_smem(n1, 2, true), st>>>(J);
-    // every odd line twice (L2 traffic), the even rows once, the coarse right-hand side
+    // algorithmic bytes: every odd line ONCE (the duplicate solve of each odd line is L2 traffic the fusion pays,
+    // not compulsory traffic), the even rows once, the coarse right-hand side
     CM_BYTES((double)(ny / 2) * n1 * 80.0 + (double)(ny / 2 + 1) * n1 * 80.0 + (double)grid * ((nx >> 1) + 1) * 8.0);
   } else {
     J.colour = mode == 3 ? 0 : colour;

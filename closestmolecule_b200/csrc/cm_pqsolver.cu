@@ -337,7 +337,7 @@ size_t pqs_workspace_bytes(int nx, int ny, int restart) {
 static double* align_ws(void* ws) { return (double*)(((uintptr_t)ws + 63) & ~(uintptr_t)63); }
 
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
-              void* ws, size_t ws_bytes, cudaStream_t st) {
+              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready) {
   PQSolver S;
   int rc = pqs_layout(S, nx, ny, restart, align_ws(ws), read_knobs());
   if (rc) return rc;
@@ -348,8 +348,9 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
   CM_CUDA(cudaMemsetAsync(S.has_extra, 0, sizeof(int), st));
   int wide = 0;
-  if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err, st, 0,
-                              -1, S.QQx, S.has_extra, &wide)))
+  // blocks_ready: the assembly sweep wrote PP / PQ / QP / QQ / sp / sq itself (7-point pattern by construction)
+  if (!blocks_ready && (rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err, st, 0,
+                                               -1, S.QQx, S.has_extra, &wide)))
     return rc;
   if (wide && (rc = st_lump_extras(nx, ny, S.QQ, S.QQx, S.QQl, st))) return rc;
   for (int l = 0; l < S.nlev; ++l) {
@@ -519,7 +520,8 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
 }
 
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
-                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st, int Ld_forced) {
+                   const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st, int Ld_forced,
+                   bool blocks_ready) {
   PQSolver S;
   double* base = align_ws(ws);
   int rc = pqs_layout(S, nx, ny, restart, base, read_knobs());
@@ -544,8 +546,8 @@ int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* n
     }
   CM_CUDA(cudaMemsetAsync(S.err, 0, sizeof(int), st));
   CM_CUDA(cudaMemsetAsync(S.has_extra, 0, sizeof(int), st));
-  if ((rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err,
-                              st, I.rb[0], I.re[0])))  // 7-point rows only on the multi-GPU path
+  if (!blocks_ready && (rc = st_extract_blocks(nx, ny, nrowptr, ncol, vals, S.PP, S.PQ, S.QP, S.QQ, S.sp, S.sq, S.err,
+                                               st, I.rb[0], I.re[0])))  // 7-point rows only on the multi-GPU path
     return rc;
   for (int l = 0; l < I.Ld; ++l) {
     PQSLevel& L = S.lev[l];
@@ -835,22 +837,33 @@ static int pqc_pack_f32(PQContext* C, cudaStream_t st) {
   return CM_OK;
 }
 
-int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st) {
+int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st,
+                  bool blocks_ready) {
   PQContext* C = static_cast<PQContext*>(ctx);
   PQSolver& S = C->S;
   int rc;
   if (!C->dist) {
     // same operator hierarchy as the first generation (the kernels of the cycle differ, the factors do not)
-    if ((rc = pqs_setup(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, st))) return rc;
+    if ((rc = pqs_setup(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, st, blocks_ready))) return rc;
     int wide = 0;
-    CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CM_CUDA(cudaStreamSynchronize(st));
+    if (!blocks_ready) {
+      CM_CUDA(cudaMemcpyAsync(&wide, S.has_extra, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CM_CUDA(cudaStreamSynchronize(st));
+    }
     C->wide = wide;
     return wide ? (int)CM_OK : pqc_pack_f32(C, st);
   }
-  if ((rc = pqs_setup_dist(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, &C->D, st, C->I.Ld)))
+  if ((rc = pqs_setup_dist(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, &C->D, st, C->I.Ld,
+                           blocks_ready)))
     return rc;
   return pqc_pack_f32(C, st);
+}
+
+int pqs_ctx_blocks(void* ctx, cm_pq_blocks* out) {
+  PQContext* C = static_cast<PQContext*>(ctx);
+  const PQSolver& S = C->S;
+  out->PP = S.PP; out->PQ = S.PQ; out->QP = S.QP; out->QQ = S.QQ; out->sp = S.sp; out->sq = S.sq;
+  return CM_OK;
 }
 
 // one V-cycle on the p-block, level l: x = approx. A_l^{-1} b

@@ -213,7 +213,7 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
                 const double2* __restrict__ coords, const int* __restrict__ nrowptr,
                 const double2* __restrict__ u, const double* __restrict__ p_old,
                 const double2* __restrict__ load, double* __restrict__ vals,
-                double2* __restrict__ b) {
+                double2* __restrict__ b, const cm_pq_blocks blk) {
   extern __shared__ double sm[];  // 2 row buffers x kAccPerVertex x kTX
   const int tid = threadIdx.x;
   const bool isB = tid >= kTX;
@@ -315,17 +315,35 @@ pq_sweep_kernel(const cm_pq_params P, const int nx, const int ny, const int rows
         double2* row = reinterpret_cast<double2*>(vals + 4 * (size_t)rp) + (isB ? deg : 0);
         const int e0 = isB ? 2 : 0;
         int k = 0;
+        // optional second copy of the row in the stencil form of the linear solver (cm_pq_blocks: diagonals
+        // [7][nv], slot s = this loop's s) + the row equilibration 1 / max |entry|: what cm_pqs_ctx_setup would
+        // otherwise extract from `vals` in a pass of its own
+        const bool wblk = blk.PP != nullptr;
+        const size_t nvb = (size_t)n1 * (ny + 1);
+        double* __restrict__ B0 = isB ? blk.QP : blk.PP;
+        double* __restrict__ B1 = isB ? blk.QQ : blk.PQ;
+        double rmax = 0.0;
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
           const int dx = (s == 0 || s == 2) ? -1 : ((s == 4 || s == 6) ? 1 : 0);
           const int dy = (s < 2) ? -1 : (s > 4 ? 1 : 0);
           const int jx = vx + dx, jy = jq + dy;
-          if (jx < 0 || jx > nx || jy < 0 || jy > ny) continue;
-          row[k] = make_double2(accLo[(4 * s + e0) * kTX + t], accLo[(4 * s + e0 + 1) * kTX + t]);
+          if (jx < 0 || jx > nx || jy < 0 || jy > ny) {
+            if (wblk) { B0[(size_t)s * nvb + v] = 0.0; B1[(size_t)s * nvb + v] = 0.0; }
+            continue;
+          }
+          const double a0 = accLo[(4 * s + e0) * kTX + t], a1 = accLo[(4 * s + e0 + 1) * kTX + t];
+          row[k] = make_double2(a0, a1);
+          if (wblk) {
+            B0[(size_t)s * nvb + v] = a0;
+            B1[(size_t)s * nvb + v] = a1;
+            rmax = fmax(rmax, fmax(fabs(a0), fabs(a1)));
+          }
           accLo[(4 * s + e0) * kTX + t] = 0.0;
           accLo[(4 * s + e0 + 1) * kTX + t] = 0.0;
           ++k;
         }
+        if (wblk) (isB ? blk.sq : blk.sp)[v] = rmax > 0.0 ? 1.0 / rmax : 1.0;
       }
     }
   }
@@ -335,7 +353,7 @@ template <int NQ, int GKIND, bool QGEN>
 static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                         const int* nrowptr, const double* u, const double* p_old,
                         const double* load, double* vals, double* b, cudaStream_t st, int row_begin,
-                        int row_end) {
+                        int row_end, const cm_pq_blocks& blk) {
   if (row_end < 0) { row_begin = 0; row_end = ny + 1; }
   const int nrows = row_end - row_begin;
   if (nrows <= 0) return CM_OK;
@@ -368,13 +386,14 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, true>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, row_begin, row_end, (const double2*)coords, nrowptr, (const double2*)u,
-                                  p_old, (const double2*)load, vals, (double2*)b);
+                                  p_old, (const double2*)load, vals, (double2*)b, blk);
+    if (blk.PP != nullptr) CM_BYTES((double)nrows * (nx + 1) * (28 * 8.0 + 16.0));   // stencil blocks + scalings
     prof_end(kProfAssembly, st);
   } else {
     auto kern = pq_sweep_kernel<NQ, GKIND, QGEN, false>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 2 * kTX, smem, st>>>(P, nx, ny, rows, row_begin, row_end, (const double2*)coords, nrowptr, (const double2*)u,
-                                  p_old, (const double2*)load, vals, (double2*)b);
+                                  p_old, (const double2*)load, vals, (double2*)b, cm_pq_blocks{});
   }
   CM_LAUNCH_CHECK();
   return CM_OK;
@@ -382,14 +401,16 @@ static int launch_sweep(const cm_pq_params& P, int nx, int ny, const double* coo
 
 int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coords,
                       const int* nrowptr, const double* u, const double* p_old, const double* load,
-                      double* vals, double* b, cudaStream_t st, int row_begin, int row_end) {
+                      double* vals, double* b, cudaStream_t st, int row_begin, int row_end,
+                      const cm_pq_blocks* blocks) {
   const int nq = nq_of_degree(P.degree);
+  const cm_pq_blocks blk = (blocks != nullptr && vals != nullptr) ? *blocks : cm_pq_blocks{};
   const bool plain = P.q_react == 0.0 && P.q_adv == 1.0 && P.q_x2p == 1.0 && P.q_x2q == 0.0 &&
                      P.q_divr == 0.0 && P.q_ibp == 0.0 && P.supg_stab == 0.0;
 #define CM_SW(NQ_, GK_)                                                                          \
   if (nq == NQ_ && P.gkind == GK_)                                                               \
-    return plain ? launch_sweep<NQ_, GK_, false>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end) \
-                 : launch_sweep<NQ_, GK_, true>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end);
+    return plain ? launch_sweep<NQ_, GK_, false>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end, blk) \
+                 : launch_sweep<NQ_, GK_, true>(P, nx, ny, coords, nrowptr, u, p_old, load, vals, b, st, row_begin, row_end, blk);
   CM_SW(6, CM_G_NONE)
   CM_SW(6, CM_G_POWER)
   CM_SW(6, CM_G_GSTAR)

@@ -135,15 +135,33 @@ class DistributedPQNewton:
         self.history = []
         self.phase_events = None
 
+    def _blocks(self):
+        """the solver's stencil blocks, written by the assembly sweep itself (CM_ASSEMBLE_BLOCKS=0: extracted in setup)"""
+        import os
+        if os.environ.get("CM_ASSEMBLE_BLOCKS", "1") == "0":
+            return None
+        if getattr(self, "_blk", None) is None:
+            self._blk = _capi.PQBlocksC()
+            _capi.check(self.lib.cm_pqs_ctx_blocks(self.pqs, C.byref(self._blk)))
+        return self._blk
+
     def _assemble(self, want_jac):
         ctx, asm, form, mesh = self.ctx, self.asm, self.form, self.mesh
         ctx.exchange_state()
         p_old = form.p_old.vector() if form.p_old is not None else None
-        _capi.check(self.lib.cm_assemble_pq_cells_structured_rows(
-            C.byref(form.params), mesh.nx, mesh.ny, _capi.ptr(mesh.coords), _capi.ptr(asm.topo.nrowptr),
-            _capi.ptr(self.u), _capi.ptr(p_old), _capi.ptr(asm.load), _capi.ptr(asm.vals) if want_jac else None,
-            _capi.ptr(asm.b), ctx.rb, ctx.re, _capi.stream_ptr()))
-        asm.apply_bcs(self.bc, self.u, with_matrix=want_jac)
+        blk = self._blocks() if want_jac else None
+        if blk is not None:
+            _capi.check(self.lib.cm_assemble_pq_cells_structured_blocks(
+                C.byref(form.params), mesh.nx, mesh.ny, _capi.ptr(mesh.coords), _capi.ptr(asm.topo.nrowptr),
+                _capi.ptr(self.u), _capi.ptr(p_old), _capi.ptr(asm.load), _capi.ptr(asm.vals), _capi.ptr(asm.b),
+                C.byref(blk), ctx.rb, ctx.re, _capi.stream_ptr()))
+        else:
+            _capi.check(self.lib.cm_assemble_pq_cells_structured_rows(
+                C.byref(form.params), mesh.nx, mesh.ny, _capi.ptr(mesh.coords), _capi.ptr(asm.topo.nrowptr),
+                _capi.ptr(self.u), _capi.ptr(p_old), _capi.ptr(asm.load), _capi.ptr(asm.vals) if want_jac else None,
+                _capi.ptr(asm.b), ctx.rb, ctx.re, _capi.stream_ptr()))
+        asm.apply_bcs(self.bc, self.u, with_matrix=want_jac, blocks=blk)
+        return blk is not None
 
     def residual_norm(self):
         self._assemble(False)
@@ -162,11 +180,14 @@ class DistributedPQNewton:
                 e.record()
                 marks.append(e)
         mark()
-        self._assemble(True)
+        blocks_ready = self._assemble(True)
         mark()
         t = asm.topo
-        _capi.check(self.lib.cm_pqs_ctx_setup(self.pqs, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(asm.vals),
-                                              _capi.stream_ptr()))
+        if blocks_ready:
+            _capi.check(self.lib.cm_pqs_ctx_setup_from_blocks(self.pqs, _capi.stream_ptr()))
+        else:
+            _capi.check(self.lib.cm_pqs_ctx_setup(self.pqs, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol), _capi.ptr(asm.vals),
+                                                  _capi.stream_ptr()))
         mark()
         it, rr = C.c_int32(0), C.c_double(0.0)
         rc = self.lib.cm_pqs_ctx_solve(self.pqs, _capi.ptr(asm.b), _capi.ptr(self.dx), self.rtol_lin, 0.0,

@@ -60,7 +60,21 @@ class StructuredPQLinearSolver:
                 "coarse_cluster", "graphs", "wide_q_block")
         return dict(zip(keys, list(out)))
 
-    def setup(self):
+    def blocks(self):
+        """Where the assembly sweep may write the stencil form of the Jacobian (None: extract it in setup).
+        CM_ASSEMBLE_BLOCKS=0 keeps the extraction pass."""
+        import os
+        if os.environ.get("CM_ASSEMBLE_BLOCKS", "1") == "0" or not getattr(self.asm, "writes_blocks", lambda: False)():
+            return None
+        if getattr(self, "_blocks", None) is None:
+            self._blocks = _capi.PQBlocksC()
+            _capi.check(self.lib.cm_pqs_ctx_blocks(self.ctx, C.byref(self._blocks)))
+        return self._blocks
+
+    def setup(self, blocks_ready=False):
+        if blocks_ready:
+            _capi.check(self.lib.cm_pqs_ctx_setup_from_blocks(self.ctx, _capi.stream_ptr()))
+            return
         t = self.asm.topo
         _capi.check(self.lib.cm_pqs_ctx_setup(self.ctx, _capi.ptr(t.nrowptr), _capi.ptr(t.ncol),
                                               _capi.ptr(self.asm.vals), _capi.stream_ptr()))
@@ -342,10 +356,18 @@ class NonlinearVariationalSolver:
                 e.record()
                 marks.append(e)
         mark()
-        asm.assemble(u, want_jac=True)
-        mark()
-        asm.apply_bcs(self._bc, u, with_matrix=True)
-        lin.setup()
+        # structured P-Q path: the sweep writes the solver's stencil blocks next to the CSR values (no extraction pass)
+        blk = lin.blocks() if hasattr(lin, "blocks") else None
+        if blk is not None:
+            asm.assemble(u, want_jac=True, blocks=blk)
+            mark()
+            asm.apply_bcs(self._bc, u, with_matrix=True, blocks=blk)
+            lin.setup(blocks_ready=True)
+        else:
+            asm.assemble(u, want_jac=True)
+            mark()
+            asm.apply_bcs(self._bc, u, with_matrix=True)
+            lin.setup()
         mark()
         ok = lin.solve(asm.b, self._dx, kp["relative_tolerance"], kp["absolute_tolerance"],
                        kp["maximum_iterations"])

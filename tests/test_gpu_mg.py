@@ -314,6 +314,64 @@ def _supg_solver(nx, ny, restart=40):
     return asm, (lambda: StructuredPQLinearSolver(asm, restart=restart))
 
 
+@pytest.mark.parametrize("nx,ny", [(40, 24), (256, 128), (300, 130)])
+def test_sweep_writes_the_solver_blocks(nx, ny):
+    """The assembly sweep can write the stencil form of the Jacobian and the row scalings straight into the solver
+    workspace (cm_assemble_pq_cells_structured_blocks + cm_apply_dirichlet_blocks): bit-identical to what
+    cm_pqs_ctx_setup extracts from the CSR values, and the solve through cm_pqs_ctx_setup_from_blocks gives the
+    same iterations and the same answer."""
+    import ctypes as C
+    from closestmolecule_b200.manufactured import p_exact, q_exact
+    from closestmolecule_b200.solver import StructuredPQLinearSolver
+    P1 = cm.FiniteElement("CG", "triangle", 1)
+    mesh = cm.RectangleMesh(cm.Point(0, 0), cm.Point(1, 1), nx, ny)
+    V = cm.FunctionSpace(mesh, cm.MixedElement([P1, P1]))
+    bd = cm.MeshFunction("size_t", mesh, 1, 0)
+    cm.CompiledSubDomain("near(x[0],0) && on_boundary").mark(bd, 31)
+    form = cm.PQPrimalForm.manufactured(V, "supg")
+    bcs = [cm.DirichletBC(V.sub(0), p_exact, "on_boundary"), cm.DirichletBC(V.sub(1), q_exact, bd, 31)]
+    s = cm.NonlinearVariationalSolver(cm.NonlinearVariationalProblem(form, cm.Function(V), bcs))
+    asm = s.asm
+    X = mesh.coords
+    u = torch.empty(2 * mesh.num_vertices(), dtype=torch.float64, device=mesh.device)
+    u[0::2] = p_exact(X[:, 0], X[:, 1])
+    u[1::2] = q_exact(X[:, 0], X[:, 1]) * (1 + 1e-3 * torch.sin(7 * X[:, 0] + 3 * X[:, 1]))
+    bc = asm._bc_tables(bcs)
+    lin = StructuredPQLinearSolver(asm, restart=40)
+    blk = lin.blocks()
+    assert blk is not None and asm.writes_blocks()
+    nv = mesh.num_vertices()
+    base = lin.ws.data_ptr()
+
+    def view(p, n):
+        off = p - base
+        assert 0 <= off and off + 8 * n <= lin.ws.numel() and off % 8 == 0
+        return lin.ws[off:off + 8 * n].view(torch.float64)
+
+    names = ("PP", "PQ", "QP", "QQ", "sp", "sq")
+    arrs = {k: view(getattr(blk, k), (7 if len(k) == 2 and k[0] in "PQ" and k[1] in "PQ" else 1) * nv) for k in names}
+    for a in arrs.values():
+        a.fill_(float("nan"))
+    asm.assemble(u, True, blocks=blk)
+    asm.apply_bcs(bc, u, True, blocks=blk)
+    got = {k: a.clone() for k, a in arrs.items()}
+    assert all(torch.isfinite(a).all() for a in got.values())
+    lin.setup(blocks_ready=True)
+    dx1 = torch.zeros_like(asm.b)
+    assert lin.solve(asm.b, dx1, 1e-11, 0.0, 200)
+    it1 = lin.last_iterations
+    # the extraction path on the same CSR values
+    for a in arrs.values():
+        a.fill_(float("nan"))
+    lin.setup()
+    for k in names:
+        assert torch.equal(got[k], arrs[k]), k
+    dx2 = torch.zeros_like(asm.b)
+    assert lin.solve(asm.b, dx2, 1e-11, 0.0, 200)
+    assert lin.last_iterations == it1
+    assert torch.equal(dx1, dx2)
+
+
 @pytest.mark.parametrize("nx,ny", [(64, 32), (256, 128), (1024, 512)])
 def test_kernel_generations_agree(nx, ny, monkeypatch):
     """The same Jacobian solved by the first-generation path (two-kernel sweeps, full residual / restriction /
