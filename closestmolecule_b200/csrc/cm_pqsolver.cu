@@ -75,6 +75,9 @@ struct PQKnobs {
   int coarse_smem = 1;      // shared-memory resident cycle (one CTA) from the first level whose arrays fit
   int q_concurrent = 1;     // q-block sweeps on a second stream, concurrently with the p-block V-cycle
   int post_coarse = -1;     // post-smoothing sweeps on the levels >= coarse_from (-1: same as post)
+  int post_smem = 1;        // post-smoothing sweeps inside the shared-memory resident cycle (65 x 33 and coarser at 16 Mi
+                            // cells): 1 instead of 2 keeps the 11 GMRES iterations and shortens the cycle by ~10 us; on the
+                            // levels above it costs an iteration (measured, profiles/README.md)
   int coarse_from = 2;
   int gmres_host = 0;       // diagnostics: second-generation preconditioner under the host-driven GMRES (1 GPU)
   int precond_v1 = 0;       // diagnostics: first-generation preconditioner under the device-resident GMRES (1 GPU)
@@ -111,6 +114,7 @@ static PQKnobs read_knobs() {
   K.coarse_smem = env_int("CM_COARSE_SMEM", 1, 0);
   K.q_concurrent = env_int("CM_Q_CONCURRENT", 1, 0);
   K.post_coarse = env_int("CM_MG_POST_COARSE", -1, 1);
+  K.post_smem = env_int("CM_MG_POST_SMEM", 1, 1);
   K.coarse_from = env_int("CM_MG_COARSE_FROM", 2, 0);
   K.gmres_host = env_int("CM_GMRES_HOST", 0, 0);
   K.precond_v1 = env_int("CM_PRECOND_V1", 0, 0);
@@ -882,7 +886,8 @@ static int vcycle2(PQContext* C, int l, const double* b, double* x, cudaStream_t
     CoarseCycle cc{};
     cc.nlev = S.nlev - l;
     cc.pre = S.pre_smooth;
-    cc.post = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse : S.post_smooth;
+    cc.post = (C->K.post_coarse > 0 && l >= C->K.coarse_from) ? C->K.post_coarse
+              : (l >= C->Lsm && C->Lsm >= 2 && C->K.post_smem < S.post_smooth ? C->K.post_smem : S.post_smooth);
     cc.Ainv = S.dense_coarse ? S.Ainv : nullptr;
     for (int k = 0; k < cc.nlev; ++k) {
       const PQSLevel& Lk = S.lev[l + k];
