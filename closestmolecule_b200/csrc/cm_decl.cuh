@@ -135,6 +135,7 @@ int st_residual(int nx, int ny, const double* A, const double* b, const double* 
 int st_restrict(int nxc, int nyc, const double* rf, double* rc, cudaStream_t st, int R0 = 0, int R1 = -1);
 int st_prolong_add(int nxc, int nyc, const double* ec, double* xf, cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st, int R0 = 0, int R1 = -1);
+int st_init_attributes();
 int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
                    cudaStream_t st, int r0 = 0, int r1 = -1);
 int st_zebra(int nx, int ny, int colour, const double* A, const double* lf, const double* iu,
@@ -154,12 +155,12 @@ int assemble_pq_sweep(const cm_pq_params& P, int nx, int ny, const double* coord
 // cm_pqsolver.cu
 size_t pqs_workspace_bytes(int nx, int ny, int restart);
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
-              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready = false);
+              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready = false, bool no_check = false);
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
               int maxit, void* ws, size_t ws_bytes, int* iters, double* resid, cudaStream_t st);
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
                    const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st,
-                   int Ld_forced = -1, bool blocks_ready = false);
+                   int Ld_forced = -1, bool blocks_ready = false, bool no_check = false);
 void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const cm_dist* D);
 int pqs_destroy(void* ctx);
 int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st,

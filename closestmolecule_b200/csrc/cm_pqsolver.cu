@@ -85,6 +85,7 @@ struct PQKnobs {
   int mid_fuse = 1;         // ... with the restricted residual / the prolongation folded into the half sweeps
   int fuse_unscale = 1;     // the GMRES update kernel writes the next preconditioner input (no separate unscaling pass)
   int f32_op = 1;           // long-line smoother: operator streams from the fp32 pack (x, b and all arithmetic stay fp64)
+  int graph_setup = 1;      // replay the solver setup behind a block-writing assembly as one CUDA graph
   int graph_while = 1;      // a whole GMRES cycle as ONE graph launch (WHILE node around the iteration, condition set on the device)
   int q_low_priority = 1;   // the q-block stream gets the lowest priority: its sweeps fill the SMs / the HBM time the p-block
                             // V-cycle leaves idle on its latency-bound coarse levels instead of competing with its fine sweeps
@@ -122,6 +123,7 @@ static PQKnobs read_knobs() {
   K.mid_fuse = env_int("CM_MID_FUSE", 1, 0);
   K.fuse_unscale = env_int("CM_FUSE_UNSCALE", 1, 0);
   K.f32_op = env_int("CM_F32_OP", 1, 0);
+  K.graph_setup = env_int("CM_GRAPH_SETUP", 1, 0);
   K.graph_while = env_int("CM_GRAPH_WHILE", 1, 0);
   K.q_low_priority = env_int("CM_Q_LOW_PRIORITY", 1, 0);
   return K;
@@ -341,7 +343,7 @@ size_t pqs_workspace_bytes(int nx, int ny, int restart) {
 static double* align_ws(void* ws) { return (double*)(((uintptr_t)ws + 63) & ~(uintptr_t)63); }
 
 int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, const double* vals,
-              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready) {
+              void* ws, size_t ws_bytes, cudaStream_t st, bool blocks_ready, bool no_check) {
   PQSolver S;
   int rc = pqs_layout(S, nx, ny, restart, align_ws(ws), read_knobs());
   if (rc) return rc;
@@ -376,7 +378,7 @@ int pqs_setup(int nx, int ny, int restart, const int* nrowptr, const int* ncol, 
     PQSLevel& QC = S.qlev[S.nlev - 1];
     if (S.dense_coarse && (rc = st_coarse_invert(QC.nx, QC.ny, QC.A, S.Mwork, S.qAinv, S.err, st))) return rc;
   }
-  return check_err_flag(S, st, "cm_pqs_setup");
+  return no_check ? (int)CM_OK : check_err_flag(S, st, "cm_pqs_setup");
 }
 
 int pqs_solve(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
@@ -525,7 +527,7 @@ static int vcycle_dist(PQSolver& S, const DistInfo& I, int l, double* b, double*
 
 int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* ncol,
                    const double* vals, void* ws, size_t ws_bytes, cm_dist* D, cudaStream_t st, int Ld_forced,
-                   bool blocks_ready) {
+                   bool blocks_ready, bool no_check) {
   PQSolver S;
   double* base = align_ws(ws);
   int rc = pqs_layout(S, nx, ny, restart, base, read_knobs());
@@ -584,7 +586,7 @@ int pqs_setup_dist(int nx, int ny, int restart, const int* nrowptr, const int* n
   PQSLevel& C = S.lev[S.nlev - 1];
   if (S.dense_coarse && (rc = st_coarse_invert(C.nx, C.ny, C.A, S.Mwork, S.Ainv, S.err, st))) return rc;
   if ((rc = st_line_factor(nx, ny, S.QQ, S.qlf, S.qiu, S.qcu, S.err, st, I.rb[0], I.re[0]))) return rc;
-  return check_err_flag(S, st, "cm_pqs_setup_dist");
+  return no_check ? (int)CM_OK : check_err_flag(S, st, "cm_pqs_setup_dist");
 }
 
 int pqs_solve_dist(int nx, int ny, int restart, const double* b, double* x, double rtol, double atol,
@@ -697,6 +699,7 @@ struct PQContext {
   cudaStream_t cap = nullptr;
   CachedGraph g_iter, g_final;
   CachedGraph g_cycle;   // [condition] -> WHILE { one GMRES iteration } -> [solve y, x += Z y]
+  CachedGraph g_setup;   // the whole setup behind a block-writing assembly (workspace pointers only: replayable)
   long long cycle_iter_launches = 0, cycle_fixed_launches = 0;
   double cycle_iter_bytes = 0.0, cycle_fixed_bytes = 0.0;
   bool while_ok = true;
@@ -708,6 +711,7 @@ static void pqc_destroy(PQContext* C) {
   C->g_iter.destroy();
   C->g_final.destroy();
   C->g_cycle.destroy();
+  C->g_setup.destroy();
   if (C->cap) cudaStreamDestroy(C->cap);
   if (C->s2) cudaStreamDestroy(C->s2);
   if (C->ev_fork) cudaEventDestroy(C->ev_fork);
@@ -802,7 +806,8 @@ void* pqs_create(int nx, int ny, int restart, void* ws, size_t ws_bytes, const c
       C->K.q_concurrent = 0;
     }
   }
-  if (mg_init_attributes() != CM_OK || mg_mid_init_attributes() != CM_OK || mg_coarse_smem_init_attributes() != CM_OK) {
+  if (mg_init_attributes() != CM_OK || mg_mid_init_attributes() != CM_OK || mg_coarse_smem_init_attributes() != CM_OK ||
+      st_init_attributes() != CM_OK) {
     delete C;
     return nullptr;
   }
@@ -841,11 +846,28 @@ static int pqc_pack_f32(PQContext* C, cudaStream_t st) {
   return CM_OK;
 }
 
+template <class F>
+static int run_cached(PQContext* C, CachedGraph& g, cudaStream_t st, F&& body);
+
 int pqs_ctx_setup(void* ctx, const int* nrowptr, const int* ncol, const double* vals, cudaStream_t st,
                   bool blocks_ready) {
   PQContext* C = static_cast<PQContext*>(ctx);
   PQSolver& S = C->S;
   int rc;
+  if (blocks_ready && C->K.graph_setup) {
+    // the assembly sweep wrote the stencil blocks: everything the setup touches lives in the workspace, so the
+    // ~35 small launches (line factors, Galerkin products, packs, ghost rows of the operator, coarse inverse) are
+    // one cached graph; only the error flag is read back afterwards
+    rc = run_cached(C, C->g_setup, st, [&](cudaStream_t s_) -> int {
+      int e = C->dist ? pqs_setup_dist(C->nx, C->ny, C->restart, nullptr, nullptr, nullptr, C->ws, C->ws_bytes, &C->D, s_,
+                                       C->I.Ld, true, true)
+                      : pqs_setup(C->nx, C->ny, C->restart, nullptr, nullptr, nullptr, C->ws, C->ws_bytes, s_, true, true);
+      return e ? e : pqc_pack_f32(C, s_);
+    });
+    if (rc) return rc;
+    C->wide = 0;
+    return check_err_flag(S, st, "cm_pqs_ctx_setup");
+  }
   if (!C->dist) {
     // same operator hierarchy as the first generation (the kernels of the cycle differ, the factors do not)
     if ((rc = pqs_setup(C->nx, C->ny, C->restart, nrowptr, ncol, vals, C->ws, C->ws_bytes, st, blocks_ready))) return rc;

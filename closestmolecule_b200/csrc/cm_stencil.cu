@@ -1114,6 +1114,16 @@ int st_rap(int nxc, int nyc, const double* Af, double* Ac, cudaStream_t st, int 
   return CM_OK;
 }
 
+// opt-in shared-memory sizes of the setup kernels, once per process and outside any stream capture (cm_pqs_create)
+int st_init_attributes() {
+  static std::atomic<bool> done{false};
+  if (done.load()) return CM_OK;
+  CM_CUDA(cudaFuncSetAttribute(line_factor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CM_CUDA(cudaFuncSetAttribute(coarse_invert_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  done.store(true);
+  return CM_OK;
+}
+
 int st_line_factor(int nx, int ny, const double* A, double* lf, double* iu, double* cu, int* err,
                    cudaStream_t st, int r0, int r1) {
   if (r1 < 0) { r0 = 0; r1 = ny + 1; }
