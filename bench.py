@@ -148,7 +148,11 @@ def workload_config(args, nx, ny):
     cells = 2 * nx * ny
     variant = getattr(args, "variant", "supg").upper()
     solver = ("pivoting banded LU (cm_blu_*) + 1 refinement step" if getattr(args, "linear_solver", "gmres") == "lu"
-              else f"GMRES({RESTART}) + field split + V(1,2) multigrid / zebra line relaxation")
+              else f"flexible GMRES({RESTART}) on the fp64 operator + field split + V(1,2) multigrid / zebra line relaxation"
+                   + ("" if os.environ.get("CM_F32_OP", "1") == "0" else
+                      "; preconditioner detail: the long-line smoother reads its off-line diagonals and line factors "
+                      "from an fp32 copy (x, b, residuals, transfers, Galerkin products, Krylov vectors and every "
+                      "product / sum are fp64; the solve converges to linear_rtol in the fp64 residual)"))
     if gpus > 1 and not getattr(args, "instances", False):
         kind = "weak scaling: the mesh grows with the GPUs" if getattr(args, "weak", False) else "strong scaling"
         return {"workload": f"P-Q CG1xCG1 manufactured {variant} Newton step on ONE RectangleMesh {nx}x{ny} "
